@@ -1,0 +1,73 @@
+"""Deterministic synthetic inputs for the benchmark and parity configurations.
+
+Pure numpy input generation - no covariance or kriging arithmetic happens here.  Shared by
+`bench.py`, the tests and `tests/golden/make_golden.py` so that every arm sees identical inputs.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def global_grid(res_deg: float) -> tuple[np.ndarray, np.ndarray]:
+    """Cell-centre latitudes / longitudes of a regular global grid (5 deg -> 36 x 72, 1 deg -> 180 x 360)."""
+    lats = np.arange(-90 + res_deg / 2, 90, res_deg, dtype=np.float64)
+    lons = np.arange(-180 + res_deg / 2, 180, res_deg, dtype=np.float64)
+    return lats, lons
+
+
+def ellipse_fields(lats: np.ndarray, lons: np.ndarray, land_mask: bool = False):
+    """Smooth, longitude-periodic ellipse parameter fields (Lx > Ly everywhere), each (nlat, nlon).
+
+    Lx in 900..2700 km, Ly in 600..1200 km, theta in +-0.6 rad, stdev in 0.8..1.2.  With
+    `land_mask` about 30 % of the cells are masked (returned as numpy MaskedArrays).
+    """
+    lon_g, lat_g = np.meshgrid(np.deg2rad(lons), np.deg2rad(lats))
+    Lx = 1800.0 + 900.0 * np.cos(lat_g) * np.cos(2 * lon_g)
+    Ly = 900.0 + 300.0 * np.sin(2 * lat_g) * np.sin(lon_g)
+    theta = 0.6 * np.sin(lon_g) * np.cos(lat_g)
+    stdev = 0.8 + 0.4 * np.cos(lat_g) ** 2
+    if land_mask:
+        land = (np.sin(3 * lon_g + 0.7) * np.cos(2 * lat_g - 0.3) + 0.35 * np.sin(lat_g)) > 0.42
+        Lx, Ly, theta, stdev = (np.ma.masked_where(land, a) for a in (Lx, Ly, theta, stdev))
+    return Lx, Ly, theta, stdev
+
+
+def month_observations(month: int, n_cells: int, n_min: int = 600, n_max: int = 1600):
+    """Observation cells and values for synthetic month `month` (config 2): sorted unique idx, N(0,1) obs."""
+    rng = np.random.default_rng(month)
+    n = int(rng.integers(n_min, n_max + 1))
+    idx = np.sort(rng.choice(n_cells, size=n, replace=False)).astype(np.int64)
+    obs = rng.standard_normal(n)
+    return idx, obs
+
+
+def fixed_observations(seed: int, n_cells: int, n_obs: int):
+    """`n_obs` distinct sorted cells and N(0,1) values (config 4 uses seed 4, n_obs 20 000)."""
+    rng = np.random.default_rng(seed)
+    idx = np.sort(rng.choice(n_cells, size=n_obs, replace=False)).astype(np.int64)
+    return idx, rng.standard_normal(n_obs)
+
+
+def hadcrut_style_error_cov(idx: np.ndarray, nlon: int, seed: int = 7, n_groups: int = 12):
+    """Obs-space (n x n) "HadCRUT-style" error covariance: sum_g s_g^2 1_g 1_g^T + diag(u^2).
+
+    Groups are longitude bands ("platform groups"); s_g ~ U(0.05, 0.2), u ~ U(0.2, 0.4).  Mirrors
+    the block + diagonal structure produced by reference `error_covariance.py:99-186`.
+    """
+    rng = np.random.default_rng(seed)
+    s = rng.uniform(0.05, 0.2, size=n_groups)
+    u = rng.uniform(0.2, 0.4, size=len(idx))
+    g = ((idx % nlon) * n_groups) // nlon
+    E = (g[:, None] == g[None, :]) * (s[g] ** 2)[:, None]
+    E = E + np.diag(u ** 2)
+    return np.ascontiguousarray(E, dtype=np.float64)
+
+
+def full_grid_error_cov(idx: np.ndarray, n_cells: int, nlon: int, seed: int = 7):
+    """Full-grid (M x M) variant: NaN off the observed cells' block and a zero diagonal at
+    unobserved cells, exercising the subset + zero/NaN-diagonal filter (reference kriging.py:94-120)."""
+    E = np.full((n_cells, n_cells), np.nan)
+    E[np.arange(n_cells), np.arange(n_cells)] = 0.0
+    E[np.ix_(idx, idx)] = hadcrut_style_error_cov(idx, nlon, seed)
+    return E

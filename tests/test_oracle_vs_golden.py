@@ -1,0 +1,114 @@
+"""The oracle restatement against the committed golden vectors (CPU only).
+
+Goldens come from the unmodified reference (tests/golden/make_golden.py) and from the reference's
+own GeoStats.jl known-answer file.  Covariance: bit-exact in float64 (same arithmetic order, same
+scipy entry points) - asserted at 1e-13 to allow for a different libm/scipy build on another host.
+"""
+
+import warnings
+
+import numpy as np
+import pytest
+from conftest import from_triu, load_golden, max_norm_rel, max_rel
+
+from glomargridding_b200 import synthetic as synth
+from oracle import (EllipseOracle, extended_inverse, ordinary_kriging, simple_kriging,
+                    stochastic_kriging)
+from oracle.variogram import geostats_setup
+
+SMALL = load_golden("ellipse_small.npz")
+
+
+def _case(name):
+    parts = name.split("_")
+    v = float(parts[0][2:])
+    meth = "Modified_Met_Office" if parts[1] == "mod" else "Met_Office"
+    prec = np.float64 if parts[2] == "f64" else np.float32
+    return v, meth, prec, "masked" in parts, (6000.0 if "maxdist" in parts else None)
+
+
+@pytest.mark.parametrize("name", [str(c) for c in SMALL["cases"]])
+def test_ellipse_small_full_matrix(name):
+    v, meth, prec, masked, max_dist = _case(name)
+    lats, lons = SMALL["lats"], SMALL["lons"]
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons, land_mask=masked)
+    got = EllipseOracle(Lx, Ly, th, sd, lats, lons, v, meth, max_dist, prec).build()
+    want = from_triu(SMALL[name])
+    assert got.dtype == prec and got.shape == want.shape
+    assert max_rel(got, want) <= (1e-13 if prec == np.float64 else 1e-6)
+    assert np.array_equal(got, got.T)
+    if max_dist is not None:
+        assert (want == 0).sum() > 0 and np.array_equal(got == 0, want == 0)
+
+
+@pytest.mark.parametrize("tag,res", [("5deg", 5.0), ("1deg", 1.0)])
+def test_ellipse_sampled_pairs(tag, res):
+    g = load_golden(f"ellipse_pairs_{tag}.npz")
+    lats, lons = synth.global_grid(res)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    for name in [k for k in g.files if k.startswith("nu")]:
+        v = float(name.split("_")[0][2:])
+        meth = "Modified_Met_Office" if name.endswith("_mod") else "Met_Office"
+        o = EllipseOracle(Lx, Ly, th, sd, lats, lons, v, meth)
+        assert max_rel(o.pairs(g["i"], g["j"]), g[name]) <= 1e-13, name
+
+
+def test_geostats_known_answer():
+    """Reference test/test_kriging.py:67-192 (OrdinaryKriging vs GeoStats.jl), default allclose tol."""
+    g = load_golden("geostats_ok.npz")
+    cov, idx, obs = geostats_setup()
+    assert np.array_equal(idx, g["idx"])
+    with np.errstate(all="ignore"):
+        res = ordinary_kriging(cov, idx, obs)
+    assert np.allclose(g["expected"], res["field"].reshape(20, 20))
+
+
+@pytest.mark.parametrize("tag", ["spd", "indef"])
+def test_kriging_small(tag):
+    g = load_golden("kriging_small.npz")
+    cov = g[f"{tag}_cov"]
+    assert (g[f"{tag}_min_eig"] > 0) == (tag == "spd")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sk = simple_kriging(cov, g["idx"], g["obs"], g["E_full"], mean=0.25)
+        ok = ordinary_kriging(cov, g["idx"], g["obs"], g["E_full"])
+        ok0 = ordinary_kriging(cov, g["idx"], g["obs"], None)
+    assert np.array_equal(ok["idx"], g["kept_idx"]) and len(ok["idx"]) == len(g["idx"]) - 1
+    for key, got in [("sk_field", sk["field"]), ("sk_unc", sk["uncertainty"]), ("sk_mask", sk["constraint_mask"]),
+                     ("sk_weights", sk["weights"]), ("ok_field", ok["field"]), ("ok_unc", ok["uncertainty"]),
+                     ("ok_mask", ok["constraint_mask"]), ("ok_weights", ok["weights"]),
+                     ("ok_noE_field", ok0["field"]), ("ok_noE_unc", ok0["uncertainty"])]:
+        assert max_norm_rel(got, g[f"{tag}_{key}"]) <= 1e-11, key
+
+
+def test_kriging_diag_only_variant_matches():
+    g = load_golden("kriging_small.npz")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = ordinary_kriging(g["spd_cov"], g["idx"], g["obs"], g["E_full"], big_temporaries=True)
+        b = ordinary_kriging(g["spd_cov"], g["idx"], g["obs"], g["E_full"], big_temporaries=False)
+    for k in ("uncertainty", "constraint_mask"):
+        assert max_norm_rel(a[k], b[k]) <= 1e-12
+
+
+def test_stochastic_small_injected_draws():
+    g = load_golden("kriging_small.npz")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        st = stochastic_kriging(g["spd_cov"], g["idx"], g["obs"], g["E_full"], simulated_state=g["st_state"],
+                                simulated_obs_noise=g["st_noise"])
+    for key, got in [("st_result", st["result"]), ("st_epsilon", st["epsilon"]),
+                     ("st_gridded_field", st["gridded_field"]), ("st_simulated_grid", st["simulated_grid"]),
+                     ("st_unc", st["uncertainty"]), ("st_mask", st["constraint_mask"]),
+                     ("st_ok_weights", st["weights"]), ("st_sk_weights", st["simple_weights"])]:
+        assert max_norm_rel(got, g[key]) <= 1e-10, key
+
+
+@pytest.mark.parametrize("n", [10, 25, 100])
+def test_extended_inverse(n):
+    g = load_golden("kriging_small.npz")
+    S = g[f"ext_inv_{n}_S"]
+    got = extended_inverse(np.linalg.inv(S))
+    assert np.allclose(got, g[f"ext_inv_{n}"])
+    S_ext = np.block([[S, np.ones((n, 1))], [np.ones((1, n)), 0]])
+    assert np.allclose(got, np.linalg.inv(S_ext))
