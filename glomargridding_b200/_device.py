@@ -1,0 +1,44 @@
+"""Device-buffer plumbing (PyTorch owns every allocation; the C ABI only sees raw pointers)."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import GlomarB200Error
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise GlomarB200Error("glomargridding_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_device(a, dtype=torch.float64) -> torch.Tensor:
+    """numpy / torch (any device) -> contiguous CUDA tensor of `dtype` on the current device."""
+    dev = require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=dtype).contiguous()
+    arr = np.ascontiguousarray(np.ma.getdata(a))
+    return torch.from_numpy(arr).to(device=dev, dtype=dtype, non_blocking=False).contiguous()
+
+
+def to_host(t: torch.Tensor, pinned: bool = True) -> np.ndarray:
+    """CUDA tensor -> numpy array.  Large results land in pinned host memory (torch's caching host
+    allocator reuses the block across calls), which is what keeps D2H at PCIe speed."""
+    if t.device.type != "cuda":
+        return t.numpy()
+    if pinned and t.numel() * t.element_size() >= (1 << 20):
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
+    return t.cpu().numpy()
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()

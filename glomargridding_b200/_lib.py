@@ -1,0 +1,82 @@
+"""ctypes binding of `libglomar_b200.so` (C ABI declared in `include/glomar_b200.h`).
+
+There is no CPU fallback: importing the compute classes on a machine without the built library, or
+calling them without a CUDA device, raises.  Build the library with `python __graft_entry__.py`
+(or `make -C glomargridding_b200/csrc`).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libglomar_b200.so")
+
+_lib = None
+
+
+class GlomarB200Error(RuntimeError):
+    """A libglomar_b200 entry point returned a non-zero status."""
+
+
+def _declare(lib):
+    p, i64, dbl, i32 = c_void_p, c_int64, c_double, c_int
+    sigs = {
+        "gmg_version": (c_int, []),
+        "gmg_strerror": (c_char_p, [c_int]),
+        "gmg_last_cuda_error": (c_int, []),
+        "gmg_ellipse_ws_bytes": (c_int, [i64, POINTER(c_size_t)]),
+        "gmg_ellipse_prepare_f64": (c_int, [p, p, p, p, p, p, i64, dbl, p, c_size_t, p]),
+        "gmg_ellipse_cov_f64": (c_int, [p, i64, i64, i64, dbl, i32, dbl, i32, p, i64, i32, p]),
+        "gmg_ellipse_pairs_f64": (c_int, [p, i64, p, p, i64, dbl, i32, i32, p, p]),
+        "gmg_bessel_kv_f64": (c_int, [dbl, p, i64, i32, p, p]),
+        "gmg_matern_f64": (c_int, [p, dbl, i32, p, i64, p, p]),
+        "gmg_haversine_f64": (c_int, [p, p, i64, i64, i64, p, i64, p]),
+    }
+    optional = {
+        "gmg_gather_obs_f64": (c_int, [p, i64, i64, p, i64, p, i64, p, i64, p, i64, p]),
+        "gmg_potrf_f64": (c_int, [p, i64, i64, p, p, c_size_t, p]),
+        "gmg_potrf_ws_bytes": (c_int, [i64, POINTER(c_size_t)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    for name, (res, args) in optional.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    _ = (c_uint64, np)
+
+
+def lib():
+    """The loaded library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GlomarB200Error(
+                f"{LIB_PATH} not found: build it with `python __graft_entry__.py` "
+                "(glomargridding_b200 has no CPU fallback)"
+            )
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().gmg_strerror(status).decode()
+        raise GlomarB200Error(f"{what} failed with status {status}: {msg}")
+
+
+def exported_symbols() -> list[str]:
+    """Every `gmg_*` symbol declared in include/glomar_b200.h (parsed from the header)."""
+    import re
+
+    header = os.path.join(os.path.dirname(_HERE), "include", "glomar_b200.h")
+    with open(header) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\b(gmg_[a-z0-9_]+)\s*\(", text)))

@@ -1,0 +1,596 @@
+// K1/K2: Paciorek-Schervish non-stationary Matern covariance tiles for sm_100a.
+//
+// Replaces (reference, paths relative to its root):
+//   glomar_gridding/ellipse/covariance.py:205-248  _calculate_covariance (pre-terms, diagonal)
+//   glomar_gridding/ellipse/covariance.py:250-403  the three build strategies + mirror
+//   glomar_gridding/ellipse/covariance.py:405-468  c_ij_anisotropic_array (the pair formula)
+//   glomar_gridding/ellipse/covariance.py:512-654  Sigma rotation, 2x2 det, haversine, displacements
+//
+// Design: one CTA computes one 64x64 tile of C in FP64.  Per-point terms
+// (lat, lon, cos lat / 2, Sigma / 2, stdev * det^(1/4), stdev^2) are packed once per build by
+// `ellipse_prepare_kernel` (64 B per point) and staged in shared memory for the tile's 64 row
+// points and 64 column points.  Each thread owns two adjacent columns (held in registers) and 8
+// rows (broadcast from shared memory), so a warp stores 512 contiguous bytes per row with 16-byte
+// vector stores.  Inside the square diagonal block of a row shard only the upper-triangle tiles are
+// computed; the lower ones are written as the transpose of their mirror tile through a padded
+// shared-memory tile, so the FP64 work is halved and both stores stay coalesced.
+// The formula is sign-symmetric under i <-> j (IEEE add/mul are commutative and the wrap is odd),
+// so the mirrored entries are bit-identical to evaluating them in the reference's i<j orientation.
+//
+// The Matern factor x^nu K_nu(x) / (Gamma(nu) 2^(nu-1)) is evaluated as g(x) e^-x with
+//   nu = 0.5 / 1.5 / 2.5 : g = 1, 1 + x, 1 + x + x^2/3              (closed forms)
+//   otherwise            : g from a piecewise degree-12 polynomial table in the mantissa of x
+//                          (4 linear sub-intervals per octave, 2^-20 <= x < 2^10), built on the
+//                          device from the Temme/CF2 Bessel-K in bessel_k.cuh for the build's nu;
+//                          lanes outside the table range fall back to the direct evaluation.
+#include "gmg_common.cuh"
+#include "bessel_k.cuh"
+#include "../../include/glomar_b200.h"
+
+namespace {
+
+constexpr double kEarthRadiusKm = 6371.0;           // reference constants.py:18
+constexpr double kPi = 3.141592653589793;           // np.pi
+constexpr double kTwoPi = 6.283185307179586;        // 2 * np.pi, reference ellipse/covariance.py:37
+
+constexpr int kTile = 64;
+constexpr int kThreads = 256;
+constexpr int kTileLd = kTile + 1;                  // odd leading dimension: conflict-free transposed reads
+
+// Matern table geometry
+constexpr int kTabEmin = -20;
+constexpr int kTabEmax = 10;                        // exclusive
+constexpr int kTabSub = 4;
+constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 120
+constexpr int kTabDeg = 12;
+constexpr int kTabCoef = kTabDeg + 1;
+constexpr int kTabDoubles = kTabNint * kTabCoef;            // 1560
+
+enum { MODE_NU05 = 0, MODE_NU15 = 1, MODE_NU25 = 2, MODE_TABLE = 3, MODE_DIRECT = 4 };
+
+// packed per-point record, 8 doubles
+enum { P_LAT = 0, P_LON = 1, P_HCOS = 2, P_H00 = 3, P_H01 = 4, P_H11 = 5, P_W = 6, P_VAR = 7, P_N = 8 };
+
+__global__ void __launch_bounds__(256) ellipse_prepare_kernel(
+    const double* __restrict__ Lx, const double* __restrict__ Ly, const double* __restrict__ theta,
+    const double* __restrict__ stdev, const double* __restrict__ lat, const double* __restrict__ lon,
+    int64_t N, double* __restrict__ params) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    // reference `_sigma_rot_func_multi`, ellipse/covariance.py:512-533
+    double st, ct;
+    sincos(theta[i], &st, &ct);
+    const double c2 = ct * ct, s2 = st * st, cs = ct * st;
+    const double lx2 = Lx[i] * Lx[i], ly2 = Ly[i] * Ly[i];
+    const double s00 = __dadd_rn(__dmul_rn(c2, lx2), __dmul_rn(s2, ly2));
+    const double s01 = __dmul_rn(cs, lx2 - ly2);
+    const double s11 = __dadd_rn(__dmul_rn(s2, lx2), __dmul_rn(c2, ly2));
+    const double det = __dsub_rn(__dmul_rn(s00, s11), __dmul_rn(s01, s01));   // :543-547
+    const double sd = stdev[i];
+    double* p = params + i * P_N;
+    p[P_LAT] = lat[i];
+    p[P_LON] = lon[i];
+    p[P_HCOS] = 0.5 * cos(lat[i]);          // 0.5*(cos a + cos b) == 0.5 cos a + 0.5 cos b exactly
+    p[P_H00] = 0.5 * s00;                   // 0.5*(S_i + S_j)   == 0.5 S_i + 0.5 S_j     exactly
+    p[P_H01] = 0.5 * s01;
+    p[P_H11] = 0.5 * s11;
+    p[P_W] = sd * sqrt(sqrt(det));          // stdev_i * det_i^(1/4): sqrt(sqrt_det_i sqrt_det_j) = q_i q_j
+    p[P_VAR] = sd * sd;                     // diagonal, :246
+}
+
+// One block per table interval: sample g at Chebyshev nodes, transform to monomial coefficients in
+// t = (m - c_k) * 8 in [-1, 1] where m in [1, 2) is the mantissa of x and c_k the sub-interval centre.
+__global__ void __launch_bounds__(32) matern_table_kernel(GmgBesselConsts bc, double* __restrict__ table) {
+    __shared__ double f[kTabCoef];
+    __shared__ double cheb[kTabCoef];
+    const int interval = blockIdx.x;
+    const int e = kTabEmin + interval / kTabSub;
+    const int k = interval % kTabSub;
+    const double centre = ldexp(1.125 + 0.25 * k, e);
+    const double halfw = ldexp(0.125, e);
+    const int t = threadIdx.x;
+    if (t < kTabCoef) {
+        const double node = cospi((t + 0.5) / kTabCoef);
+        f[t] = gmg_matern_scaled(bc, centre + halfw * node);
+    }
+    __syncthreads();
+    if (t < kTabCoef) {
+        double acc = 0.0;
+        for (int j = 0; j < kTabCoef; ++j) acc += f[j] * cospi(t * (j + 0.5) / kTabCoef);
+        cheb[t] = acc * (t == 0 ? 1.0 : 2.0) / kTabCoef;
+    }
+    __syncthreads();
+    if (t == 0) {
+        // Chebyshev -> monomial via T_{n+1} = 2 t T_n - T_{n-1}
+        double mono[kTabCoef], tn[kTabCoef], tp[kTabCoef], tmp[kTabCoef];
+        for (int j = 0; j < kTabCoef; ++j) { mono[j] = 0.0; tn[j] = 0.0; tp[j] = 0.0; }
+        tp[0] = 1.0;                   // T_0
+        tn[1] = 1.0;                   // T_1
+        mono[0] += cheb[0];
+        mono[1] += cheb[1];
+        for (int n = 2; n < kTabCoef; ++n) {
+            for (int j = 0; j < kTabCoef; ++j) tmp[j] = (j > 0 ? 2.0 * tn[j - 1] : 0.0) - tp[j];
+            for (int j = 0; j < kTabCoef; ++j) { tp[j] = tn[j]; tn[j] = tmp[j]; mono[j] += cheb[n] * tmp[j]; }
+        }
+        for (int j = 0; j < kTabCoef; ++j) table[j * kTabNint + interval] = mono[j];   // [coef][interval]
+    }
+}
+
+struct MaternCtx {
+    GmgBesselConsts bc;
+    const double* table;   // shared-memory (tile kernel) or global (pairs kernel) pointer, [coef][interval]
+    int geom_f32;          // decide the longitude wrap in float32 like the reference's precision=float32 path
+};
+
+template <int MODE>
+__device__ __forceinline__ double matern_scaled_eval(const MaternCtx& m, double x) {
+    if (MODE == MODE_NU05) return 1.0;
+    if (MODE == MODE_NU15) return 1.0 + x;
+    if (MODE == MODE_NU25) return fma(x, fma(x, 1.0 / 3.0, 1.0), 1.0);
+    if (MODE == MODE_TABLE) {
+        const int hi = __double2hiint(x);
+        const int lo = __double2loint(x);
+        const int idx = ((hi >> 20) - (1023 + kTabEmin)) * kTabSub + ((hi >> 18) & 3);
+        if ((unsigned)idx < (unsigned)kTabNint) {     // also rejects x <= 0, inf, NaN (sign/exponent bits)
+            const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+            const double centre = __hiloint2double(0x3FF20000 | (hi & 0x000C0000), 0);
+            const double t = (mant - centre) * 8.0;
+            const double* c = m.table + idx;
+            double p = c[kTabDeg * kTabNint];
+#pragma unroll
+            for (int k = kTabDeg - 1; k >= 0; --k) p = fma(p, t, c[k * kTabNint]);
+            return p;
+        }
+    }
+    return gmg_matern_scaled(m.bc, x);
+}
+
+struct PointRegs { double lat, lon, hcos, h00, h01, h11, w; };
+
+// The pair formula: reference `c_ij_anisotropic_array`, ellipse/covariance.py:441-466, with
+//   sqrt(sqrt_det_i sqrt_det_j / det) = q_i q_j rsqrt(det)   and   sqrt(Q / det) = sqrt(Q rsqrt(det)^2).
+template <int MODE, int DISP>
+__device__ __forceinline__ double cov_pair(const PointRegs& a, const PointRegs& b, const MaternCtx& m,
+                                           double max_dist) {
+    double dy = a.lat - b.lat;                              // :631 orientation (i) - (j)
+    double dx = a.lon - b.lon;                              // :632 exact IEEE subtract of host radians
+    const double dlon_raw = dx;
+    if (m.geom_f32) {
+        // precision=float32: the reference holds radians as float32 and subtracts / compares / wraps in
+        // float32 (np.pi and TWO_PI are weak scalars), which decides the 180-degree ties differently
+        // from a float64 subtract of the same values.  Inputs here are exactly float32-representable.
+        float d = __fsub_rn((float)a.lon, (float)b.lon);
+        if (d > (float)kPi) d = __fsub_rn(d, (float)kTwoPi);
+        if (d < -(float)kPi) d = __fadd_rn(d, (float)kTwoPi);
+        dx = (double)d;
+        dy = (double)__fsub_rn((float)a.lat, (float)b.lat);
+    } else {
+        if (dx > kPi) dx -= kTwoPi;                         // :633 strict >
+        if (dx < -kPi) dx += kTwoPi;                        // :634 strict <
+    }
+    if (DISP == GMG_DISP_MODIFIED_MET_OFFICE) dx *= (a.hcos + b.hcos);   // :636-637, after the wrap
+    dy *= kEarthRadiusKm;                                   // :639
+    dx *= kEarthRadiusKm;
+    const double s0 = a.h00 + b.h00, s1 = a.h01 + b.h01, s3 = a.h11 + b.h11;   // :451
+    const double det = s0 * s3 - s1 * s1;                   // :452
+    const double r = rsqrt(det);
+    const double q = dx * (dx * s3 - dy * s1) + dy * (dy * s0 - dx * s1);      // :459-461
+    const double t = q * r * r;                             // Q / det
+    const double x = m.bc.two_sqrt_nu * sqrt(t);            // :457 inner = 2 sqrt(nu) tau
+    double c = (a.w * b.w) * r * matern_scaled_eval<MODE>(m, x) * exp(-x);     // :447-455, :465-466
+    if (max_dist >= 0.0) {                                  // :256-266, `_haversine_multi` :572-588
+        const double sl = sin(0.5 * (a.lat - b.lat)), so = sin(0.5 * dlon_raw);
+        const double h = sl * sl + (2.0 * a.hcos) * (2.0 * b.hcos) * so * so;
+        if (kEarthRadiusKm * (2.0 * asin(sqrt(h))) > max_dist) c = 0.0;
+    }
+    return c;
+}
+
+struct EllipseArgs {
+    const double* params;
+    const double* table;
+    void* out;
+    int64_t N, row0, nrows, ld;
+    int tiles_r, tiles_c, tile_b0, symmetric;
+    int64_t n_tri;
+    double max_dist;
+    int vec2;
+    int geom_f32;
+    GmgBesselConsts bc;
+};
+
+template <typename OutT> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+template <typename OutT>
+__device__ __forceinline__ void store_pair(OutT* p, double v0, double v1, bool second, bool vec2) {
+    if (vec2 && second) {
+        typename Vec2<OutT>::type v;
+        v.x = (OutT)v0;
+        v.y = (OutT)v1;
+        *reinterpret_cast<typename Vec2<OutT>::type*>(p) = v;
+    } else {
+        p[0] = (OutT)v0;
+        if (second) p[1] = (OutT)v1;
+    }
+}
+
+template <int MODE, int DISP, typename OutT>
+__global__ void __launch_bounds__(kThreads, 2) ellipse_cov_tile_kernel(const EllipseArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    double* rowp = smem;                              // [P_N][kTile]
+    double* colp = rowp + P_N * kTile;                // [P_N][kTile]
+    double* tileT = colp + P_N * kTile;               // [kTile][kTileLd]
+    double* stab = tileT + kTile * kTileLd;           // [kTabCoef][kTabNint] (MODE_TABLE only)
+
+    // ---- which tile -------------------------------------------------------------------------
+    int ta, tb;
+    bool mirror = false;
+    {
+        const int64_t id = blockIdx.x;
+        if (a.symmetric) {
+            if (id < a.n_tri) {
+                // row-major upper triangle of the tiles_r x tiles_r diagonal block
+                const double n2 = 2.0 * a.tiles_r + 1.0;
+                int r = (int)floor((n2 - sqrt(n2 * n2 - 8.0 * (double)id)) * 0.5);
+                auto off = [&](int rr) { return (int64_t)rr * a.tiles_r - (int64_t)rr * (rr - 1) / 2; };
+                while (r > 0 && off(r) > id) --r;
+                while (off(r + 1) <= id) ++r;
+                ta = r;
+                const int bp = r + (int)(id - off(r));
+                tb = a.tile_b0 + bp;
+                mirror = bp > r;
+            } else {
+                const int64_t rest = id - a.n_tri;
+                const int wide = a.tiles_c - a.tiles_r;
+                ta = (int)(rest / wide);
+                const int c = (int)(rest % wide);
+                tb = c < a.tile_b0 ? c : c + a.tiles_r;
+            }
+        } else {
+            ta = (int)(id / a.tiles_c);
+            tb = (int)(id % a.tiles_c);
+        }
+    }
+    const int64_t i0 = a.row0 + (int64_t)ta * kTile;   // global index of the tile's first row point
+    const int64_t j0 = (int64_t)tb * kTile;            // global index of the tile's first column point
+    const int64_t row_end = a.row0 + a.nrows;
+
+    // ---- stage per-point terms (AoS in global -> SoA in shared) --------------------------------
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 2 * kTile * P_N; e += kThreads) {
+        const int which = e / (kTile * P_N);           // 0 rows, 1 cols
+        const int rem = e % (kTile * P_N);
+        const int pt = rem / P_N, f = rem % P_N;
+        const int64_t g = (which ? j0 : i0) + pt;
+        const double v = (g < a.N) ? a.params[g * P_N + f] : 1.0;
+        (which ? colp : rowp)[f * kTile + pt] = v;
+    }
+    MaternCtx m;
+    m.bc = a.bc;
+    m.table = stab;
+    m.geom_f32 = a.geom_f32;
+    if (MODE == MODE_TABLE) {
+        for (int e = tid; e < kTabDoubles; e += kThreads) stab[e] = a.table[e];
+    }
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int jl = 2 * lane;
+    PointRegs c0, c1;
+    c0.lat = colp[P_LAT * kTile + jl];     c1.lat = colp[P_LAT * kTile + jl + 1];
+    c0.lon = colp[P_LON * kTile + jl];     c1.lon = colp[P_LON * kTile + jl + 1];
+    c0.hcos = colp[P_HCOS * kTile + jl];   c1.hcos = colp[P_HCOS * kTile + jl + 1];
+    c0.h00 = colp[P_H00 * kTile + jl];     c1.h00 = colp[P_H00 * kTile + jl + 1];
+    c0.h01 = colp[P_H01 * kTile + jl];     c1.h01 = colp[P_H01 * kTile + jl + 1];
+    c0.h11 = colp[P_H11 * kTile + jl];     c1.h11 = colp[P_H11 * kTile + jl + 1];
+    c0.w = colp[P_W * kTile + jl];         c1.w = colp[P_W * kTile + jl + 1];
+    const int64_t gj = j0 + jl;
+    const bool col0_ok = gj < a.N, col1_ok = gj + 1 < a.N;
+    OutT* out = reinterpret_cast<OutT*>(a.out);
+
+#pragma unroll 2
+    for (int r = 0; r < kTile / 8; ++r) {
+        const int il = warp * (kTile / 8) + r;
+        const int64_t gi = i0 + il;
+        PointRegs p;
+        p.lat = rowp[P_LAT * kTile + il];
+        p.lon = rowp[P_LON * kTile + il];
+        p.hcos = rowp[P_HCOS * kTile + il];
+        p.h00 = rowp[P_H00 * kTile + il];
+        p.h01 = rowp[P_H01 * kTile + il];
+        p.h11 = rowp[P_H11 * kTile + il];
+        p.w = rowp[P_W * kTile + il];
+        double v0 = cov_pair<MODE, DISP>(p, c0, m, a.max_dist);
+        double v1 = cov_pair<MODE, DISP>(p, c1, m, a.max_dist);
+        const double var = rowp[P_VAR * kTile + il];
+        if (gi == gj) v0 = var;                       // diagonal = stdev^2, :246
+        if (gi == gj + 1) v1 = var;
+        if (gi < row_end && col0_ok)
+            store_pair<OutT>(out + (gi - a.row0) * a.ld + gj, v0, v1, col1_ok, a.vec2 != 0);
+        if (mirror) {
+            tileT[il * kTileLd + jl] = v0;
+            tileT[il * kTileLd + jl + 1] = v1;
+        }
+    }
+    if (!mirror) return;
+    __syncthreads();
+    // ---- transposed tile: rows j0.. of C, columns i0.. (inside the shard's square block) ----------
+#pragma unroll 2
+    for (int r = 0; r < kTile / 8; ++r) {
+        const int jj = warp * (kTile / 8) + r;
+        const int64_t grow = j0 + jj;                 // global row of the mirrored entry
+        if (grow >= row_end || grow >= a.N) continue;
+        OutT* dst = out + (grow - a.row0) * a.ld + i0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ii = lane + 32 * h;
+            if (i0 + ii < row_end) dst[ii] = (OutT)tileT[ii * kTileLd + jj];
+        }
+    }
+}
+
+template <int MODE, int DISP>
+__global__ void __launch_bounds__(256) ellipse_pairs_kernel(const double* __restrict__ params,
+                                                            const double* __restrict__ table,
+                                                            GmgBesselConsts bc, const int64_t* __restrict__ is,
+                                                            const int64_t* __restrict__ js, int64_t n,
+                                                            double* __restrict__ out) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    MaternCtx m;
+    m.bc = bc;
+    m.table = table;
+    m.geom_f32 = 0;
+    PointRegs a, b;
+    const double* pa = params + is[k] * P_N;
+    const double* pb = params + js[k] * P_N;
+    a.lat = pa[P_LAT]; a.lon = pa[P_LON]; a.hcos = pa[P_HCOS]; a.h00 = pa[P_H00]; a.h01 = pa[P_H01];
+    a.h11 = pa[P_H11]; a.w = pa[P_W];
+    b.lat = pb[P_LAT]; b.lon = pb[P_LON]; b.hcos = pb[P_HCOS]; b.h00 = pb[P_H00]; b.h01 = pb[P_H01];
+    b.h11 = pb[P_H11]; b.w = pb[P_W];
+    out[k] = cov_pair<MODE, DISP>(a, b, m, -1.0);
+}
+
+__global__ void __launch_bounds__(256) bessel_kv_kernel(GmgBesselConsts bc, const double* __restrict__ x,
+                                                        int64_t n, int scaled, double* __restrict__ out) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out[k] = scaled ? gmg_bessel_kve(bc, x[k]) : gmg_bessel_kv(bc, x[k]);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) matern_kernel(GmgBesselConsts bc, const double* __restrict__ table,
+                                                     const double* __restrict__ x, int64_t n,
+                                                     double* __restrict__ out) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    MaternCtx m;
+    m.bc = bc;
+    m.table = table;
+    m.geom_f32 = 0;
+    out[k] = matern_scaled_eval<MODE>(m, x[k]) * exp(-x[k]);
+}
+
+__global__ void __launch_bounds__(256) haversine_kernel(const double* __restrict__ lat,
+                                                        const double* __restrict__ lon, int64_t N,
+                                                        int64_t row0, int64_t nrows, double* __restrict__ D,
+                                                        int64_t ld) {
+    // reference distances.py:191-218 (sklearn haversine_distances * 6371): asin form
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = row0 + blockIdx.y;
+    if (j >= N || blockIdx.y >= nrows) return;
+    const double sl = sin(0.5 * (lat[i] - lat[j])), so = sin(0.5 * (lon[i] - lon[j]));
+    const double h = sl * sl + cos(lat[i]) * cos(lat[j]) * so * so;
+    D[(int64_t)blockIdx.y * ld + j] = kEarthRadiusKm * (2.0 * asin(sqrt(h)));
+}
+
+int resolve_mode(double nu, int matern_mode) {
+    if (matern_mode == GMG_MATERN_DIRECT) return MODE_DIRECT;
+    if (matern_mode == GMG_MATERN_TABLE) return MODE_TABLE;
+    if (nu == 0.5) return MODE_NU05;
+    if (nu == 1.5) return MODE_NU15;
+    if (nu == 2.5) return MODE_NU25;
+    return (nu <= 10.0) ? MODE_TABLE : MODE_DIRECT;   // table accuracy degrades for large nu
+}
+
+// workspace layout: [Matern table, kTabDoubles doubles, padded to 256 B][params, N x 8 doubles]
+constexpr size_t kTableBytes = ((size_t)kTabDoubles * sizeof(double) + 255) / 256 * 256;
+size_t params_bytes(int64_t N) { return gmg_align_up((size_t)N * P_N * sizeof(double), 256); }
+inline const double* ws_table(const void* ws) { return reinterpret_cast<const double*>(ws); }
+inline const double* ws_params(const void* ws) {
+    return reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + kTableBytes);
+}
+
+template <int MODE, int DISP, typename OutT>
+int launch_tiles(const EllipseArgs& a, int64_t n_ctas, cudaStream_t s) {
+    size_t smem = (size_t)(2 * P_N * kTile + kTile * kTileLd) * sizeof(double);
+    if (MODE == MODE_TABLE) smem += (size_t)kTabDoubles * sizeof(double);
+    auto kern = ellipse_cov_tile_kernel<MODE, DISP, OutT>;
+    GMG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)n_ctas, kThreads, smem, s>>>(a);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+template <int MODE, int DISP>
+int launch_tiles_out(const EllipseArgs& a, int64_t n, int f32, cudaStream_t s) {
+    return f32 ? launch_tiles<MODE, DISP, float>(a, n, s) : launch_tiles<MODE, DISP, double>(a, n, s);
+}
+
+template <int MODE>
+int launch_tiles_disp(const EllipseArgs& a, int64_t n, int disp, int f32, cudaStream_t s) {
+    return disp == GMG_DISP_MODIFIED_MET_OFFICE
+               ? launch_tiles_out<MODE, GMG_DISP_MODIFIED_MET_OFFICE>(a, n, f32, s)
+               : launch_tiles_out<MODE, GMG_DISP_MET_OFFICE>(a, n, f32, s);
+}
+
+template <int MODE>
+int launch_pairs_disp(const double* params, const double* table, const GmgBesselConsts& bc, const int64_t* i,
+                      const int64_t* j, int64_t n, int disp, double* out, cudaStream_t s) {
+    const unsigned blocks = (unsigned)gmg_ceil_div(n, 256);
+    if (disp == GMG_DISP_MODIFIED_MET_OFFICE)
+        ellipse_pairs_kernel<MODE, GMG_DISP_MODIFIED_MET_OFFICE><<<blocks, 256, 0, s>>>(params, table, bc, i, j, n, out);
+    else
+        ellipse_pairs_kernel<MODE, GMG_DISP_MET_OFFICE><<<blocks, 256, 0, s>>>(params, table, bc, i, j, n, out);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gmg_ellipse_ws_bytes(int64_t N, size_t* bytes) {
+    if (N <= 0) return -1;
+    if (!bytes) return -2;
+    *bytes = kTableBytes + params_bytes(N);
+    return GMG_OK;
+}
+
+int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* theta, const double* stdev,
+                            const double* lat_rad, const double* lon_rad, int64_t N, double nu, void* ws,
+                            size_t ws_bytes, gmg_stream_t stream) {
+    if (!Lx) return -1;
+    if (!Ly) return -2;
+    if (!theta) return -3;
+    if (!stdev) return -4;
+    if (!lat_rad) return -5;
+    if (!lon_rad) return -6;
+    if (N <= 0) return -7;
+    if (!(nu > 0.0)) return -8;
+    if (!ws) return -9;
+    size_t need;
+    gmg_ellipse_ws_bytes(N, &need);
+    if (ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15)) return GMG_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* params = const_cast<double*>(ws_params(ws));
+    double* table = const_cast<double*>(ws_table(ws));
+    ellipse_prepare_kernel<<<(unsigned)gmg_ceil_div(N, 256), 256, 0, s>>>(Lx, Ly, theta, stdev, lat_rad, lon_rad,
+                                                                           N, params);
+    GMG_LAUNCH_CHECK();
+    const GmgBesselConsts bc = gmg_make_bessel_consts(nu);
+    matern_table_kernel<<<kTabNint, 32, 0, s>>>(bc, table);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, double nu, int disp_method,
+                        double max_dist_km, int matern_mode, void* C_rows, int64_t ld, int store_f32,
+                        gmg_stream_t stream) {
+    if (!ws) return -1;
+    if (N <= 0) return -2;
+    if (row0 < 0 || row0 >= N) return -3;
+    if (nrows <= 0 || row0 + nrows > N) return -4;
+    if (!(nu > 0.0)) return -5;
+    if (disp_method != GMG_DISP_MET_OFFICE && disp_method != GMG_DISP_MODIFIED_MET_OFFICE) return -6;
+    if (matern_mode < 0 || matern_mode > 2) return -8;
+    if (!C_rows) return -9;
+    if (ld < N) return -10;
+    EllipseArgs a;
+    a.params = ws_params(ws);
+    a.table = ws_table(ws);
+    a.out = C_rows;
+    a.N = N; a.row0 = row0; a.nrows = nrows; a.ld = ld;
+    a.tiles_r = (int)gmg_ceil_div(nrows, kTile);
+    a.tiles_c = (int)gmg_ceil_div(N, kTile);
+    a.symmetric = (row0 % kTile == 0) ? 1 : 0;
+    a.tile_b0 = (int)(row0 / kTile);
+    a.n_tri = (int64_t)a.tiles_r * (a.tiles_r + 1) / 2;
+    a.max_dist = (max_dist_km >= 0.0) ? max_dist_km : -1.0;
+    const size_t elt = store_f32 ? sizeof(float) : sizeof(double);
+    a.vec2 = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(C_rows) % (2 * elt)) == 0);
+    a.geom_f32 = store_f32 ? 1 : 0;
+    a.bc = gmg_make_bessel_consts(nu);
+    const int64_t n_ctas = a.symmetric ? a.n_tri + (int64_t)a.tiles_r * (a.tiles_c - a.tiles_r)
+                                       : (int64_t)a.tiles_r * a.tiles_c;
+    if (n_ctas > 0x7fffffffLL) return GMG_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (resolve_mode(nu, matern_mode)) {
+        case MODE_NU05: return launch_tiles_disp<MODE_NU05>(a, n_ctas, disp_method, store_f32, s);
+        case MODE_NU15: return launch_tiles_disp<MODE_NU15>(a, n_ctas, disp_method, store_f32, s);
+        case MODE_NU25: return launch_tiles_disp<MODE_NU25>(a, n_ctas, disp_method, store_f32, s);
+        case MODE_TABLE: return launch_tiles_disp<MODE_TABLE>(a, n_ctas, disp_method, store_f32, s);
+        default: return launch_tiles_disp<MODE_DIRECT>(a, n_ctas, disp_method, store_f32, s);
+    }
+}
+
+int gmg_ellipse_pairs_f64(const void* ws, int64_t N, const int64_t* i, const int64_t* j, int64_t npairs,
+                          double nu, int disp_method, int matern_mode, double* out, gmg_stream_t stream) {
+    if (!ws) return -1;
+    if (N <= 0) return -2;
+    if (!i) return -3;
+    if (!j) return -4;
+    if (npairs < 0) return -5;
+    if (!(nu > 0.0)) return -6;
+    if (disp_method != GMG_DISP_MET_OFFICE && disp_method != GMG_DISP_MODIFIED_MET_OFFICE) return -7;
+    if (matern_mode < 0 || matern_mode > 2) return -8;
+    if (!out) return -9;
+    if (npairs == 0) return GMG_OK;
+    const double* params = ws_params(ws);
+    const double* table = ws_table(ws);
+    const GmgBesselConsts bc = gmg_make_bessel_consts(nu);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (resolve_mode(nu, matern_mode)) {
+        case MODE_NU05: return launch_pairs_disp<MODE_NU05>(params, table, bc, i, j, npairs, disp_method, out, s);
+        case MODE_NU15: return launch_pairs_disp<MODE_NU15>(params, table, bc, i, j, npairs, disp_method, out, s);
+        case MODE_NU25: return launch_pairs_disp<MODE_NU25>(params, table, bc, i, j, npairs, disp_method, out, s);
+        case MODE_TABLE: return launch_pairs_disp<MODE_TABLE>(params, table, bc, i, j, npairs, disp_method, out, s);
+        default: return launch_pairs_disp<MODE_DIRECT>(params, table, bc, i, j, npairs, disp_method, out, s);
+    }
+}
+
+int gmg_bessel_kv_f64(double nu, const double* x, int64_t n, int scaled, double* out, gmg_stream_t stream) {
+    if (!(nu >= 0.0)) return -1;
+    if (!x) return -2;
+    if (n < 0) return -3;
+    if (!out) return -5;
+    if (n == 0) return GMG_OK;
+    bessel_kv_kernel<<<(unsigned)gmg_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        gmg_make_bessel_consts(nu), x, n, scaled, out);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+int gmg_matern_f64(const void* ws, double nu, int matern_mode, const double* x, int64_t n, double* out,
+                   gmg_stream_t stream) {
+    if (!(nu > 0.0)) return -2;
+    if (matern_mode < 0 || matern_mode > 2) return -3;
+    if (!x) return -4;
+    if (n < 0) return -5;
+    if (!out) return -6;
+    if (n == 0) return GMG_OK;
+    const int mode = resolve_mode(nu, matern_mode);
+    if (mode == MODE_TABLE && !ws) return -1;
+    const double* table = ws ? ws_table(ws) : nullptr;   // the table sits at the start of any ellipse workspace
+    const GmgBesselConsts bc = gmg_make_bessel_consts(nu);
+    const unsigned blocks = (unsigned)gmg_ceil_div(n, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (mode) {
+        case MODE_NU05: matern_kernel<MODE_NU05><<<blocks, 256, 0, s>>>(bc, table, x, n, out); break;
+        case MODE_NU15: matern_kernel<MODE_NU15><<<blocks, 256, 0, s>>>(bc, table, x, n, out); break;
+        case MODE_NU25: matern_kernel<MODE_NU25><<<blocks, 256, 0, s>>>(bc, table, x, n, out); break;
+        case MODE_TABLE: matern_kernel<MODE_TABLE><<<blocks, 256, 0, s>>>(bc, table, x, n, out); break;
+        default: matern_kernel<MODE_DIRECT><<<blocks, 256, 0, s>>>(bc, table, x, n, out); break;
+    }
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+int gmg_haversine_f64(const double* lat_rad, const double* lon_rad, int64_t N, int64_t row0, int64_t nrows,
+                      double* D_rows, int64_t ld, gmg_stream_t stream) {
+    if (!lat_rad) return -1;
+    if (!lon_rad) return -2;
+    if (N <= 0) return -3;
+    if (row0 < 0 || row0 >= N) return -4;
+    if (nrows <= 0 || row0 + nrows > N || nrows > 65535) return -5;
+    if (!D_rows) return -6;
+    if (ld < N) return -7;
+    dim3 grid((unsigned)gmg_ceil_div(N, 256), (unsigned)nrows);
+    haversine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lat_rad, lon_rad, N, row0, nrows, D_rows, ld);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+}  // extern "C"

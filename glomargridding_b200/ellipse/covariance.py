@@ -1,0 +1,232 @@
+"""`EllipseCovarianceBuilder`: drop-in for `glomar_gridding.ellipse.EllipseCovarianceBuilder`.
+
+Same constructor signature, attributes and methods as the reference class
+(`glomar_gridding/ellipse/covariance.py:40-509`); the N x N build runs as one tiled FP64 CUDA kernel
+(`gmg_ellipse_cov_f64`, `csrc/ellipse_cov.cu`) instead of the reference's pair-index / numpy
+pipeline.  Host code here only does what the reference's constructor does on O(N) data (casting,
+mask compression, `np.deg2rad`); all per-pair arithmetic is on the GPU and there is no CPU fallback.
+
+Differences from the reference, by design:
+
+* `covariance_method` / `batch_size` are validated exactly like the reference but do not change how
+  the matrix is computed (one kernel; no 10 000-point "low_memory" switch, no warning).
+* The result lives on the GPU (`cov_ns_device`, a CUDA `torch.Tensor`).  `cov_ns` is materialised as
+  a numpy array (dtype `precision`) on first access, so chaining the builder into the kriging classes
+  never round-trips the matrix through the host.
+* `rows=(row0, nrows)` builds only a row block (how the build shards across GPUs).
+* With `precision=np.float32` the inputs are rounded to float32 exactly where the reference rounds them
+  (`:121-129`), the arithmetic is FP64 and the result is rounded to float32 on store; the reference's
+  float32 path differs from its own float64 path by ~1e-6 relative, which is also how close the two
+  implementations are in that mode.
+* The reference's progress `print`s are not reproduced.
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import _device as dev
+from .._lib import check, lib
+from ..types import CovarianceMethod, DeltaXMethod
+from ..utils import cov_2_cor, mask_array
+
+import ctypes
+
+_DISP = {"Met_Office": 0, "Modified_Met_Office": 1}
+_MATERN = {"auto": 0, "table": 1, "direct": 2}
+
+
+class EllipseCovarianceBuilder:
+    """Compute covariance from ellipse parameters and positions on a B200.
+
+    Parameters are those of the reference class (`ellipse/covariance.py:95-109`):
+    `Lx, Ly, theta, stdev` (2-D arrays or MaskedArrays, theta in radians), `lats`, `lons` (degrees),
+    `v` (Matern shape), `delta_x_method`, `max_dist` (km or None), `precision`, `covariance_method`,
+    `batch_size`.
+
+    Extensions (keyword-only): `rows=(row0, nrows)` builds only that row block of the compressed
+    matrix; `matern_mode` in {"auto", "table", "direct"} selects how K_nu is evaluated.
+    """
+
+    def __init__(
+        self,
+        Lx: np.ndarray,
+        Ly: np.ndarray,
+        theta: np.ndarray,
+        stdev: np.ndarray,
+        lats: np.ndarray,
+        lons: np.ndarray,
+        v: float,
+        delta_x_method: DeltaXMethod | None = "Modified_Met_Office",
+        max_dist: float | None = None,
+        precision=np.float32,
+        covariance_method: CovarianceMethod = "array",
+        batch_size: int | None = None,
+        *,
+        rows: tuple[int, int] | None = None,
+        matern_mode: str = "auto",
+    ) -> None:
+        if max_dist is not None and not isinstance(max_dist, (int, float)):
+            raise ValueError("max_dist must be a number")  # reference :116-117
+        if precision not in (np.float32, np.float64):
+            raise ValueError("precision must be numpy.float32 or numpy.float64")
+        if matern_mode not in _MATERN:
+            raise ValueError(f"Unknown matern_mode: {matern_mode}")
+
+        self.v = v
+        self.precision = precision
+        self.Lx = mask_array(np.ma.asanyarray(Lx).astype(precision))
+        self.Ly = mask_array(np.ma.asanyarray(Ly).astype(precision))
+        self.theta = mask_array(np.ma.asanyarray(theta).astype(precision))
+        self.stdev = mask_array(np.ma.asanyarray(stdev).astype(precision))
+        self.max_dist = max_dist
+        self.delta_x_method: DeltaXMethod | None = delta_x_method
+        self.lats = np.asarray(lats).astype(precision)
+        self.lons = np.asarray(lons).astype(precision)
+        self.covariance_method: CovarianceMethod = covariance_method
+        self.batch_size = batch_size
+        self.matern_mode = matern_mode
+
+        self.xy_shape = self.Lx.shape
+        self.n_elements = np.prod(self.xy_shape)
+
+        self._get_mask()
+        self._rows = rows
+        self._calculate_covariance()
+
+    # -- host-side O(N) set-up, as reference `_get_mask` :149-180 --------------------------------
+    def _get_mask(self) -> None:
+        self.data_has_mask = np.ma.is_masked(self.Lx)
+        if self.data_has_mask:
+            self.data_mask = np.ma.getmaskarray(self.Lx)
+            self.covar_size = np.sum(np.logical_not(self.data_mask))
+        else:
+            self.data_mask = np.zeros_like(np.ma.getdata(self.Lx), dtype=bool)
+            self.covar_size = self.n_elements
+        self.Lx_compressed = self.Lx.compressed()
+        self.Ly_compressed = self.Ly.compressed()
+        self.theta_compressed = self.theta.compressed()
+        self.stdev_compressed = self.stdev.compressed()
+
+        self.x_grid, self.y_grid = np.meshgrid(self.lons, self.lats)  # row-major (lat, lon), :166
+        self.x_mask = np.ma.masked_where(self.data_mask, self.x_grid)
+        self.y_mask = np.ma.masked_where(self.data_mask, self.y_grid)
+        self.lat_grid_compressed = self.y_mask.compressed()
+        self.lon_grid_compressed = self.x_mask.compressed()
+        self.lat_grid_compressed_rad = np.deg2rad(self.lat_grid_compressed)  # :171-172
+        self.lon_grid_compressed_rad = np.deg2rad(self.lon_grid_compressed)
+        self.xy_compressed = np.column_stack([self.lon_grid_compressed, self.lat_grid_compressed])
+        self.xy_full = np.column_stack([self.x_mask.flatten(), self.y_mask.flatten()])
+
+    def _validate(self) -> None:
+        # same errors, same order of checks as reference `_get_disp_fn` :182-203 and the dispatch :226-236
+        if self.delta_x_method not in _DISP:
+            raise ValueError(f"Unknown 'delta_x_method' value: {self.delta_x_method}")
+        if self.covariance_method not in ("low_memory", "array", "batched"):
+            raise ValueError(f"Unknown covariance_method: {self.covariance_method}")
+        if self.covariance_method == "batched" and self.batch_size is None:
+            raise ValueError("batch_size must be set if using 'batched' method")
+
+    # -- device build --------------------------------------------------------------------------
+    def _prepare_device(self) -> None:
+        L = lib()
+        N = int(len(self.Lx_compressed))
+        self._N = N
+        ws_bytes = ctypes.c_size_t()
+        check(L.gmg_ellipse_ws_bytes(N, ctypes.byref(ws_bytes)), "gmg_ellipse_ws_bytes")
+        self._ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev.require_cuda())
+        ins = [dev.to_device(a) for a in (self.Lx_compressed, self.Ly_compressed, self.theta_compressed,
+                                          self.stdev_compressed, self.lat_grid_compressed_rad,
+                                          self.lon_grid_compressed_rad)]
+        check(L.gmg_ellipse_prepare_f64(*[t.data_ptr() for t in ins], N, float(self.v), self._ws.data_ptr(),
+                                        ws_bytes.value, dev.stream_ptr()), "gmg_ellipse_prepare_f64")
+        self._inputs_device = ins  # keep alive until the stream has consumed them
+
+    def _calculate_covariance(self) -> None:
+        self._validate()
+        self._prepare_device()
+        N = self._N
+        row0, nrows = (0, N) if self._rows is None else (int(self._rows[0]), int(self._rows[1]))
+        if row0 < 0 or nrows <= 0 or row0 + nrows > N:
+            raise ValueError(f"rows={self._rows} outside the {N} unmasked grid points")
+        self.row0, self.nrows = row0, nrows
+        f32 = self.precision == np.float32
+        out = torch.empty((nrows, N), dtype=torch.float32 if f32 else torch.float64, device=self._ws.device)
+        check(lib().gmg_ellipse_cov_f64(self._ws.data_ptr(), N, row0, nrows, float(self.v),
+                                        _DISP[self.delta_x_method],
+                                        -1.0 if self.max_dist is None else float(self.max_dist),
+                                        _MATERN[self.matern_mode], out.data_ptr(), N, int(f32),
+                                        dev.stream_ptr()), "gmg_ellipse_cov_f64")
+        self.cov_ns_device = out
+        self._cov_ns_host = None
+
+    # -- results ---------------------------------------------------------------------------------
+    @property
+    def cov_ns(self) -> np.ndarray:
+        """The covariance as a numpy array of dtype `precision` (copied from the GPU on first use)."""
+        if self._cov_ns_host is None:
+            self._cov_ns_host = dev.to_host(self.cov_ns_device)
+        return self._cov_ns_host
+
+    @cov_ns.setter
+    def cov_ns(self, value) -> None:
+        if isinstance(value, torch.Tensor):
+            self.cov_ns_device, self._cov_ns_host = value, None
+        else:
+            self._cov_ns_host = np.asarray(value)
+            self.cov_ns_device = None
+
+    # reference computes these on the host at :219-224; kept as cheap O(N) attributes for users
+    @property
+    def sigmas(self) -> np.ndarray:
+        ct, st = np.cos(self.theta_compressed), np.sin(self.theta_compressed)
+        c2, s2, cs = ct ** 2, st ** 2, ct * st
+        lx2, ly2 = self.Lx_compressed ** 2, self.Ly_compressed ** 2
+        off = cs * (lx2 - ly2)
+        return np.column_stack([c2 * lx2 + s2 * ly2, off, off, s2 * lx2 + c2 * ly2]).astype(self.precision)
+
+    @property
+    def sqrt_dets(self) -> np.ndarray:
+        s = self.sigmas
+        return np.sqrt(s[:, 0] * s[:, 3] - s[:, 1] * s[:, 2])
+
+    @property
+    def gamma_v_term(self) -> float:
+        import math
+
+        return math.gamma(self.v) * (2 ** (self.v - 1))
+
+    @property
+    def sqrt_v_term(self) -> float:
+        return float(np.sqrt(self.v) * 2)
+
+    def c_ij_anisotropic_array(self, i_s, j_s) -> np.ndarray:
+        """Covariances between pairs of ellipses (reference `:405-468`), evaluated on the GPU."""
+        i_t = dev.to_device(np.asarray(i_s), torch.int64)
+        j_t = dev.to_device(np.asarray(j_s), torch.int64)
+        out = torch.empty(i_t.numel(), dtype=torch.float64, device=i_t.device)
+        check(lib().gmg_ellipse_pairs_f64(self._ws.data_ptr(), self._N, i_t.data_ptr(), j_t.data_ptr(),
+                                          i_t.numel(), float(self.v), _DISP[self.delta_x_method],
+                                          _MATERN[self.matern_mode], out.data_ptr(), dev.stream_ptr()),
+              "gmg_ellipse_pairs_f64")
+        return out.cpu().numpy().astype(self.precision)
+
+    def calculate_cor(self) -> None:
+        """Correlation matrix from the covariance matrix (reference `:470-473`)."""
+        self.cor_ns = cov_2_cor(self.cov_ns)
+
+    def uncompress_cov(self, diag_fill_value: Any = np.nan, fill_value: Any = np.nan) -> None:
+        """Scatter the compressed matrix into full-grid size (reference `:475-509`); overwrites `cov_ns`."""
+        cov = self.cov_ns
+        flat = np.asarray(self.data_mask).flatten()
+        if not np.sum(~flat) == cov.shape[0]:
+            raise ValueError("Data mask and coordinates cannot be aligned")
+        M = flat.size
+        out = np.full((M, M), fill_value, dtype=self.precision)
+        out[np.arange(M), np.arange(M)] = diag_fill_value
+        keep = np.flatnonzero(~flat)
+        out[np.ix_(keep, keep)] = cov
+        self.cov_ns = out

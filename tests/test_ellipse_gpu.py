@@ -1,0 +1,155 @@
+"""Parity of the CUDA ellipse-covariance path against the oracle and the reference goldens.
+
+Tolerance: 1e-10 entrywise relative (BASELINE.json north_star) with the 1e-290 absolute floor of
+SURVEY.md §8(d).  All calls go through the Python classes, i.e. through the C ABI.
+"""
+
+import numpy as np
+import pytest
+from conftest import from_triu, load_golden, max_rel
+
+from glomargridding_b200 import synthetic as synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def Builder():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    return EllipseCovarianceBuilder
+
+
+SMALL = load_golden("ellipse_small.npz")
+
+
+def _case(name):
+    parts = name.split("_")
+    return (float(parts[0][2:]), "Modified_Met_Office" if parts[1] == "mod" else "Met_Office",
+            np.float64 if parts[2] == "f64" else np.float32, "masked" in parts,
+            6000.0 if "maxdist" in parts else None)
+
+
+@pytest.mark.parametrize("name", [str(c) for c in SMALL["cases"]])
+def test_small_grid_vs_reference_golden(Builder, name):
+    v, meth, prec, masked, max_dist = _case(name)
+    lats, lons = SMALL["lats"], SMALL["lons"]
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons, land_mask=masked)
+    b = Builder(Lx, Ly, th, sd, lats, lons, v=v, delta_x_method=meth, max_dist=max_dist, precision=prec)
+    got, want = b.cov_ns, from_triu(SMALL[name])
+    assert got.dtype == prec and got.shape == want.shape
+    assert np.array_equal(got, got.T)
+    if prec == np.float64:
+        assert max_rel(got, want) <= TOL
+    else:
+        # the reference's own float32 criterion (test/test_ellipse.py:212)
+        assert np.allclose(got, want, rtol=1e-5)
+    if max_dist is not None:
+        assert np.array_equal(got == 0, want == 0)
+    assert np.array_equal(np.diag(got), (b.stdev_compressed ** 2).astype(prec))
+
+
+@pytest.mark.parametrize("mode", ["table", "direct"])
+@pytest.mark.parametrize("v", [0.5, 1.5, 2.5, 2.2, 0.3, 7.25])
+def test_matern_modes_agree_with_oracle(Builder, v, mode):
+    from oracle import EllipseOracle
+
+    lats, lons = synth.global_grid(15.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    got = Builder(Lx, Ly, th, sd, lats, lons, v=v, precision=np.float64, matern_mode=mode).cov_ns
+    want = EllipseOracle(Lx, Ly, th, sd, lats, lons, v).build()
+    assert max_rel(got, want) <= TOL
+
+
+@pytest.mark.parametrize("v,meth", [(1.5, "Modified_Met_Office"), (2.2, "Modified_Met_Office"),
+                                    (0.5, "Met_Office"), (2.2, "Met_Office")])
+def test_5deg_full_matrix_vs_oracle(Builder, v, meth):
+    from oracle import EllipseOracle
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    got = Builder(Lx, Ly, th, sd, lats, lons, v=v, delta_x_method=meth, precision=np.float64).cov_ns
+    want = EllipseOracle(Lx, Ly, th, sd, lats, lons, v, meth).build()
+    assert got.shape == (2592, 2592)
+    assert max_rel(got, want) <= TOL
+    assert np.array_equal(got, got.T)
+
+
+@pytest.mark.parametrize("tag,res", [("5deg", 5.0), ("1deg", 1.0)])
+def test_sampled_pairs_vs_reference_golden(Builder, tag, res):
+    """`c_ij_anisotropic_array(i_s, j_s)` on the pairs the reference itself evaluated (incl. +-pi wrap ties)."""
+    g = load_golden(f"ellipse_pairs_{tag}.npz")
+    lats, lons = synth.global_grid(res)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    for name in [k for k in g.files if k.startswith("nu")]:
+        v = float(name.split("_")[0][2:])
+        meth = "Modified_Met_Office" if name.endswith("_mod") else "Met_Office"
+        b = Builder(Lx, Ly, th, sd, lats, lons, v=v, delta_x_method=meth, precision=np.float64, rows=(0, 64))
+        got = b.c_ij_anisotropic_array(g["i"], g["j"])
+        assert max_rel(got, g[name]) <= TOL, name
+
+
+def test_1deg_row_blocks_vs_golden_pairs_and_symmetry(Builder):
+    """Full-size (N = 64 800) build in row blocks: entries sampled by the reference, block symmetry,
+    exact diagonal - the size-independent checks of SURVEY.md §8(d)."""
+    import torch
+
+    g = load_golden("ellipse_pairs_1deg.npz")
+    lats, lons = synth.global_grid(1.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    N = 64800
+    gi, gj, want = g["i"].astype(np.int64), g["j"].astype(np.int64), g["nu2.2_mod"]
+    checked = 0
+    for row0, nrows in [(0, 4096), (30016, 4096), (64800 - 4000, 4000)]:
+        b = Builder(Lx, Ly, th, sd, lats, lons, v=2.2, precision=np.float64, rows=(row0, nrows))
+        blk = b.cov_ns_device
+        assert blk.shape == (nrows, N)
+        sq = blk[:, row0:row0 + nrows]
+        assert torch.equal(sq, sq.T)                       # mirrored tiles are bit-identical
+        sd_c = torch.from_numpy(b.stdev_compressed[row0:row0 + nrows]).cuda()
+        assert torch.equal(torch.diagonal(sq), sd_c * sd_c)
+        for a, c in ((gi, gj), (gj, gi)):                   # both orientations of every sampled pair
+            sel = (a >= row0) & (a < row0 + nrows)
+            got = blk[torch.from_numpy(a[sel] - row0).cuda(), torch.from_numpy(c[sel]).cuda()].cpu().numpy()
+            assert max_rel(got, want[sel]) <= TOL
+            checked += int(sel.sum())
+    assert checked > 3000
+
+
+def test_row_block_equals_full_build(Builder):
+    lats, lons = synth.global_grid(10.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons, land_mask=True)
+    full = Builder(Lx, Ly, th, sd, lats, lons, v=2.2, precision=np.float64).cov_ns
+    N = full.shape[0]
+    for row0, nrows in [(0, 64), (64, 100), (128, N - 128), (70, 33), (N - 1, 1)]:
+        blk = Builder(Lx, Ly, th, sd, lats, lons, v=2.2, precision=np.float64, rows=(row0, nrows)).cov_ns
+        assert np.array_equal(blk, full[row0:row0 + nrows])
+
+
+def test_api_errors_and_attributes(Builder):
+    lats, lons = synth.global_grid(20.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons, land_mask=True)
+    with pytest.raises(ValueError, match="max_dist must be a number"):
+        Builder(Lx, Ly, th, sd, lats, lons, v=1.5, max_dist="far")
+    with pytest.raises(ValueError, match="Unknown 'delta_x_method' value"):
+        Builder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="nope")
+    with pytest.raises(ValueError, match="Unknown covariance_method"):
+        Builder(Lx, Ly, th, sd, lats, lons, v=1.5, covariance_method="nope")
+    with pytest.raises(ValueError, match="batch_size must be set"):
+        Builder(Lx, Ly, th, sd, lats, lons, v=1.5, covariance_method="batched")
+    b = Builder(Lx, Ly, th, sd, lats, lons, v=0.5, covariance_method="batched", batch_size=100)
+    n = int((~np.ma.getmaskarray(Lx)).sum())
+    assert b.cov_ns.dtype == np.float32 and b.cov_ns.shape == (n, n) and b.covar_size == n
+    assert b.xy_shape == Lx.shape and b.n_elements == Lx.size
+    assert b.sigmas.shape == (n, 4) and b.sqrt_dets.shape == (n,)
+    b.calculate_cor()
+    assert np.isclose(1, np.max(np.diag(b.cor_ns)))       # reference test/test_ellipse.py:215-217
+    b.uncompress_cov()
+    assert b.cov_ns.shape == (Lx.size, Lx.size)            # reference test/test_ellipse.py:387-388
+    assert np.isnan(b.cov_ns).sum() > 0
