@@ -202,9 +202,9 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
 
     def step():
-        check(L.gmg_ellipse_prepare_f64(*[t.data_ptr() for t in ins], N, args.nu, ws.data_ptr(), ws_bytes,
+        check(L.gmg_ellipse_prepare_f64(*[t.data_ptr() for t in ins], N, args.nu, 1, ws.data_ptr(), ws_bytes,
                                         stream.cuda_stream), "prepare")
-        check(L.gmg_ellipse_cov_f64(ws.data_ptr(), N, row0, nrows, args.nu, 1, -1.0, 0, out.data_ptr(), N, 0,
+        check(L.gmg_ellipse_cov_f64(ws.data_ptr(), N, row0, nrows, args.nu, -1.0, 0, out.data_ptr(), N, 0,
                                     stream.cuda_stream), "cov")
 
     def barrier():
@@ -228,7 +228,7 @@ def run_b200(args):
         for _ in range(min(args.steps, 5)):
             k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             k0.record(stream)
-            check(L.gmg_ellipse_cov_f64(ws.data_ptr(), N, row0, nrows, args.nu, 1, -1.0, 0, out.data_ptr(), N, 0,
+            check(L.gmg_ellipse_cov_f64(ws.data_ptr(), N, row0, nrows, args.nu, -1.0, 0, out.data_ptr(), N, 0,
                                         stream.cuda_stream), "cov")
             k1.record(stream)
             k1.synchronize()

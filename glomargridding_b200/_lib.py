@@ -30,9 +30,9 @@ def _declare(lib):
         "gmg_strerror": (c_char_p, [c_int]),
         "gmg_last_cuda_error": (c_int, []),
         "gmg_ellipse_ws_bytes": (c_int, [i64, POINTER(c_size_t)]),
-        "gmg_ellipse_prepare_f64": (c_int, [p, p, p, p, p, p, i64, dbl, p, c_size_t, p]),
-        "gmg_ellipse_cov_f64": (c_int, [p, i64, i64, i64, dbl, i32, dbl, i32, p, i64, i32, p]),
-        "gmg_ellipse_pairs_f64": (c_int, [p, i64, p, p, i64, dbl, i32, i32, p, p]),
+        "gmg_ellipse_prepare_f64": (c_int, [p, p, p, p, p, p, i64, dbl, i32, p, c_size_t, p]),
+        "gmg_ellipse_cov_f64": (c_int, [p, i64, i64, i64, dbl, dbl, i32, p, i64, i32, p]),
+        "gmg_ellipse_pairs_f64": (c_int, [p, i64, p, p, i64, dbl, i32, p, p]),
         "gmg_bessel_kv_f64": (c_int, [dbl, p, i64, i32, p, p]),
         "gmg_matern_f64": (c_int, [p, dbl, i32, p, i64, p, p]),
         "gmg_haversine_f64": (c_int, [p, p, i64, i64, i64, p, i64, p]),

@@ -40,11 +40,12 @@ constexpr int kTileLd = kTile + 1;                  // odd leading dimension: co
 // Matern table geometry
 constexpr int kTabEmin = -20;
 constexpr int kTabEmax = 10;                        // exclusive
-constexpr int kTabSub = 4;
-constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 120
-constexpr int kTabDeg = 12;
+constexpr int kTabSubLog2 = 4;
+constexpr int kTabSub = 1 << kTabSubLog2;                   // linear sub-intervals of the mantissa per octave
+constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 480
+constexpr int kTabDeg = 7;
 constexpr int kTabCoef = kTabDeg + 1;
-constexpr int kTabDoubles = kTabNint * kTabCoef;            // 1560
+constexpr int kTabDoubles = kTabNint * kTabCoef;            // 3840 (30.7 KB)
 
 enum { MODE_NU05 = 0, MODE_NU15 = 1, MODE_NU25 = 2, MODE_TABLE = 3, MODE_DIRECT = 4 };
 
@@ -54,7 +55,7 @@ enum { P_LAT = 0, P_LON = 1, P_HCOS = 2, P_H00 = 3, P_H01 = 4, P_H11 = 5, P_W = 
 __global__ void __launch_bounds__(256) ellipse_prepare_kernel(
     const double* __restrict__ Lx, const double* __restrict__ Ly, const double* __restrict__ theta,
     const double* __restrict__ stdev, const double* __restrict__ lat, const double* __restrict__ lon,
-    int64_t N, double* __restrict__ params) {
+    int64_t N, int disp_method, double* __restrict__ params) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
     // reference `_sigma_rot_func_multi`, ellipse/covariance.py:512-533
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(256) ellipse_prepare_kernel(
     double* p = params + i * P_N;
     p[P_LAT] = lat[i];
     p[P_LON] = lon[i];
-    p[P_HCOS] = 0.5 * cos(lat[i]);          // 0.5*(cos a + cos b) == 0.5 cos a + 0.5 cos b exactly
+    // 0.5*(cos a + cos b) == 0.5 cos a + 0.5 cos b exactly; "Met_Office" has no cos-latitude factor (0.5 + 0.5 = 1)
+    p[P_HCOS] = disp_method == GMG_DISP_MODIFIED_MET_OFFICE ? 0.5 * cos(lat[i]) : 0.5;
     p[P_H00] = 0.5 * s00;                   // 0.5*(S_i + S_j)   == 0.5 S_i + 0.5 S_j     exactly
     p[P_H01] = 0.5 * s01;
     p[P_H11] = 0.5 * s11;
@@ -79,15 +81,15 @@ __global__ void __launch_bounds__(256) ellipse_prepare_kernel(
 }
 
 // One block per table interval: sample g at Chebyshev nodes, transform to monomial coefficients in
-// t = (m - c_k) * 8 in [-1, 1] where m in [1, 2) is the mantissa of x and c_k the sub-interval centre.
+// t = (m - c_k) * 2 kTabSub in [-1, 1] where m in [1, 2) is the mantissa of x and c_k the sub-interval centre.
 __global__ void __launch_bounds__(32) matern_table_kernel(GmgBesselConsts bc, double* __restrict__ table) {
     __shared__ double f[kTabCoef];
     __shared__ double cheb[kTabCoef];
     const int interval = blockIdx.x;
     const int e = kTabEmin + interval / kTabSub;
     const int k = interval % kTabSub;
-    const double centre = ldexp(1.125 + 0.25 * k, e);
-    const double halfw = ldexp(0.125, e);
+    const double centre = ldexp(1.0 + (k + 0.5) / kTabSub, e);
+    const double halfw = ldexp(0.5 / kTabSub, e);
     const int t = threadIdx.x;
     if (t < kTabCoef) {
         const double node = cospi((t + 0.5) / kTabCoef);
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(32) matern_table_kernel(GmgBesselConsts bc, do
 struct MaternCtx {
     GmgBesselConsts bc;
     const double* table;   // shared-memory (tile kernel) or global (pairs kernel) pointer, [coef][interval]
-    int geom_f32;          // decide the longitude wrap in float32 like the reference's precision=float32 path
+    double x_scale;        // 2 sqrt(nu) * R: inner = x_scale * sqrt(Q_rad / det)
 };
 
 template <int MODE>
@@ -130,11 +132,12 @@ __device__ __forceinline__ double matern_scaled_eval(const MaternCtx& m, double 
     if (MODE == MODE_TABLE) {
         const int hi = __double2hiint(x);
         const int lo = __double2loint(x);
-        const int idx = ((hi >> 20) - (1023 + kTabEmin)) * kTabSub + ((hi >> 18) & 3);
+        const int idx = ((hi >> 20) - (1023 + kTabEmin)) * kTabSub + ((hi >> (20 - kTabSubLog2)) & (kTabSub - 1));
         if ((unsigned)idx < (unsigned)kTabNint) {     // also rejects x <= 0, inf, NaN (sign/exponent bits)
             const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
-            const double centre = __hiloint2double(0x3FF20000 | (hi & 0x000C0000), 0);
-            const double t = (mant - centre) * 8.0;
+            const int cbits = (hi & ((kTabSub - 1) << (20 - kTabSubLog2))) | (1 << (19 - kTabSubLog2));
+            const double centre = __hiloint2double(0x3FF00000 | cbits, 0);
+            const double t = (mant - centre) * (double)(2 * kTabSub);
             const double* c = m.table + idx;
             double p = c[kTabDeg * kTabNint];
 #pragma unroll
@@ -147,15 +150,122 @@ __device__ __forceinline__ double matern_scaled_eval(const MaternCtx& m, double 
 
 struct PointRegs { double lat, lon, hcos, h00, h01, h11, w; };
 
-// The pair formula: reference `c_ij_anisotropic_array`, ellipse/covariance.py:441-466, with
-//   sqrt(sqrt_det_i sqrt_det_j / det) = q_i q_j rsqrt(det)   and   sqrt(Q / det) = sqrt(Q rsqrt(det)^2).
-template <int MODE, int DISP>
-__device__ __forceinline__ double cov_pair(const PointRegs& a, const PointRegs& b, const MaternCtx& m,
-                                           double max_dist) {
-    double dy = a.lat - b.lat;                              // :631 orientation (i) - (j)
-    double dx = a.lon - b.lon;                              // :632 exact IEEE subtract of host radians
-    const double dlon_raw = dx;
-    if (m.geom_f32) {
+__device__ __forceinline__ PointRegs load_point(const double* p) {     // p: 8 consecutive doubles (AoS)
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *reinterpret_cast<const double2*>(p + 2);
+    const double2 c = *reinterpret_cast<const double2*>(p + 4);
+    PointRegs r;
+    r.lat = a.x; r.lon = a.y; r.hcos = b.x; r.h00 = b.y; r.h01 = c.x; r.h11 = c.y; r.w = p[6];
+    return r;
+}
+
+// ---- straight-line FP64 helpers for the hot loop ------------------------------------------------------
+// The kernel is bound by the FP64 pipe (64 lanes / SM: one warp-wide FP64 instruction per 2 cycles per SM
+// sub-partition), so the loop body is written to minimise FP64 instructions and to contain no branches.
+// The CUDA libm sqrt / rsqrt / exp carry special-case branches and slow-path calls (ncu r01: 222 issued
+// instructions per pair for 72 FP64 ones, "wait" stalls dominant); arguments here are positive and normal,
+// so a cubically convergent refinement of the MUFU.RSQ64H seed and a table-driven exp suffice.  Anything
+// unusual (x >= 700, x outside the Matern table, NaN from a non-positive determinant) is flagged and
+// recomputed on a cold path with the libm functions.
+
+// 2^(-j/64), j = 0..63, correctly rounded (mpmath); staged in shared memory by every CTA
+__device__ const double kExp2Neg64[64] = {
+    1.0, 0.9892280131939755, 0.9785720620877001, 0.9680308967461472,
+    0.9576032806985737, 0.9472879907934828, 0.93708381705515, 0.9269895625416927,
+    0.9170040432046712, 0.9071260877501994, 0.8973545375015536, 0.8876882462632606,
+    0.8781260801866497, 0.8686669176368531, 0.859309649061239, 0.8500531768592617,
+    0.8408964152537145, 0.8318382901633682, 0.8228777390769825, 0.8140137109286739,
+    0.8052451659746271, 0.7965710756711335, 0.7879904225539432, 0.7795022001189185,
+    0.7711054127039704, 0.7627990753722692, 0.7545822137967114, 0.7464538641456324,
+    0.7384130729697497, 0.7304588970903235, 0.7225904034885233, 0.714806669195985,
+    0.7071067811865476, 0.6994898362691556, 0.691954940981916, 0.6845012114872953,
+    0.6771277734684463, 0.6698337620266515, 0.6626183215798707, 0.6554806057623822,
+    0.6484197773255048, 0.6414350080393891, 0.6345254785958666, 0.6276903785123455,
+    0.620928906036742, 0.614240268053435, 0.6076236799902345, 0.6010783657263515,
+    0.5946035575013605, 0.5881984958251406, 0.5818624293887887, 0.5755946149764913,
+    0.5693943173783458, 0.5632608093041209, 0.5571933712979462, 0.5511912916539204,
+    0.5452538663326288, 0.5393803988785599, 0.5335702003384118, 0.5278225891802786,
+    0.5221368912137069, 0.5165124395106142, 0.5109485743270583, 0.5054446430258502};
+
+// 1/sqrt(a), a > 0 normal: MUFU seed (rel. error < 2^-22) and one cubically convergent step
+//   e = 1 - a r^2,  r <- r + r e (1/2 + 3/8 e)      (error ~ 5/16 e^3 < 2^-64)       5 FP64 instructions
+__device__ __forceinline__ double rsqrt_pos(double a) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    const double e = fma(-(a * r), r, 1.0);
+    return fma(r * e, fma(e, 0.375, 0.5), r);
+}
+
+// exp(-x) for 0 <= x < 700 (result normal):  k = rint(64 x / ln 2),  exp(-x) = 2^-(k>>6) T[k&63] exp(s),
+// s = k ln2/64 - x in [-ln2/128, ln2/128] (Cody-Waite, k ln2_hi exact for k < 2^17), degree-5 Taylor
+// (truncation s^6/720 < 3.5e-17).  9 FP64 instructions + one shared-memory load.
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ sexp) {
+    const double kMagic = 6755399441055744.0;                     // 1.5 * 2^52
+    const double t = fma(x, 92.33248261689366, kMagic);           // 64 / ln 2
+    const int k = __double2loint(t);
+    const double kf = t - kMagic;
+    double s = fma(kf, 0.010830424695086549, -x);                 // ln2/64 hi (33 significant bits)
+    s = fma(kf, 1.162596423439437e-12, s);                        // ln2/64 lo
+    double p = 8.33333333333333333333e-03;                        // 1/5!
+    p = fma(p, s, 4.16666666666666666667e-02);                    // 1/4!
+    p = fma(p, s, 1.66666666666666666667e-01);                    // 1/3!
+    p = fma(p, s, 0.5);
+    p = fma(p, s, 1.0);
+    const double ts = sexp[k & 63];
+    p = fma(ts * s, p, ts);                                       // T (1 + s p)
+    return __hiloint2double(__double2hiint(p) - ((k >> 6) << 20), __double2loint(p));
+}
+
+// g(x) of the fast path; `slow` is set when the lane must be recomputed by `cov_pair_slow`.
+template <int MODE>
+__device__ __forceinline__ double matern_scaled_fast(const MaternCtx& m, double x, bool& slow) {
+    slow = !(x < 700.0);                                          // also catches NaN
+    if (MODE == MODE_NU05) return 1.0;
+    if (MODE == MODE_NU15) return 1.0 + x;
+    if (MODE == MODE_NU25) return fma(x, fma(x, 1.0 / 3.0, 1.0), 1.0);
+    if (MODE == MODE_DIRECT) { slow = true; return 0.0; }         // validation mode: always the cold path
+    const int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int idx = ((hi >> 20) - (1023 + kTabEmin)) * kTabSub + ((hi >> (20 - kTabSubLog2)) & (kTabSub - 1));
+    slow = slow || ((unsigned)idx >= (unsigned)kTabNint);
+    idx = min(max(idx, 0), kTabNint - 1);
+    const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+    const int cbits = (hi & (((kTabSub - 1) << (20 - kTabSubLog2)))) | (1 << (19 - kTabSubLog2));
+    const double centre = __hiloint2double(0x3FF00000 | cbits, 0);
+    const double t = (mant - centre) * (double)(2 * kTabSub);
+    const double* c = m.table + idx;
+    double p = c[kTabDeg * kTabNint];
+#pragma unroll
+    for (int k = kTabDeg - 1; k >= 0; --k) p = fma(p, t, c[k * kTabNint]);
+    return p;
+}
+
+// longitude wrap, reference ellipse/covariance.py:633-634:  dx > pi -> dx - 2 pi,  dx < -pi -> dx + 2 pi
+// (strict).  |dx| <= 2 pi, so this is dx - copysign(2 pi, dx) when |dx| > pi; the comparison is done on the
+// bit pattern in the integer pipe (IEEE doubles of one sign order like integers) to keep it off the FP64
+// pipe, and the subtraction of +0.0 in the other case is exact.
+__device__ __forceinline__ double wrap_lon(double dx) {
+    const unsigned hi = (unsigned)__double2hiint(dx);
+    const unsigned lo = (unsigned)__double2loint(dx);
+    const unsigned ahi = hi & 0x7fffffffu;
+    const bool gt = (ahi > 0x400921FBu) || (ahi == 0x400921FBu && lo > 0x54442D18u);   // |dx| > np.pi
+    const unsigned whi = gt ? (0x401921FBu | (hi & 0x80000000u)) : 0u;                 // copysign(2 pi, dx)
+    const unsigned wlo = gt ? 0x54442D18u : 0u;
+    return dx - __hiloint2double((int)whi, (int)wlo);
+}
+
+// Geometry shared by the fast and slow paths: reference `c_ij_anisotropic_array`,
+// ellipse/covariance.py:441-463, with
+//   sqrt(sqrt_det_i sqrt_det_j / det) = q_i q_j rsqrt(det)   and   inner = 2 sqrt(nu) R sqrt(Q) rsqrt(det)
+// where Q is the quadratic form of the displacements in RADIANS (the Earth radius of :639 is folded into the
+// constant).  For "Met_Office" the prepare kernel stores hcos = 0.5, so (a.hcos + b.hcos) == 1.0 exactly and
+// the mean-cos-latitude factor of "Modified_Met_Office" (:636-637) drops out without a second code path.
+struct PairGeom { double det, q, dx, dy; };
+
+template <bool GEOM_F32>
+__device__ __forceinline__ PairGeom pair_geom(const PointRegs& a, const PointRegs& b) {
+    double dy, dx;
+    if (GEOM_F32) {
         // precision=float32: the reference holds radians as float32 and subtracts / compares / wraps in
         // float32 (np.pi and TWO_PI are weak scalars), which decides the 180-degree ties differently
         // from a float64 subtract of the same values.  Inputs here are exactly float32-representable.
@@ -165,25 +275,46 @@ __device__ __forceinline__ double cov_pair(const PointRegs& a, const PointRegs& 
         dx = (double)d;
         dy = (double)__fsub_rn((float)a.lat, (float)b.lat);
     } else {
-        if (dx > kPi) dx -= kTwoPi;                         // :633 strict >
-        if (dx < -kPi) dx += kTwoPi;                        // :634 strict <
+        dy = a.lat - b.lat;                                 // :631 orientation (i) - (j)
+        dx = wrap_lon(a.lon - b.lon);                       // :632-634 exact IEEE subtract of host radians
     }
-    if (DISP == GMG_DISP_MODIFIED_MET_OFFICE) dx *= (a.hcos + b.hcos);   // :636-637, after the wrap
-    dy *= kEarthRadiusKm;                                   // :639
-    dx *= kEarthRadiusKm;
+    dx *= (a.hcos + b.hcos);                                // :636-637, after the wrap
     const double s0 = a.h00 + b.h00, s1 = a.h01 + b.h01, s3 = a.h11 + b.h11;   // :451
-    const double det = s0 * s3 - s1 * s1;                   // :452
-    const double r = rsqrt(det);
-    const double q = dx * (dx * s3 - dy * s1) + dy * (dy * s0 - dx * s1);      // :459-461
-    const double t = q * r * r;                             // Q / det
-    const double x = m.bc.two_sqrt_nu * sqrt(t);            // :457 inner = 2 sqrt(nu) tau
-    double c = (a.w * b.w) * r * matern_scaled_eval<MODE>(m, x) * exp(-x);     // :447-455, :465-466
-    if (max_dist >= 0.0) {                                  // :256-266, `_haversine_multi` :572-588
-        const double sl = sin(0.5 * (a.lat - b.lat)), so = sin(0.5 * dlon_raw);
-        const double h = sl * sl + (2.0 * a.hcos) * (2.0 * b.hcos) * so * so;
-        if (kEarthRadiusKm * (2.0 * asin(sqrt(h))) > max_dist) c = 0.0;
-    }
-    return c;
+    PairGeom g;
+    g.det = fma(s0, s3, -(s1 * s1));                        // :452
+    g.q = dx * fma(dx, s3, -(dy * s1)) + dy * fma(dy, s0, -(dx * s1));         // :459-461
+    g.dx = dx;
+    g.dy = dy;
+    return g;
+}
+
+template <int MODE, bool GEOM_F32>
+__device__ __forceinline__ double cov_pair(const PointRegs& a, const PointRegs& b, const MaternCtx& m,
+                                           const double* __restrict__ sexp, bool& slow) {
+    const PairGeom g = pair_geom<GEOM_F32>(a, b);
+    const double r = rsqrt_pos(g.det);
+    const double x = (m.x_scale * g.q) * rsqrt_pos(g.q) * r;                    // :457 inner
+    const double gm = matern_scaled_fast<MODE>(m, x, slow);
+    return ((a.w * b.w) * r) * gm * exp_neg(x, sexp);                           // :447-455, :465-466
+}
+
+// Cold path for flagged lanes: libm sqrt / exp, Temme-CF2 Bessel-K; any x (incl. underflow to 0 and NaN).
+// Takes pointers (to the 64 B point records and to the context) so that the hot loop never spills its
+// registers to the stack to make the call.
+template <int MODE, bool GEOM_F32>
+__device__ __noinline__ double cov_pair_slow(const double* pa, const double* pb, const MaternCtx* m) {
+    const PointRegs a = load_point(pa), b = load_point(pb);
+    const PairGeom g = pair_geom<GEOM_F32>(a, b);
+    const double x = m->x_scale * sqrt(g.q / g.det);
+    return (a.w * b.w) * rsqrt(g.det) * matern_scaled_eval<MODE>(*m, x) * exp(-x);
+}
+
+// `_haversine_multi`, ellipse/covariance.py:572-588 (only when max_dist is set, :256-266)
+__device__ __noinline__ bool beyond_max_dist(const double* pa, const double* pb, double max_dist) {
+    const double lat0 = pa[P_LAT], lat1 = pb[P_LAT];
+    const double sl = sin(0.5 * (lat0 - lat1)), so = sin(0.5 * (pa[P_LON] - pb[P_LON]));
+    const double h = sl * sl + cos(lat0) * cos(lat1) * so * so;
+    return kEarthRadiusKm * (2.0 * asin(sqrt(h))) > max_dist;
 }
 
 struct EllipseArgs {
@@ -195,7 +326,6 @@ struct EllipseArgs {
     int64_t n_tri;
     double max_dist;
     int vec2;
-    int geom_f32;
     GmgBesselConsts bc;
 };
 
@@ -216,13 +346,16 @@ __device__ __forceinline__ void store_pair(OutT* p, double v0, double v1, bool s
     }
 }
 
-template <int MODE, int DISP, typename OutT>
+template <int MODE, bool MAXDIST, typename OutT>
 __global__ void __launch_bounds__(kThreads, 2) ellipse_cov_tile_kernel(const EllipseArgs a) {
+    constexpr bool GEOM_F32 = sizeof(OutT) == 4;
     extern __shared__ __align__(16) double smem[];
-    double* rowp = smem;                              // [P_N][kTile]
-    double* colp = rowp + P_N * kTile;                // [P_N][kTile]
-    double* tileT = colp + P_N * kTile;               // [kTile][kTileLd]
+    double* rowp = smem;                              // [kTile][P_N]  (AoS: one row point = 64 B, LDS.128 broadcast)
+    double* colp = rowp + P_N * kTile;                // [kTile][P_N]
+    double* sexp = colp + P_N * kTile;                // [64]
+    double* tileT = sexp + 64;                        // [kTile][kTileLd]
     double* stab = tileT + kTile * kTileLd;           // [kTabCoef][kTabNint] (MODE_TABLE only)
+    __shared__ MaternCtx sctx;                        // for the cold path
 
     // ---- which tile -------------------------------------------------------------------------
     int ta, tb;
@@ -257,35 +390,31 @@ __global__ void __launch_bounds__(kThreads, 2) ellipse_cov_tile_kernel(const Ell
     const int64_t j0 = (int64_t)tb * kTile;            // global index of the tile's first column point
     const int64_t row_end = a.row0 + a.nrows;
 
-    // ---- stage per-point terms (AoS in global -> SoA in shared) --------------------------------
+    // ---- stage per-point terms (64 B records, coalesced) and the tables -----------------------
     const int tid = threadIdx.x;
     for (int e = tid; e < 2 * kTile * P_N; e += kThreads) {
         const int which = e / (kTile * P_N);           // 0 rows, 1 cols
         const int rem = e % (kTile * P_N);
-        const int pt = rem / P_N, f = rem % P_N;
-        const int64_t g = (which ? j0 : i0) + pt;
-        const double v = (g < a.N) ? a.params[g * P_N + f] : 1.0;
-        (which ? colp : rowp)[f * kTile + pt] = v;
+        const int64_t g = (which ? j0 : i0) + rem / P_N;
+        // out-of-range points get benign values (1.0 everywhere: det = 1 > 0, q = 0 -> cold path, never stored)
+        (which ? colp : rowp)[rem] = (g < a.N) ? a.params[g * P_N + rem % P_N] : 1.0;
     }
+    if (tid < 64) sexp[tid] = kExp2Neg64[tid];
     MaternCtx m;
     m.bc = a.bc;
     m.table = stab;
-    m.geom_f32 = a.geom_f32;
+    m.x_scale = a.bc.two_sqrt_nu * kEarthRadiusKm;
     if (MODE == MODE_TABLE) {
         for (int e = tid; e < kTabDoubles; e += kThreads) stab[e] = a.table[e];
     }
+    if (tid == 0) sctx = m;
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
     const int jl = 2 * lane;
-    PointRegs c0, c1;
-    c0.lat = colp[P_LAT * kTile + jl];     c1.lat = colp[P_LAT * kTile + jl + 1];
-    c0.lon = colp[P_LON * kTile + jl];     c1.lon = colp[P_LON * kTile + jl + 1];
-    c0.hcos = colp[P_HCOS * kTile + jl];   c1.hcos = colp[P_HCOS * kTile + jl + 1];
-    c0.h00 = colp[P_H00 * kTile + jl];     c1.h00 = colp[P_H00 * kTile + jl + 1];
-    c0.h01 = colp[P_H01 * kTile + jl];     c1.h01 = colp[P_H01 * kTile + jl + 1];
-    c0.h11 = colp[P_H11 * kTile + jl];     c1.h11 = colp[P_H11 * kTile + jl + 1];
-    c0.w = colp[P_W * kTile + jl];         c1.w = colp[P_W * kTile + jl + 1];
+    const double* pc0 = colp + jl * P_N;
+    const double* pc1 = pc0 + P_N;
+    const PointRegs c0 = load_point(pc0), c1 = load_point(pc1);
     const int64_t gj = j0 + jl;
     const bool col0_ok = gj < a.N, col1_ok = gj + 1 < a.N;
     OutT* out = reinterpret_cast<OutT*>(a.out);
@@ -294,17 +423,18 @@ __global__ void __launch_bounds__(kThreads, 2) ellipse_cov_tile_kernel(const Ell
     for (int r = 0; r < kTile / 8; ++r) {
         const int il = warp * (kTile / 8) + r;
         const int64_t gi = i0 + il;
-        PointRegs p;
-        p.lat = rowp[P_LAT * kTile + il];
-        p.lon = rowp[P_LON * kTile + il];
-        p.hcos = rowp[P_HCOS * kTile + il];
-        p.h00 = rowp[P_H00 * kTile + il];
-        p.h01 = rowp[P_H01 * kTile + il];
-        p.h11 = rowp[P_H11 * kTile + il];
-        p.w = rowp[P_W * kTile + il];
-        double v0 = cov_pair<MODE, DISP>(p, c0, m, a.max_dist);
-        double v1 = cov_pair<MODE, DISP>(p, c1, m, a.max_dist);
-        const double var = rowp[P_VAR * kTile + il];
+        const double* pr = rowp + il * P_N;
+        const PointRegs p = load_point(pr);
+        bool slow0, slow1;
+        double v0 = cov_pair<MODE, GEOM_F32>(p, c0, m, sexp, slow0);
+        double v1 = cov_pair<MODE, GEOM_F32>(p, c1, m, sexp, slow1);
+        if (slow0) v0 = cov_pair_slow<MODE, GEOM_F32>(pr, pc0, &sctx);
+        if (slow1) v1 = cov_pair_slow<MODE, GEOM_F32>(pr, pc1, &sctx);
+        if (MAXDIST) {                                // :256-266 pairs beyond max_dist stay 0
+            if (beyond_max_dist(pr, pc0, a.max_dist)) v0 = 0.0;
+            if (beyond_max_dist(pr, pc1, a.max_dist)) v1 = 0.0;
+        }
+        const double var = pr[P_VAR];
         if (gi == gj) v0 = var;                       // diagonal = stdev^2, :246
         if (gi == gj + 1) v1 = var;
         if (gi < row_end && col0_ok)
@@ -331,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 2) ellipse_cov_tile_kernel(const Ell
     }
 }
 
-template <int MODE, int DISP>
+template <int MODE>
 __global__ void __launch_bounds__(256) ellipse_pairs_kernel(const double* __restrict__ params,
                                                             const double* __restrict__ table,
                                                             GmgBesselConsts bc, const int64_t* __restrict__ is,
@@ -342,15 +472,13 @@ __global__ void __launch_bounds__(256) ellipse_pairs_kernel(const double* __rest
     MaternCtx m;
     m.bc = bc;
     m.table = table;
-    m.geom_f32 = 0;
-    PointRegs a, b;
+    m.x_scale = bc.two_sqrt_nu * kEarthRadiusKm;
     const double* pa = params + is[k] * P_N;
     const double* pb = params + js[k] * P_N;
-    a.lat = pa[P_LAT]; a.lon = pa[P_LON]; a.hcos = pa[P_HCOS]; a.h00 = pa[P_H00]; a.h01 = pa[P_H01];
-    a.h11 = pa[P_H11]; a.w = pa[P_W];
-    b.lat = pb[P_LAT]; b.lon = pb[P_LON]; b.hcos = pb[P_HCOS]; b.h00 = pb[P_H00]; b.h01 = pb[P_H01];
-    b.h11 = pb[P_H11]; b.w = pb[P_W];
-    out[k] = cov_pair<MODE, DISP>(a, b, m, -1.0);
+    bool slow;
+    double v = cov_pair<MODE, false>(load_point(pa), load_point(pb), m, kExp2Neg64, slow);   // as the tile kernel
+    if (slow) v = cov_pair_slow<MODE, false>(pa, pb, &m);
+    out[k] = v;
 }
 
 __global__ void __launch_bounds__(256) bessel_kv_kernel(GmgBesselConsts bc, const double* __restrict__ x,
@@ -369,7 +497,7 @@ __global__ void __launch_bounds__(256) matern_kernel(GmgBesselConsts bc, const d
     MaternCtx m;
     m.bc = bc;
     m.table = table;
-    m.geom_f32 = 0;
+    m.x_scale = 0.0;
     out[k] = matern_scaled_eval<MODE>(m, x[k]) * exp(-x[k]);
 }
 
@@ -403,37 +531,28 @@ inline const double* ws_params(const void* ws) {
     return reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + kTableBytes);
 }
 
-template <int MODE, int DISP, typename OutT>
+template <int MODE, bool MAXDIST, typename OutT>
 int launch_tiles(const EllipseArgs& a, int64_t n_ctas, cudaStream_t s) {
-    size_t smem = (size_t)(2 * P_N * kTile + kTile * kTileLd) * sizeof(double);
+    size_t smem = (size_t)(2 * P_N * kTile + 64 + kTile * kTileLd) * sizeof(double);
     if (MODE == MODE_TABLE) smem += (size_t)kTabDoubles * sizeof(double);
-    auto kern = ellipse_cov_tile_kernel<MODE, DISP, OutT>;
+    auto kern = ellipse_cov_tile_kernel<MODE, MAXDIST, OutT>;
     GMG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)n_ctas, kThreads, smem, s>>>(a);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
 }
 
-template <int MODE, int DISP>
-int launch_tiles_out(const EllipseArgs& a, int64_t n, int f32, cudaStream_t s) {
-    return f32 ? launch_tiles<MODE, DISP, float>(a, n, s) : launch_tiles<MODE, DISP, double>(a, n, s);
+template <int MODE>
+int launch_tiles_mode(const EllipseArgs& a, int64_t n, int f32, cudaStream_t s) {
+    const bool md = a.max_dist >= 0.0;
+    if (f32) return md ? launch_tiles<MODE, true, float>(a, n, s) : launch_tiles<MODE, false, float>(a, n, s);
+    return md ? launch_tiles<MODE, true, double>(a, n, s) : launch_tiles<MODE, false, double>(a, n, s);
 }
 
 template <int MODE>
-int launch_tiles_disp(const EllipseArgs& a, int64_t n, int disp, int f32, cudaStream_t s) {
-    return disp == GMG_DISP_MODIFIED_MET_OFFICE
-               ? launch_tiles_out<MODE, GMG_DISP_MODIFIED_MET_OFFICE>(a, n, f32, s)
-               : launch_tiles_out<MODE, GMG_DISP_MET_OFFICE>(a, n, f32, s);
-}
-
-template <int MODE>
-int launch_pairs_disp(const double* params, const double* table, const GmgBesselConsts& bc, const int64_t* i,
-                      const int64_t* j, int64_t n, int disp, double* out, cudaStream_t s) {
-    const unsigned blocks = (unsigned)gmg_ceil_div(n, 256);
-    if (disp == GMG_DISP_MODIFIED_MET_OFFICE)
-        ellipse_pairs_kernel<MODE, GMG_DISP_MODIFIED_MET_OFFICE><<<blocks, 256, 0, s>>>(params, table, bc, i, j, n, out);
-    else
-        ellipse_pairs_kernel<MODE, GMG_DISP_MET_OFFICE><<<blocks, 256, 0, s>>>(params, table, bc, i, j, n, out);
+int launch_pairs(const double* params, const double* table, const GmgBesselConsts& bc, const int64_t* i,
+                 const int64_t* j, int64_t n, double* out, cudaStream_t s) {
+    ellipse_pairs_kernel<MODE><<<(unsigned)gmg_ceil_div(n, 256), 256, 0, s>>>(params, table, bc, i, j, n, out);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
 }
@@ -450,8 +569,8 @@ int gmg_ellipse_ws_bytes(int64_t N, size_t* bytes) {
 }
 
 int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* theta, const double* stdev,
-                            const double* lat_rad, const double* lon_rad, int64_t N, double nu, void* ws,
-                            size_t ws_bytes, gmg_stream_t stream) {
+                            const double* lat_rad, const double* lon_rad, int64_t N, double nu, int disp_method,
+                            void* ws, size_t ws_bytes, gmg_stream_t stream) {
     if (!Lx) return -1;
     if (!Ly) return -2;
     if (!theta) return -3;
@@ -460,7 +579,8 @@ int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* th
     if (!lon_rad) return -6;
     if (N <= 0) return -7;
     if (!(nu > 0.0)) return -8;
-    if (!ws) return -9;
+    if (disp_method != GMG_DISP_MET_OFFICE && disp_method != GMG_DISP_MODIFIED_MET_OFFICE) return -9;
+    if (!ws) return -10;
     size_t need;
     gmg_ellipse_ws_bytes(N, &need);
     if (ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15)) return GMG_ERR_WORKSPACE;
@@ -468,7 +588,7 @@ int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* th
     double* params = const_cast<double*>(ws_params(ws));
     double* table = const_cast<double*>(ws_table(ws));
     ellipse_prepare_kernel<<<(unsigned)gmg_ceil_div(N, 256), 256, 0, s>>>(Lx, Ly, theta, stdev, lat_rad, lon_rad,
-                                                                           N, params);
+                                                                           N, disp_method, params);
     GMG_LAUNCH_CHECK();
     const GmgBesselConsts bc = gmg_make_bessel_consts(nu);
     matern_table_kernel<<<kTabNint, 32, 0, s>>>(bc, table);
@@ -476,18 +596,16 @@ int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* th
     return GMG_OK;
 }
 
-int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, double nu, int disp_method,
-                        double max_dist_km, int matern_mode, void* C_rows, int64_t ld, int store_f32,
-                        gmg_stream_t stream) {
+int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, double nu, double max_dist_km,
+                        int matern_mode, void* C_rows, int64_t ld, int store_f32, gmg_stream_t stream) {
     if (!ws) return -1;
     if (N <= 0) return -2;
     if (row0 < 0 || row0 >= N) return -3;
     if (nrows <= 0 || row0 + nrows > N) return -4;
     if (!(nu > 0.0)) return -5;
-    if (disp_method != GMG_DISP_MET_OFFICE && disp_method != GMG_DISP_MODIFIED_MET_OFFICE) return -6;
-    if (matern_mode < 0 || matern_mode > 2) return -8;
-    if (!C_rows) return -9;
-    if (ld < N) return -10;
+    if (matern_mode < 0 || matern_mode > 2) return -7;
+    if (!C_rows) return -8;
+    if (ld < N) return -9;
     EllipseArgs a;
     a.params = ws_params(ws);
     a.table = ws_table(ws);
@@ -501,43 +619,41 @@ int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, 
     a.max_dist = (max_dist_km >= 0.0) ? max_dist_km : -1.0;
     const size_t elt = store_f32 ? sizeof(float) : sizeof(double);
     a.vec2 = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(C_rows) % (2 * elt)) == 0);
-    a.geom_f32 = store_f32 ? 1 : 0;
     a.bc = gmg_make_bessel_consts(nu);
     const int64_t n_ctas = a.symmetric ? a.n_tri + (int64_t)a.tiles_r * (a.tiles_c - a.tiles_r)
                                        : (int64_t)a.tiles_r * a.tiles_c;
     if (n_ctas > 0x7fffffffLL) return GMG_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     switch (resolve_mode(nu, matern_mode)) {
-        case MODE_NU05: return launch_tiles_disp<MODE_NU05>(a, n_ctas, disp_method, store_f32, s);
-        case MODE_NU15: return launch_tiles_disp<MODE_NU15>(a, n_ctas, disp_method, store_f32, s);
-        case MODE_NU25: return launch_tiles_disp<MODE_NU25>(a, n_ctas, disp_method, store_f32, s);
-        case MODE_TABLE: return launch_tiles_disp<MODE_TABLE>(a, n_ctas, disp_method, store_f32, s);
-        default: return launch_tiles_disp<MODE_DIRECT>(a, n_ctas, disp_method, store_f32, s);
+        case MODE_NU05: return launch_tiles_mode<MODE_NU05>(a, n_ctas, store_f32, s);
+        case MODE_NU15: return launch_tiles_mode<MODE_NU15>(a, n_ctas, store_f32, s);
+        case MODE_NU25: return launch_tiles_mode<MODE_NU25>(a, n_ctas, store_f32, s);
+        case MODE_TABLE: return launch_tiles_mode<MODE_TABLE>(a, n_ctas, store_f32, s);
+        default: return launch_tiles_mode<MODE_DIRECT>(a, n_ctas, store_f32, s);
     }
 }
 
 int gmg_ellipse_pairs_f64(const void* ws, int64_t N, const int64_t* i, const int64_t* j, int64_t npairs,
-                          double nu, int disp_method, int matern_mode, double* out, gmg_stream_t stream) {
+                          double nu, int matern_mode, double* out, gmg_stream_t stream) {
     if (!ws) return -1;
     if (N <= 0) return -2;
     if (!i) return -3;
     if (!j) return -4;
     if (npairs < 0) return -5;
     if (!(nu > 0.0)) return -6;
-    if (disp_method != GMG_DISP_MET_OFFICE && disp_method != GMG_DISP_MODIFIED_MET_OFFICE) return -7;
-    if (matern_mode < 0 || matern_mode > 2) return -8;
-    if (!out) return -9;
+    if (matern_mode < 0 || matern_mode > 2) return -7;
+    if (!out) return -8;
     if (npairs == 0) return GMG_OK;
     const double* params = ws_params(ws);
     const double* table = ws_table(ws);
     const GmgBesselConsts bc = gmg_make_bessel_consts(nu);
     cudaStream_t s = (cudaStream_t)stream;
     switch (resolve_mode(nu, matern_mode)) {
-        case MODE_NU05: return launch_pairs_disp<MODE_NU05>(params, table, bc, i, j, npairs, disp_method, out, s);
-        case MODE_NU15: return launch_pairs_disp<MODE_NU15>(params, table, bc, i, j, npairs, disp_method, out, s);
-        case MODE_NU25: return launch_pairs_disp<MODE_NU25>(params, table, bc, i, j, npairs, disp_method, out, s);
-        case MODE_TABLE: return launch_pairs_disp<MODE_TABLE>(params, table, bc, i, j, npairs, disp_method, out, s);
-        default: return launch_pairs_disp<MODE_DIRECT>(params, table, bc, i, j, npairs, disp_method, out, s);
+        case MODE_NU05: return launch_pairs<MODE_NU05>(params, table, bc, i, j, npairs, out, s);
+        case MODE_NU15: return launch_pairs<MODE_NU15>(params, table, bc, i, j, npairs, out, s);
+        case MODE_NU25: return launch_pairs<MODE_NU25>(params, table, bc, i, j, npairs, out, s);
+        case MODE_TABLE: return launch_pairs<MODE_TABLE>(params, table, bc, i, j, npairs, out, s);
+        default: return launch_pairs<MODE_DIRECT>(params, table, bc, i, j, npairs, out, s);
     }
 }
 

@@ -141,8 +141,9 @@ class EllipseCovarianceBuilder:
         ins = [dev.to_device(a) for a in (self.Lx_compressed, self.Ly_compressed, self.theta_compressed,
                                           self.stdev_compressed, self.lat_grid_compressed_rad,
                                           self.lon_grid_compressed_rad)]
-        check(L.gmg_ellipse_prepare_f64(*[t.data_ptr() for t in ins], N, float(self.v), self._ws.data_ptr(),
-                                        ws_bytes.value, dev.stream_ptr()), "gmg_ellipse_prepare_f64")
+        check(L.gmg_ellipse_prepare_f64(*[t.data_ptr() for t in ins], N, float(self.v),
+                                        _DISP[self.delta_x_method], self._ws.data_ptr(), ws_bytes.value,
+                                        dev.stream_ptr()), "gmg_ellipse_prepare_f64")
         self._inputs_device = ins  # keep alive until the stream has consumed them
 
     def _calculate_covariance(self) -> None:
@@ -156,7 +157,6 @@ class EllipseCovarianceBuilder:
         f32 = self.precision == np.float32
         out = torch.empty((nrows, N), dtype=torch.float32 if f32 else torch.float64, device=self._ws.device)
         check(lib().gmg_ellipse_cov_f64(self._ws.data_ptr(), N, row0, nrows, float(self.v),
-                                        _DISP[self.delta_x_method],
                                         -1.0 if self.max_dist is None else float(self.max_dist),
                                         _MATERN[self.matern_mode], out.data_ptr(), N, int(f32),
                                         dev.stream_ptr()), "gmg_ellipse_cov_f64")
@@ -209,8 +209,7 @@ class EllipseCovarianceBuilder:
         j_t = dev.to_device(np.asarray(j_s), torch.int64)
         out = torch.empty(i_t.numel(), dtype=torch.float64, device=i_t.device)
         check(lib().gmg_ellipse_pairs_f64(self._ws.data_ptr(), self._N, i_t.data_ptr(), j_t.data_ptr(),
-                                          i_t.numel(), float(self.v), _DISP[self.delta_x_method],
-                                          _MATERN[self.matern_mode], out.data_ptr(), dev.stream_ptr()),
+                                          i_t.numel(), float(self.v), _MATERN[self.matern_mode], out.data_ptr(), dev.stream_ptr()),
               "gmg_ellipse_pairs_f64")
         return out.cpu().numpy().astype(self.precision)
 

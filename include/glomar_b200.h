@@ -57,10 +57,13 @@ int gmg_ellipse_ws_bytes(int64_t N, size_t* bytes);
  * and the Matern table for `nu`, packed into `ws`.
  * replaces `_sigma_rot_func_multi` (:512-533), `_det_22_multi` (:543-547) and the pre-terms of
  * `_calculate_covariance` (:218-224).  lat/lon are RADIANS as produced by numpy.deg2rad on the host
- * (:171-172) so that the +-pi longitude-wrap ties are decided on bit-identical inputs. */
+ * (:171-172) so that the +-pi longitude-wrap ties are decided on bit-identical inputs.
+ * `disp_method` selects the displacement function of `_get_disp_fn` (:182-203): it only changes the
+ * per-point mean-cos-latitude term, so it is fixed here and not passed to the build calls. */
 int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* theta,
                             const double* stdev, const double* lat_rad, const double* lon_rad,
-                            int64_t N, double nu, void* ws, size_t ws_bytes, gmg_stream_t stream);
+                            int64_t N, double nu, int disp_method, void* ws, size_t ws_bytes,
+                            gmg_stream_t stream);
 
 /* Rows [row0, row0 + nrows) of the symmetric N x N covariance, written to `C_rows`
  * (nrows x N, leading dimension `ld` elements, FP64 or - if store_f32 - FP32 rounded on store).
@@ -70,13 +73,13 @@ int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* th
  * (:405-468), the displacement helpers (:591-654), `_haversine_multi` (:572-588), the mirror
  * (:277, :401) and the diagonal add (:246).  Row blocks are how the build shards across GPUs. */
 int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, double nu,
-                        int disp_method, double max_dist_km, int matern_mode, void* C_rows,
-                        int64_t ld, int store_f32, gmg_stream_t stream);
+                        double max_dist_km, int matern_mode, void* C_rows, int64_t ld,
+                        int store_f32, gmg_stream_t stream);
 
 /* Covariance of arbitrary index pairs (i[k], j[k]) - no diagonal term, no max_dist.
  * replaces `EllipseCovarianceBuilder.c_ij_anisotropic_array(i_s, j_s)` (:405-468). */
 int gmg_ellipse_pairs_f64(const void* ws, int64_t N, const int64_t* i, const int64_t* j,
-                          int64_t npairs, double nu, int disp_method, int matern_mode, double* out,
+                          int64_t npairs, double nu, int matern_mode, double* out,
                           gmg_stream_t stream);
 
 /* out[k] = K_nu(x[k]) (scaled != 0: e^x K_nu(x)), Temme/CF2 on device.
