@@ -14,7 +14,8 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_uint
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libglomar_b200.so")
+# GLOMAR_B200_LIB selects another build of the same library (kernel experiments); never a fallback
+LIB_PATH = os.environ.get("GLOMAR_B200_LIB") or os.path.join(_HERE, "libglomar_b200.so")
 
 _lib = None
 

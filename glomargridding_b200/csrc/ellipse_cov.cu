@@ -6,21 +6,22 @@
 //   glomar_gridding/ellipse/covariance.py:405-468  c_ij_anisotropic_array (the pair formula)
 //   glomar_gridding/ellipse/covariance.py:512-654  Sigma rotation, 2x2 det, haversine, displacements
 //
-// Design: one CTA computes one 64x64 tile of C in FP64.  Per-point terms
-// (lat, lon, cos lat / 2, Sigma / 2, stdev * det^(1/4), stdev^2) are packed once per build by
-// `ellipse_prepare_kernel` (64 B per point) and staged in shared memory for the tile's 64 row
-// points and 64 column points.  Each thread owns two adjacent columns (held in registers) and 8
-// rows (broadcast from shared memory), so a warp stores 512 contiguous bytes per row with 16-byte
-// vector stores.  Inside the square diagonal block of a row shard only the upper-triangle tiles are
-// computed; the lower ones are written as the transpose of their mirror tile through a padded
+// Design: a persistent grid (2 CTAs per SM) loops over 64 x 64 tiles of C in FP64.
+// Per-point terms (lat, lon, cos lat / 2, Sigma / 2, stdev * det^(1/4), stdev^2) are packed once per
+// build by `ellipse_prepare_kernel` (64 B per point, record-major and field-major copies) and fetched
+// with cp.async into a double-buffered shared-memory stage for the tile's 64 row points and 64 column
+// points while the previous tile is computed.  Each thread owns two adjacent columns (held in
+// registers) and 8 rows (broadcast from shared memory), so a warp stores 512 contiguous bytes per row
+// with 16-byte vector stores.  Inside the square diagonal block of a row shard only the upper-triangle
+// tiles are computed; the lower ones are written as the transpose of their mirror tile through a padded
 // shared-memory tile, so the FP64 work is halved and both stores stay coalesced.
 // The formula is sign-symmetric under i <-> j (IEEE add/mul are commutative and the wrap is odd),
 // so the mirrored entries are bit-identical to evaluating them in the reference's i<j orientation.
 //
 // The Matern factor x^nu K_nu(x) / (Gamma(nu) 2^(nu-1)) is evaluated as g(x) e^-x with
 //   nu = 0.5 / 1.5 / 2.5 : g = 1, 1 + x, 1 + x + x^2/3              (closed forms)
-//   otherwise            : g from a piecewise degree-12 polynomial table in the mantissa of x
-//                          (4 linear sub-intervals per octave, 2^-20 <= x < 2^10), built on the
+//   otherwise            : g from a piecewise degree-7 polynomial table in the mantissa of x
+//                          (16 linear sub-intervals per octave, 2^-12 <= x < 2^10), built on the
 //                          device from the Temme/CF2 Bessel-K in bessel_k.cuh for the build's nu;
 //                          lanes outside the table range fall back to the direct evaluation.
 #include "gmg_common.cuh"
@@ -38,14 +39,15 @@ constexpr int kThreads = 256;
 constexpr int kTileLd = kTile + 1;                  // odd leading dimension: conflict-free transposed reads
 
 // Matern table geometry
-constexpr int kTabEmin = -20;
+constexpr int kTabEmin = -12;
 constexpr int kTabEmax = 10;                        // exclusive
 constexpr int kTabSubLog2 = 4;
 constexpr int kTabSub = 1 << kTabSubLog2;                   // linear sub-intervals of the mantissa per octave
-constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 480
+constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 352
 constexpr int kTabDeg = 7;
 constexpr int kTabCoef = kTabDeg + 1;
-constexpr int kTabDoubles = kTabNint * kTabCoef;            // 3840 (30.7 KB)
+constexpr int kTabDoubles = kTabNint * kTabCoef;            // 2816 (22.5 KB), layout [interval][coef]
+static_assert(kTabCoef == 8, "the table record is read as four 16-byte loads");
 
 enum { MODE_NU05 = 0, MODE_NU15 = 1, MODE_NU25 = 2, MODE_TABLE = 3, MODE_DIRECT = 4 };
 
@@ -55,29 +57,41 @@ enum { P_LAT = 0, P_LON = 1, P_HCOS = 2, P_H00 = 3, P_H01 = 4, P_H11 = 5, P_W = 
 __global__ void __launch_bounds__(256) ellipse_prepare_kernel(
     const double* __restrict__ Lx, const double* __restrict__ Ly, const double* __restrict__ theta,
     const double* __restrict__ stdev, const double* __restrict__ lat, const double* __restrict__ lon,
-    int64_t N, int disp_method, double* __restrict__ params) {
+    int64_t N, int64_t npad, int disp_method, double* __restrict__ aos, double* __restrict__ soa) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    // reference `_sigma_rot_func_multi`, ellipse/covariance.py:512-533
-    double st, ct;
-    sincos(theta[i], &st, &ct);
-    const double c2 = ct * ct, s2 = st * st, cs = ct * st;
-    const double lx2 = Lx[i] * Lx[i], ly2 = Ly[i] * Ly[i];
-    const double s00 = __dadd_rn(__dmul_rn(c2, lx2), __dmul_rn(s2, ly2));
-    const double s01 = __dmul_rn(cs, lx2 - ly2);
-    const double s11 = __dadd_rn(__dmul_rn(s2, lx2), __dmul_rn(c2, ly2));
-    const double det = __dsub_rn(__dmul_rn(s00, s11), __dmul_rn(s01, s01));   // :543-547
-    const double sd = stdev[i];
-    double* p = params + i * P_N;
-    p[P_LAT] = lat[i];
-    p[P_LON] = lon[i];
-    // 0.5*(cos a + cos b) == 0.5 cos a + 0.5 cos b exactly; "Met_Office" has no cos-latitude factor (0.5 + 0.5 = 1)
-    p[P_HCOS] = disp_method == GMG_DISP_MODIFIED_MET_OFFICE ? 0.5 * cos(lat[i]) : 0.5;
-    p[P_H00] = 0.5 * s00;                   // 0.5*(S_i + S_j)   == 0.5 S_i + 0.5 S_j     exactly
-    p[P_H01] = 0.5 * s01;
-    p[P_H11] = 0.5 * s11;
-    p[P_W] = sd * sqrt(sqrt(det));          // stdev_i * det_i^(1/4): sqrt(sqrt_det_i sqrt_det_j) = q_i q_j
-    p[P_VAR] = sd * sd;                     // diagonal, :246
+    if (i >= npad + kTile) return;
+    double rec[P_N];
+    if (i < N) {
+        // reference `_sigma_rot_func_multi`, ellipse/covariance.py:512-533
+        double st, ct;
+        sincos(theta[i], &st, &ct);
+        const double c2 = ct * ct, s2 = st * st, cs = ct * st;
+        const double lx2 = Lx[i] * Lx[i], ly2 = Ly[i] * Ly[i];
+        const double s00 = __dadd_rn(__dmul_rn(c2, lx2), __dmul_rn(s2, ly2));
+        const double s01 = __dmul_rn(cs, lx2 - ly2);
+        const double s11 = __dadd_rn(__dmul_rn(s2, lx2), __dmul_rn(c2, ly2));
+        const double det = __dsub_rn(__dmul_rn(s00, s11), __dmul_rn(s01, s01));   // :543-547
+        const double sd = stdev[i];
+        rec[P_LAT] = lat[i];
+        rec[P_LON] = lon[i];
+        // 0.5*(cos a + cos b) == 0.5 cos a + 0.5 cos b exactly; "Met_Office" has no cos-latitude factor
+        // (0.5 + 0.5 == 1)
+        rec[P_HCOS] = disp_method == GMG_DISP_MODIFIED_MET_OFFICE ? 0.5 * cos(lat[i]) : 0.5;
+        rec[P_H00] = 0.5 * s00;                 // 0.5*(S_i + S_j)   == 0.5 S_i + 0.5 S_j     exactly
+        rec[P_H01] = 0.5 * s01;
+        rec[P_H11] = 0.5 * s11;
+        rec[P_W] = sd * sqrt(sqrt(det));        // stdev_i * det_i^(1/4): sqrt(sqrt_det_i sqrt_det_j) = q_i q_j
+        rec[P_VAR] = sd * sd;                   // diagonal, :246
+    } else {
+        // padding points of partial tiles: benign values (det = 1 > 0, q = 0 -> cold path), never stored
+#pragma unroll
+        for (int f = 0; f < P_N; ++f) rec[f] = 1.0;
+    }
+#pragma unroll
+    for (int f = 0; f < P_N; ++f) {
+        aos[i * P_N + f] = rec[f];
+        if (i < npad) soa[f * npad + i] = rec[f];
+    }
 }
 
 // One block per table interval: sample g at Chebyshev nodes, transform to monomial coefficients in
@@ -114,15 +128,30 @@ __global__ void __launch_bounds__(32) matern_table_kernel(GmgBesselConsts bc, do
             for (int j = 0; j < kTabCoef; ++j) tmp[j] = (j > 0 ? 2.0 * tn[j - 1] : 0.0) - tp[j];
             for (int j = 0; j < kTabCoef; ++j) { tp[j] = tn[j]; tn[j] = tmp[j]; mono[j] += cheb[n] * tmp[j]; }
         }
-        for (int j = 0; j < kTabCoef; ++j) table[j * kTabNint + interval] = mono[j];   // [coef][interval]
+        for (int j = 0; j < kTabCoef; ++j) table[interval * kTabCoef + j] = mono[j];   // [interval][coef]
     }
 }
 
 struct MaternCtx {
     GmgBesselConsts bc;
-    const double* table;   // shared-memory (tile kernel) or global (pairs kernel) pointer, [coef][interval]
+    const double* table;   // shared-memory (tile kernel) or global (pairs kernel) pointer, [interval][coef]
     double x_scale;        // 2 sqrt(nu) * R: inner = x_scale * sqrt(Q_rad / det)
 };
+
+// degree-7 Horner on one 64 B table record (four 16-byte loads)
+__device__ __forceinline__ double table_horner(const double* c, double t) {
+    const double2 c01 = *reinterpret_cast<const double2*>(c);
+    const double2 c23 = *reinterpret_cast<const double2*>(c + 2);
+    const double2 c45 = *reinterpret_cast<const double2*>(c + 4);
+    const double2 c67 = *reinterpret_cast<const double2*>(c + 6);
+    double p = fma(c67.y, t, c67.x);
+    p = fma(p, t, c45.y);
+    p = fma(p, t, c45.x);
+    p = fma(p, t, c23.y);
+    p = fma(p, t, c23.x);
+    p = fma(p, t, c01.y);
+    return fma(p, t, c01.x);
+}
 
 template <int MODE>
 __device__ __forceinline__ double matern_scaled_eval(const MaternCtx& m, double x) {
@@ -138,11 +167,7 @@ __device__ __forceinline__ double matern_scaled_eval(const MaternCtx& m, double 
             const int cbits = (hi & ((kTabSub - 1) << (20 - kTabSubLog2))) | (1 << (19 - kTabSubLog2));
             const double centre = __hiloint2double(0x3FF00000 | cbits, 0);
             const double t = (mant - centre) * (double)(2 * kTabSub);
-            const double* c = m.table + idx;
-            double p = c[kTabDeg * kTabNint];
-#pragma unroll
-            for (int k = kTabDeg - 1; k >= 0; --k) p = fma(p, t, c[k * kTabNint]);
-            return p;
+            return table_horner(m.table + idx * kTabCoef, t);
         }
     }
     return gmg_matern_scaled(m.bc, x);
@@ -168,7 +193,11 @@ __device__ __forceinline__ PointRegs load_point(const double* p) {     // p: 8 c
 // unusual (x >= 700, x outside the Matern table, NaN from a non-positive determinant) is flagged and
 // recomputed on a cold path with the libm functions.
 
-// 2^(-j/64), j = 0..63, correctly rounded (mpmath); staged in shared memory by every CTA
+// 2^(-j/64), j = 0..63, correctly rounded (mpmath).  Every CTA stages kExpRep = 16 interleaved copies in
+// shared memory, entry j of copy c at [j * 16 + c]: a 64-bit shared load is served per half-warp, and lane l
+// reads copy l & 15, i.e. always its own bank pair - the data-dependent lookup is conflict-free
+// (ncu r01b: 4.8 wavefronts per lookup with a single copy).
+constexpr int kExpRep = 16;
 __device__ const double kExp2Neg64[64] = {
     1.0, 0.9892280131939755, 0.9785720620877001, 0.9680308967461472,
     0.9576032806985737, 0.9472879907934828, 0.93708381705515, 0.9269895625416927,
@@ -187,45 +216,61 @@ __device__ const double kExp2Neg64[64] = {
     0.5452538663326288, 0.5393803988785599, 0.5335702003384118, 0.5278225891802786,
     0.5221368912137069, 0.5165124395106142, 0.5109485743270583, 0.5054446430258502};
 
+// FP64 literals of the hot loop live in constant memory: a DFMA can take a c[bank][offset] operand directly,
+// whereas a 64-bit immediate costs two extra MOV issue slots per use once registers are short (ncu r01c: the
+// loop was issue-bound, 53 non-FP64 instructions per pair for 45 FP64 ones).
+struct HotConsts {
+    double magic, inv_ln2_64, ln2_64_hi, ln2_64_lo, c5, c4, c3, half, one, c38, pi, third;
+};
+__constant__ HotConsts kHot = {6755399441055744.0,        // 1.5 * 2^52
+                               92.33248261689366,         // 64 / ln 2
+                               0.010830424695086549,      // ln2/64 hi (33 significant bits)
+                               1.162596423439437e-12,     // ln2/64 lo
+                               8.33333333333333333333e-03, 4.16666666666666666667e-02,
+                               1.66666666666666666667e-01, 0.5, 1.0, 0.375, 3.141592653589793,
+                               1.0 / 3.0};
+
 // 1/sqrt(a), a > 0 normal: MUFU seed (rel. error < 2^-22) and one cubically convergent step
 //   e = 1 - a r^2,  r <- r + r e (1/2 + 3/8 e)      (error ~ 5/16 e^3 < 2^-64)       5 FP64 instructions
 __device__ __forceinline__ double rsqrt_pos(double a) {
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    const double e = fma(-(a * r), r, 1.0);
-    return fma(r * e, fma(e, 0.375, 0.5), r);
+    const double e = fma(-(a * r), r, kHot.one);
+    return fma(r * e, fma(e, kHot.c38, kHot.half), r);
 }
 
 // exp(-x) for 0 <= x < 700 (result normal):  k = rint(64 x / ln 2),  exp(-x) = 2^-(k>>6) T[k&63] exp(s),
 // s = k ln2/64 - x in [-ln2/128, ln2/128] (Cody-Waite, k ln2_hi exact for k < 2^17), degree-5 Taylor
 // (truncation s^6/720 < 3.5e-17).  9 FP64 instructions + one shared-memory load.
+template <int STRIDE>
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ sexp) {
-    const double kMagic = 6755399441055744.0;                     // 1.5 * 2^52
-    const double t = fma(x, 92.33248261689366, kMagic);           // 64 / ln 2
+    const double t = fma(x, kHot.inv_ln2_64, kHot.magic);
     const int k = __double2loint(t);
-    const double kf = t - kMagic;
-    double s = fma(kf, 0.010830424695086549, -x);                 // ln2/64 hi (33 significant bits)
-    s = fma(kf, 1.162596423439437e-12, s);                        // ln2/64 lo
-    double p = 8.33333333333333333333e-03;                        // 1/5!
-    p = fma(p, s, 4.16666666666666666667e-02);                    // 1/4!
-    p = fma(p, s, 1.66666666666666666667e-01);                    // 1/3!
-    p = fma(p, s, 0.5);
-    p = fma(p, s, 1.0);
-    const double ts = sexp[k & 63];
+    const double kf = t - kHot.magic;
+    double s = fma(kf, kHot.ln2_64_hi, -x);
+    s = fma(kf, kHot.ln2_64_lo, s);
+    double p = fma(kHot.c5, s, kHot.c4);                          // 1/5!, 1/4!
+    p = fma(p, s, kHot.c3);                                       // 1/3!
+    p = fma(p, s, kHot.half);
+    p = fma(p, s, kHot.one);
+    const double ts = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(sexp) +
+                                                       (k & 63) * (STRIDE * (int)sizeof(double)));
     p = fma(ts * s, p, ts);                                       // T (1 + s p)
-    return __hiloint2double(__double2hiint(p) - ((k >> 6) << 20), __double2loint(p));
+    // 2^-(k >> 6): subtract (k >> 6) << 20 from the high word = (k & ~63) * 2^14, one LOP3 + one IMAD
+    return __hiloint2double(__double2hiint(p) - (k & ~63) * 16384, __double2loint(p));
 }
 
 // g(x) of the fast path; `slow` is set when the lane must be recomputed by `cov_pair_slow`.
 template <int MODE>
 __device__ __forceinline__ double matern_scaled_fast(const MaternCtx& m, double x, bool& slow) {
-    slow = !(x < 700.0);                                          // also catches NaN
-    if (MODE == MODE_NU05) return 1.0;
-    if (MODE == MODE_NU15) return 1.0 + x;
-    if (MODE == MODE_NU25) return fma(x, fma(x, 1.0 / 3.0, 1.0), 1.0);
-    if (MODE == MODE_DIRECT) { slow = true; return 0.0; }         // validation mode: always the cold path
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
+    // !(0 <= x < 700) on the high word in the integer pipe (700.0 = 0x4085E000_00000000); also catches NaN
+    slow = (unsigned)hi >= 0x4085E000u;
+    if (MODE == MODE_NU05) return kHot.one;
+    if (MODE == MODE_NU15) return kHot.one + x;
+    if (MODE == MODE_NU25) return fma(x, fma(x, kHot.third, kHot.one), kHot.one);
+    if (MODE == MODE_DIRECT) { slow = true; return 0.0; }         // validation mode: always the cold path
     int idx = ((hi >> 20) - (1023 + kTabEmin)) * kTabSub + ((hi >> (20 - kTabSubLog2)) & (kTabSub - 1));
     slow = slow || ((unsigned)idx >= (unsigned)kTabNint);
     idx = min(max(idx, 0), kTabNint - 1);
@@ -233,22 +278,15 @@ __device__ __forceinline__ double matern_scaled_fast(const MaternCtx& m, double 
     const int cbits = (hi & (((kTabSub - 1) << (20 - kTabSubLog2)))) | (1 << (19 - kTabSubLog2));
     const double centre = __hiloint2double(0x3FF00000 | cbits, 0);
     const double t = (mant - centre) * (double)(2 * kTabSub);
-    const double* c = m.table + idx;
-    double p = c[kTabDeg * kTabNint];
-#pragma unroll
-    for (int k = kTabDeg - 1; k >= 0; --k) p = fma(p, t, c[k * kTabNint]);
-    return p;
+    return table_horner(m.table + idx * kTabCoef, t);
 }
 
 // longitude wrap, reference ellipse/covariance.py:633-634:  dx > pi -> dx - 2 pi,  dx < -pi -> dx + 2 pi
-// (strict).  |dx| <= 2 pi, so this is dx - copysign(2 pi, dx) when |dx| > pi; the comparison is done on the
-// bit pattern in the integer pipe (IEEE doubles of one sign order like integers) to keep it off the FP64
-// pipe, and the subtraction of +0.0 in the other case is exact.
+// (strict).  |dx| <= 2 pi, so this is dx - copysign(2 pi, dx) when |dx| > pi: one DSETP, one DADD and three
+// integer instructions; the subtraction of +0.0 in the other case is exact.
 __device__ __forceinline__ double wrap_lon(double dx) {
+    const bool gt = fabs(dx) > kHot.pi;                                                // |dx| > np.pi, strict
     const unsigned hi = (unsigned)__double2hiint(dx);
-    const unsigned lo = (unsigned)__double2loint(dx);
-    const unsigned ahi = hi & 0x7fffffffu;
-    const bool gt = (ahi > 0x400921FBu) || (ahi == 0x400921FBu && lo > 0x54442D18u);   // |dx| > np.pi
     const unsigned whi = gt ? (0x401921FBu | (hi & 0x80000000u)) : 0u;                 // copysign(2 pi, dx)
     const unsigned wlo = gt ? 0x54442D18u : 0u;
     return dx - __hiloint2double((int)whi, (int)wlo);
@@ -288,42 +326,46 @@ __device__ __forceinline__ PairGeom pair_geom(const PointRegs& a, const PointReg
     return g;
 }
 
-template <int MODE, bool GEOM_F32>
+template <int MODE, bool GEOM_F32, int EXPSTRIDE>
 __device__ __forceinline__ double cov_pair(const PointRegs& a, const PointRegs& b, const MaternCtx& m,
                                            const double* __restrict__ sexp, bool& slow) {
     const PairGeom g = pair_geom<GEOM_F32>(a, b);
     const double r = rsqrt_pos(g.det);
     const double x = (m.x_scale * g.q) * rsqrt_pos(g.q) * r;                    // :457 inner
     const double gm = matern_scaled_fast<MODE>(m, x, slow);
-    return ((a.w * b.w) * r) * gm * exp_neg(x, sexp);                           // :447-455, :465-466
+    return ((a.w * b.w) * r) * gm * exp_neg<EXPSTRIDE>(x, sexp);                           // :447-455, :465-466
 }
 
 // Cold path for flagged lanes: libm sqrt / exp, Temme-CF2 Bessel-K; any x (incl. underflow to 0 and NaN).
 // Takes pointers (to the 64 B point records and to the context) so that the hot loop never spills its
 // registers to the stack to make the call.
 template <int MODE, bool GEOM_F32>
-__device__ __noinline__ double cov_pair_slow(const double* pa, const double* pb, const MaternCtx* m) {
-    const PointRegs a = load_point(pa), b = load_point(pb);
+__device__ __noinline__ double cov_pair_slow(const double* pa, const double* pb, int sb, const MaternCtx* m) {
+    const PointRegs a = load_point(pa);
+    PointRegs b;                                     // second point: field f at pb[f * sb]
+    b.lat = pb[P_LAT * sb]; b.lon = pb[P_LON * sb]; b.hcos = pb[P_HCOS * sb]; b.h00 = pb[P_H00 * sb];
+    b.h01 = pb[P_H01 * sb]; b.h11 = pb[P_H11 * sb]; b.w = pb[P_W * sb];
     const PairGeom g = pair_geom<GEOM_F32>(a, b);
     const double x = m->x_scale * sqrt(g.q / g.det);
     return (a.w * b.w) * rsqrt(g.det) * matern_scaled_eval<MODE>(*m, x) * exp(-x);
 }
 
 // `_haversine_multi`, ellipse/covariance.py:572-588 (only when max_dist is set, :256-266)
-__device__ __noinline__ bool beyond_max_dist(const double* pa, const double* pb, double max_dist) {
-    const double lat0 = pa[P_LAT], lat1 = pb[P_LAT];
-    const double sl = sin(0.5 * (lat0 - lat1)), so = sin(0.5 * (pa[P_LON] - pb[P_LON]));
+__device__ __noinline__ bool beyond_max_dist(const double* pa, const double* pb, int sb, double max_dist) {
+    const double lat0 = pa[P_LAT], lat1 = pb[P_LAT * sb];
+    const double sl = sin(0.5 * (lat0 - lat1)), so = sin(0.5 * (pa[P_LON] - pb[P_LON * sb]));
     const double h = sl * sl + cos(lat0) * cos(lat1) * so * so;
     return kEarthRadiusKm * (2.0 * asin(sqrt(h))) > max_dist;
 }
 
 struct EllipseArgs {
-    const double* params;
+    const double* aos;      // [npad + kTile][P_N] point records (rows of a tile: one 16 B cp.async per thread)
+    const double* soa;      // [P_N][npad]         the same, field-major (columns of a tile)
     const double* table;
     void* out;
-    int64_t N, row0, nrows, ld;
+    int64_t N, npad, row0, nrows, ld;
     int tiles_r, tiles_c, tile_b0, symmetric;
-    int64_t n_tri;
+    int64_t n_tri, n_tiles;
     double max_dist;
     int vec2;
     GmgBesselConsts bc;
@@ -346,119 +388,202 @@ __device__ __forceinline__ void store_pair(OutT* p, double v0, double v1, bool s
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct TileId { int ta, tb; bool mirror; };
+
+// Tile `id` of the launch -> (row tile, column tile).  In symmetric mode (row0 aligned to the tile size) the
+// first n_tri ids enumerate the upper triangle of the tiles_r x tiles_r block on the diagonal - rows r and
+// tiles_r-1-r are folded into one strip of tiles_r+1 tiles, so the decode is one integer division - and
+// those tiles are also written transposed; the remaining ids are the columns left and right of that block.
+__device__ __forceinline__ TileId decode_tile(const EllipseArgs& a, int64_t id) {
+    TileId t;
+    t.mirror = false;
+    if (a.symmetric) {
+        if (id < a.n_tri) {
+            const int T = a.tiles_r, w = T + 1;
+            const int pr = (int)(id / w), k = (int)(id - (int64_t)pr * w);
+            int r, off;
+            if (k < T - pr) { r = pr; off = k; } else { r = T - 1 - pr; off = k - (T - pr); }
+            t.ta = r;
+            t.tb = a.tile_b0 + r + off;
+            t.mirror = off > 0;
+        } else {
+            const int64_t rest = id - a.n_tri;
+            const int wide = a.tiles_c - a.tiles_r;
+            t.ta = (int)(rest / wide);
+            const int c = (int)(rest - (int64_t)t.ta * wide);
+            t.tb = c < a.tile_b0 ? c : c + a.tiles_r;
+        }
+    } else {
+        t.ta = (int)(id / a.tiles_c);
+        t.tb = (int)(id - (int64_t)t.ta * a.tiles_c);
+    }
+    return t;
+}
+
+#ifndef K1_MINB
+#define K1_MINB 2
+#endif
+#ifndef K1_UNROLL
+#define K1_UNROLL 1
+#endif
+
+// Persistent kernel: K1_MINB CTAs per SM, each looping over tiles id = blockIdx.x, += gridDim.x.  The exp and
+// Matern tables are staged once per CTA; the 2 x 4 KB of per-point records of the NEXT tile are fetched with
+// cp.async into the other half of a double buffer while the current tile is computed.
 template <int MODE, bool MAXDIST, typename OutT>
-__global__ void __launch_bounds__(kThreads, 2) ellipse_cov_tile_kernel(const EllipseArgs a) {
+__global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(const EllipseArgs a) {
     constexpr bool GEOM_F32 = sizeof(OutT) == 4;
     extern __shared__ __align__(16) double smem[];
-    double* rowp = smem;                              // [kTile][P_N]  (AoS: one row point = 64 B, LDS.128 broadcast)
-    double* colp = rowp + P_N * kTile;                // [kTile][P_N]
-    double* sexp = colp + P_N * kTile;                // [64]
-    double* tileT = sexp + 64;                        // [kTile][kTileLd]
-    double* stab = tileT + kTile * kTileLd;           // [kTabCoef][kTabNint] (MODE_TABLE only)
+    double* rowp = smem;                              // [2][kTile][P_N]  records (one LDS.128 broadcast per 2 fields)
+    double* colp = rowp + 2 * P_N * kTile;            // [2][P_N][kTile]  field-major (conflict-free LDS.128)
+    double* sexp = colp + 2 * P_N * kTile;            // [64][kExpRep]
+    double* tileT = sexp + 64 * kExpRep;              // [kTile][kTileLd]
+    double* stab = tileT + kTile * kTileLd;           // [kTabNint][kTabCoef] (MODE_TABLE only)
     __shared__ MaternCtx sctx;                        // for the cold path
 
-    // ---- which tile -------------------------------------------------------------------------
-    int ta, tb;
-    bool mirror = false;
-    {
-        const int64_t id = blockIdx.x;
-        if (a.symmetric) {
-            if (id < a.n_tri) {
-                // row-major upper triangle of the tiles_r x tiles_r diagonal block
-                const double n2 = 2.0 * a.tiles_r + 1.0;
-                int r = (int)floor((n2 - sqrt(n2 * n2 - 8.0 * (double)id)) * 0.5);
-                auto off = [&](int rr) { return (int64_t)rr * a.tiles_r - (int64_t)rr * (rr - 1) / 2; };
-                while (r > 0 && off(r) > id) --r;
-                while (off(r + 1) <= id) ++r;
-                ta = r;
-                const int bp = r + (int)(id - off(r));
-                tb = a.tile_b0 + bp;
-                mirror = bp > r;
-            } else {
-                const int64_t rest = id - a.n_tri;
-                const int wide = a.tiles_c - a.tiles_r;
-                ta = (int)(rest / wide);
-                const int c = (int)(rest % wide);
-                tb = c < a.tile_b0 ? c : c + a.tiles_r;
-            }
-        } else {
-            ta = (int)(id / a.tiles_c);
-            tb = (int)(id % a.tiles_c);
-        }
-    }
-    const int64_t i0 = a.row0 + (int64_t)ta * kTile;   // global index of the tile's first row point
-    const int64_t j0 = (int64_t)tb * kTile;            // global index of the tile's first column point
-    const int64_t row_end = a.row0 + a.nrows;
-
-    // ---- stage per-point terms (64 B records, coalesced) and the tables -----------------------
     const int tid = threadIdx.x;
-    for (int e = tid; e < 2 * kTile * P_N; e += kThreads) {
-        const int which = e / (kTile * P_N);           // 0 rows, 1 cols
-        const int rem = e % (kTile * P_N);
-        const int64_t g = (which ? j0 : i0) + rem / P_N;
-        // out-of-range points get benign values (1.0 everywhere: det = 1 > 0, q = 0 -> cold path, never stored)
-        (which ? colp : rowp)[rem] = (g < a.N) ? a.params[g * P_N + rem % P_N] : 1.0;
-    }
-    if (tid < 64) sexp[tid] = kExp2Neg64[tid];
+    const int warp = tid >> 5, lane = tid & 31;
+    const int jl = 2 * lane;
+    const int64_t row_end = a.row0 + a.nrows;
+    OutT* out = reinterpret_cast<OutT*>(a.out);
+
+    auto stage = [&](int buf, const TileId& t) {      // 2 x 16 B per thread
+        const int64_t i0 = a.row0 + (int64_t)t.ta * kTile, j0 = (int64_t)t.tb * kTile;
+        cp_async16(rowp + buf * (P_N * kTile) + 2 * tid, a.aos + i0 * P_N + 2 * tid);
+        const int f = tid >> 5, part = tid & 31;       // field f, points 2 part, 2 part + 1
+        cp_async16(colp + buf * (P_N * kTile) + f * kTile + 2 * part, a.soa + f * a.npad + j0 + 2 * part);
+    };
+
+    int64_t id = blockIdx.x;
+    if (id >= a.n_tiles) return;
+    TileId t = decode_tile(a, id);
+    stage(0, t);
+    cp_async_commit();
+
+    for (int e = tid; e < 64 * kExpRep; e += kThreads) sexp[e] = kExp2Neg64[e / kExpRep];
     MaternCtx m;
     m.bc = a.bc;
     m.table = stab;
     m.x_scale = a.bc.two_sqrt_nu * kEarthRadiusKm;
     if (MODE == MODE_TABLE) {
-        for (int e = tid; e < kTabDoubles; e += kThreads) stab[e] = a.table[e];
+        for (int e = tid; e < kTabDoubles / 2; e += kThreads)
+            reinterpret_cast<double2*>(stab)[e] = reinterpret_cast<const double2*>(a.table)[e];
     }
     if (tid == 0) sctx = m;
-    __syncthreads();
+    const double* sexp_lane = sexp + (lane & (kExpRep - 1));
 
-    const int warp = tid >> 5, lane = tid & 31;
-    const int jl = 2 * lane;
-    const double* pc0 = colp + jl * P_N;
-    const double* pc1 = pc0 + P_N;
-    const PointRegs c0 = load_point(pc0), c1 = load_point(pc1);
-    const int64_t gj = j0 + jl;
-    const bool col0_ok = gj < a.N, col1_ok = gj + 1 < a.N;
-    OutT* out = reinterpret_cast<OutT*>(a.out);
-
-#pragma unroll 2
-    for (int r = 0; r < kTile / 8; ++r) {
-        const int il = warp * (kTile / 8) + r;
-        const int64_t gi = i0 + il;
-        const double* pr = rowp + il * P_N;
-        const PointRegs p = load_point(pr);
-        bool slow0, slow1;
-        double v0 = cov_pair<MODE, GEOM_F32>(p, c0, m, sexp, slow0);
-        double v1 = cov_pair<MODE, GEOM_F32>(p, c1, m, sexp, slow1);
-        if (slow0) v0 = cov_pair_slow<MODE, GEOM_F32>(pr, pc0, &sctx);
-        if (slow1) v1 = cov_pair_slow<MODE, GEOM_F32>(pr, pc1, &sctx);
-        if (MAXDIST) {                                // :256-266 pairs beyond max_dist stay 0
-            if (beyond_max_dist(pr, pc0, a.max_dist)) v0 = 0.0;
-            if (beyond_max_dist(pr, pc1, a.max_dist)) v1 = 0.0;
+    int buf = 0;
+    for (;;) {
+        const int64_t id_next = id + gridDim.x;
+        const bool has_next = id_next < a.n_tiles;
+        TileId tn = t;
+        if (has_next) {
+            tn = decode_tile(a, id_next);
+            stage(buf ^ 1, tn);
         }
-        const double var = pr[P_VAR];
-        if (gi == gj) v0 = var;                       // diagonal = stdev^2, :246
-        if (gi == gj + 1) v1 = var;
-        if (gi < row_end && col0_ok)
-            store_pair<OutT>(out + (gi - a.row0) * a.ld + gj, v0, v1, col1_ok, a.vec2 != 0);
+        cp_async_commit();
+        cp_async_wait<1>();                           // this tile's records have landed (the next may be in flight)
+        __syncthreads();
+
+        const double* rp = rowp + buf * (P_N * kTile);
+        const double* cp = colp + buf * (P_N * kTile);
+        const int64_t i0 = a.row0 + (int64_t)t.ta * kTile;   // global index of the tile's first row point
+        const int64_t j0 = (int64_t)t.tb * kTile;            // global index of the tile's first column point
+        const bool mirror = t.mirror;
+
+        PointRegs c0, c1;
+        {
+            auto ld2 = [&](int f, double& x0, double& x1) {
+                const double2 v = *reinterpret_cast<const double2*>(cp + f * kTile + jl);
+                x0 = v.x;
+                x1 = v.y;
+            };
+            ld2(P_LAT, c0.lat, c1.lat);   ld2(P_LON, c0.lon, c1.lon);   ld2(P_HCOS, c0.hcos, c1.hcos);
+            ld2(P_H00, c0.h00, c1.h00);   ld2(P_H01, c0.h01, c1.h01);   ld2(P_H11, c0.h11, c1.h11);
+            ld2(P_W, c0.w, c1.w);
+        }
+        // CTA-uniform tile classification, so that the per-row epilogue of the common case (a full tile off the
+        // diagonal) is one vector store: `diag` = the tile touches the matrix diagonal, `full` = all 64 x 64
+        // entries are inside the row block / matrix and the output admits 16 B (8 B for float) vector stores.
+        const int64_t dlt = j0 - i0;                  // column index - row index at the tile origin
+        const bool diag = dlt > -(int64_t)kTile && dlt < (int64_t)kTile;
+        const bool full = (i0 + kTile <= row_end) && (j0 + kTile <= a.N) && a.vec2;
+        const int dl = diag ? (int)dlt : (1 << 20);   // il == jl + dl  <=>  global row == global column
+        const int rows_ok = (int)min((int64_t)kTile, row_end - i0);
+        const int cols_ok = (int)min((int64_t)kTile, a.N - j0);
+        OutT* orow = out + (i0 - a.row0 + warp * (kTile / 8)) * a.ld + (j0 + jl);
+
+        // software pipeline: the next row's record is fetched from shared memory while this row is computed
+        // (ncu r01b: 12 % of the stall samples sat on the first use of the row record)
+        PointRegs pnext = load_point(rp + warp * (kTile / 8) * P_N);
+        constexpr int kRowUnroll = K1_UNROLL;
+#pragma unroll kRowUnroll
+        for (int r = 0; r < kTile / 8; ++r) {
+            const int il = warp * (kTile / 8) + r;
+            const double* pr = rp + il * P_N;
+            const PointRegs p = pnext;
+            if (r + 1 < kTile / 8) pnext = load_point(pr + P_N);
+            bool slow0, slow1;
+            double v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
+            double v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
+            if (slow0 | slow1) {                      // one cold branch for both pairs
+                if (slow0) v0 = cov_pair_slow<MODE, GEOM_F32>(pr, cp + jl, kTile, &sctx);
+                if (slow1) v1 = cov_pair_slow<MODE, GEOM_F32>(pr, cp + jl + 1, kTile, &sctx);
+            }
+            if (MAXDIST) {                            // :256-266 pairs beyond max_dist stay 0
+                if (beyond_max_dist(pr, cp + jl, kTile, a.max_dist)) v0 = 0.0;
+                if (beyond_max_dist(pr, cp + jl + 1, kTile, a.max_dist)) v1 = 0.0;
+            }
+            if (diag) {                               // diagonal = stdev^2, :246
+                const double var = pr[P_VAR];
+                if (il == jl + dl) v0 = var;
+                if (il == jl + 1 + dl) v1 = var;
+            }
+            if (full) {
+                typename Vec2<OutT>::type v;
+                v.x = (OutT)v0;
+                v.y = (OutT)v1;
+                *reinterpret_cast<typename Vec2<OutT>::type*>(orow) = v;
+            } else if (il < rows_ok && jl < cols_ok) {
+                store_pair<OutT>(orow, v0, v1, jl + 1 < cols_ok, a.vec2 != 0);
+            }
+            orow += a.ld;
+            if (mirror) {
+                tileT[il * kTileLd + jl] = v0;
+                tileT[il * kTileLd + jl + 1] = v1;
+            }
+        }
         if (mirror) {
-            tileT[il * kTileLd + jl] = v0;
-            tileT[il * kTileLd + jl + 1] = v1;
-        }
-    }
-    if (!mirror) return;
-    __syncthreads();
-    // ---- transposed tile: rows j0.. of C, columns i0.. (inside the shard's square block) ----------
+            __syncthreads();
+            // ---- transposed tile: rows j0.. of C, columns i0.. (inside the shard's square block) ------
 #pragma unroll 2
-    for (int r = 0; r < kTile / 8; ++r) {
-        const int jj = warp * (kTile / 8) + r;
-        const int64_t grow = j0 + jj;                 // global row of the mirrored entry
-        if (grow >= row_end || grow >= a.N) continue;
-        OutT* dst = out + (grow - a.row0) * a.ld + i0;
+            for (int r = 0; r < kTile / 8; ++r) {
+                const int jj = warp * (kTile / 8) + r;
+                const int64_t grow = j0 + jj;         // global row of the mirrored entry
+                if (grow >= row_end || grow >= a.N) continue;
+                OutT* dst = out + (grow - a.row0) * a.ld + i0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int ii = lane + 32 * h;
-            if (i0 + ii < row_end) dst[ii] = (OutT)tileT[ii * kTileLd + jj];
+                for (int h = 0; h < 2; ++h) {
+                    const int ii = lane + 32 * h;
+                    if (i0 + ii < row_end) dst[ii] = (OutT)tileT[ii * kTileLd + jj];
+                }
+            }
         }
+        if (!has_next) break;
+        __syncthreads();                              // all reads of buf / tileT done before they are refilled
+        id = id_next;
+        t = tn;
+        buf ^= 1;
     }
+    cp_async_wait<0>();
 }
 
 template <int MODE>
@@ -476,8 +601,8 @@ __global__ void __launch_bounds__(256) ellipse_pairs_kernel(const double* __rest
     const double* pa = params + is[k] * P_N;
     const double* pb = params + js[k] * P_N;
     bool slow;
-    double v = cov_pair<MODE, false>(load_point(pa), load_point(pb), m, kExp2Neg64, slow);   // as the tile kernel
-    if (slow) v = cov_pair_slow<MODE, false>(pa, pb, &m);
+    double v = cov_pair<MODE, false, 1>(load_point(pa), load_point(pb), m, kExp2Neg64, slow);   // as the tile kernel
+    if (slow) v = cov_pair_slow<MODE, false>(pa, pb, 1, &m);
     out[k] = v;
 }
 
@@ -523,21 +648,34 @@ int resolve_mode(double nu, int matern_mode) {
     return (nu <= 10.0) ? MODE_TABLE : MODE_DIRECT;   // table accuracy degrades for large nu
 }
 
-// workspace layout: [Matern table, kTabDoubles doubles, padded to 256 B][params, N x 8 doubles]
+// workspace layout: [Matern table, padded to 256 B][records (npad + kTile) x 8 doubles][fields 8 x npad doubles]
 constexpr size_t kTableBytes = ((size_t)kTabDoubles * sizeof(double) + 255) / 256 * 256;
-size_t params_bytes(int64_t N) { return gmg_align_up((size_t)N * P_N * sizeof(double), 256); }
+inline int64_t pad_points(int64_t N) { return gmg_ceil_div(N, kTile) * kTile; }
+inline size_t aos_bytes(int64_t N) { return gmg_align_up((size_t)(pad_points(N) + kTile) * P_N * sizeof(double), 256); }
+inline size_t soa_bytes(int64_t N) { return gmg_align_up((size_t)pad_points(N) * P_N * sizeof(double), 256); }
 inline const double* ws_table(const void* ws) { return reinterpret_cast<const double*>(ws); }
-inline const double* ws_params(const void* ws) {
+inline const double* ws_aos(const void* ws) {
     return reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + kTableBytes);
+}
+inline const double* ws_soa(const void* ws, int64_t N) {
+    return reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + kTableBytes + aos_bytes(N));
 }
 
 template <int MODE, bool MAXDIST, typename OutT>
 int launch_tiles(const EllipseArgs& a, int64_t n_ctas, cudaStream_t s) {
-    size_t smem = (size_t)(2 * P_N * kTile + 64 + kTile * kTileLd) * sizeof(double);
+    size_t smem = (size_t)(4 * P_N * kTile + 64 * kExpRep + kTile * kTileLd) * sizeof(double);
     if (MODE == MODE_TABLE) smem += (size_t)kTabDoubles * sizeof(double);
     auto kern = ellipse_cov_tile_kernel<MODE, MAXDIST, OutT>;
     GMG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)n_ctas, kThreads, smem, s>>>(a);
+    // persistent grid: K1_MINB resident CTAs per SM (cached per device)
+    static int sm_count[64] = {0};
+    int dev = 0;
+    GMG_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return GMG_ERR_UNSUPPORTED;
+    if (sm_count[dev] == 0)
+        GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    const int64_t grid = n_ctas < (int64_t)K1_MINB * sm_count[dev] ? n_ctas : (int64_t)K1_MINB * sm_count[dev];
+    kern<<<(unsigned)grid, kThreads, smem, s>>>(a);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
 }
@@ -564,7 +702,7 @@ extern "C" {
 int gmg_ellipse_ws_bytes(int64_t N, size_t* bytes) {
     if (N <= 0) return -1;
     if (!bytes) return -2;
-    *bytes = kTableBytes + params_bytes(N);
+    *bytes = kTableBytes + aos_bytes(N) + soa_bytes(N);
     return GMG_OK;
 }
 
@@ -585,10 +723,11 @@ int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* th
     gmg_ellipse_ws_bytes(N, &need);
     if (ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15)) return GMG_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
-    double* params = const_cast<double*>(ws_params(ws));
     double* table = const_cast<double*>(ws_table(ws));
-    ellipse_prepare_kernel<<<(unsigned)gmg_ceil_div(N, 256), 256, 0, s>>>(Lx, Ly, theta, stdev, lat_rad, lon_rad,
-                                                                           N, disp_method, params);
+    const int64_t npad = pad_points(N);
+    ellipse_prepare_kernel<<<(unsigned)gmg_ceil_div(npad + kTile, 256), 256, 0, s>>>(
+        Lx, Ly, theta, stdev, lat_rad, lon_rad, N, npad, disp_method, const_cast<double*>(ws_aos(ws)),
+        const_cast<double*>(ws_soa(ws, N)));
     GMG_LAUNCH_CHECK();
     const GmgBesselConsts bc = gmg_make_bessel_consts(nu);
     matern_table_kernel<<<kTabNint, 32, 0, s>>>(bc, table);
@@ -607,7 +746,9 @@ int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, 
     if (!C_rows) return -8;
     if (ld < N) return -9;
     EllipseArgs a;
-    a.params = ws_params(ws);
+    a.aos = ws_aos(ws);
+    a.soa = ws_soa(ws, N);
+    a.npad = pad_points(N);
     a.table = ws_table(ws);
     a.out = C_rows;
     a.N = N; a.row0 = row0; a.nrows = nrows; a.ld = ld;
@@ -622,7 +763,7 @@ int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, 
     a.bc = gmg_make_bessel_consts(nu);
     const int64_t n_ctas = a.symmetric ? a.n_tri + (int64_t)a.tiles_r * (a.tiles_c - a.tiles_r)
                                        : (int64_t)a.tiles_r * a.tiles_c;
-    if (n_ctas > 0x7fffffffLL) return GMG_ERR_UNSUPPORTED;
+    a.n_tiles = n_ctas;
     cudaStream_t s = (cudaStream_t)stream;
     switch (resolve_mode(nu, matern_mode)) {
         case MODE_NU05: return launch_tiles_mode<MODE_NU05>(a, n_ctas, store_f32, s);
@@ -644,7 +785,7 @@ int gmg_ellipse_pairs_f64(const void* ws, int64_t N, const int64_t* i, const int
     if (matern_mode < 0 || matern_mode > 2) return -7;
     if (!out) return -8;
     if (npairs == 0) return GMG_OK;
-    const double* params = ws_params(ws);
+    const double* params = ws_aos(ws);
     const double* table = ws_table(ws);
     const GmgBesselConsts bc = gmg_make_bessel_consts(nu);
     cudaStream_t s = (cudaStream_t)stream;

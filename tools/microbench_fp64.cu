@@ -109,6 +109,22 @@ int main() {
     float t_16816 = time_ms([&] { dmma16816_kernel<4><<<blocks, 256>>>(d, iters / 4, 1.0000001, 1e-9); }, 5);
     double d16816_tf = 2.0 * 2048.0 * blocks * 8.0 * (iters / 4) * 4 / (t_16816 * 1e-3) / 1e12;
 
+    // DFMA issue-to-issue latency of a dependent chain and how many independent chains per SM sub-partition
+    // saturate the pipe: one CTA per SM, W warps per sub-partition, ILP independent chains per thread.
+    // cycles per DFMA per sub-partition = clock * time / (iters * ILP * W)
+    auto sweep = [&](int warps_per_smsp, int ilp) {
+        const int threads = 128 * warps_per_smsp;
+        float t;
+        if (ilp == 1) t = time_ms([&] { dfma_kernel<1><<<sms, threads>>>(d, iters, 1.0000001, 1e-9); }, 3);
+        else if (ilp == 2) t = time_ms([&] { dfma_kernel<2><<<sms, threads>>>(d, iters, 1.0000001, 1e-9); }, 3);
+        else t = time_ms([&] { dfma_kernel<4><<<sms, threads>>>(d, iters, 1.0000001, 1e-9); }, 3);
+        return (double)p.clockRate * 1e3 * t * 1e-3 / ((double)iters * ilp * warps_per_smsp);
+    };
+    fprintf(stderr, "DFMA cycles per warp-instruction per sub-partition (2.0 = pipe saturated):\n");
+    for (int w : {1, 2, 3, 4, 6, 8})
+        fprintf(stderr, "  warps/SMSP=%d: ILP1 %.2f  ILP2 %.2f  ILP4 %.2f\n", w, sweep(w, 1), sweep(w, 2), sweep(w, 4));
+    const double dfma_latency = sweep(1, 1);
+
     size_t bytes = (size_t)8 << 30;   // 8 GiB, far larger than the 126 MB L2
     double2 *a, *b; CK(cudaMalloc(&a, bytes)); CK(cudaMalloc(&b, bytes));
     size_t n2 = bytes / sizeof(double2);
@@ -118,8 +134,8 @@ int main() {
     size_t free_b, total_b; CK(cudaMemGetInfo(&free_b, &total_b));
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d, \"dfma_tflops\": %.2f, \"dmma_m8n8k4_tflops\": %.2f, "
            "\"dmma_m16n8k16_tflops\": %.2f, \"store_only_gbs\": %.1f, \"copy_rw_gbs\": %.1f, \"memset_gbs\": %.1f, "
-           "\"hbm_total_gb\": %.1f}\n",
+           "\"hbm_total_gb\": %.1f, \"dfma_dependent_latency_cycles\": %.1f}\n",
            p.name, sms, p.clockRate, fma_tf, d884_tf, d16816_tf, bytes / (t_st * 1e-3) / 1e9,
-           2.0 * bytes / (t_cp * 1e-3) / 1e9, bytes / (t_ms * 1e-3) / 1e9, total_b / 1e9);
+           2.0 * bytes / (t_cp * 1e-3) / 1e9, bytes / (t_ms * 1e-3) / 1e9, total_b / 1e9, dfma_latency);
     return 0;
 }
