@@ -1,0 +1,289 @@
+"""Host-side driver of the device kriging pipeline (gather -> Cholesky -> two triangular solves -> apply).
+
+PyTorch owns the device buffers; every arithmetic step is a `libglomar_b200.so` entry point
+(`include/glomar_b200.h`).  `KrigeBatch` runs any number of independent kriging problems that share one
+covariance matrix - one problem for the `SimpleKriging` / `OrdinaryKriging` / `StochasticKriging` classes,
+hundreds of months for the batched driver (`glomargridding_b200.batched`) - as ONE sequence of launches
+(the batch index is `blockIdx.z`), not as per-problem streams of small kernels.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from warnings import warn
+
+import numpy as np
+import torch
+
+from . import _device as dev
+from ._lib import check, lib
+
+NB = 128      # factorisation block = GEMM tile of the library
+SLAB = 256    # rows per partial sum of the apply pass
+
+SOLVE_DESC = np.dtype([("S", "u8"), ("lds", "i8"), ("Linv", "u8"), ("R", "u8"), ("ldr", "i8"), ("P", "u8"),
+                       ("ldp", "i8"), ("info", "u8"), ("n", "i4"), ("nrhs", "i4")])
+KRIGE_DESC = np.dtype([("idx", "u8"), ("E", "u8"), ("lde", "i8"), ("y", "u8"), ("S", "u8"), ("lds", "i8"),
+                       ("Cx", "u8"), ("ldx", "i8"), ("T", "u8"), ("ldt", "i8"), ("partial", "u8"), ("out", "u8"),
+                       ("n", "i4"), ("ordinary", "i4")])
+assert SOLVE_DESC.itemsize == 72 and KRIGE_DESC.itemsize == 104
+
+OUT_FIELD, OUT_U2, OUT_MASK, OUT_ALPHA, OUT_ROWDOT = range(5)
+
+
+def _even(x: int) -> int:
+    return x + (x & 1)
+
+
+def solve_ws(n: int) -> tuple[int, int, int]:
+    """(doubles for the inverted diagonal blocks, doubles for the coefficient strip, its leading dimension)."""
+    a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    check(lib().gmg_solve_ws_doubles(n, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "gmg_solve_ws_doubles")
+    return a.value, b.value, c.value
+
+
+def _desc_tensor(arr: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(device)
+
+
+def factor_inplace(S: torch.Tensor, n: int, what: str = "matrix") -> dict:
+    """S[:n, :n] (row-major, leading dimension S.stride(0), even) <- lower Cholesky factor L (the strict upper
+    triangle keeps its old contents).  Returns the solve workspace (inverted diagonal blocks etc.).
+
+    Raises numpy.linalg.LinAlgError if a pivot is not positive."""
+    assert S.is_cuda and S.dtype == torch.float64 and S.stride(1) == 1 and S.stride(0) % 2 == 0
+    lin, pdb, ldp = solve_ws(n)
+    ws = {"Linv": torch.empty(lin, dtype=torch.float64, device=S.device),
+          "P": torch.empty(pdb, dtype=torch.float64, device=S.device),
+          "info": torch.zeros(1, dtype=torch.int32, device=S.device), "ldp": ldp}
+    d = np.zeros(1, dtype=SOLVE_DESC)
+    d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"], d["n"] = (
+        S.data_ptr(), S.stride(0), ws["Linv"].data_ptr(), ws["P"].data_ptr(), ldp, ws["info"].data_ptr(), n)
+    dt = _desc_tensor(d, S.device)
+    check(lib().gmg_potrf_batched_f64(dt.data_ptr(), 1, n, dev.stream_ptr()), "gmg_potrf_batched_f64")
+    code = int(ws["info"].item())
+    if code != 0:
+        raise np.linalg.LinAlgError(
+            f"{what} is not positive definite (Cholesky pivot {code} of {n} is not positive); "
+            "apply glomar_gridding.covariance_tools.eigenvalue_clip or use delta_x_method='Met_Office'")
+    return ws
+
+
+def cholesky_solve_inplace(S: torch.Tensor, R: torch.Tensor, what: str = "matrix", lu_fallback: bool = True) -> None:
+    """R <- S^-1 R for one symmetric S (n x n, overwritten by its factors): Cholesky on DMMA tiles, or - if S is
+    not positive definite and `lu_fallback` - LU with partial pivoting like the reference's np.linalg.solve."""
+    n = S.shape[0]
+    assert R.is_cuda and R.dtype == torch.float64 and R.stride(1) == 1 and R.stride(0) % 2 == 0
+    keep = S.clone() if lu_fallback else None
+    d = np.zeros(1, dtype=SOLVE_DESC)
+    d["R"], d["ldr"], d["n"], d["nrhs"] = R.data_ptr(), R.stride(0), n, R.shape[1]
+    try:
+        ws = factor_inplace(S, n, what)
+    except np.linalg.LinAlgError:
+        if not lu_fallback:
+            raise
+        warn(f"{what} is not positive definite; solving by LU with partial pivoting (slow path)")
+        S.copy_(keep)
+        piv = torch.empty(n + 2, dtype=torch.float64, device=S.device)
+        info = torch.zeros(1, dtype=torch.int32, device=S.device)
+        d["S"], d["lds"], d["P"], d["info"] = S.data_ptr(), S.stride(0), piv.data_ptr(), info.data_ptr()
+        dt = _desc_tensor(d, S.device)
+        check(lib().gmg_gesv_batched_f64(dt.data_ptr(), 1, R.shape[1], dev.stream_ptr()), "gmg_gesv_batched_f64")
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        return
+    d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"] = (
+        S.data_ptr(), S.stride(0), ws["Linv"].data_ptr(), ws["P"].data_ptr(), ws["ldp"], ws["info"].data_ptr())
+    dt = _desc_tensor(d, S.device)
+    check(lib().gmg_potrs_batched_f64(dt.data_ptr(), 1, n, R.shape[1], dev.stream_ptr()), "gmg_potrs_batched_f64")
+    torch.cuda.current_stream().synchronize()   # the descriptor / workspace tensors die with this frame
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, transa: bool = False, transb: bool = False,
+         out: torch.Tensor | None = None, alpha: float = 1.0, beta: float = 0.0) -> torch.Tensor:
+    """alpha op(A) op(B) + beta out on DMMA tiles (row-major, contiguous, even leading dimensions)."""
+    m, k = (A.shape[1], A.shape[0]) if transa else A.shape
+    k2, n = (B.shape[1], B.shape[0]) if transb else B.shape
+    assert k == k2, (A.shape, B.shape, transa, transb)
+    assert A.stride(1) == 1 and B.stride(1) == 1 and A.stride(0) % 2 == 0 and B.stride(0) % 2 == 0
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float64, device=A.device)
+    check(lib().gmg_gemm_f64(int(transa), int(transb), m, n, k, alpha, A.data_ptr(), A.stride(0), B.data_ptr(),
+                             B.stride(0), beta, out.data_ptr(), out.stride(0), dev.stream_ptr()), "gmg_gemm_f64")
+    return out
+
+
+def apply_reduce(cov: torch.Tensor, Cx: torch.Tensor, T: torch.Tensor, y: torch.Tensor, ordinary: bool) -> torch.Tensor:
+    """One apply pass (`gmg_krige_apply_batched_f64`) for given device operands.
+
+    cov (M, M): only its diagonal is read; Cx (n, >=M) = C_cross; T (n, >=M [+1]) transposed weights
+    (column M = S^-1 1 if `ordinary`); y (n,).  Returns the (5, M) result rows (OUT_* indices)."""
+    M, n = cov.shape[0], T.shape[0]
+    assert Cx.stride(1) == 1 and T.stride(1) == 1 and y.is_contiguous()
+    slabs = (n + SLAB - 1) // SLAB
+    partial = torch.empty(3 * slabs * M, dtype=torch.float64, device=cov.device)
+    out = torch.empty((5, M), dtype=torch.float64, device=cov.device)
+    kd = np.zeros(1, dtype=KRIGE_DESC)
+    kd[0] = (0, 0, n, y.data_ptr(), 0, 0, Cx.data_ptr(), Cx.stride(0), T.data_ptr(), T.stride(0),
+             partial.data_ptr(), out.data_ptr(), n, int(ordinary))
+    kdt = _desc_tensor(kd, cov.device)
+    check(lib().gmg_krige_apply_batched_f64(cov.data_ptr(), M, cov.stride(0), kdt.data_ptr(), 1, n,
+                                            dev.stream_ptr()), "gmg_krige_apply_batched_f64")
+    torch.cuda.current_stream().synchronize()   # descriptor / workspace tensors die with this frame
+    return out
+
+
+def padded(a, rows: int | None = None, cols: int | None = None) -> torch.Tensor:
+    """Host or device matrix -> float64 CUDA tensor with an even leading dimension (zero padded)."""
+    t = dev.to_device(a, torch.float64) if not isinstance(a, torch.Tensor) else a.to(dev.require_cuda(), torch.float64)
+    r, c = t.shape
+    out = torch.zeros((rows or r, _even(cols or c)), dtype=torch.float64, device=t.device)
+    out[:r, :c] = t
+    return out
+
+
+class KrigeBatch:
+    """`B` kriging problems against one covariance matrix, solved together on the current device.
+
+    problems: sequence of (idx int64[n], obs float64[n], error_cov float64[n, n] | None), already filtered
+    by `Kriging.subset_error_covariance`.  After `run()`:
+      out[b]  (5, M) tensor rows: field, variance before clamping, constraint mask, alpha, rowdot(W, C_cross^T)
+      T[b]    (n, ldt) tensor: S^-1 C_cross (simple-kriging weights, transposed); column M = S^-1 1 if ordinary
+      Cx[b]   (n, ldx) tensor: C[idx, :]
+    """
+
+    def __init__(self, cov: torch.Tensor, problems, ordinary: bool):
+        assert cov.is_cuda and cov.dtype == torch.float64 and cov.dim() == 2 and cov.stride(1) == 1
+        self.cov, self.ordinary = cov, bool(ordinary)
+        self.M = M = cov.shape[0]
+        device = cov.device
+        B = self.B = len(problems)
+        ns = [int(len(p[0])) for p in problems]
+        if min(ns) <= 0:
+            raise ValueError("a kriging problem needs at least one observation")
+        self.ns, self.n_max = ns, max(ns)
+        self.ldx, self.ldt = _even(M), _even(M + 1)
+        lds = [_even(n) for n in ns]
+        ws = [solve_ws(n) for n in ns]
+        slabs = [(n + SLAB - 1) // SLAB for n in ns]
+
+        def pool(sizes):
+            offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            return torch.empty(int(offs[-1]), dtype=torch.float64, device=device), offs
+
+        self._S, oS = pool([n * l for n, l in zip(ns, lds)])
+        self._Cx, oX = pool([n * self.ldx for n in ns])
+        self._T, oT = pool([n * self.ldt for n in ns])
+        self._Linv, oL = pool([w[0] for w in ws])
+        self._P, oP = pool([w[1] for w in ws])
+        self._partial, oPa = pool([3 * s * M for s in slabs])
+        self.out = torch.empty((B, 5, M), dtype=torch.float64, device=device)
+        self.info = torch.zeros(B, dtype=torch.int32, device=device)
+        # inputs: one H2D copy each (idx, obs, error covariances), pinned staging handled by torch
+        offs_n = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+        self._idx = torch.from_numpy(np.concatenate([np.asarray(p[0], dtype=np.int64) for p in problems])).to(device)
+        self._y = torch.from_numpy(np.concatenate([np.asarray(p[1], dtype=np.float64) for p in problems])).to(device)
+        has_E = [p[2] is not None for p in problems]
+        offs_E = np.concatenate([[0], np.cumsum([n * n if h else 0 for n, h in zip(ns, has_E)])]).astype(np.int64)
+        if any(has_E):
+            flat = np.concatenate([np.ascontiguousarray(p[2], dtype=np.float64).reshape(-1)
+                                   for p in problems if p[2] is not None])
+            self._E = torch.from_numpy(flat).to(device)
+        else:
+            self._E = None
+
+        kd = np.zeros(B, dtype=KRIGE_DESC)
+        sd = np.zeros(B, dtype=SOLVE_DESC)
+        f8 = 8
+        for b in range(B):
+            n = ns[b]
+            S_ptr = self._S.data_ptr() + f8 * int(oS[b])
+            T_ptr = self._T.data_ptr() + f8 * int(oT[b])
+            kd[b] = (self._idx.data_ptr() + f8 * int(offs_n[b]),
+                     (self._E.data_ptr() + f8 * int(offs_E[b])) if has_E[b] else 0, n,
+                     self._y.data_ptr() + f8 * int(offs_n[b]), S_ptr, lds[b],
+                     self._Cx.data_ptr() + f8 * int(oX[b]), self.ldx, T_ptr, self.ldt,
+                     self._partial.data_ptr() + f8 * int(oPa[b]), self.out.data_ptr() + f8 * 5 * M * b, n,
+                     int(self.ordinary))
+            sd[b] = (S_ptr, lds[b], self._Linv.data_ptr() + f8 * int(oL[b]), T_ptr, self.ldt,
+                     self._P.data_ptr() + f8 * int(oP[b]), ws[b][2], self.info.data_ptr() + 4 * b, n,
+                     M + (1 if self.ordinary else 0))
+        self._kd, self._sd = _desc_tensor(kd, device), _desc_tensor(sd, device)
+        self._kd_np, self._sd_np = kd, sd
+        self._oS, self._oX, self._oT, self._lds = oS, oX, oT, lds
+        self._ran = False
+
+    # -- views -----------------------------------------------------------------------------------------
+    def T(self, b: int) -> torch.Tensor:
+        return self._T[int(self._oT[b]):int(self._oT[b + 1])].view(self.ns[b], self.ldt)
+
+    def Cx(self, b: int) -> torch.Tensor:
+        return self._Cx[int(self._oX[b]):int(self._oX[b + 1])].view(self.ns[b], self.ldx)
+
+    def S(self, b: int) -> torch.Tensor:
+        return self._S[int(self._oS[b]):int(self._oS[b + 1])].view(self.ns[b], self._lds[b])
+
+    # -- pipeline --------------------------------------------------------------------------------------
+    def run(self, allow_lu_fallback: bool = True) -> "KrigeBatch":
+        """gather -> Cholesky -> two triangular solves -> apply.  Systems whose Cholesky meets a non-positive
+        pivot are re-gathered and solved by LU with partial pivoting (what the reference does for every system),
+        with a warning; an exactly singular system raises numpy.linalg.LinAlgError like numpy does."""
+        L, s = lib(), dev.stream_ptr()
+        C, M, ldc = self.cov.data_ptr(), self.M, self.cov.stride(0)
+        nrhs = M + (1 if self.ordinary else 0)
+        check(L.gmg_krige_gather_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, s), "gather")
+        check(L.gmg_potrf_batched_f64(self._sd.data_ptr(), self.B, self.n_max, s), "gmg_potrf_batched_f64")
+        info = self.info.cpu().numpy()               # synchronises: the factorisation outcome decides the path
+        bad = np.flatnonzero(info)
+        self.lu_fallback = bad.tolist()
+        if bad.size == 0:
+            check(L.gmg_potrs_batched_f64(self._sd.data_ptr(), self.B, self.n_max, nrhs, s), "gmg_potrs_batched_f64")
+        else:
+            if not allow_lu_fallback:
+                self.raise_if_not_spd(info)
+            warn(f"C[idx, idx] + E is not positive definite for {bad.size} of {self.B} kriging system(s) "
+                 f"(first: system {int(bad[0])}, Cholesky pivot {int(info[bad[0]])}); solving those by LU with "
+                 "partial pivoting like the reference does - slow path, consider "
+                 "glomar_gridding.covariance_tools.eigenvalue_clip or delta_x_method='Met_Office'")
+            good = np.flatnonzero(info == 0)
+            self.info.zero_()
+            kd_bad = _desc_tensor(self._kd_np[bad], self.cov.device)
+            sd_bad = _desc_tensor(self._sd_np[bad], self.cov.device)
+            n_bad = max(self.ns[int(b)] for b in bad)
+            check(L.gmg_krige_gather_batched_f64(C, M, ldc, kd_bad.data_ptr(), int(bad.size), n_bad, s), "gather")
+            check(L.gmg_gesv_batched_f64(sd_bad.data_ptr(), int(bad.size), nrhs, s), "gmg_gesv_batched_f64")
+            if good.size:
+                sd_good = _desc_tensor(self._sd_np[good], self.cov.device)
+                n_good = max(self.ns[int(b)] for b in good)
+                check(L.gmg_potrs_batched_f64(sd_good.data_ptr(), int(good.size), n_good, nrhs, s),
+                      "gmg_potrs_batched_f64")
+            if np.any(self.info.cpu().numpy()):
+                raise np.linalg.LinAlgError("Singular matrix")
+        check(L.gmg_krige_apply_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, s), "apply")
+        self._ran = True
+        return self
+
+    def raise_if_not_spd(self, info=None) -> None:
+        info = self.info.cpu().numpy() if info is None else info
+        bad = np.flatnonzero(info)
+        if bad.size:
+            b = int(bad[0])
+            raise np.linalg.LinAlgError(
+                f"observation covariance C[idx, idx] + E of problem {b} is not positive definite "
+                f"(Cholesky pivot {int(info[b])} of {self.ns[b]} is not positive); apply "
+                "glomar_gridding.covariance_tools.eigenvalue_clip to the covariance or use "
+                "delta_x_method='Met_Office'")
+
+    def weights(self, b: int, ordinary: bool | None = None) -> torch.Tensor:
+        """The reference's `kriging_weights` for problem b: (M, n) simple or (M, n + 1) ordinary."""
+        ordinary = self.ordinary if ordinary is None else ordinary
+        if ordinary and not self.ordinary:
+            raise ValueError("ordinary weights need an ordinary-kriging batch")
+        n, M = self.ns[b], self.M
+        T = self.T(b)
+        W = torch.empty((M, n + (1 if ordinary else 0)), dtype=torch.float64, device=T.device)
+        o_ptr = T.data_ptr() + 8 * M if ordinary else None
+        a_ptr = self.out[b, OUT_ALPHA].data_ptr() if ordinary else None
+        check(lib().gmg_krige_weights_f64(T.data_ptr(), self.ldt, o_ptr, self.ldt, a_ptr, n, M, W.data_ptr(),
+                                          W.stride(0), dev.stream_ptr()), "gmg_krige_weights_f64")
+        return W

@@ -38,19 +38,23 @@ def _declare(lib):
         "gmg_matern_f64": (c_int, [p, dbl, i32, p, i64, p, p]),
         "gmg_haversine_f64": (c_int, [p, p, i64, i64, i64, p, i64, p]),
     }
-    optional = {
-        "gmg_gather_obs_f64": (c_int, [p, i64, i64, p, i64, p, i64, p, i64, p, i64, p]),
-        "gmg_potrf_f64": (c_int, [p, i64, i64, p, p, c_size_t, p]),
-        "gmg_potrf_ws_bytes": (c_int, [i64, POINTER(c_size_t)]),
-    }
+    u64 = c_uint64
+    sigs.update({
+        "gmg_gemm_f64": (c_int, [i32, i32, i64, i64, i64, dbl, p, i64, p, i64, dbl, p, i64, p]),
+        "gmg_solve_ws_doubles": (c_int, [i64, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+        "gmg_potrf_batched_f64": (c_int, [p, i32, i64, p]),
+        "gmg_potrs_batched_f64": (c_int, [p, i32, i64, i64, p]),
+        "gmg_gesv_batched_f64": (c_int, [p, i32, i64, p]),
+        "gmg_krige_gather_batched_f64": (c_int, [p, i64, i64, p, i32, i64, p]),
+        "gmg_krige_apply_batched_f64": (c_int, [p, i64, i64, p, i32, i64, p]),
+        "gmg_krige_weights_f64": (c_int, [p, i64, p, i64, p, i64, i64, p, i64, p]),
+        "gmg_extended_inverse_f64": (c_int, [p, i64, i64, p, p, i64, p]),
+        "gmg_normal_f64": (c_int, [p, i64, u64, u64, p]),
+        "gmg_tril_f64": (c_int, [p, i64, i64, p]),
+    })
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    for name, (res, args) in optional.items():
-        if hasattr(lib, name):
-            fn = getattr(lib, name)
-            fn.restype, fn.argtypes = res, args
-    _ = (c_uint64, np)
 
 
 def lib():

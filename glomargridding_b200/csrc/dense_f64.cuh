@@ -1,0 +1,167 @@
+// FP64 dense building blocks for the kriging path on sm_100a: a DMMA (mma.sync m8n8k4 f64) GEMM tile
+// mainloop with a 3-stage cp.async pipeline, shared by the GEMM entry point, the blocked Cholesky and the
+// blocked triangular solves (dense_f64.cu, kriging.cu).
+//
+// Why mma.sync and not tcgen05: tcgen05.mma has no f64 kind on sm_100a (ptxas rejects it); the FP64 tensor
+// path is the DMMA.8x8x4 instruction that mma.sync.m8n8k4.f64 lowers to (measured 37.1 TFLOP/s on B200,
+// profiles/r01_microbench_fp64.json, against 34.2 TFLOP/s for plain DFMA).
+//
+// All matrices are ROW-MAJOR with leading dimensions in elements.  Pointers and leading dimensions must be
+// multiples of 2 doubles (16 B) because tiles are fetched with 16-byte cp.async.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace gmg {
+
+constexpr int BM = 128;            // CTA tile rows
+constexpr int BN = 128;            // CTA tile columns
+constexpr int BK = 16;             // k-slab per pipeline stage (4 DMMA k-steps)
+constexpr int STAGES = 3;
+constexpr int GEMM_THREADS = 512;  // 16 warps as 4 (m) x 4 (n), warp tile 32 x 32 = 4 x 4 DMMA tiles
+constexpr int LDK = BK + 4;        // [row][k] operand tile: 20 doubles -> the 8 x 4 fragment is conflict-free
+constexpr int LDN = BN + 4;        // [k][col] operand tile: 132 doubles -> the 4 x 8 fragment is conflict-free
+constexpr int TILE_DOUBLES = (BM * LDK > BK * LDN) ? BM * LDK : BK * LDN;   // 2560
+constexpr size_t GEMM_SMEM_BYTES = (size_t)STAGES * 2 * TILE_DOUBLES * sizeof(double);   // 122 880
+
+struct TileArgs {
+    const double* A;   // op(A) is m x k:  TA ? stored k x m : stored m x k
+    const double* B;   // op(B) is k x n:  TB ? stored n x k : stored k x n
+    const double* C;   // m x n, read only when beta != 0 (may alias D)
+    double* D;         // m x n
+    int m, n, k;
+    int64_t lda, ldb, ldc, ldd;
+    double alpha, beta;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Fetch one [rows][BK] k-slab of a matrix stored rows x k (row-major) into a [row][k] tile (ld = LDK).
+__device__ __forceinline__ void load_rowk(double* s, const double* G, int64_t ld, int row0, int rows_total, int k0,
+                                          int k_total, int tid) {
+#pragma unroll
+    for (int c = tid; c < BM * (BK / 2); c += GEMM_THREADS) {
+        const int r = c / (BK / 2), c2 = c % (BK / 2);
+        const int gr = row0 + r, gk = k0 + 2 * c2;
+        int bytes = (gr < rows_total) ? (k_total - gk) * 8 : 0;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const double* src = bytes ? G + (int64_t)gr * ld + gk : G;
+        cp_async16_zfill(s + r * LDK + 2 * c2, src, bytes);
+    }
+}
+
+// Fetch one [BK][cols] k-slab of a matrix stored k x cols (row-major) into a [k][col] tile (ld = LDN).
+__device__ __forceinline__ void load_kcol(double* s, const double* G, int64_t ld, int col0, int cols_total, int k0,
+                                          int k_total, int tid) {
+#pragma unroll
+    for (int c = tid; c < BK * (BN / 2); c += GEMM_THREADS) {
+        const int r = c / (BN / 2), c2 = c % (BN / 2);
+        const int gk = k0 + r, gc = col0 + 2 * c2;
+        int bytes = (gk < k_total) ? (cols_total - gc) * 8 : 0;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const double* src = bytes ? G + (int64_t)gk * ld + gc : G;
+        cp_async16_zfill(s + r * LDN + 2 * c2, src, bytes);
+    }
+}
+
+// D[m0.., n0..] = alpha op(A) op(B) + beta C for one BM x BN tile.  `smem` = GEMM_SMEM_BYTES, 16 B aligned.
+// Every thread of the 512-thread CTA must call this (it contains __syncthreads).
+// In-place note: a CTA reads all of its A / B slabs before the epilogue writes D, so D may alias rows of A
+// or B that only THIS tile reads (used by the panel solve and the triangular solves).
+template <bool TA, bool TB>
+__device__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int grp = lane >> 2, t4 = lane & 3;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int nk = (g.k + BK - 1) / BK;
+    auto load_stage = [&](int kt) {
+        double* sA = smem + (size_t)(kt % STAGES) * 2 * TILE_DOUBLES;
+        double* sB = sA + TILE_DOUBLES;
+        if (TA) load_kcol(sA, g.A, g.lda, m0, g.m, kt * BK, g.k, tid);
+        else    load_rowk(sA, g.A, g.lda, m0, g.m, kt * BK, g.k, tid);
+        if (TB) load_rowk(sB, g.B, g.ldb, n0, g.n, kt * BK, g.k, tid);
+        else    load_kcol(sB, g.B, g.ldb, n0, g.n, kt * BK, g.k, tid);
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s);
+        cp_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_wait<STAGES - 2>();
+        __syncthreads();                     // slab kt has landed; slab kt-1's buffer is free for the prefetch
+        if (kt + STAGES - 1 < nk) load_stage(kt + STAGES - 1);
+        cp_commit();
+        const double* sA = smem + (size_t)(kt % STAGES) * 2 * TILE_DOUBLES;
+        const double* sB = sA + TILE_DOUBLES;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                a[i] = TA ? sA[(k4 * 4 + t4) * LDN + wm * 32 + i * 8 + grp]
+                          : sA[(wm * 32 + i * 8 + grp) * LDK + k4 * 4 + t4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                b[j] = TB ? sB[(wn * 32 + j * 8 + grp) * LDK + k4 * 4 + t4]
+                          : sB[(k4 * 4 + t4) * LDN + wn * 32 + j * 8 + grp];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_wait<0>();
+    __syncthreads();                         // all warps done with shared memory (callers may reuse it)
+
+    const bool vec_ok = ((g.ldd & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.D) & 15) == 0) &&
+                        ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + wm * 32 + i * 8 + grp;
+        if (row >= g.m) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + wn * 32 + j * 8 + 2 * t4;
+            if (col >= g.n) continue;
+            double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+            double* d = g.D + (int64_t)row * g.ldd + col;
+            if (col + 1 < g.n && vec_ok) {
+                if (g.beta != 0.0) {
+                    const double2 c = *reinterpret_cast<const double2*>(g.C + (int64_t)row * g.ldc + col);
+                    v0 = fma(g.beta, c.x, v0);
+                    v1 = fma(g.beta, c.y, v1);
+                }
+                *reinterpret_cast<double2*>(d) = make_double2(v0, v1);
+            } else {
+                if (g.beta != 0.0) v0 = fma(g.beta, g.C[(int64_t)row * g.ldc + col], v0);
+                d[0] = v0;
+                if (col + 1 < g.n) {
+                    if (g.beta != 0.0) v1 = fma(g.beta, g.C[(int64_t)row * g.ldc + col + 1], v1);
+                    d[1] = v1;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace gmg

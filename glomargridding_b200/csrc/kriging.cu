@@ -1,0 +1,267 @@
+// K3 / K6 / K7: assembly of the observation system and application of the kriging weights.
+//
+// Replaces (reference, paths relative to its root):
+//   glomar_gridding/kriging.py:337-342, :571-583   obs_obs_cov / obs_grid_cov gathers, "+= error_cov", Lagrange row
+//   glomar_gridding/kriging.py:417, :677-679       kriging_weights @ obs
+//   glomar_gridding/kriging.py:432-435, :694-701   diag(C - W @ C_cross) [- alpha]
+//   glomar_gridding/kriging.py:487-491, :772-776   diag(C[:, idx] @ W_simple^T) / diag(C)
+//   glomar_gridding/stochastic.py:233-243, :292-297  the same for StochasticKriging
+// The reference forms M x M products to read their diagonals (2 M^2 n flops and an M^2 temporary each); here
+// one pass over T = S^-1 [C_cross | 1] and C_cross produces the three column reductions everything derives from:
+//   yT[m] = sum_a y[a] T[a, m]      d[m] = sum_a T[a, m] Cx[a, m]      oc[m] = sum_a o[a] Cx[a, m]
+// The pass is HBM-bound (2 n M 8 bytes read); partial sums over 256-row slabs are written to a workspace and
+// combined in a fixed order by the finalising kernel, so results are bit-reproducible run to run.
+#include "gmg_common.cuh"
+#include "../../include/glomar_b200.h"
+
+namespace {
+
+constexpr int kSlab = 256;            // rows per partial sum
+constexpr int kColsPerBlock = 256;    // one column per thread: a warp reads 256 contiguous bytes per row
+
+static_assert(sizeof(GmgKrigeDesc) == 104, "GmgKrigeDesc layout is part of the C ABI");
+
+// grid = (ceil((M + 1) / 256), n_max, batch): row a of S, Cx and T for every system
+__global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ C, int64_t M, int64_t ldc,
+                                                     const GmgKrigeDesc* __restrict__ descs) {
+    const GmgKrigeDesc d = descs[blockIdx.z];
+    const int a = blockIdx.y;
+    if (a >= d.n) return;
+    const int64_t ia = d.idx[a];
+    const double* crow = C + ia * ldc;
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m < M) {
+        const double v = crow[m];
+        d.Cx[(int64_t)a * d.ldx + m] = v;
+        d.T[(int64_t)a * d.ldt + m] = v;
+    } else if (m == M && d.ordinary) {
+        d.T[(int64_t)a * d.ldt + M] = 1.0;      // right-hand side for o = S^-1 1 (Lagrange column, :579-583)
+    }
+    // S row: the first ceil(n / 256) column blocks also fill S[a, :]
+    if (m < d.n) {
+        double s = crow[d.idx[m]];
+        if (d.E) s += d.E[(int64_t)a * d.lde + m];   // :342, :576
+        d.S[(int64_t)a * d.lds + m] = s;
+    }
+}
+
+// grid = (ceil(M / 256), ceil(n_max / kSlab), batch)
+__global__ void __launch_bounds__(kColsPerBlock) reduce_kernel(int64_t M, const GmgKrigeDesc* __restrict__ descs) {
+    const GmgKrigeDesc d = descs[blockIdx.z];
+    const int a0 = blockIdx.y * kSlab;
+    if (a0 >= d.n) return;
+    const int a1 = min(d.n, a0 + kSlab);
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    __shared__ double sy[kSlab], so[kSlab];
+    for (int e = threadIdx.x; e < a1 - a0; e += blockDim.x) {
+        sy[e] = d.y[a0 + e];
+        so[e] = d.ordinary ? d.T[(int64_t)(a0 + e) * d.ldt + M] : 0.0;
+    }
+    __syncthreads();
+    if (m >= M) return;
+    double yT = 0.0, dd = 0.0, oc = 0.0;
+    const double* t = d.T + (int64_t)a0 * d.ldt + m;
+    const double* x = d.Cx + (int64_t)a0 * d.ldx + m;
+#pragma unroll 4
+    for (int a = 0; a < a1 - a0; ++a) {
+        const double tv = t[(int64_t)a * d.ldt], xv = x[(int64_t)a * d.ldx];
+        yT = fma(sy[a], tv, yT);
+        dd = fma(tv, xv, dd);
+        oc = fma(so[a], xv, oc);
+    }
+    const int64_t slabs = (d.n + kSlab - 1) / kSlab;
+    double* p = d.partial + (int64_t)blockIdx.y * M + m;
+    p[0] = yT;
+    p[slabs * M] = dd;
+    p[2 * slabs * M] = oc;
+}
+
+// grid = (ceil(M / 256), 1, batch)
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ C, int64_t M, int64_t ldc,
+                                                       const GmgKrigeDesc* __restrict__ descs) {
+    const GmgKrigeDesc d = descs[blockIdx.z];
+    if (d.n <= 0) return;
+    // scalar reductions over the observations: 1^T o and o^T y (each block recomputes them; n is small
+    // next to M and the order of summation is fixed)
+    __shared__ double red[2][256];
+    double so = 0.0, soy = 0.0;
+    if (d.ordinary) {
+        for (int a = threadIdx.x; a < d.n; a += blockDim.x) {
+            const double o = d.T[(int64_t)a * d.ldt + M];
+            so += o;
+            soy = fma(o, d.y[a], soy);
+        }
+    }
+    red[0][threadIdx.x] = so;
+    red[1][threadIdx.x] = soy;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + s];
+            red[1][threadIdx.x] += red[1][threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    const double sum_o = red[0][0], o_dot_y = red[1][0];
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int64_t slabs = (d.n + kSlab - 1) / kSlab;
+    double yT = 0.0, dd = 0.0, oc = 0.0;
+    for (int64_t s = 0; s < slabs; ++s) {
+        yT += d.partial[s * M + m];
+        dd += d.partial[(slabs + s) * M + m];
+        oc += d.partial[(2 * slabs + s) * M + m];
+    }
+    const double cmm = C[m * ldc + m];
+    double field = yT, rowdot = dd, alpha = 0.0, u2 = cmm - dd;
+    if (d.ordinary) {
+        alpha = (oc - 1.0) / sum_o;              // Schur complement of the bordered system (:579-586)
+        field = yT - alpha * o_dot_y;            // W_ext @ [y; 0]                              (:677-679)
+        rowdot = dd - alpha * oc;                // rowdot(W, Cx^T)
+        u2 = cmm - rowdot - alpha - alpha;       // diag(C - W_ext @ Cx_ext) - alpha            (:699-701)
+    }
+    d.out[m] = field;
+    d.out[M + m] = u2;
+    d.out[2 * M + m] = dd / cmm;                 // constraint mask uses the SIMPLE weights       (:772-776)
+    d.out[3 * M + m] = alpha;
+    d.out[4 * M + m] = rowdot;
+}
+
+// W[m, a] = T[a, m] - o[a] alpha[m],  W[m, n] = alpha[m]: 32 x 32 transpose tiles through shared memory
+__global__ void __launch_bounds__(256) weights_kernel(const double* __restrict__ T, int64_t ldt,
+                                                      const double* __restrict__ o, int64_t o_stride,
+                                                      const double* __restrict__ alpha, int64_t n, int64_t M,
+                                                      double* __restrict__ W, int64_t ldw) {
+    __shared__ double tile[32][33];
+    const int64_t m0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t a = a0 + r, m = m0 + tx;
+        tile[r][tx] = (a < n && m < M) ? T[a * ldt + m] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t m = m0 + r, a = a0 + tx;
+        if (m < M && a < n) {
+            double v = tile[tx][r];
+            if (alpha) v = fma(-o[a * o_stride], alpha[m], v);
+            W[m * ldw + a] = v;
+        }
+    }
+    if (alpha && blockIdx.y == 0 && threadIdx.x < 32) {
+        const int64_t m = m0 + threadIdx.x;
+        if (m < M) W[m * ldw + n] = alpha[m];
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs, int batch,
+                                 int64_t n_max, gmg_stream_t stream) {
+    if (!C) return -1;
+    if (M <= 0) return -2;
+    if (ldc < M) return -3;
+    if (!descs) return -4;
+    if (batch <= 0 || batch > 65535) return -5;
+    if (n_max <= 0 || n_max > 65535 || n_max > M) return -6;
+    dim3 grid((unsigned)gmg_ceil_div(M + 1, 256), (unsigned)n_max, (unsigned)batch);
+    gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C, M, ldc, descs);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+int gmg_krige_apply_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs, int batch,
+                                int64_t n_max, gmg_stream_t stream) {
+    if (!C) return -1;
+    if (M <= 0) return -2;
+    if (ldc < M) return -3;
+    if (!descs) return -4;
+    if (batch <= 0 || batch > 65535) return -5;
+    if (n_max <= 0) return -6;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned cb = (unsigned)gmg_ceil_div(M, kColsPerBlock);
+    reduce_kernel<<<dim3(cb, (unsigned)gmg_ceil_div(n_max, kSlab), (unsigned)batch), kColsPerBlock, 0, s>>>(M, descs);
+    GMG_LAUNCH_CHECK();
+    finalize_kernel<<<dim3(cb, 1, (unsigned)batch), 256, 0, s>>>(C, M, ldc, descs);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+int gmg_krige_weights_f64(const double* T, int64_t ldt, const double* o, int64_t o_stride, const double* alpha,
+                          int64_t n, int64_t M, double* W, int64_t ldw, gmg_stream_t stream) {
+    if (!T) return -1;
+    if (ldt < M) return -2;
+    if (alpha && !o) return -3;
+    if (n <= 0) return -6;
+    if (M <= 0) return -7;
+    if (!W) return -8;
+    if (ldw < n + (alpha ? 1 : 0)) return -9;
+    dim3 grid((unsigned)gmg_ceil_div(M, 32), (unsigned)gmg_ceil_div(n, 32));
+    if (grid.y > 65535) return GMG_ERR_UNSUPPORTED;
+    weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, ldt, o, o_stride, alpha, n, M, W, ldw);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+}  // extern "C"
+
+// ---- bordered (Lagrange-extended) inverse --------------------------------------------------------------------
+// replaces `_extended_inverse`, glomar_gridding/kriging.py:815-829 (Guttman 1946 block inverse with B = 1, d = 0):
+//   e = S^-1 1,  f = -(1^T e),  K = S^-1 + e e^T / f,  result = [[K, -e/f], [-e^T/f, 1/f]]
+namespace {
+
+__global__ void __launch_bounds__(256) rowsum_kernel(const double* __restrict__ A, int64_t n, int64_t ld,
+                                                     double* __restrict__ e) {
+    // one warp per row, fixed summation order
+    const int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double s = 0.0;
+    for (int64_t j = lane; j < n; j += 32) s += A[row * ld + j];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) e[row] = s;
+}
+
+__global__ void __launch_bounds__(256) bordered_kernel(const double* __restrict__ A, int64_t n, int64_t ld,
+                                                       const double* __restrict__ e, double* __restrict__ out,
+                                                       int64_t ldo) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += 256) s += e[j];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    const double finv = 1.0 / (0.0 - red[0]);
+    const int64_t i = blockIdx.y;
+    const int64_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j > n) return;
+    double v;
+    if (i < n && j < n) v = A[i * ld + j] + e[i] * (finv * e[j]);
+    else if (i < n) v = -(finv * e[i]);
+    else if (j < n) v = -(finv * e[j]);
+    else v = finv;
+    out[i * ldo + j] = v;
+}
+
+}  // namespace
+
+extern "C" int gmg_extended_inverse_f64(const double* inv, int64_t n, int64_t ld, double* ws_e, double* out,
+                                        int64_t ldo, gmg_stream_t stream) {
+    if (!inv) return -1;
+    if (n <= 0 || n >= 65535) return -2;
+    if (ld < n) return -3;
+    if (!ws_e) return -4;
+    if (!out) return -5;
+    if (ldo < n + 1) return -6;
+    cudaStream_t s = (cudaStream_t)stream;
+    rowsum_kernel<<<(unsigned)gmg_ceil_div(n, 8), 256, 0, s>>>(inv, n, ld, ws_e);
+    GMG_LAUNCH_CHECK();
+    bordered_kernel<<<dim3((unsigned)gmg_ceil_div(n + 1, 256), (unsigned)(n + 1)), 256, 0, s>>>(inv, n, ld, ws_e, out, ldo);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}

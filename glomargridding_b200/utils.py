@@ -101,3 +101,25 @@ def sizeof_fmt(num: float, suffix: str = "B") -> str:
             return f"{num:3.1f}{unit}{suffix}"
         num /= 1024.0
     return f"{num:.1f}Yi{suffix}"
+
+
+def intersect_mtlb(a: np.ndarray, b: np.ndarray):
+    """Intersection of two arrays and the index of each common value in `a` and in `b`
+    (reference `utils.py:246-279`)."""
+    a1, ia = np.unique(a, return_index=True)
+    b1, ib = np.unique(b, return_index=True)
+    both = np.sort(np.concatenate((a1, b1)))
+    common = both[:-1][both[1:] == both[:-1]]
+    return common, ia[np.isin(a1, common)], ib[np.isin(b1, common)]
+
+
+def get_spatial_mean(grid_obs: np.ndarray, covx: np.ndarray) -> float:
+    """Best linear unbiased estimate of a constant mean, (1^T C^-1 1)^-1 (1^T C^-1 z)
+    (reference `utils.py:766-793`); C^-1 [1, z] by the device Cholesky."""
+    from . import _dense as dn
+
+    n = len(grid_obs)
+    R = dn.padded(np.column_stack([np.ones(n), np.asarray(grid_obs, dtype=np.float64)]))
+    dn.cholesky_solve_inplace(dn.padded(np.asarray(covx)), R, "covx")
+    x = R[:, :2].cpu().numpy()
+    return float(x[:, 1].sum() / x[:, 0].sum())

@@ -97,6 +97,110 @@ int gmg_matern_f64(const void* ws, double nu, int matern_mode, const double* x, 
 int gmg_haversine_f64(const double* lat_rad, const double* lon_rad, int64_t N, int64_t row0,
                       int64_t nrows, double* D_rows, int64_t ld, gmg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dense FP64 linear algebra of the kriging path (DMMA = mma.sync m8n8k4 f64 tiles)
+ * replaces the LAPACK/BLAS calls of glomar_gridding/kriging.py:343,585,768 (np.linalg.solve),
+ * stochastic.py:159 (np.linalg.inv) and the `@` products at kriging.py:378,634, stochastic.py:210-216
+ * All matrices row-major; pointers and leading dimensions must be multiples of 2 doubles (16 B).
+ * ------------------------------------------------------------------------------------------- */
+
+/* C (m x n) = alpha op(A) op(B) + beta C;  op(X) = X or X^T (trans != 0); A stored m x k (k x m if transa),
+ * B stored k x n (n x k if transb). */
+int gmg_gemm_f64(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha,
+                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+                 int64_t ldc, gmg_stream_t stream);
+
+/* One symmetric positive definite system per descriptor (array in DEVICE memory, built by the caller). */
+typedef struct GmgSolveDesc {
+    double* S;      /* n x n, lower triangle read; overwritten by the Cholesky factor L (lower)     */
+    int64_t lds;
+    double* Linv;   /* workspace: ceil(n/128) inverted 128 x 128 diagonal blocks of L               */
+    double* R;      /* n x nrhs right-hand sides, overwritten by S^-1 R                             */
+    int64_t ldr;
+    double* P;      /* workspace: coefficient strip, `p_doubles` of gmg_solve_ws_doubles            */
+    int64_t ldp;    /* leading dimension of the forward strip, `ldp` of gmg_solve_ws_doubles        */
+    int* info;      /* 0, or the order of the first non-positive pivot (LAPACK potrf convention)    */
+    int32_t n;
+    int32_t nrhs;
+} GmgSolveDesc;
+
+/* Workspace sizes (in doubles) for one system of order n. */
+int gmg_solve_ws_doubles(int64_t n, int64_t* linv_doubles, int64_t* p_doubles, int64_t* ldp);
+
+/* S = L L^T for `batch` systems (n_max = largest order in the batch): blocked right-looking
+ * Cholesky, trailing update on DMMA tiles.  *info must be zeroed by the caller. */
+int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, gmg_stream_t stream);
+
+/* R <- S^-1 R for the factored systems: R <- L^-1 R then R <- L^-T R, each block step one GEMM
+ * (diagonal blocks were inverted by gmg_potrf_batched_f64). */
+int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max,
+                          gmg_stream_t stream);
+
+/* Indefinite-safe fallback: R <- S^-1 R by LU with partial pivoting (what the reference's
+ * np.linalg.solve does, kriging.py:343, :585, :768).  S is the FULL n x n matrix (both triangles) and is
+ * overwritten by its LU factors; pivots go to the descriptor's P workspace; *info = k + 1 for an exactly
+ * zero pivot.  One CTA per system: meant for the matrices Cholesky rejects, not for speed. */
+int gmg_gesv_batched_f64(const GmgSolveDesc* descs, int batch, int64_t nrhs_max, gmg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kriging assembly and application
+ * ------------------------------------------------------------------------------------------- */
+
+/* One kriging problem (descriptor array in DEVICE memory).  T is the n x M "transposed weights"
+ * matrix S^-1 C_cross with an extra column M holding o = S^-1 1 when `ordinary` (leading
+ * dimension ldr >= M + 1). */
+typedef struct GmgKrigeDesc {
+    const int64_t* idx;  /* n observation cells                                                    */
+    const double* E;     /* n x n error covariance or NULL                                         */
+    int64_t lde;
+    const double* y;     /* n observations                                                         */
+    double* S;           /* n x n  out: C[idx, idx] + E                                            */
+    int64_t lds;
+    double* Cx;          /* n x M  out: C[idx, :]                                                  */
+    int64_t ldx;
+    double* T;           /* n x (M [+1])  out: copy of Cx (+ ones column) = right-hand sides       */
+    int64_t ldt;
+    double* partial;     /* workspace: 3 * ceil(n/256) * M doubles                                 */
+    double* out;         /* 5 x M: field, u2 (variance before clamping), mask, alpha, rowdot       */
+    int32_t n;
+    int32_t ordinary;    /* 0 simple kriging, 1 ordinary kriging (Lagrange-extended system)        */
+} GmgKrigeDesc;
+
+/* S = C[idx, idx] + E, Cx = C[idx, :], T = [Cx | 1]     (reference kriging.py:337-342, :571-583) */
+int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs,
+                                 int batch, int64_t n_max, gmg_stream_t stream);
+
+/* From T = S^-1 [Cx | 1]:  field = W y, variance = diag(C) - rowdot(W, Cx^T) [- 2 alpha], constraint
+ * mask = rowdot(W_simple, Cx^T) / diag(C), alpha = Lagrange multiplier column, without forming W
+ * (M x n) or the reference's M x M temporaries (kriging.py:417, :434-435, :487-491, :677-679, :699-701,
+ * :772-776).  Ordinary kriging uses the Schur complement of the bordered system:
+ * alpha = (o^T Cx - 1) / (1^T o), W = (S^-1 Cx - o alpha^T)^T. */
+int gmg_krige_apply_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs,
+                                int batch, int64_t n_max, gmg_stream_t stream);
+
+/* Materialise the reference's `kriging_weights`: W (M x n, or M x (n+1) with the Lagrange column when
+ * alpha != NULL) from T (n x M) :  W[m, a] = T[a, m] - o[a] alpha[m],  W[m, n] = alpha[m]. */
+int gmg_krige_weights_f64(const double* T, int64_t ldt, const double* o, int64_t o_stride,
+                          const double* alpha, int64_t n, int64_t M, double* W, int64_t ldw,
+                          gmg_stream_t stream);
+
+/* Inverse of [[S, 1], [1^T, 0]] from S^-1 (n x n) by the bordered-matrix identity; `ws_e` = n doubles.
+ * replaces `_extended_inverse`, glomar_gridding/kriging.py:815-829. */
+int gmg_extended_inverse_f64(const double* inv, int64_t n, int64_t ld, double* ws_e, double* out,
+                             int64_t ldo, gmg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stochastic draws   replaces glomar_gridding/stochastic.py:395-502 (np.random.multivariate_normal)
+ * A draw is X = Z L^T with L from gmg_potrf_batched_f64 (upper triangle cleared by gmg_tril_f64),
+ * Z from gmg_normal_f64 and the product by gmg_gemm_f64.
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[0..n) ~ N(0, 1): Philox4x32-10 counter (offset + pair index) keyed by `seed`, Box-Muller. */
+int gmg_normal_f64(double* out, int64_t n, uint64_t seed, uint64_t offset, gmg_stream_t stream);
+
+/* Zero the strict upper triangle of the row-major n x n matrix A. */
+int gmg_tril_f64(double* A, int64_t n, int64_t ld, gmg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
