@@ -1,12 +1,16 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: 1-degree global (N = 64 800) non-stationary ellipse Matern covariance
-build, general nu via Bessel-K (BASELINE.json configs[2], the configuration the headline metric
-"ellipse-cov entries/s @1 degree grid" is quoted on), row-block sharded across the GPUs of one box.
+"""Benchmark of the hot path (BASELINE.json metric: "ellipse-cov entries/s @1deg grid; kriged months/s").
+
+Primary line value: 1-degree global (N = 64 800) non-stationary ellipse Matern covariance build, general nu via
+Bessel-K (BASELINE.json configs[2], the configuration "ellipse-cov entries/s @1deg grid" is quoted on), row-block
+sharded across the GPUs of one box.  The second half of the metric, "kriged months/s" (configs[1]: 480 synthetic
+months of 5-degree ordinary kriging, sharded by month), is measured in the same run and reported under
+`"kriging"` in the same JSON line, with its own roofline, e2e and cpu_baseline objects.
 
     python bench.py --gpus N --steps K --warmup W            # this implementation
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port)
 
-One JSON line on stdout (rank 0).  See DESIGN.md §Measurement for what each key means.
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
 """
 
 from __future__ import annotations
@@ -17,15 +21,18 @@ import os
 import sys
 import threading
 import time
+import warnings
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "ellipse-cov entries/s @1deg grid"
+METRIC = "ellipse-cov entries/s @1deg grid; kriged months/s"
 UNIT = "entries/s"
 TILE = 64
+DMMA_PEAK_TFLOPS = 37.1     # mma.sync m8n8k4 f64, measured on this pool's B200 (profiles/r01_microbench_fp64.json)
+DFMA_PEAK_TFLOPS = 34.2     # plain DFMA, same file
 
 
 def parse_args():
@@ -38,8 +45,12 @@ def parse_args():
     ap.add_argument("--nu", type=float, default=2.2)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-rows", type=int, default=192, help="rows of the 1-degree matrix the CPU baseline evaluates")
+    ap.add_argument("--months", type=int, default=480)
+    ap.add_argument("--month-steps", type=int, default=3)
+    ap.add_argument("--cpu-months", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kriging", action="store_true")
     return ap.parse_args()
 
 
@@ -52,6 +63,18 @@ def workload(res, nu):
             "N": lats.size * lons.size}
 
 
+def month_problems(months, n_cells, nlon):
+    """Synthetic months of SURVEY.md §8(d): month m has default_rng(m) observations and a HadCRUT-style n x n
+    error covariance (12 longitude-band blocks + diagonal)."""
+    from glomargridding_b200 import synthetic as synth
+
+    out = []
+    for m in months:
+        idx, obs = synth.month_observations(m, n_cells)
+        out.append((idx, obs, synth.hadcrut_style_error_cov(idx, nlon, seed=m)))
+    return out
+
+
 def row_block(N, rank, world):
     """Contiguous row block of rank `rank`, aligned to the 64-row tile so mirrored tiles stay inside it."""
     tiles = (N + TILE - 1) // TILE
@@ -60,13 +83,21 @@ def row_block(N, rank, world):
     return t0 * TILE, min(N, t1 * TILE) - t0 * TILE
 
 
+def config_dict(args, wl, world):
+    return {"workload": f"{args.res:g}deg global grid ({wl['N']} cells) ellipse Matern covariance, nu={args.nu:g} "
+                        f"(general nu via Bessel-K), Modified_Met_Office, FP64 [BASELINE configs[2]]; secondary: "
+                        f"5deg grid ordinary kriging of {args.months} synthetic months [configs[1]]",
+            "N": wl["N"], "nu": args.nu, "sharding": f"row blocks x{world}; months round-robin x{world}",
+            "l2": "output (8*N^2/world bytes per GPU) is far larger than the 126 MB L2; no flush needed"}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's algorithm on a bounded sample of the same workload
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(wl, n_rows):
-    """Time the reference's pair formula (oracle port of `c_ij_anisotropic_array`) on every i<j pair
-    whose row index lies in a contiguous block of `n_rows` rows in the middle of the matrix.  The
-    reference evaluates N(N-1)/2 pairs to fill N^2 entries, so entries/s = 2 * pairs/s."""
+def cpu_cov_sample(wl, n_rows):
+    """Time the reference's pair formula (oracle port of `c_ij_anisotropic_array`) on every i<j pair whose row
+    index lies in a contiguous block of `n_rows` rows in the middle of the matrix.  The reference evaluates
+    N(N-1)/2 pairs to fill N^2 entries, so entries/s = 2 * pairs/s."""
     from oracle import EllipseOracle
 
     N = wl["N"]
@@ -84,21 +115,50 @@ def cpu_sample(wl, n_rows):
     return 2.0 * pairs / dt, pairs, dt
 
 
+def cpu_kriging_sample(n_months):
+    """The reference's per-month workflow (oracle port, M x M temporaries included like the reference):
+    OrdinaryKriging construct + solve + get_uncertainty on the first `n_months` synthetic months."""
+    from glomargridding_b200 import synthetic as synth
+    from oracle import EllipseOracle, ordinary_kriging
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5, "Met_Office").build()
+    probs = month_problems(range(n_months), cov.shape[0], lons.size)
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for idx, obs, E in probs:
+            ordinary_kriging(cov, idx, obs, E, big_temporaries=True)
+    dt = time.perf_counter() - t0
+    return n_months / dt, dt
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = workload(args.res, args.nu)
     for _ in range(min(args.warmup, 1)):
-        cpu_sample(wl, 8)
+        cpu_cov_sample(wl, 8)
     vals, times = [], []
     for _ in range(args.steps):
-        v, pairs, dt = cpu_sample(wl, args.cpu_rows)
+        v, pairs, dt = cpu_cov_sample(wl, args.cpu_rows)
         vals.append(v)
         times.append(dt)
     value = float(np.mean(vals))
     sample = (f"all i<j pairs with i in a {args.cpu_rows}-row block of the {wl['N']}-cell matrix per step "
-              f"({pairs} pairs), numpy/scipy single thread; entries/s = 2*pairs/s")
+              f"({pairs} pairs), numpy/scipy (the reference's covariance build is single-threaded); "
+              f"entries/s = 2*pairs/s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3),
@@ -108,14 +168,15 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_kriging:
+        mps, dt = cpu_kriging_sample(args.cpu_months)
+        line["kriging"] = {"metric": "kriged months/s", "value": mps, "unit": "months/s",
+                           "cpu_baseline": {"value": mps, "unit": "months/s", "cores": host_threads(), "kind": "port",
+                                            "sample": f"{args.cpu_months} of the {args.months} months ({dt:.1f} s): "
+                                                      "OrdinaryKriging construct + solve + get_uncertainty, numpy "
+                                                      "LAPACK/BLAS on all host threads"},
+                           "e2e": {"value": mps, "unit": "months/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def config_dict(args, wl, world):
-    return {"workload": f"{args.res:g}deg global grid ({wl['N']} cells) ellipse Matern covariance, nu={args.nu:g} "
-                        f"(general nu via Bessel-K), Modified_Met_Office, FP64",
-            "N": wl["N"], "nu": args.nu, "sharding": f"row blocks x{world}",
-            "l2": "output (8*N^2/world bytes per GPU) is far larger than the 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -166,16 +227,21 @@ class ClockSampler:
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def load_json(path, default):
+    try:
+        with open(os.path.join(ROOT, path)) as f:
+            return json.load(f)
+    except Exception:
+        return default
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
-    import ctypes
-
     import torch
     import torch.distributed as dist
 
-    from glomargridding_b200 import _device as dev
     from glomargridding_b200._lib import check, lib
     from glomargridding_b200.ellipse import EllipseCovarianceBuilder
 
@@ -187,10 +253,22 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = torch.device("cuda", local)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     wl = workload(args.res, args.nu)
     N = wl["N"]
     row0, nrows = row_block(N, rank, world)
     L = lib()
+    warmup = max(args.warmup, 3)
 
     # ---- device-resident inputs (the builder's own host prep, done once) ------------------------
     probe = EllipseCovarianceBuilder(wl["Lx"], wl["Ly"], wl["theta"], wl["stdev"], wl["lats"], wl["lons"],
@@ -201,18 +279,16 @@ def run_b200(args):
     out = torch.empty((nrows, N), dtype=torch.float64, device=device)
     stream = torch.cuda.current_stream()
 
-    def step():
-        check(L.gmg_ellipse_prepare_f64(*[t.data_ptr() for t in ins], N, args.nu, 1, ws.data_ptr(), ws_bytes,
-                                        stream.cuda_stream), "prepare")
+    def cov_kernel():
         check(L.gmg_ellipse_cov_f64(ws.data_ptr(), N, row0, nrows, args.nu, -1.0, 0, out.data_ptr(), N, 0,
                                     stream.cuda_stream), "cov")
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step():
+        check(L.gmg_ellipse_prepare_f64(*[t.data_ptr() for t in ins], N, args.nu, 1, ws.data_ptr(), ws_bytes,
+                                        stream.cuda_stream), "prepare")
+        cov_kernel()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -228,16 +304,11 @@ def run_b200(args):
         for _ in range(min(args.steps, 5)):
             k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             k0.record(stream)
-            check(L.gmg_ellipse_cov_f64(ws.data_ptr(), N, row0, nrows, args.nu, -1.0, 0, out.data_ptr(), N, 0,
-                                        stream.cuda_stream), "cov")
+            cov_kernel()
             k1.record(stream)
             k1.synchronize()
             kernel_ms.append(k0.elapsed_time(k1))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = max_over_ranks(total_ms) / args.steps
     value = float(N) * float(N) / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API: host inputs -> numpy cov_ns (pinned) ------------------
@@ -255,49 +326,129 @@ def run_b200(args):
         for _ in range(args.e2e_steps):
             e2e_step()
         barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = 6 * N * 8
-        e2e = {"value": float(N) * float(N) / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+        dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        e2e = {"value": float(N) * float(N) / dt, "unit": UNIT, "h2d_bytes_per_step": 6 * N * 8,
                "d2h_bytes_per_step": int(nrows) * N * 8, "steps": args.e2e_steps,
-               "note": "EllipseCovarianceBuilder(host arrays).cov_ns -> numpy in pinned host memory, per rank row block"}
+               "note": "EllipseCovarianceBuilder(host arrays).cov_ns -> numpy in pinned host memory, per rank row "
+                       "block; the 8*N^2/world-byte device->host copy of the matrix dominates"}
+    del out
+    torch.cuda.empty_cache()
+
+    kriging = None
+    if not args.no_kriging:
+        kriging = run_months(args, rank, world, device, barrier, max_over_ranks, local)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
+    peaks = load_json("MEASURED_PEAKS.json", {})
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     k_ms = float(np.mean(kernel_ms))
     achieved = 8.0 * nrows * N / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "ellipse_cov_tile_kernel<TABLE, Modified_Met_Office, f64>",
+    prof = load_json("profiles/r01_ellipse_full_traffic.json", {})
+    traffic = prof.get("dram_bytes_per_launch") if world == 1 and abs(args.nu - prof.get("nu", -1)) < 1e-12 else None
+    roofline = {"bound": "hbm", "kernel": "ellipse_cov_tile_kernel<TABLE, f64> (persistent, 2 CTAs/SM)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s",
-                "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": 8 * int(nrows) * N,
-                "note": "8 B written per entry; the kernel is FP64-pipe bound for general nu (see DESIGN.md)"}
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "traffic": traffic, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": 8 * int(nrows) * N,
+                "note": "8 B written per entry (SURVEY 8d).  The general-nu kernel is FP64-pipe bound, not HBM "
+                        "bound: ~53 FP64 instructions per evaluated pair (profiles/r01_ellipse_summary.md) against "
+                        f"a {DFMA_PEAK_TFLOPS} TFLOP/s DFMA pipe; see fp64_pipe_frac",
+                "fp64_pipe_frac": prof.get("fp64_pipe_pct_of_peak")}
     cpu = None
     if not args.no_cpu_baseline:
-        v, pairs, dt = cpu_sample(wl, args.cpu_rows)
+        v, pairs, dt = cpu_cov_sample(wl, args.cpu_rows)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"all i<j pairs with i in a {args.cpu_rows}-row block ({pairs} pairs, {dt:.1f} s), "
-                         f"numpy/scipy oracle port, single thread; entries/s = 2*pairs/s"}
+                         f"numpy/scipy oracle port (the reference's build is single-threaded); entries/s = 2*pairs/s"}
+        if kriging is not None:
+            mps, dtk = cpu_kriging_sample(args.cpu_months)
+            kriging["cpu_baseline"] = {"value": mps, "unit": "months/s", "cores": host_threads(), "kind": "port",
+                                       "sample": f"{args.cpu_months} of the {args.months} months ({dtk:.1f} s): "
+                                                 "OrdinaryKriging construct + solve + get_uncertainty, numpy "
+                                                 "LAPACK/BLAS on all host threads"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, wl, world),
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": 3 * args.steps, "roofline": roofline,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "kriging": kriging,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_months(args, rank, world, device, barrier, max_over_ranks, local):
+    """kriged months/s: `--months` synthetic 5-degree months, ordinary kriging, months round-robin over ranks."""
+    import torch
+
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200 import synthetic as synth
+    from glomargridding_b200.batched import krige_batch, shard
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office",
+                                   precision=np.float64).cov_ns_device
+    M = cov.shape[0]
+    mine = shard(args.months, rank, world)
+    probs = month_problems(mine, M, lons.size)
+    kb = dn.KrigeBatch(cov, probs, ordinary=True)      # inputs resident in HBM before the timed region
+    for _ in range(2):
+        kb.run()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.month_steps):
+            kb.run()
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.month_steps
+    ns = np.array(kb.ns, dtype=np.float64)
+    flops = float((ns ** 3 / 3 + 2 * ns ** 2 * (M + 1)).sum())          # Cholesky + two triangular solves
+    tflops_local = flops / (ms * 1e-3) / 1e12
+    nblk = int(np.ceil(kb.n_max / 128))
+    launches = 1 + (3 * nblk - 2) + 4 * nblk + 2
+    del kb
+    torch.cuda.empty_cache()
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                r = krige_batch(cov, probs, "ordinary")
+            return r["field"][0, 0]
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": args.months / dt, "unit": "months/s",
+               "h2d_bytes_per_step": int(sum(8 * (len(p[0]) ** 2 + 2 * len(p[0])) for p in probs)),
+               "d2h_bytes_per_step": int(len(probs) * 5 * M * 8), "steps": 1,
+               "note": "krige_batch(cov on device, host idx/obs/error_cov per month) -> numpy field, uncertainty, "
+                       "constraint mask; per-rank share of the months"}
+    return {"metric": "kriged months/s", "value": args.months / (ms * 1e-3), "unit": "months/s",
+            "ms_per_step": ms, "steps": args.month_steps, "months": args.months,
+            "config": {"workload": f"5deg grid (M={M}) ordinary kriging, {args.months} synthetic months, n~U(600,1600) "
+                                   "obs, HadCRUT-style error covariance, Met_Office ellipse covariance (SPD), "
+                                   "construct + solve + uncertainty + constraint mask per month"},
+            "clocks": clocks.summary(), "gpu_launches": launches * args.month_steps,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tile (DMMA m8n8k4 f64) inside trsm_step / potrf_update",
+                         "achieved": tflops_local, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": tflops_local / DMMA_PEAK_TFLOPS, "traffic": None,
+                         "peak_source": "measured mma.sync f64 peak, profiles/r01_microbench_fp64.json "
+                                        "(MEASURED_PEAKS.json has no FP64 figure)",
+                         "note": "algorithmic flops n^3/3 + 2 n^2 (M+1) per month (SURVEY 8d) over the whole "
+                                 "gather+factor+solve+apply step of this rank"},
+            "e2e": e2e}
 
 
 if __name__ == "__main__":

@@ -1,0 +1,97 @@
+"""Many kriging problems against one covariance matrix in one go (BASELINE.json config 2: 480 months of 5-degree
+ordinary kriging, sharded by month across the GPUs of a box).
+
+The reference has no batched entry point - a user loops `OrdinaryKriging(cov, idx_m, obs_m, E_m)` over months
+(`glomar_gridding/kriging.py:494-812`, notebook cells 31-40).  `krige_batch` is that loop, run as ONE sequence of
+batched launches per chunk of months (`_dense.KrigeBatch`: the month index is `blockIdx.z` of every kernel).
+Each problem goes through exactly the constructor logic of the classes (error-covariance subsetting and the
+NaN / zero-diagonal filter with its warning), so results are identical to the per-month classes.
+
+Multi-GPU: problems are independent, so rank r of `world` takes problems r, r + world, ... (`shard`), with no
+data-path collective; `gather_results` collects the M-vectors on every rank with one all_gather (gloo or nccl).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _dense as dn
+from .kriging import OrdinaryKriging, SimpleKriging, _as_device_cov, _finish_uncertainty
+
+
+def shard(n_items: int, rank: int, world: int) -> list[int]:
+    """Round-robin ownership of independent problems (months, ensemble members)."""
+    return list(range(rank, n_items, world))
+
+
+def _bytes_per_problem(n: int, M: int) -> int:
+    lin, pdb, _ = dn.solve_ws(n)
+    slabs = (n + dn.SLAB - 1) // dn.SLAB
+    return 8 * (n * (n + 2) + 2 * n * (M + 2) + lin + pdb + 3 * slabs * M + 5 * M + n * n)
+
+
+def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_bytes: int | None = None,
+                return_device: bool = False):
+    """Kriged field, uncertainty and constraint mask for every (idx, obs, error_cov) in `problems`.
+
+    Returns a dict of (len(problems), M) arrays: "field", "uncertainty", "constraint_mask" (numpy, or CUDA
+    tensors "field", "variance", "constraint_mask" if `return_device`).  `max_bytes` bounds the device
+    memory of one chunk of problems (default: 40 % of the free memory)."""
+    if method not in ("ordinary", "simple"):
+        raise ValueError(f"Unknown kriging method: {method}")
+    cls = OrdinaryKriging if method == "ordinary" else SimpleKriging
+    cov = _as_device_cov(covariance)
+    M = cov.shape[0]
+    # the classes' constructor logic (subset E, drop NaN / zero-diagonal observations, warn) per problem
+    prepared = []
+    for idx, obs, E in problems:
+        k = cls.__new__(cls)
+        k.covariance, k.idx, k.obs, k.error_cov = covariance, np.asarray(idx), np.asarray(obs), E
+        k._batch = k._user_weights = None
+        k.subset_error_covariance()
+        prepared.append(k._problem())
+    if max_bytes is None:
+        free, _ = torch.cuda.mem_get_info(cov.device)
+        max_bytes = int(0.4 * free)
+    out = torch.empty((len(prepared), 5, M), dtype=torch.float64, device=cov.device)
+    start = 0
+    while start < len(prepared):
+        used, stop = 0, start
+        while stop < len(prepared):
+            need = _bytes_per_problem(len(prepared[stop][0]), M)
+            if stop > start and used + need > max_bytes:
+                break
+            used += need
+            stop += 1
+        batch = dn.KrigeBatch(cov, prepared[start:stop], ordinary=method == "ordinary").run()
+        out[start:stop] = batch.out
+        del batch
+        start = stop
+    if return_device:
+        field = out[:, dn.OUT_FIELD] + (mean if method == "simple" else 0.0)
+        return {"field": field, "variance": out[:, dn.OUT_U2], "constraint_mask": out[:, dn.OUT_MASK]}
+    o = out.cpu().numpy()
+    field = o[:, dn.OUT_FIELD] + (mean if method == "simple" else 0.0)
+    unc = np.stack([_finish_uncertainty(o[b, dn.OUT_U2], np.float64) for b in range(o.shape[0])]) if len(o) else o[:, 0]
+    return {"field": field, "uncertainty": unc, "constraint_mask": o[:, dn.OUT_MASK]}
+
+
+def gather_results(local: np.ndarray, n_items: int, rank: int, world: int) -> np.ndarray:
+    """Reassemble per-rank result rows (sharded by `shard`) into problem order on every rank."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+
+    M = local.shape[1]
+    per = (n_items + world - 1) // world
+    use_cuda = dist.get_backend() == "nccl"
+    buf = torch.zeros((per, M), dtype=torch.float64, device="cuda" if use_cuda else "cpu")
+    buf[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(buf.device)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    out = np.empty((n_items, M), dtype=np.float64)
+    for r in range(world):
+        rows = shard(n_items, r, world)
+        out[rows] = parts[r][: len(rows)].cpu().numpy()
+    return out

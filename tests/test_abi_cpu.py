@@ -1,0 +1,91 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol declared in
+include/glomar_b200.h, descriptor layouts match, and the product package fails loudly without a GPU
+(no compute calls are made here)."""
+
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from glomargridding_b200._lib import LIB_PATH, exported_symbols, lib
+
+    assert os.path.exists(LIB_PATH), "run `python __graft_entry__.py` first"
+    L = lib()
+    names = exported_symbols()
+    assert len(names) >= 20
+    missing = [s for s in names if not hasattr(L, s)]
+    assert not missing, missing
+    assert L.gmg_version() >= 100
+    assert L.gmg_strerror(2).decode().startswith("matrix is not positive definite")
+    assert b"invalid argument" in L.gmg_strerror(-3)
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected before any CUDA call: negative return = 1-based argument index."""
+    from glomargridding_b200._lib import lib
+
+    L = lib()
+    nbytes = ctypes.c_size_t()
+    assert L.gmg_ellipse_ws_bytes(0, ctypes.byref(nbytes)) == -1
+    assert L.gmg_ellipse_ws_bytes(100, ctypes.byref(nbytes)) == 0 and nbytes.value > 100 * 64 * 2
+    assert L.gmg_ellipse_cov_f64(None, 10, 0, 10, 1.5, -1.0, 0, None, 10, 0, None) == -1
+    assert L.gmg_gemm_f64(0, 0, -1, 1, 1, 1.0, None, 2, None, 2, 0.0, None, 2, None) == -3
+    a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    assert L.gmg_solve_ws_doubles(300, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)) == 0
+    assert (a.value, b.value, c.value) == (3 * 128 * 128, 128 * 384, 384)
+    assert L.gmg_potrf_batched_f64(None, 1, 10, None) == -1
+
+
+def test_descriptor_layouts_match_the_header():
+    from glomargridding_b200 import _dense as dn
+
+    assert dn.SOLVE_DESC.itemsize == 72 and dn.KRIGE_DESC.itemsize == 104
+    assert list(dn.SOLVE_DESC.names) == ["S", "lds", "Linv", "R", "ldr", "P", "ldp", "info", "n", "nrhs"]
+    header = open(os.path.join(ROOT, "include", "glomar_b200.h")).read()
+    for name in dn.SOLVE_DESC.names + dn.KRIGE_DESC.names:
+        assert name in header
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from glomargridding_b200 import synthetic as synth
+    from glomargridding_b200._lib import GlomarB200Error
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+    from glomargridding_b200.kriging import OrdinaryKriging
+
+    lats, lons = synth.global_grid(30.0)
+    with pytest.raises(GlomarB200Error, match="no CPU fallback"):
+        EllipseCovarianceBuilder(*synth.ellipse_fields(lats, lons), lats, lons, v=1.5)
+    with pytest.raises(GlomarB200Error, match="no CPU fallback"):
+        OrdinaryKriging(np.eye(4), np.array([0, 2]), np.array([1.0, 2.0])).solve()
+
+
+def test_product_never_imports_the_oracle():
+    code = ("import sys; sys.path.insert(0, %r); import glomargridding_b200, glomargridding_b200.ellipse, "
+            "glomargridding_b200.kriging, glomargridding_b200.stochastic, glomargridding_b200.batched; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'" % ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "glomargridding_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_install_as_glomar_gridding_aliases_import_paths():
+    code = ("import sys; sys.path.insert(0, %r); import glomargridding_b200 as g; g.install_as_glomar_gridding(); "
+            "from glomar_gridding.ellipse import EllipseCovarianceBuilder; "
+            "from glomar_gridding.kriging import SimpleKriging, OrdinaryKriging, kriging_simple; "
+            "from glomar_gridding.stochastic import StochasticKriging, scipy_mv_normal_draw; "
+            "from glomar_gridding.utils import adjust_small_negative, cov_2_cor" % ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True)

@@ -374,3 +374,30 @@ def test_normal_generator_moments(K):
     assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 5 * np.sqrt(2 / n)
     assert abs(np.mean(z ** 3)) < 5 * np.sqrt(15 / n) and abs(np.mean(z ** 4) - 3) < 5 * np.sqrt(96 / n)
     assert np.isfinite(z).all() and np.unique(z).size > 0.999 * n
+
+
+# ---- batched months (BASELINE.json config 2) ----------------------------------------------------------------
+def test_batched_months_equal_per_month_classes(K):
+    from glomargridding_b200.batched import krige_batch
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(10.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    b = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office", precision=np.float64)
+    M = b.cov_ns.shape[0]
+    problems = []
+    for m in range(7):
+        idx, obs = synth.month_observations(m, M, n_min=40, n_max=300)
+        problems.append((idx, obs, synth.hadcrut_style_error_cov(idx, lons.size, seed=m)))
+    # one full-grid error covariance with a zero diagonal at an observed cell: the filter must run per problem
+    idx, obs = synth.month_observations(99, M, n_min=50, n_max=60)
+    E_full = synth.full_grid_error_cov(idx, M, lons.size)
+    E_full[idx[3], idx[3]] = 0.0
+    problems.append((idx, obs, E_full))
+    for method, cls in (("ordinary", K.OrdinaryKriging), ("simple", K.SimpleKriging)):
+        res = quiet(krige_batch, b.cov_ns_device, problems, method, max_bytes=40 << 20)   # forces several chunks
+        for m, (idx, obs, E) in enumerate(problems):
+            one = quiet(cls, b.cov_ns_device, idx.copy(), obs.copy(), E.copy())
+            assert np.array_equal(res["field"][m], quiet(one.solve))
+            assert np.array_equal(res["uncertainty"][m], quiet(one.get_uncertainty))
+            assert np.array_equal(res["constraint_mask"][m], quiet(one.constraint_mask))
