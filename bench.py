@@ -121,6 +121,7 @@ def cpu_kriging_sample(n_months):
     from glomargridding_b200 import synthetic as synth
     from oracle import EllipseOracle, ordinary_kriging
 
+    use_all_host_threads()
     lats, lons = synth.global_grid(5.0)
     Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
     cov = EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5, "Met_Office").build()
@@ -141,6 +142,16 @@ def host_threads():
         return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
         return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core for LAPACK/BLAS."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
 
 
 def run_reference(args):
@@ -250,7 +261,19 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator is created: keep stdout to the one
+        # JSON line by pointing fd 1 at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     device = torch.device("cuda", local)
 
     def barrier():
@@ -358,7 +381,7 @@ def run_b200(args):
                         f"a {DFMA_PEAK_TFLOPS} TFLOP/s DFMA pipe; see fp64_pipe_frac",
                 "fp64_pipe_frac": prof.get("fp64_pipe_pct_of_peak")}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (the reference arm covers N > 1)
         v, pairs, dt = cpu_cov_sample(wl, args.cpu_rows)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"all i<j pairs with i in a {args.cpu_rows}-row block ({pairs} pairs, {dt:.1f} s), "

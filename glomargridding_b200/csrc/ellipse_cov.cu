@@ -21,9 +21,10 @@
 // The Matern factor x^nu K_nu(x) / (Gamma(nu) 2^(nu-1)) is evaluated as g(x) e^-x with
 //   nu = 0.5 / 1.5 / 2.5 : g = 1, 1 + x, 1 + x + x^2/3              (closed forms)
 //   otherwise            : g from a piecewise degree-7 polynomial table in the mantissa of x
-//                          (16 linear sub-intervals per octave, 2^-12 <= x < 2^10), built on the
+//                          (16 linear sub-intervals per octave, 2^-12 <= x < 2^9), built on the
 //                          device from the Temme/CF2 Bessel-K in bessel_k.cuh for the build's nu;
 //                          lanes outside the table range fall back to the direct evaluation.
+#include <type_traits>
 #include "gmg_common.cuh"
 #include "bessel_k.cuh"
 #include "../../include/glomar_b200.h"
@@ -40,13 +41,13 @@ constexpr int kTileLd = kTile + 1;                  // odd leading dimension: co
 
 // Matern table geometry
 constexpr int kTabEmin = -12;
-constexpr int kTabEmax = 10;                        // exclusive
+constexpr int kTabEmax = 9;                         // exclusive: the table ends at x = 512 < 700
 constexpr int kTabSubLog2 = 4;
 constexpr int kTabSub = 1 << kTabSubLog2;                   // linear sub-intervals of the mantissa per octave
-constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 352
+constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 336
 constexpr int kTabDeg = 7;
 constexpr int kTabCoef = kTabDeg + 1;
-constexpr int kTabDoubles = kTabNint * kTabCoef;            // 2816 (22.5 KB), layout [interval][coef]
+constexpr int kTabDoubles = kTabNint * kTabCoef;            // 2688 (21.5 KB), layout [interval][coef]
 static_assert(kTabCoef == 8, "the table record is read as four 16-byte loads");
 
 enum { MODE_NU05 = 0, MODE_NU15 = 1, MODE_NU25 = 2, MODE_TABLE = 3, MODE_DIRECT = 4 };
@@ -193,42 +194,57 @@ __device__ __forceinline__ PointRegs load_point(const double* p) {     // p: 8 c
 // unusual (x >= 700, x outside the Matern table, NaN from a non-positive determinant) is flagged and
 // recomputed on a cold path with the libm functions.
 
-// 2^(-j/64), j = 0..63, correctly rounded (mpmath).  Every CTA stages kExpRep = 16 interleaved copies in
+// 2^(-j/128), j = 0..127, correctly rounded (mpmath).  Every CTA stages kExpRep = 16 interleaved copies in
 // shared memory, entry j of copy c at [j * 16 + c]: a 64-bit shared load is served per half-warp, and lane l
 // reads copy l & 15, i.e. always its own bank pair - the data-dependent lookup is conflict-free
 // (ncu r01b: 4.8 wavefronts per lookup with a single copy).
 constexpr int kExpRep = 16;
-__device__ const double kExp2Neg64[64] = {
-    1.0, 0.9892280131939755, 0.9785720620877001, 0.9680308967461472,
-    0.9576032806985737, 0.9472879907934828, 0.93708381705515, 0.9269895625416927,
-    0.9170040432046712, 0.9071260877501994, 0.8973545375015536, 0.8876882462632606,
-    0.8781260801866497, 0.8686669176368531, 0.859309649061239, 0.8500531768592617,
-    0.8408964152537145, 0.8318382901633682, 0.8228777390769825, 0.8140137109286739,
-    0.8052451659746271, 0.7965710756711335, 0.7879904225539432, 0.7795022001189185,
-    0.7711054127039704, 0.7627990753722692, 0.7545822137967114, 0.7464538641456324,
-    0.7384130729697497, 0.7304588970903235, 0.7225904034885233, 0.714806669195985,
-    0.7071067811865476, 0.6994898362691556, 0.691954940981916, 0.6845012114872953,
-    0.6771277734684463, 0.6698337620266515, 0.6626183215798707, 0.6554806057623822,
-    0.6484197773255048, 0.6414350080393891, 0.6345254785958666, 0.6276903785123455,
-    0.620928906036742, 0.614240268053435, 0.6076236799902345, 0.6010783657263515,
-    0.5946035575013605, 0.5881984958251406, 0.5818624293887887, 0.5755946149764913,
-    0.5693943173783458, 0.5632608093041209, 0.5571933712979462, 0.5511912916539204,
-    0.5452538663326288, 0.5393803988785599, 0.5335702003384118, 0.5278225891802786,
-    0.5221368912137069, 0.5165124395106142, 0.5109485743270583, 0.5054446430258502};
+constexpr int kExpTab = 128;
+__device__ const double kExp2Neg[kExpTab] = {
+    1.0, 0.9945994234836332, 0.9892280131939755, 0.9838856116165879,
+    0.9785720620877001, 0.9732872087896166, 0.9680308967461472, 0.9628029718180625,
+    0.9576032806985737, 0.9524316709088371, 0.9472879907934828, 0.9421720895161673,
+    0.93708381705515, 0.9320230241988945, 0.9269895625416927, 0.921983284479313,
+    0.9170040432046712, 0.9120516927035267, 0.9071260877501994, 0.902227083903312,
+    0.8973545375015536, 0.8925083056594675, 0.8876882462632606, 0.8828942179666364,
+    0.8781260801866497, 0.8733836930995845, 0.8686669176368531, 0.8639756154809188,
+    0.859309649061239, 0.8546688815502315, 0.8500531768592617, 0.8454623996346526,
+    0.8408964152537145, 0.8363550898207983, 0.8318382901633682, 0.8273458838280972,
+    0.8228777390769825, 0.8184337248834822, 0.8140137109286739, 0.8096175675974319,
+    0.8052451659746271, 0.8008963778413467, 0.7965710756711335, 0.7922691326262469,
+    0.7879904225539432, 0.7837348199827765, 0.7795022001189185, 0.7752924388425,
+    0.7711054127039704, 0.766940998920478, 0.7627990753722692, 0.7586795205991074,
+    0.7545822137967114, 0.7505070348132128, 0.7464538641456324, 0.7424225829363762,
+    0.7384130729697497, 0.7344252166684909, 0.7304588970903235, 0.7265139979245263,
+    0.7225904034885233, 0.7186879987244912, 0.714806669195985, 0.7109463010845828,
+    0.7071067811865476, 0.7032879969095077, 0.6994898362691556, 0.6957121878859631,
+    0.691954940981916, 0.6882179853772651, 0.6845012114872953, 0.6808045103191124,
+    0.6771277734684463, 0.6734708931164729, 0.6698337620266515, 0.6662162735415808,
+    0.6626183215798707, 0.659039800633032, 0.6554806057623822, 0.6519406325959679,
+    0.6484197773255048, 0.6449179367033329, 0.6414350080393891, 0.637970889198196,
+    0.6345254785958666, 0.6310986751971254, 0.6276903785123455, 0.6243004885946024,
+    0.620928906036742, 0.6175755319684667, 0.614240268053435, 0.6109230164863788,
+    0.6076236799902345, 0.6043421618132908, 0.6010783657263515, 0.5978321960199137,
+    0.5946035575013605, 0.5913923554921705, 0.5881984958251406, 0.5850218848416251,
+    0.5818624293887887, 0.5787200368168756, 0.5755946149764913, 0.5724860722159021,
+    0.5693943173783458, 0.5663192597993596, 0.5632608093041209, 0.5602188762048034,
+    0.5571933712979462, 0.5541842058618394, 0.5511912916539204, 0.5482145409081884,
+    0.5452538663326288, 0.5423091811066546, 0.5393803988785599, 0.5364674337629878,
+    0.5335702003384118, 0.530688613644631, 0.5278225891802786, 0.5249720429003436,
+    0.5221368912137069, 0.5193170509806894, 0.5165124395106142, 0.5137229745593819,
+    0.5109485743270583, 0.5081891574554765, 0.5054446430258502, 0.5027149505564014};
 
 // FP64 literals of the hot loop live in constant memory: a DFMA can take a c[bank][offset] operand directly,
 // whereas a 64-bit immediate costs two extra MOV issue slots per use once registers are short (ncu r01c: the
 // loop was issue-bound, 53 non-FP64 instructions per pair for 45 FP64 ones).
 struct HotConsts {
-    double magic, inv_ln2_64, ln2_64_hi, ln2_64_lo, c5, c4, c3, half, one, c38, pi, third;
+    double magic, inv_ln2_128, ln2_128, c4, c3, half, one, c38, pi, third, tab_scale;
 };
 __constant__ HotConsts kHot = {6755399441055744.0,        // 1.5 * 2^52
-                               92.33248261689366,         // 64 / ln 2
-                               0.010830424695086549,      // ln2/64 hi (33 significant bits)
-                               1.162596423439437e-12,     // ln2/64 lo
-                               8.33333333333333333333e-03, 4.16666666666666666667e-02,
-                               1.66666666666666666667e-01, 0.5, 1.0, 0.375, 3.141592653589793,
-                               1.0 / 3.0};
+                               184.6649652337873,        // 128 / ln 2
+                               0.0054152123481245725,      // ln 2 / 128, correctly rounded
+                               4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5, 1.0, 0.375,
+                               3.141592653589793, 1.0 / 3.0, (double)(2 * kTabSub)};
 
 // 1/sqrt(a), a > 0 normal: MUFU seed (rel. error < 2^-22) and one cubically convergent step
 //   e = 1 - a r^2,  r <- r + r e (1/2 + 3/8 e)      (error ~ 5/16 e^3 < 2^-64)       5 FP64 instructions
@@ -239,25 +255,25 @@ __device__ __forceinline__ double rsqrt_pos(double a) {
     return fma(r * e, fma(e, kHot.c38, kHot.half), r);
 }
 
-// exp(-x) for 0 <= x < 700 (result normal):  k = rint(64 x / ln 2),  exp(-x) = 2^-(k>>6) T[k&63] exp(s),
-// s = k ln2/64 - x in [-ln2/128, ln2/128] (Cody-Waite, k ln2_hi exact for k < 2^17), degree-5 Taylor
-// (truncation s^6/720 < 3.5e-17).  9 FP64 instructions + one shared-memory load.
+// exp(-x) for 0 <= x < 700 (result normal):  k = rint(128 x / ln 2),  exp(-x) = 2^-(k>>7) T[k&127] exp(s),
+// s = k ln2/128 - x in [-ln2/256, ln2/256].  The FMA forms k * c - x exactly and rounds once, so the only
+// reduction error is k * |c - ln2/128| <= 9e4 * 6e-19 = 5e-14 absolute at x = 700 (1e-14 at x = 100): no
+// Cody-Waite second constant is needed at the 1e-10 parity target.  Degree-4 Taylor (truncation s^5/120 <
+// 1.2e-15).  8 FP64 instructions + one shared-memory load.
 template <int STRIDE>
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ sexp) {
-    const double t = fma(x, kHot.inv_ln2_64, kHot.magic);
+    const double t = fma(x, kHot.inv_ln2_128, kHot.magic);
     const int k = __double2loint(t);
     const double kf = t - kHot.magic;
-    double s = fma(kf, kHot.ln2_64_hi, -x);
-    s = fma(kf, kHot.ln2_64_lo, s);
-    double p = fma(kHot.c5, s, kHot.c4);                          // 1/5!, 1/4!
-    p = fma(p, s, kHot.c3);                                       // 1/3!
+    const double s = fma(kf, kHot.ln2_128, -x);
+    double p = fma(kHot.c4, s, kHot.c3);                          // 1/4!, 1/3!
     p = fma(p, s, kHot.half);
     p = fma(p, s, kHot.one);
     const double ts = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(sexp) +
-                                                       (k & 63) * (STRIDE * (int)sizeof(double)));
+                                                       (k & (kExpTab - 1)) * (STRIDE * (int)sizeof(double)));
     p = fma(ts * s, p, ts);                                       // T (1 + s p)
-    // 2^-(k >> 6): subtract (k >> 6) << 20 from the high word = (k & ~63) * 2^14, one LOP3 + one IMAD
-    return __hiloint2double(__double2hiint(p) - (k & ~63) * 16384, __double2loint(p));
+    // 2^-(k >> 7): subtract (k >> 7) << 20 from the high word = (k & ~127) * 2^13, one LOP3 + one IMAD
+    return __hiloint2double(__double2hiint(p) - (k & ~(kExpTab - 1)) * 8192, __double2loint(p));
 }
 
 // g(x) of the fast path; `slow` is set when the lane must be recomputed by `cov_pair_slow`.
@@ -265,20 +281,29 @@ template <int MODE>
 __device__ __forceinline__ double matern_scaled_fast(const MaternCtx& m, double x, bool& slow) {
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
-    // !(0 <= x < 700) on the high word in the integer pipe (700.0 = 0x4085E000_00000000); also catches NaN
-    slow = (unsigned)hi >= 0x4085E000u;
-    if (MODE == MODE_NU05) return kHot.one;
-    if (MODE == MODE_NU15) return kHot.one + x;
-    if (MODE == MODE_NU25) return fma(x, fma(x, kHot.third, kHot.one), kHot.one);
-    if (MODE == MODE_DIRECT) { slow = true; return 0.0; }         // validation mode: always the cold path
-    int idx = ((hi >> 20) - (1023 + kTabEmin)) * kTabSub + ((hi >> (20 - kTabSubLog2)) & (kTabSub - 1));
-    slow = slow || ((unsigned)idx >= (unsigned)kTabNint);
-    idx = min(max(idx, 0), kTabNint - 1);
+    if (MODE != MODE_TABLE) {
+        // !(0 <= x < 700) on the high word in the integer pipe (700.0 = 0x4085E000_00000000); also catches NaN
+        slow = (unsigned)hi >= 0x4085E000u;
+        if (MODE == MODE_NU05) return kHot.one;
+        if (MODE == MODE_NU15) return kHot.one + x;
+        if (MODE == MODE_NU25) return fma(x, fma(x, kHot.third, kHot.one), kHot.one);
+        slow = true;                                              // MODE_DIRECT (validation): always the cold path
+        return 0.0;
+    }
+    // Integer instructions run at half rate on sm_100 (profiles/r01_microbench_xu.txt: a LOP3 costs 2 cycles of
+    // its pipe per warp), so the index arithmetic is kept to 6 of them.  With a positive x the interval index
+    // (exponent - emin) * 16 + top 4 mantissa bits is simply (hi >> 16) - 16 * (1023 + emin); one unsigned
+    // compare rejects everything outside [2^emin, 2^emax) - which includes x >= 700 (emax = 9), x <= 0 and NaN.
+    static_assert(kTabSubLog2 == 4 && kTabEmax <= 9, "index arithmetic below assumes 16 sub-intervals, table end <= 512");
+    const unsigned u = (unsigned)((hi >> 16) - kTabSub * (1023 + kTabEmin));
+    slow = u >= (unsigned)kTabNint;
+    const unsigned idx = min(u, (unsigned)(kTabNint - 1));
     const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
-    const int cbits = (hi & (((kTabSub - 1) << (20 - kTabSubLog2)))) | (1 << (19 - kTabSubLog2));
-    const double centre = __hiloint2double(0x3FF00000 | cbits, 0);
-    const double t = (mant - centre) * (double)(2 * kTabSub);
-    return table_horner(m.table + idx * kTabCoef, t);
+    // t = (mant - centre) * 32 = mant * 32 - (33 + 2 sub): the subtrahend is the integer-valued double
+    // 1.(2 sub + 1) x 2^5, whose high word is 0x40400000 | sub << 16 | 1 << 15 - one LOP3 on hi
+    const double c32 = __hiloint2double((hi & 0x000F0000) | 0x40408000, 0);
+    const double t = fma(mant, kHot.tab_scale, -c32);
+    return table_horner(reinterpret_cast<const double*>(reinterpret_cast<const char*>(m.table) + idx * (kTabCoef * 8)), t);
 }
 
 // longitude wrap, reference ellipse/covariance.py:633-634:  dx > pi -> dx - 2 pi,  dx < -pi -> dx + 2 pi
@@ -340,7 +365,7 @@ __device__ __forceinline__ double cov_pair(const PointRegs& a, const PointRegs& 
 // Takes pointers (to the 64 B point records and to the context) so that the hot loop never spills its
 // registers to the stack to make the call.
 template <int MODE, bool GEOM_F32>
-__device__ __noinline__ double cov_pair_slow(const double* pa, const double* pb, int sb, const MaternCtx* m) {
+__device__ __forceinline__ double cov_pair_slow(const double* pa, const double* pb, int sb, const MaternCtx* m) {
     const PointRegs a = load_point(pa);
     PointRegs b;                                     // second point: field f at pb[f * sb]
     b.lat = pb[P_LAT * sb]; b.lon = pb[P_LON * sb]; b.hcos = pb[P_HCOS * sb]; b.h00 = pb[P_H00 * sb];
@@ -351,11 +376,35 @@ __device__ __noinline__ double cov_pair_slow(const double* pa, const double* pb,
 }
 
 // `_haversine_multi`, ellipse/covariance.py:572-588 (only when max_dist is set, :256-266)
-__device__ __noinline__ bool beyond_max_dist(const double* pa, const double* pb, int sb, double max_dist) {
+__device__ __forceinline__ bool beyond_max_dist(const double* pa, const double* pb, int sb, double max_dist) {
     const double lat0 = pa[P_LAT], lat1 = pb[P_LAT * sb];
     const double sl = sin(0.5 * (lat0 - lat1)), so = sin(0.5 * (pa[P_LON] - pb[P_LON * sb]));
     const double h = sl * sl + cos(lat0) * cos(lat1) * so * so;
     return kEarthRadiusKm * (2.0 * asin(sqrt(h))) > max_dist;
+}
+
+// dynamic shared-memory layout of the tile kernel, in doubles from the start of the extern array
+constexpr int kSmRow = 0;                                  // [2][kTile][P_N]  records (LDS.128 broadcast)
+constexpr int kSmCol = kSmRow + 2 * P_N * kTile;           // [2][P_N][kTile]  field-major (conflict-free LDS.128)
+constexpr int kSmExp = kSmCol + 2 * P_N * kTile;           // [kExpTab][kExpRep]
+constexpr int kSmCtx = kSmExp + kExpTab * kExpRep;         // MaternCtx for the cold path (16 doubles reserved)
+constexpr int kSmTileT = kSmCtx + 16;                      // [kTile][kTileLd]
+constexpr int kSmTab = kSmTileT + kTile * kTileLd;         // [kTabNint][kTabCoef] (MODE_TABLE only)
+static_assert(sizeof(MaternCtx) <= 16 * sizeof(double), "MaternCtx must fit its shared-memory slot");
+
+// Cold paths of the tile kernel.  They take OFFSETS into the dynamic shared memory, not pointers: a generic
+// pointer to shared memory costs an S2UR SR_CgaCtaId + address arithmetic where it is formed, which the compiler
+// otherwise re-materialises inside the hot loop (ncu r01: 5.6 % of the stall samples).
+template <int MODE, bool GEOM_F32>
+__device__ __noinline__ double tile_pair_slow(int row_off, int col_off) {
+    extern __shared__ __align__(16) double smem[];
+    const MaternCtx* m = reinterpret_cast<const MaternCtx*>(smem + kSmCtx);
+    return cov_pair_slow<MODE, GEOM_F32>(smem + row_off, smem + col_off, kTile, m);
+}
+
+__device__ __noinline__ bool tile_beyond_max_dist(int row_off, int col_off, double max_dist) {
+    extern __shared__ __align__(16) double smem[];
+    return beyond_max_dist(smem + row_off, smem + col_off, kTile, max_dist);
 }
 
 struct EllipseArgs {
@@ -434,6 +483,9 @@ __device__ __forceinline__ TileId decode_tile(const EllipseArgs& a, int64_t id) 
 #ifndef K1_UNROLL
 #define K1_UNROLL 1
 #endif
+#ifndef K1_EXPERIMENT
+#define K1_EXPERIMENT 0
+#endif
 
 // Persistent kernel: K1_MINB CTAs per SM, each looping over tiles id = blockIdx.x, += gridDim.x.  The exp and
 // Matern tables are staged once per CTA; the 2 x 4 KB of per-point records of the NEXT tile are fetched with
@@ -442,12 +494,11 @@ template <int MODE, bool MAXDIST, typename OutT>
 __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(const EllipseArgs a) {
     constexpr bool GEOM_F32 = sizeof(OutT) == 4;
     extern __shared__ __align__(16) double smem[];
-    double* rowp = smem;                              // [2][kTile][P_N]  records (one LDS.128 broadcast per 2 fields)
-    double* colp = rowp + 2 * P_N * kTile;            // [2][P_N][kTile]  field-major (conflict-free LDS.128)
-    double* sexp = colp + 2 * P_N * kTile;            // [64][kExpRep]
-    double* tileT = sexp + 64 * kExpRep;              // [kTile][kTileLd]
-    double* stab = tileT + kTile * kTileLd;           // [kTabNint][kTabCoef] (MODE_TABLE only)
-    __shared__ MaternCtx sctx;                        // for the cold path
+    double* rowp = smem + kSmRow;
+    double* colp = smem + kSmCol;
+    double* sexp = smem + kSmExp;
+    double* tileT = smem + kSmTileT;
+    double* stab = smem + kSmTab;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -468,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
     stage(0, t);
     cp_async_commit();
 
-    for (int e = tid; e < 64 * kExpRep; e += kThreads) sexp[e] = kExp2Neg64[e / kExpRep];
+    for (int e = tid; e < kExpTab * kExpRep; e += kThreads) sexp[e] = kExp2Neg[e / kExpRep];
     MaternCtx m;
     m.bc = a.bc;
     m.table = stab;
@@ -477,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         for (int e = tid; e < kTabDoubles / 2; e += kThreads)
             reinterpret_cast<double2*>(stab)[e] = reinterpret_cast<const double2*>(a.table)[e];
     }
-    if (tid == 0) sctx = m;
+    if (tid == 0) *reinterpret_cast<MaternCtx*>(smem + kSmCtx) = m;
     const double* sexp_lane = sexp + (lane & (kExpRep - 1));
 
     int buf = 0;
@@ -493,7 +544,6 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         cp_async_wait<1>();                           // this tile's records have landed (the next may be in flight)
         __syncthreads();
 
-        const double* rp = rowp + buf * (P_N * kTile);
         const double* cp = colp + buf * (P_N * kTile);
         const int64_t i0 = a.row0 + (int64_t)t.ta * kTile;   // global index of the tile's first row point
         const int64_t j0 = (int64_t)t.tb * kTile;            // global index of the tile's first column point
@@ -521,45 +571,68 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         const int cols_ok = (int)min((int64_t)kTile, a.N - j0);
         OutT* orow = out + (i0 - a.row0 + warp * (kTile / 8)) * a.ld + (j0 + jl);
 
-        // software pipeline: the next row's record is fetched from shared memory while this row is computed
-        // (ncu r01b: 12 % of the stall samples sat on the first use of the row record)
-        PointRegs pnext = load_point(rp + warp * (kTile / 8) * P_N);
-        constexpr int kRowUnroll = K1_UNROLL;
+        // Row loop.  FAST = the common tile (full, off the diagonal, no max_dist): the epilogue is one vector
+        // store and there is no per-row branch besides the cold-path check.  The next row's record is fetched
+        // from shared memory while this row is computed (ncu r01b: 12 % of the stall samples sat on its first use).
+        const int row_off0 = kSmRow + buf * (P_N * kTile) + warp * (kTile / 8) * P_N;
+        const int col_off = kSmCol + buf * (P_N * kTile) + jl;
+        auto rows = [&](auto fast_tag, auto mirror_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value, MIRROR = decltype(mirror_tag)::value;
+            PointRegs pnext = load_point(smem + row_off0);
+            constexpr int kRowUnroll = K1_UNROLL;
 #pragma unroll kRowUnroll
-        for (int r = 0; r < kTile / 8; ++r) {
-            const int il = warp * (kTile / 8) + r;
-            const double* pr = rp + il * P_N;
-            const PointRegs p = pnext;
-            if (r + 1 < kTile / 8) pnext = load_point(pr + P_N);
-            bool slow0, slow1;
-            double v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
-            double v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
-            if (slow0 | slow1) {                      // one cold branch for both pairs
-                if (slow0) v0 = cov_pair_slow<MODE, GEOM_F32>(pr, cp + jl, kTile, &sctx);
-                if (slow1) v1 = cov_pair_slow<MODE, GEOM_F32>(pr, cp + jl + 1, kTile, &sctx);
+            for (int r = 0; r < kTile / 8; ++r) {
+                const int il = warp * (kTile / 8) + r;
+                const int row_off = row_off0 + r * P_N;
+                const PointRegs p = pnext;
+                if (r + 1 < kTile / 8) pnext = load_point(smem + row_off + P_N);
+                bool slow0, slow1;
+#if K1_EXPERIMENT == 2      // stores only: no pair arithmetic (kernel-experiment builds, never shipped)
+                double v0 = p.lat + c0.lat, v1 = p.lat + c1.lat;
+                slow0 = slow1 = false;
+#else
+                double v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
+                double v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
+#endif
+                if (slow0 | slow1) {                  // one cold branch for both pairs
+                    if (slow0) v0 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off);
+                    if (slow1) v1 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off + 1);
+                }
+                if (MAXDIST) {                        // :256-266 pairs beyond max_dist stay 0
+                    if (tile_beyond_max_dist(row_off, col_off, a.max_dist)) v0 = 0.0;
+                    if (tile_beyond_max_dist(row_off, col_off + 1, a.max_dist)) v1 = 0.0;
+                }
+                if (!FAST && diag) {                  // diagonal = stdev^2, :246
+                    const double var = smem[row_off + P_VAR];
+                    if (il == jl + dl) v0 = var;
+                    if (il == jl + 1 + dl) v1 = var;
+                }
+#if K1_EXPERIMENT == 1      // arithmetic only: the store is kept reachable but never taken
+                if (v0 == 123.456789 && v1 == 987.654321)
+#else
+                if (FAST || full)
+#endif
+                {
+                    typename Vec2<OutT>::type v;
+                    v.x = (OutT)v0;
+                    v.y = (OutT)v1;
+                    *reinterpret_cast<typename Vec2<OutT>::type*>(orow) = v;
+                } else if (il < rows_ok && jl < cols_ok) {
+                    store_pair<OutT>(orow, v0, v1, jl + 1 < cols_ok, a.vec2 != 0);
+                }
+                orow += a.ld;
+                if (MIRROR) {
+                    tileT[il * kTileLd + jl] = v0;
+                    tileT[il * kTileLd + jl + 1] = v1;
+                }
             }
-            if (MAXDIST) {                            // :256-266 pairs beyond max_dist stay 0
-                if (beyond_max_dist(pr, cp + jl, kTile, a.max_dist)) v0 = 0.0;
-                if (beyond_max_dist(pr, cp + jl + 1, kTile, a.max_dist)) v1 = 0.0;
-            }
-            if (diag) {                               // diagonal = stdev^2, :246
-                const double var = pr[P_VAR];
-                if (il == jl + dl) v0 = var;
-                if (il == jl + 1 + dl) v1 = var;
-            }
-            if (full) {
-                typename Vec2<OutT>::type v;
-                v.x = (OutT)v0;
-                v.y = (OutT)v1;
-                *reinterpret_cast<typename Vec2<OutT>::type*>(orow) = v;
-            } else if (il < rows_ok && jl < cols_ok) {
-                store_pair<OutT>(orow, v0, v1, jl + 1 < cols_ok, a.vec2 != 0);
-            }
-            orow += a.ld;
-            if (mirror) {
-                tileT[il * kTileLd + jl] = v0;
-                tileT[il * kTileLd + jl + 1] = v1;
-            }
+        };
+        using T_ = std::true_type;
+        using F_ = std::false_type;
+        if (full && !diag) {
+            if (mirror) rows(T_{}, T_{}); else rows(T_{}, F_{});
+        } else {
+            if (mirror) rows(F_{}, T_{}); else rows(F_{}, F_{});
         }
         if (mirror) {
             __syncthreads();
@@ -587,6 +660,11 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
 }
 
 template <int MODE>
+__device__ __noinline__ double pairs_slow(const double* pa, const double* pb, const MaternCtx* m) {
+    return cov_pair_slow<MODE, false>(pa, pb, 1, m);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256) ellipse_pairs_kernel(const double* __restrict__ params,
                                                             const double* __restrict__ table,
                                                             GmgBesselConsts bc, const int64_t* __restrict__ is,
@@ -601,8 +679,8 @@ __global__ void __launch_bounds__(256) ellipse_pairs_kernel(const double* __rest
     const double* pa = params + is[k] * P_N;
     const double* pb = params + js[k] * P_N;
     bool slow;
-    double v = cov_pair<MODE, false, 1>(load_point(pa), load_point(pb), m, kExp2Neg64, slow);   // as the tile kernel
-    if (slow) v = cov_pair_slow<MODE, false>(pa, pb, 1, &m);
+    double v = cov_pair<MODE, false, 1>(load_point(pa), load_point(pb), m, kExp2Neg, slow);   // as the tile kernel
+    if (slow) v = pairs_slow<MODE>(pa, pb, &m);
     out[k] = v;
 }
 
@@ -663,7 +741,7 @@ inline const double* ws_soa(const void* ws, int64_t N) {
 
 template <int MODE, bool MAXDIST, typename OutT>
 int launch_tiles(const EllipseArgs& a, int64_t n_ctas, cudaStream_t s) {
-    size_t smem = (size_t)(4 * P_N * kTile + 64 * kExpRep + kTile * kTileLd) * sizeof(double);
+    size_t smem = (size_t)kSmTab * sizeof(double);
     if (MODE == MODE_TABLE) smem += (size_t)kTabDoubles * sizeof(double);
     auto kern = ellipse_cov_tile_kernel<MODE, MAXDIST, OutT>;
     GMG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
