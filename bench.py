@@ -433,10 +433,10 @@ def run_months(args, rank, world, device, barrier, max_over_ranks, local):
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.month_steps
     ns = np.array(kb.ns, dtype=np.float64)
-    flops = float((ns ** 3 / 3 + 2 * ns ** 2 * (M + 1)).sum())          # Cholesky + two triangular solves
+    flops = float((ns ** 3 / 3 + ns ** 2 * (M + 2)).sum())     # Cholesky + the forward triangular solve
     tflops_local = flops / (ms * 1e-3) / 1e12
     nblk = int(np.ceil(kb.n_max / 128))
-    launches = 1 + (3 * nblk - 2) + 4 * nblk + 2
+    launches = 1 + (3 * nblk - 2) + 2 * nblk + 2
     del kb
     torch.cuda.empty_cache()
     e2e = None
@@ -469,8 +469,10 @@ def run_months(args, rank, world, device, barrier, max_over_ranks, local):
                          "frac": tflops_local / DMMA_PEAK_TFLOPS, "traffic": None,
                          "peak_source": "measured mma.sync f64 peak, profiles/r01_microbench_fp64.json "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
-                         "note": "algorithmic flops n^3/3 + 2 n^2 (M+1) per month (SURVEY 8d) over the whole "
-                                 "gather+factor+solve+apply step of this rank"},
+                         "note": "flops actually executed, n^3/3 + n^2 (M+2) per month, over the whole "
+                                 "gather+factor+solve+apply step of this rank.  SURVEY 8d counts 2 n^2 M for two "
+                                 "triangular solves; field / variance / mask only need the forward one "
+                                 "(d = ||L^-1 c||^2), so half of that work is not done at all"},
             "e2e": e2e}
 
 

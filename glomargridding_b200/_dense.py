@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _device as dev
-from ._lib import check, lib
+from ._lib import GlomarB200Error, check, lib
 
 NB = 128      # factorisation block = GEMM tile of the library
 SLAB = 256    # rows per partial sum of the apply pass
@@ -43,7 +43,51 @@ def solve_ws(n: int) -> tuple[int, int, int]:
 
 
 def _desc_tensor(arr: np.ndarray, device) -> torch.Tensor:
-    return torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(device)
+    return torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(device)
+
+
+def _h2d(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+_STAGE = None
+
+
+def _h2d_concat(arrays, total: int, device, chunk_bytes: int = 256 << 20) -> torch.Tensor:
+    """Flattened concatenation of host float64 arrays on the device, staged through two pinned buffers so that
+    the host-side packing of one chunk overlaps the H2D copy of the previous one (the per-month n x n error
+    covariances are the bulk of the kriging path's host-to-device traffic)."""
+    out = torch.empty(total, dtype=torch.float64, device=device)
+    cap = max(chunk_bytes // 8, max(int(a.size) for a in arrays))
+    global _STAGE
+    if _STAGE is None or _STAGE[0].numel() < cap:       # pinned allocations are slow (~0.3 s): keep them
+        _STAGE = [torch.empty(cap, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+    stage = _STAGE
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    pos, cur, fill, which = 0, 0, 0, 0
+    used = [False, False]
+
+    def flush():
+        nonlocal pos, fill, which
+        if fill:
+            out[pos:pos + fill].copy_(stage[which][:fill], non_blocking=True)
+            done[which].record()
+            used[which] = True
+            pos += fill
+            fill = 0
+            which ^= 1
+            if used[which]:
+                done[which].synchronize()
+
+    for a in arrays:
+        flat = np.asarray(a, dtype=np.float64).reshape(-1)
+        if fill + flat.size > cap:
+            flush()
+        stage[which][fill:fill + flat.size].numpy()[:] = flat
+        fill += flat.size
+    flush()
+    torch.cuda.current_stream().synchronize()
+    return out
 
 
 def factor_inplace(S: torch.Tensor, n: int, what: str = "matrix") -> dict:
@@ -95,7 +139,7 @@ def cholesky_solve_inplace(S: torch.Tensor, R: torch.Tensor, what: str = "matrix
     d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"] = (
         S.data_ptr(), S.stride(0), ws["Linv"].data_ptr(), ws["P"].data_ptr(), ws["ldp"], ws["info"].data_ptr())
     dt = _desc_tensor(d, S.device)
-    check(lib().gmg_potrs_batched_f64(dt.data_ptr(), 1, n, R.shape[1], dev.stream_ptr()), "gmg_potrs_batched_f64")
+    check(lib().gmg_potrs_batched_f64(dt.data_ptr(), 1, n, R.shape[1], 3, dev.stream_ptr()), "gmg_potrs_batched_f64")
     torch.cuda.current_stream().synchronize()   # the descriptor / workspace tensors die with this frame
 
 
@@ -127,7 +171,7 @@ def apply_reduce(cov: torch.Tensor, Cx: torch.Tensor, T: torch.Tensor, y: torch.
     kd[0] = (0, 0, n, y.data_ptr(), 0, 0, Cx.data_ptr(), Cx.stride(0), T.data_ptr(), T.stride(0),
              partial.data_ptr(), out.data_ptr(), n, int(ordinary))
     kdt = _desc_tensor(kd, cov.device)
-    check(lib().gmg_krige_apply_batched_f64(cov.data_ptr(), M, cov.stride(0), kdt.data_ptr(), 1, n,
+    check(lib().gmg_krige_apply_batched_f64(cov.data_ptr(), M, cov.stride(0), kdt.data_ptr(), 1, n, 0,
                                             dev.stream_ptr()), "gmg_krige_apply_batched_f64")
     torch.cuda.current_stream().synchronize()   # descriptor / workspace tensors die with this frame
     return out
@@ -148,8 +192,10 @@ class KrigeBatch:
     problems: sequence of (idx int64[n], obs float64[n], error_cov float64[n, n] | None), already filtered
     by `Kriging.subset_error_covariance`.  After `run()`:
       out[b]  (5, M) tensor rows: field, variance before clamping, constraint mask, alpha, rowdot(W, C_cross^T)
-      T[b]    (n, ldt) tensor: S^-1 C_cross (simple-kriging weights, transposed); column M = S^-1 1 if ordinary
-      Cx[b]   (n, ldx) tensor: C[idx, :]
+    `run()` stops after the FORWARD triangular solve: with S^-1 = L^-T L^-1 every result row is a column dot
+    product of Y = L^-1 [C_cross | 1 | y], so the second solve - half of the flops - is only done by
+    `ensure_full()` (when the weights matrix itself is wanted):
+      T(b)    (n, ldt) tensor: S^-1 [C_cross | 1 | y]: simple-kriging weights transposed, column M = S^-1 1
     """
 
     def __init__(self, cov: torch.Tensor, problems, ordinary: bool):
@@ -162,7 +208,8 @@ class KrigeBatch:
         if min(ns) <= 0:
             raise ValueError("a kriging problem needs at least one observation")
         self.ns, self.n_max = ns, max(ns)
-        self.ldx, self.ldt = _even(M), _even(M + 1)
+        self.ldx, self.ldt = _even(M), _even(M + 2)
+        self.nrhs = M + 2
         lds = [_even(n) for n in ns]
         ws = [solve_ws(n) for n in ns]
         slabs = [(n + SLAB - 1) // SLAB for n in ns]
@@ -172,25 +219,19 @@ class KrigeBatch:
             return torch.empty(int(offs[-1]), dtype=torch.float64, device=device), offs
 
         self._S, oS = pool([n * l for n, l in zip(ns, lds)])
-        self._Cx, oX = pool([n * self.ldx for n in ns])
         self._T, oT = pool([n * self.ldt for n in ns])
         self._Linv, oL = pool([w[0] for w in ws])
         self._P, oP = pool([w[1] for w in ws])
         self._partial, oPa = pool([3 * s * M for s in slabs])
         self.out = torch.empty((B, 5, M), dtype=torch.float64, device=device)
         self.info = torch.zeros(B, dtype=torch.int32, device=device)
-        # inputs: one H2D copy each (idx, obs, error covariances), pinned staging handled by torch
+        # inputs: one H2D copy each (idx, obs, error covariances)
         offs_n = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
-        self._idx = torch.from_numpy(np.concatenate([np.asarray(p[0], dtype=np.int64) for p in problems])).to(device)
-        self._y = torch.from_numpy(np.concatenate([np.asarray(p[1], dtype=np.float64) for p in problems])).to(device)
+        self._idx = _h2d(np.concatenate([np.asarray(p[0], dtype=np.int64) for p in problems]), device)
+        self._y = _h2d(np.concatenate([np.asarray(p[1], dtype=np.float64) for p in problems]), device)
         has_E = [p[2] is not None for p in problems]
         offs_E = np.concatenate([[0], np.cumsum([n * n if h else 0 for n, h in zip(ns, has_E)])]).astype(np.int64)
-        if any(has_E):
-            flat = np.concatenate([np.ascontiguousarray(p[2], dtype=np.float64).reshape(-1)
-                                   for p in problems if p[2] is not None])
-            self._E = torch.from_numpy(flat).to(device)
-        else:
-            self._E = None
+        self._E = _h2d_concat([p[2] for p in problems if p[2] is not None], int(offs_E[-1]), device) if any(has_E) else None
 
         kd = np.zeros(B, dtype=KRIGE_DESC)
         sd = np.zeros(B, dtype=SOLVE_DESC)
@@ -201,67 +242,110 @@ class KrigeBatch:
             T_ptr = self._T.data_ptr() + f8 * int(oT[b])
             kd[b] = (self._idx.data_ptr() + f8 * int(offs_n[b]),
                      (self._E.data_ptr() + f8 * int(offs_E[b])) if has_E[b] else 0, n,
-                     self._y.data_ptr() + f8 * int(offs_n[b]), S_ptr, lds[b],
-                     self._Cx.data_ptr() + f8 * int(oX[b]), self.ldx, T_ptr, self.ldt,
+                     self._y.data_ptr() + f8 * int(offs_n[b]), S_ptr, lds[b], 0, self.ldx, T_ptr, self.ldt,
                      self._partial.data_ptr() + f8 * int(oPa[b]), self.out.data_ptr() + f8 * 5 * M * b, n,
                      int(self.ordinary))
             sd[b] = (S_ptr, lds[b], self._Linv.data_ptr() + f8 * int(oL[b]), T_ptr, self.ldt,
-                     self._P.data_ptr() + f8 * int(oP[b]), ws[b][2], self.info.data_ptr() + 4 * b, n,
-                     M + (1 if self.ordinary else 0))
+                     self._P.data_ptr() + f8 * int(oP[b]), ws[b][2], self.info.data_ptr() + 4 * b, n, self.nrhs)
         self._kd, self._sd = _desc_tensor(kd, device), _desc_tensor(sd, device)
         self._kd_np, self._sd_np = kd, sd
-        self._oS, self._oX, self._oT, self._lds = oS, oX, oT, lds
-        self._ran = False
+        self._oS, self._oT, self._lds, self._offs_n = oS, oT, lds, offs_n
+        self._Cx = {}                       # C_cross copies, made on demand (LU fallback, weights from outside)
+        self.full = np.zeros(B, dtype=bool)  # True once T(b) holds S^-1 [Cx | 1 | y] (both solves done)
+        self.lu_fallback: list[int] = []
 
     # -- views -----------------------------------------------------------------------------------------
     def T(self, b: int) -> torch.Tensor:
+        """S^-1 [C_cross | 1 | y] of problem b (runs the backward solve if it has not been done)."""
+        self.ensure_full([b])
+        return self._T_view(b)
+
+    def _T_view(self, b: int) -> torch.Tensor:
         return self._T[int(self._oT[b]):int(self._oT[b + 1])].view(self.ns[b], self.ldt)
 
     def Cx(self, b: int) -> torch.Tensor:
-        return self._Cx[int(self._oX[b]):int(self._oX[b + 1])].view(self.ns[b], self.ldx)
+        """C[idx, :] of problem b, (n, ldx); gathered on first use (plumbing copy)."""
+        if b not in self._Cx:
+            idx = self._idx[int(self._offs_n[b]):int(self._offs_n[b + 1])]
+            cx = torch.zeros((self.ns[b], self.ldx), dtype=torch.float64, device=self.cov.device)
+            cx[:, : self.M] = self.cov[idx, : self.M]
+            self._Cx[b] = cx
+        return self._Cx[b]
 
     def S(self, b: int) -> torch.Tensor:
         return self._S[int(self._oS[b]):int(self._oS[b + 1])].view(self.ns[b], self._lds[b])
 
     # -- pipeline --------------------------------------------------------------------------------------
     def run(self, allow_lu_fallback: bool = True) -> "KrigeBatch":
-        """gather -> Cholesky -> two triangular solves -> apply.  Systems whose Cholesky meets a non-positive
+        """gather -> Cholesky -> forward triangular solve -> apply.  Systems whose Cholesky meets a non-positive
         pivot are re-gathered and solved by LU with partial pivoting (what the reference does for every system),
         with a warning; an exactly singular system raises numpy.linalg.LinAlgError like numpy does."""
         L, s = lib(), dev.stream_ptr()
         C, M, ldc = self.cov.data_ptr(), self.M, self.cov.stride(0)
-        nrhs = M + (1 if self.ordinary else 0)
+        self.full[:] = False
         check(L.gmg_krige_gather_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, s), "gather")
         check(L.gmg_potrf_batched_f64(self._sd.data_ptr(), self.B, self.n_max, s), "gmg_potrf_batched_f64")
         info = self.info.cpu().numpy()               # synchronises: the factorisation outcome decides the path
         bad = np.flatnonzero(info)
         self.lu_fallback = bad.tolist()
         if bad.size == 0:
-            check(L.gmg_potrs_batched_f64(self._sd.data_ptr(), self.B, self.n_max, nrhs, s), "gmg_potrs_batched_f64")
-        else:
-            if not allow_lu_fallback:
-                self.raise_if_not_spd(info)
-            warn(f"C[idx, idx] + E is not positive definite for {bad.size} of {self.B} kriging system(s) "
-                 f"(first: system {int(bad[0])}, Cholesky pivot {int(info[bad[0]])}); solving those by LU with "
-                 "partial pivoting like the reference does - slow path, consider "
-                 "glomar_gridding.covariance_tools.eigenvalue_clip or delta_x_method='Met_Office'")
-            good = np.flatnonzero(info == 0)
-            self.info.zero_()
-            kd_bad = _desc_tensor(self._kd_np[bad], self.cov.device)
-            sd_bad = _desc_tensor(self._sd_np[bad], self.cov.device)
-            n_bad = max(self.ns[int(b)] for b in bad)
-            check(L.gmg_krige_gather_batched_f64(C, M, ldc, kd_bad.data_ptr(), int(bad.size), n_bad, s), "gather")
-            check(L.gmg_gesv_batched_f64(sd_bad.data_ptr(), int(bad.size), nrhs, s), "gmg_gesv_batched_f64")
-            if good.size:
-                sd_good = _desc_tensor(self._sd_np[good], self.cov.device)
-                n_good = max(self.ns[int(b)] for b in good)
-                check(L.gmg_potrs_batched_f64(sd_good.data_ptr(), int(good.size), n_good, nrhs, s),
-                      "gmg_potrs_batched_f64")
-            if np.any(self.info.cpu().numpy()):
-                raise np.linalg.LinAlgError("Singular matrix")
-        check(L.gmg_krige_apply_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, s), "apply")
-        self._ran = True
+            check(L.gmg_potrs_batched_f64(self._sd.data_ptr(), self.B, self.n_max, self.nrhs, 1, s),
+                  "gmg_potrs_batched_f64")
+            check(L.gmg_krige_apply_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, 1, s), "apply")
+            return self
+        if not allow_lu_fallback:
+            self.raise_if_not_spd(info)
+        warn(f"C[idx, idx] + E is not positive definite for {bad.size} of {self.B} kriging system(s) "
+             f"(first: system {int(bad[0])}, Cholesky pivot {int(info[bad[0]])}); solving those by LU with "
+             "partial pivoting like the reference does - slow path, consider "
+             "glomar_gridding.covariance_tools.eigenvalue_clip or delta_x_method='Met_Office'")
+        good = np.flatnonzero(info == 0)
+        self.info.zero_()
+        kd_bad_np = self._kd_np[bad].copy()
+        for i, b in enumerate(bad):
+            kd_bad_np[i]["Cx"] = self.Cx(int(b)).data_ptr()
+        kd_bad = _desc_tensor(kd_bad_np, self.cov.device)
+        sd_bad = _desc_tensor(self._sd_np[bad], self.cov.device)
+        n_bad = max(self.ns[int(b)] for b in bad)
+        check(L.gmg_krige_gather_batched_f64(C, M, ldc, kd_bad.data_ptr(), int(bad.size), n_bad, s), "gather")
+        check(L.gmg_gesv_batched_f64(sd_bad.data_ptr(), int(bad.size), self.nrhs, s), "gmg_gesv_batched_f64")
+        check(L.gmg_krige_apply_batched_f64(C, M, ldc, kd_bad.data_ptr(), int(bad.size), n_bad, 0, s), "apply")
+        self.full[bad] = True
+        if good.size:
+            kd_good = _desc_tensor(self._kd_np[good], self.cov.device)
+            sd_good = _desc_tensor(self._sd_np[good], self.cov.device)
+            n_good = max(self.ns[int(b)] for b in good)
+            check(L.gmg_potrs_batched_f64(sd_good.data_ptr(), int(good.size), n_good, self.nrhs, 1, s),
+                  "gmg_potrs_batched_f64")
+            check(L.gmg_krige_apply_batched_f64(C, M, ldc, kd_good.data_ptr(), int(good.size), n_good, 1, s), "apply")
+        if np.any(self.info.cpu().numpy()):          # also synchronises before the temporaries die
+            raise np.linalg.LinAlgError("Singular matrix")
         return self
+
+    def ensure_full(self, which=None) -> None:
+        """Second triangular solve (T <- L^-T T) for the listed problems (default: all) that still need it."""
+        todo = np.array([b for b in (range(self.B) if which is None else which) if not self.full[b]], dtype=np.int64)
+        if todo.size == 0:
+            return
+        sd = _desc_tensor(self._sd_np[todo], self.cov.device)
+        n_max = max(self.ns[int(b)] for b in todo)
+        check(lib().gmg_potrs_batched_f64(sd.data_ptr(), int(todo.size), n_max, self.nrhs, 2, dev.stream_ptr()),
+              "gmg_potrs_batched_f64")
+        torch.cuda.current_stream().synchronize()
+        self.full[todo] = True
+
+    def solve_vectors(self, b: int, V: torch.Tensor) -> torch.Tensor:
+        """S_b^-1 V for extra right-hand sides V (n, k) with the factorisation of problem b (Cholesky path)."""
+        if b in self.lu_fallback:
+            raise GlomarB200Error("extra solves are not available for a system that took the LU fallback")
+        R = padded(V)
+        d = self._sd_np[[b]].copy()
+        d["R"], d["ldr"], d["nrhs"] = R.data_ptr(), R.stride(0), V.shape[1]
+        dt = _desc_tensor(d, self.cov.device)
+        check(lib().gmg_potrs_batched_f64(dt.data_ptr(), 1, self.ns[b], V.shape[1], 3, dev.stream_ptr()),
+              "gmg_potrs_batched_f64")
+        torch.cuda.current_stream().synchronize()
+        return R[:, : V.shape[1]]
 
     def raise_if_not_spd(self, info=None) -> None:
         info = self.info.cpu().numpy() if info is None else info

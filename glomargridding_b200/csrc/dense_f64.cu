@@ -27,71 +27,178 @@ constexpr int DIAG_THREADS = 512;
 
 static_assert(sizeof(GmgSolveDesc) == 72, "GmgSolveDesc layout is part of the C ABI");
 
-// ---- diagonal block: potrf (unblocked, in shared memory) followed by the in-place inverse of L_kk ---------
+// ---- diagonal block: 128 x 128 Cholesky and the inverse of its factor, one CTA, all in shared memory ---------
 // grid = (1, 1, batch).  Reads the lower triangle of S[k0:k0+nb, k0:k0+nb], writes L_kk back into S and
 // L_kk^-1 (lower, zero above the diagonal, identity-padded to NB) into Linv + kblk * NB * NB.
+// This kernel is the serial step of the factorisation (one CTA per system per block step), so it is blocked
+// with 16 x 16 sub-blocks to cut the number of CTA-wide barriers from ~640 to ~40 (ncu r01: the unblocked
+// version took 275 us per call, 70 % of it at barriers):
+//   for each 16-column block:  warp 0 factors the 16 x 16 diagonal sub-block;
+//                              warp 0 inverts it while warps 1..4 solve the panel rows below it (one row per thread);
+//                              all 16 warps apply the rank-16 update to the trailing lower triangle (4 x 4 register tiles)
+//   inverse:  X = L^-1 by block forward substitution with the inverted 16 x 16 diagonal sub-blocks.
+constexpr int SB = 16;                          // sub-block
+constexpr int NSB = NB / SB;                    // 8
+constexpr int DIAG_G_LD = NB - SB + 1;          // staging of one block row of L X (16 x 112), odd ld
+constexpr size_t DIAG_SMEM = (size_t)(NB * DIAG_LD + NSB * SB * SB + SB * DIAG_G_LD + SB) * sizeof(double);
+
 __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolveDesc* __restrict__ descs, int kblk) {
     const GmgSolveDesc d = descs[blockIdx.z];
-    const int k0 = kblk * NB;
-    if (k0 >= d.n) return;
-    const int nb = min(NB, d.n - k0);
+    const int k0g = kblk * NB;
+    if (k0g >= d.n) return;
+    const int nb = min(NB, d.n - k0g);
     extern __shared__ __align__(16) double sm[];
     double* A = sm;                              // [NB][DIAG_LD]
+    double* Dinv = A + NB * DIAG_LD;             // [NSB][SB][SB] inverted diagonal sub-blocks
+    double* G = Dinv + NSB * SB * SB;            // [SB][DIAG_G_LD]
+    double* rd = G + SB * DIAG_G_LD;             // [SB] reciprocal diagonal of the current sub-block
     __shared__ int s_info;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_info = 0;
     for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
         const int i = e / NB, j = e % NB;
         double v = (i == j) ? 1.0 : 0.0;         // identity padding of a partial last block
-        if (i < nb && j < nb && j <= i) v = d.S[(int64_t)(k0 + i) * d.lds + k0 + j];
+        if (i < nb && j < nb && j <= i) v = d.S[(int64_t)(k0g + i) * d.lds + k0g + j];
         A[i * DIAG_LD + j] = v;
     }
     __syncthreads();
-    // right-looking Cholesky: column j scaled by 1/sqrt(pivot), then the rank-1 update of the trailing block
-    const int ti = tid % NB, tg = tid / NB;      // row ti, column group tg of 4
-    for (int j = 0; j < NB; ++j) {
-        const double piv = A[j * DIAG_LD + j];
-        if (!(piv > 0.0)) {                      // also NaN
-            if (tid == 0 && s_info == 0) s_info = k0 + j + 1;
-        }
-        const double rinv = 1.0 / sqrt(piv);
-        __syncthreads();                         // everybody has read the pivot / column before it changes
-        if (tg == 0) {
-            if (ti == j) A[j * DIAG_LD + j] = piv * rinv;
-            else if (ti > j) A[ti * DIAG_LD + j] *= rinv;
+
+    for (int kb = 0; kb < NSB; ++kb) {
+        const int k0 = kb * SB;
+        // (1) 16 x 16 diagonal sub-block, right-looking, in the registers of one warp: lane l holds row l & 15,
+        //     column values travel by shuffle (no shared-memory round trips on the critical path)
+        if (warp == 0) {
+            const int l = lane & (SB - 1);
+            double r[SB];
+            double my_rinv = 0.0;
+#pragma unroll
+            for (int c = 0; c < SB; ++c) r[c] = (c <= l) ? A[(k0 + l) * DIAG_LD + k0 + c] : 0.0;
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                const double piv = __shfl_sync(0xffffffffu, r[j], j);
+                if (!(piv > 0.0) && lane == 0 && s_info == 0) s_info = k0g + k0 + j + 1;   // also NaN
+                // 1/sqrt(piv) without libm calls (a call would spill the row registers): MUFU seed, one cubic
+                // step (< 2^-64), and sqrt(piv) = piv * rinv with one Heron correction
+                double rinv;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(piv));
+                const double e = fma(-(piv * rinv), rinv, 1.0);
+                rinv = fma(rinv * e, fma(e, 0.375, 0.5), rinv);
+                double sq = piv * rinv;
+                sq = fma(fma(-sq, sq, piv), 0.5 * rinv, sq);
+                r[j] = (l == j) ? sq : r[j] * rinv;                  // column j of L (zero above the diagonal)
+                if (l == j) my_rinv = rinv;
+#pragma unroll
+                for (int k = j + 1; k < SB; ++k) {
+                    const double lkj = __shfl_sync(0xffffffffu, r[j], k);
+                    if (l >= k) r[k] = fma(-r[j], lkj, r[k]);
+                }
+            }
+            if (lane < SB) {
+#pragma unroll
+                for (int c = 0; c < SB; ++c)
+                    if (c <= l) A[(k0 + l) * DIAG_LD + k0 + c] = r[c];
+                rd[l] = my_rinv;                                     // reciprocal diagonal 1 / L_ll
+            }
         }
         __syncthreads();
-        if (ti > j) {
-            const double lij = A[ti * DIAG_LD + j];
-            for (int k = j + 1 + tg; k <= ti; k += DIAG_THREADS / NB)
-                A[ti * DIAG_LD + k] = fma(-lij, A[k * DIAG_LD + j], A[ti * DIAG_LD + k]);
+        // (2) warp 0 inverts the sub-block (lane j = column j of the inverse, forward substitution in registers);
+        //     warps 1..4 solve the panel rows below it:  x L_kk^T = a, one row per thread
+        if (warp == 0) {
+            if (lane < SB) {
+                double x[SB];
+#pragma unroll
+                for (int i = 0; i < SB; ++i) {
+                    double acc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 0; k < i; ++k) acc = fma(-A[(k0 + i) * DIAG_LD + k0 + k], x[k], acc);
+                    x[i] = (i < lane) ? 0.0 : acc * rd[i];
+                    Dinv[(kb * SB + i) * SB + lane] = x[i];
+                }
+            }
+        } else {
+            const int i = k0 + SB + (tid - 32);
+            if (tid - 32 < NB && i < NB) {
+                double x[SB];
+#pragma unroll
+                for (int j = 0; j < SB; ++j) {
+                    double acc = A[i * DIAG_LD + k0 + j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) acc = fma(-x[k], A[(k0 + j) * DIAG_LD + k0 + k], acc);
+                    x[j] = acc * rd[j];
+                }
+#pragma unroll
+                for (int j = 0; j < SB; ++j) A[i * DIAG_LD + k0 + j] = x[j];
+            }
         }
-        // next iteration's first barrier orders these updates before the next scale
+        __syncthreads();
+        // (3) rank-16 update of the trailing lower triangle in 4 x 4 register tiles
+        const int m = NB - k0 - SB;              // trailing order (multiple of 16)
+        const int T = m / 4;                     // tiles per side
+        for (int t = tid; t < T * (T + 1) / 2; t += DIAG_THREADS) {
+            int tr = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+            while (tr * (tr + 1) / 2 > t) --tr;
+            while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+            const int tc = t - tr * (tr + 1) / 2;
+            const int i0 = k0 + SB + 4 * tr, c0 = k0 + SB + 4 * tc;
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 4
+            for (int j = 0; j < SB; ++j) {
+                double ai[4], ac[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    ai[a] = A[(i0 + a) * DIAG_LD + k0 + j];
+                    ac[a] = A[(c0 + a) * DIAG_LD + k0 + j];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fma(ai[a], ac[b], acc[a][b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (c0 + b <= i0 + a) A[(i0 + a) * DIAG_LD + c0 + b] -= acc[a][b];
+        }
         __syncthreads();
     }
     if (tid == 0 && s_info != 0) atomicCAS(d.info, 0, s_info);
     // write L_kk
     for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
         const int i = e / NB, j = e % NB;
-        if (i < nb && j <= i) d.S[(int64_t)(k0 + i) * d.lds + k0 + j] = A[i * DIAG_LD + j];
+        if (i < nb && j <= i) d.S[(int64_t)(k0g + i) * d.lds + k0g + j] = A[i * DIAG_LD + j];
     }
     __syncthreads();
-    // in-place inverse of the lower-triangular block, column by column from the right (LAPACK trti2 order):
-    //   X[j][j] = 1 / L[j][j];   X[j+1:, j] = -X[j][j] * X[j+1:, j+1:] * L[j+1:, j]
-    // Thread groups of 4 share one row (split the dot product, combine with shuffles).
-    const int row = tid >> 2, part = tid & 3;    // 128 rows x 4 partial sums
-    for (int j = NB - 1; j >= 0; --j) {
-        const double xjj = 1.0 / A[j * DIAG_LD + j];
-        double sum = 0.0;
-        if (row > j) {
-            for (int k = j + 1 + part; k <= row; k += 4) sum = fma(A[row * DIAG_LD + k], A[k * DIAG_LD + j], sum);
+    // ---- X = L^-1, in place over the lower triangle: diagonal sub-blocks first, then block rows top to bottom:
+    //      X_ij = -Dinv_i (L_i,j..i-1 X_j..i-1,j)
+    for (int e = tid; e < NSB * SB * SB; e += DIAG_THREADS) {
+        const int kb = e / (SB * SB), i = (e / SB) % SB, j = e % SB;
+        if (j <= i) A[(kb * SB + i) * DIAG_LD + kb * SB + j] = Dinv[e];
+    }
+    __syncthreads();
+    for (int bi = 1; bi < NSB; ++bi) {
+        const int i0 = bi * SB, ncols = bi * SB;
+        for (int e = tid; e < SB * ncols; e += DIAG_THREADS) {
+            const int r = e % SB, c = e / SB;    // lanes vary r: conflict-free rows of L, broadcast X[k][c]
+            double s0 = 0.0, s1 = 0.0;
+            int k = c;
+            for (; k + 1 < i0; k += 2) {
+                s0 = fma(A[(i0 + r) * DIAG_LD + k], A[k * DIAG_LD + c], s0);
+                s1 = fma(A[(i0 + r) * DIAG_LD + k + 1], A[(k + 1) * DIAG_LD + c], s1);
+            }
+            if (k < i0) s0 = fma(A[(i0 + r) * DIAG_LD + k], A[k * DIAG_LD + c], s0);
+            G[r * DIAG_G_LD + c] = s0 + s1;
         }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        __syncthreads();                         // all reads of column j (still L) done
-        if (part == 0) {
-            if (row > j) A[row * DIAG_LD + j] = -xjj * sum;
-            else if (row == j) A[j * DIAG_LD + j] = xjj;
+        __syncthreads();
+        for (int e = tid; e < SB * ncols; e += DIAG_THREADS) {
+            const int r = e % SB, c = e / SB;
+            double s = 0.0;
+            for (int q = 0; q <= r; ++q) s = fma(Dinv[(bi * SB + r) * SB + q], G[q * DIAG_G_LD + c], s);
+            A[(i0 + r) * DIAG_LD + c] = -s;
         }
         __syncthreads();
     }
@@ -259,8 +366,6 @@ int set_smem(K kern, size_t bytes) {
     return GMG_OK;
 }
 
-constexpr size_t DIAG_SMEM = (size_t)NB * DIAG_LD * sizeof(double);
-
 int ensure_attrs() {
     static bool done = false;    // per process; the attribute is per device function, set on the current device
     static int done_dev = -1;
@@ -347,23 +452,25 @@ int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, g
     return GMG_OK;
 }
 
-int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max, gmg_stream_t stream) {
+int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max, int which,
+                          gmg_stream_t stream) {
     if (!descs) return -1;
     if (batch <= 0 || batch > 65535) return -2;
     if (n_max <= 0 || n_max > 0x7fffffff) return -3;
     if (nrhs_max <= 0 || nrhs_max > 0x7fffffff) return -4;
+    if (which < 1 || which > 3) return -5;
     int rc = ensure_attrs();
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int nblk = (int)gmg_ceil_div(n_max, NB);
     const unsigned rhs_tiles = (unsigned)gmg_ceil_div(nrhs_max, BN);
-    for (int k = 0; k < nblk; ++k) {             // L Y = B
+    for (int k = 0; k < nblk && (which & GMG_SOLVE_FORWARD); ++k) {             // L Y = B
         trsm_prep_fwd_kernel<<<dim3((unsigned)k + 1, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
         GMG_LAUNCH_CHECK();
         trsm_step_fwd_kernel<<<dim3(rhs_tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
         GMG_LAUNCH_CHECK();
     }
-    for (int k = nblk - 1; k >= 0; --k) {        // L^T X = Y
+    for (int k = nblk - 1; k >= 0 && (which & GMG_SOLVE_BACKWARD); --k) {       // L^T X = Y
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
         const unsigned tiles = 1 + (rem > 0 ? (unsigned)gmg_ceil_div(rem, BM) : 0);
         trsm_prep_bwd_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);

@@ -32,10 +32,11 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
     const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (m < M) {
         const double v = crow[m];
-        d.Cx[(int64_t)a * d.ldx + m] = v;
+        if (d.Cx) d.Cx[(int64_t)a * d.ldx + m] = v;
         d.T[(int64_t)a * d.ldt + m] = v;
-    } else if (m == M && d.ordinary) {
-        d.T[(int64_t)a * d.ldt + M] = 1.0;      // right-hand side for o = S^-1 1 (Lagrange column, :579-583)
+    } else if (m == M) {
+        d.T[(int64_t)a * d.ldt + M] = 1.0;          // right-hand side for o = S^-1 1 (Lagrange column, :579-583)
+        d.T[(int64_t)a * d.ldt + M + 1] = d.y[a];   // right-hand side for S^-1 y
     }
     // S row: the first ceil(n / 256) column blocks also fill S[a, :]
     if (m < d.n) {
@@ -43,6 +44,43 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
         if (d.E) s += d.E[(int64_t)a * d.lde + m];   // :342, :576
         d.S[(int64_t)a * d.lds + m] = s;
     }
+}
+
+// Forward-only variant: T holds Y = L^-1 [Cx | 1 | y] (only the FIRST triangular solve has been done).  Because
+// S^-1 = L^-T L^-1, every quantity the kriging classes return is a column dot product of Y with itself or with
+// its two extra columns:
+//   d[m]  = Cx[:,m]^T S^-1 Cx[:,m] = sum_a Y[a,m]^2          oc[m] = 1^T S^-1 Cx[:,m] = sum_a Y[a,M]   Y[a,m]
+//   yT[m] = y^T S^-1 Cx[:,m]       = sum_a Y[a,M+1] Y[a,m]
+// so the second triangular solve (half of the flops of the whole path) is only needed when the caller asks for
+// the weights matrix itself.  One read of Y (n M 8 bytes) instead of T and Cx.
+// grid = (ceil(M / 256), ceil(n_max / kSlab), batch)
+__global__ void __launch_bounds__(kColsPerBlock) reduce_fwd_kernel(int64_t M, const GmgKrigeDesc* __restrict__ descs) {
+    const GmgKrigeDesc d = descs[blockIdx.z];
+    const int a0 = blockIdx.y * kSlab;
+    if (a0 >= d.n) return;
+    const int a1 = min(d.n, a0 + kSlab);
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    __shared__ double sy[kSlab], so[kSlab];
+    for (int e = threadIdx.x; e < a1 - a0; e += blockDim.x) {
+        so[e] = d.T[(int64_t)(a0 + e) * d.ldt + M];
+        sy[e] = d.T[(int64_t)(a0 + e) * d.ldt + M + 1];
+    }
+    __syncthreads();
+    if (m >= M) return;
+    double yT = 0.0, dd = 0.0, oc = 0.0;
+    const double* t = d.T + (int64_t)a0 * d.ldt + m;
+#pragma unroll 4
+    for (int a = 0; a < a1 - a0; ++a) {
+        const double tv = t[(int64_t)a * d.ldt];
+        yT = fma(sy[a], tv, yT);
+        dd = fma(tv, tv, dd);
+        oc = fma(so[a], tv, oc);
+    }
+    const int64_t slabs = (d.n + kSlab - 1) / kSlab;
+    double* p = d.partial + (int64_t)blockIdx.y * M + m;
+    p[0] = yT;
+    p[slabs * M] = dd;
+    p[2 * slabs * M] = oc;
 }
 
 // grid = (ceil(M / 256), ceil(n_max / kSlab), batch)
@@ -78,7 +116,7 @@ __global__ void __launch_bounds__(kColsPerBlock) reduce_kernel(int64_t M, const 
 
 // grid = (ceil(M / 256), 1, batch)
 __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ C, int64_t M, int64_t ldc,
-                                                       const GmgKrigeDesc* __restrict__ descs) {
+                                                       const GmgKrigeDesc* __restrict__ descs, int fwd_only) {
     const GmgKrigeDesc d = descs[blockIdx.z];
     if (d.n <= 0) return;
     // scalar reductions over the observations: 1^T o and o^T y (each block recomputes them; n is small
@@ -88,8 +126,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     if (d.ordinary) {
         for (int a = threadIdx.x; a < d.n; a += blockDim.x) {
             const double o = d.T[(int64_t)a * d.ldt + M];
-            so += o;
-            soy = fma(o, d.y[a], soy);
+            if (fwd_only) {                      // o = L^-1 1, T[:, M+1] = L^-1 y: 1^T S^-1 1 and 1^T S^-1 y
+                so = fma(o, o, so);
+                soy = fma(o, d.T[(int64_t)a * d.ldt + M + 1], soy);
+            } else {                             // o = S^-1 1
+                so += o;
+                soy = fma(o, d.y[a], soy);
+            }
         }
     }
     red[0][threadIdx.x] = so;
@@ -166,14 +209,14 @@ int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const 
     if (!descs) return -4;
     if (batch <= 0 || batch > 65535) return -5;
     if (n_max <= 0 || n_max > 65535 || n_max > M) return -6;
-    dim3 grid((unsigned)gmg_ceil_div(M + 1, 256), (unsigned)n_max, (unsigned)batch);
+    dim3 grid((unsigned)gmg_ceil_div(M + 1, 256), (unsigned)n_max, (unsigned)batch);   // column M: the extra RHS
     gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C, M, ldc, descs);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
 }
 
 int gmg_krige_apply_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs, int batch,
-                                int64_t n_max, gmg_stream_t stream) {
+                                int64_t n_max, int fwd_only, gmg_stream_t stream) {
     if (!C) return -1;
     if (M <= 0) return -2;
     if (ldc < M) return -3;
@@ -182,9 +225,11 @@ int gmg_krige_apply_batched_f64(const double* C, int64_t M, int64_t ldc, const G
     if (n_max <= 0) return -6;
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned cb = (unsigned)gmg_ceil_div(M, kColsPerBlock);
-    reduce_kernel<<<dim3(cb, (unsigned)gmg_ceil_div(n_max, kSlab), (unsigned)batch), kColsPerBlock, 0, s>>>(M, descs);
+    const dim3 rgrid(cb, (unsigned)gmg_ceil_div(n_max, kSlab), (unsigned)batch);
+    if (fwd_only) reduce_fwd_kernel<<<rgrid, kColsPerBlock, 0, s>>>(M, descs);
+    else reduce_kernel<<<rgrid, kColsPerBlock, 0, s>>>(M, descs);
     GMG_LAUNCH_CHECK();
-    finalize_kernel<<<dim3(cb, 1, (unsigned)batch), 256, 0, s>>>(C, M, ldc, descs);
+    finalize_kernel<<<dim3(cb, 1, (unsigned)batch), 256, 0, s>>>(C, M, ldc, descs, fwd_only);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
 }

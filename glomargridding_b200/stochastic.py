@@ -166,16 +166,22 @@ class StochasticKriging(Kriging):
         return self.gridded_field + self.epsilon
 
     def _simple_apply(self, values: np.ndarray) -> np.ndarray:
-        """W_simple @ values on the device (one apply pass over T = S^-1 C_cross)."""
+        """W_simple @ values on the device without forming W_simple: C_cross^T (S^-1 values) - one vector solve
+        with the existing Cholesky factor and one GEMM row."""
         cov = self._cov_device()
+        M = cov.shape[0]
         y = dev.to_device(np.asarray(values, dtype=np.float64), torch.float64)
-        if self._user_simple_weights is None and self._batch is not None and not getattr(self, "_simple_deleted", False):
-            o = dn.apply_reduce(cov, self._batch.Cx(0), self._batch.T(0), y, ordinary=False)
-            return o[dn.OUT_FIELD].cpu().numpy()
+        b = self._batch
+        if self._user_simple_weights is None and b is not None and not getattr(self, "_simple_deleted", False):
+            if 0 in b.lu_fallback:
+                o = dn.apply_reduce(cov, b.Cx(0), b.T(0), y, ordinary=False)
+                return o[dn.OUT_FIELD].cpu().numpy()
+            z = dn.padded(b.solve_vectors(0, y[:, None]))            # (n, 2): S^-1 values in column 0
+            return dn.gemm(z[:, :1], b.Cx(0), transa=True)[0, :M].cpu().numpy()
         W = np.asarray(self.simple_kriging_weights)
         Tt = dn.padded(np.ascontiguousarray(W.T))
         idx_t = dev.to_device(np.asarray(self.idx), torch.int64)
-        o = dn.apply_reduce(cov, dn.padded(cov[idx_t, : cov.shape[0]]), Tt, y, ordinary=False)
+        o = dn.apply_reduce(cov, dn.padded(cov[idx_t, :M]), Tt, y, ordinary=False)
         return o[dn.OUT_FIELD].cpu().numpy()
 
 

@@ -131,10 +131,14 @@ int gmg_solve_ws_doubles(int64_t n, int64_t* linv_doubles, int64_t* p_doubles, i
  * Cholesky, trailing update on DMMA tiles.  *info must be zeroed by the caller. */
 int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, gmg_stream_t stream);
 
-/* R <- S^-1 R for the factored systems: R <- L^-1 R then R <- L^-T R, each block step one GEMM
- * (diagonal blocks were inverted by gmg_potrf_batched_f64). */
+/* Triangular solves with the factored systems, each block step one GEMM (diagonal blocks were inverted
+ * by gmg_potrf_batched_f64):  which = GMG_SOLVE_FORWARD: R <- L^-1 R;  GMG_SOLVE_BACKWARD: R <- L^-T R;
+ * GMG_SOLVE_BOTH: R <- S^-1 R. */
+#define GMG_SOLVE_FORWARD 1
+#define GMG_SOLVE_BACKWARD 2
+#define GMG_SOLVE_BOTH 3
 int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max,
-                          gmg_stream_t stream);
+                          int which, gmg_stream_t stream);
 
 /* Indefinite-safe fallback: R <- S^-1 R by LU with partial pivoting (what the reference's
  * np.linalg.solve does, kriging.py:343, :585, :768).  S is the FULL n x n matrix (both triangles) and is
@@ -146,9 +150,10 @@ int gmg_gesv_batched_f64(const GmgSolveDesc* descs, int batch, int64_t nrhs_max,
  * Kriging assembly and application
  * ------------------------------------------------------------------------------------------- */
 
-/* One kriging problem (descriptor array in DEVICE memory).  T is the n x M "transposed weights"
- * matrix S^-1 C_cross with an extra column M holding o = S^-1 1 when `ordinary` (leading
- * dimension ldr >= M + 1). */
+/* One kriging problem (descriptor array in DEVICE memory).  T (n x (M + 2), leading dimension
+ * ldt >= M + 2) starts as the right-hand sides [C_cross | 1 | y] and is overwritten by the solves:
+ * after the forward solve it holds Y = L^-1 [C_cross | 1 | y], after both S^-1 [C_cross | 1 | y]
+ * (the "transposed weights", column M = o = S^-1 1). */
 typedef struct GmgKrigeDesc {
     const int64_t* idx;  /* n observation cells                                                    */
     const double* E;     /* n x n error covariance or NULL                                         */
@@ -156,9 +161,9 @@ typedef struct GmgKrigeDesc {
     const double* y;     /* n observations                                                         */
     double* S;           /* n x n  out: C[idx, idx] + E                                            */
     int64_t lds;
-    double* Cx;          /* n x M  out: C[idx, :]                                                  */
+    double* Cx;          /* n x M  out: C[idx, :]; may be NULL when only the forward-solve apply is used */
     int64_t ldx;
-    double* T;           /* n x (M [+1])  out: copy of Cx (+ ones column) = right-hand sides       */
+    double* T;           /* n x (M + 2)  out: [Cx | 1 | y] = right-hand sides                      */
     int64_t ldt;
     double* partial;     /* workspace: 3 * ceil(n/256) * M doubles                                 */
     double* out;         /* 5 x M: field, u2 (variance before clamping), mask, alpha, rowdot       */
@@ -166,17 +171,20 @@ typedef struct GmgKrigeDesc {
     int32_t ordinary;    /* 0 simple kriging, 1 ordinary kriging (Lagrange-extended system)        */
 } GmgKrigeDesc;
 
-/* S = C[idx, idx] + E, Cx = C[idx, :], T = [Cx | 1]     (reference kriging.py:337-342, :571-583) */
+/* S = C[idx, idx] + E, Cx = C[idx, :], T = [Cx | 1 | y]   (reference kriging.py:337-342, :571-583) */
 int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs,
                                  int batch, int64_t n_max, gmg_stream_t stream);
 
-/* From T = S^-1 [Cx | 1]:  field = W y, variance = diag(C) - rowdot(W, Cx^T) [- 2 alpha], constraint
- * mask = rowdot(W_simple, Cx^T) / diag(C), alpha = Lagrange multiplier column, without forming W
- * (M x n) or the reference's M x M temporaries (kriging.py:417, :434-435, :487-491, :677-679, :699-701,
- * :772-776).  Ordinary kriging uses the Schur complement of the bordered system:
- * alpha = (o^T Cx - 1) / (1^T o), W = (S^-1 Cx - o alpha^T)^T. */
+/* field = W y, variance = diag(C) - rowdot(W, Cx^T) [- 2 alpha], constraint mask = rowdot(W_simple,
+ * Cx^T) / diag(C), alpha = Lagrange multiplier column, without forming W (M x n) or the reference's
+ * M x M temporaries (kriging.py:417, :434-435, :487-491, :677-679, :699-701, :772-776).  Ordinary
+ * kriging uses the Schur complement of the bordered system: alpha = (o^T Cx - 1) / (1^T o),
+ * W = (S^-1 Cx - o alpha^T)^T.
+ * fwd_only != 0: T holds Y = L^-1 [Cx | 1 | y] (forward solve only); since S^-1 = L^-T L^-1 every
+ * result is a column dot product of Y (d = sum Y^2, ...) - the second triangular solve is skipped.
+ * fwd_only == 0: T holds S^-1 [Cx | 1 | y] and Cx must be present (LU fallback, user-supplied weights). */
 int gmg_krige_apply_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs,
-                                int batch, int64_t n_max, gmg_stream_t stream);
+                                int batch, int64_t n_max, int fwd_only, gmg_stream_t stream);
 
 /* Materialise the reference's `kriging_weights`: W (M x n, or M x (n+1) with the Lagrange column when
  * alpha != NULL) from T (n x M) :  W[m, a] = T[a, m] - o[a] alpha[m],  W[m, n] = alpha[m]. */
