@@ -371,3 +371,32 @@ class KrigeBatch:
         check(lib().gmg_krige_weights_f64(T.data_ptr(), self.ldt, o_ptr, self.ldt, a_ptr, n, M, W.data_ptr(),
                                           W.stride(0), dev.stream_ptr()), "gmg_krige_weights_f64")
         return W
+
+
+def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.Tensor, ldc: int, y: torch.Tensor,
+                   ordinary: bool) -> torch.Tensor:
+    """Factor + forward solve + apply for ONE system whose operands are already assembled on this device:
+    S (n, n) = C_obs + E (overwritten by its Cholesky factor), T (n, >= Mc + 2) = [C_cross columns | 1 | y]
+    (overwritten by L^-1 T).  `diag_base` points at the element that holds C[m0, m0] for local column 0 and
+    `ldc` is the stride to the next diagonal element minus one (the matrix leading dimension), so that local
+    column m reads its prior variance at diag_base[m * ldc + m].  Used by the column-sharded multi-GPU path.
+    Returns the (5, Mc) result rows.  Raises LinAlgError if S is not positive definite (no LU fallback here)."""
+    n = S.shape[0]
+    assert S.stride(1) == 1 and T.stride(1) == 1 and S.stride(0) % 2 == 0 and T.stride(0) % 2 == 0
+    assert T.shape[1] >= Mc + 2
+    ws = factor_inplace(S, n, "observation covariance C[idx, idx] + E")
+    slabs = (n + SLAB - 1) // SLAB
+    partial = torch.empty(3 * slabs * Mc, dtype=torch.float64, device=S.device)
+    out = torch.empty((5, Mc), dtype=torch.float64, device=S.device)
+    sd = np.zeros(1, dtype=SOLVE_DESC)
+    sd[0] = (S.data_ptr(), S.stride(0), ws["Linv"].data_ptr(), T.data_ptr(), T.stride(0), ws["P"].data_ptr(),
+             ws["ldp"], ws["info"].data_ptr(), n, Mc + 2)
+    kd = np.zeros(1, dtype=KRIGE_DESC)
+    kd[0] = (0, 0, n, y.data_ptr(), 0, 0, 0, 0, T.data_ptr(), T.stride(0), partial.data_ptr(), out.data_ptr(), n,
+             int(ordinary))
+    sdt, kdt = _desc_tensor(sd, S.device), _desc_tensor(kd, S.device)
+    L, s = lib(), dev.stream_ptr()
+    check(L.gmg_potrs_batched_f64(sdt.data_ptr(), 1, n, Mc + 2, 1, s), "gmg_potrs_batched_f64")
+    check(L.gmg_krige_apply_batched_f64(diag_base.data_ptr(), Mc, ldc, kdt.data_ptr(), 1, n, 1, s), "apply")
+    torch.cuda.current_stream().synchronize()
+    return out

@@ -74,3 +74,45 @@ def test_gather_results_gloo_world2(n_items):
     want = np.array([[100.0 * i + j for j in range(M)] for i in range(n_items)])
     for _, full in results:
         assert np.array_equal(full, want)
+
+
+def _assemble_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from glomargridding_b200.distributed import assemble_obs_system, local_rhs
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    N, n = 37, 11
+    A = rng.standard_normal((N, N))
+    C = torch.from_numpy(A @ A.T)
+    idx = torch.from_numpy(np.sort(rng.choice(N, n, replace=False)))
+    E = torch.from_numpy(np.diag(rng.uniform(0.1, 0.2, n)))
+    bounds = [0, 20, N]                      # uneven row blocks
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    S = assemble_obs_system(C[r0:r1].contiguous(), r0, idx, E)
+    T = local_rhs(C[r0:r1].contiguous(), idx, torch.arange(n, dtype=torch.float64))
+    ok = bool(torch.equal(S, C[idx][:, idx] + E)) and bool(torch.equal(T[:, : r1 - r0], C[idx][:, r0:r1])) \
+        and bool((T[:, r1 - r0] == 1).all()) and bool(torch.equal(T[:, r1 - r0 + 1], torch.arange(n, dtype=torch.float64)))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_obs_system_assembly_gloo_world2():
+    """The exchange step of the row-block sharded kriging path (distributed.py) on CPU tensors over gloo."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_assemble_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in results)
