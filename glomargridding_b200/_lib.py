@@ -34,6 +34,12 @@ def _declare(lib):
         "gmg_ellipse_prepare_f64": (c_int, [p, p, p, p, p, p, i64, dbl, i32, p, c_size_t, p]),
         "gmg_ellipse_cov_f64": (c_int, [p, i64, i64, i64, dbl, dbl, i32, p, i64, i32, p]),
         "gmg_ellipse_pairs_f64": (c_int, [p, i64, p, p, i64, dbl, i32, p, p]),
+        "gmg_ellipse_cov_p2p_f64": (c_int, [p, i64, dbl, dbl, i32, i32, i32, POINTER(c_int64), POINTER(c_void_p), i64,
+                                            i32, p]),
+        "gmg_ipc_alloc_f64": (c_int, [c_size_t, POINTER(c_void_p), p]),
+        "gmg_ipc_free_f64": (c_int, [p]),
+        "gmg_ipc_open_f64": (c_int, [p, POINTER(c_void_p)]),
+        "gmg_ipc_close_f64": (c_int, [p]),
         "gmg_bessel_kv_f64": (c_int, [dbl, p, i64, i32, p, p]),
         "gmg_matern_f64": (c_int, [p, dbl, i32, p, i64, p, p]),
         "gmg_haversine_f64": (c_int, [p, p, i64, i64, i64, p, i64, p]),

@@ -24,6 +24,7 @@
 //                          (16 linear sub-intervals per octave, 2^-12 <= x < 2^9), built on the
 //                          device from the Temme/CF2 Bessel-K in bessel_k.cuh for the build's nu;
 //                          lanes outside the table range fall back to the direct evaluation.
+#include <cstring>
 #include <type_traits>
 #include "gmg_common.cuh"
 #include "bessel_k.cuh"
@@ -383,6 +384,9 @@ __device__ __forceinline__ bool beyond_max_dist(const double* pa, const double* 
     return kEarthRadiusKm * (2.0 * asin(sqrt(h))) > max_dist;
 }
 
+constexpr int kMaxPeers = 8;
+constexpr int kMaxSeg = 5;
+
 // dynamic shared-memory layout of the tile kernel, in doubles from the start of the extern array
 constexpr int kSmRow = 0;                                  // [2][kTile][P_N]  records (LDS.128 broadcast)
 constexpr int kSmCol = kSmRow + 2 * P_N * kTile;           // [2][P_N][kTile]  field-major (conflict-free LDS.128)
@@ -418,6 +422,16 @@ struct EllipseArgs {
     double max_dist;
     int vec2;
     GmgBesselConsts bc;
+    // peer-to-peer symmetric mode (gmg_ellipse_cov_p2p_f64): rank `rank` of `world` owns rows
+    // [blk_row0[rank], blk_row0[rank + 1]) and computes every pair of the matrix exactly once together with its
+    // peers; the transposed tile is stored straight into the owner's row block over NVLink (peer_out).
+    int world, rank;
+    int nseg;                       // work segments after the n_tri diagonal-block tiles
+    int64_t seg_id0[kMaxSeg + 1];   // first tile id of each segment (seg_id0[nseg] = n_tiles)
+    int seg_blk[kMaxSeg];           // column block of the segment
+    int seg_parity[kMaxSeg];        // -1: every tile; 0 / 1: only tiles with (ta_global + tb) % 2 == parity
+    int64_t blk_row0[kMaxPeers + 1];
+    void* peer_out[kMaxPeers];
 };
 
 template <typename OutT> struct Vec2;
@@ -445,7 +459,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-struct TileId { int ta, tb; bool mirror; };
+struct TileId { int ta, tb; bool mirror; int peer; bool skip; };   // peer: block that receives the mirrored tile
 
 // Tile `id` of the launch -> (row tile, column tile).  In symmetric mode (row0 aligned to the tile size) the
 // first n_tri ids enumerate the upper triangle of the tiles_r x tiles_r block on the diagonal - rows r and
@@ -454,6 +468,39 @@ struct TileId { int ta, tb; bool mirror; };
 __device__ __forceinline__ TileId decode_tile(const EllipseArgs& a, int64_t id) {
     TileId t;
     t.mirror = false;
+    t.peer = a.rank;
+    t.skip = false;
+    if (a.world > 1 && id >= a.n_tri) {
+        // off-diagonal block segment: all tiles_r x (column tiles of the block), each mirrored into the peer
+        int sgm = 0;
+        while (sgm + 1 < a.nseg && id >= a.seg_id0[sgm + 1]) ++sgm;
+        const int blk = a.seg_blk[sgm];
+        const int ct0 = (int)(a.blk_row0[blk] / kTile);
+        const int cts = (int)((a.blk_row0[blk + 1] - a.blk_row0[blk] + kTile - 1) / kTile);
+        // Row tile fastest: CTAs that run concurrently (consecutive ids) then share the column tile, i.e. they
+        // mirror into the SAME 64-row band of the peer's block.  Remote stores that are scattered over the whole
+        // peer block run at ~40 GB/s (measured: every tile touches 16 different 2 MB pages of a mapping whose
+        // translations are not cached like local ones); banded, they reach NVLink speed.
+        const int64_t rest = id - a.seg_id0[sgm];
+        if (a.seg_parity[sgm] < 0) {
+            const int c = (int)(rest / a.tiles_r);
+            t.ta = (int)(rest - (int64_t)c * a.tiles_r);
+            t.tb = ct0 + c;
+        } else {
+            // half block: only tiles with (global row tile + column tile) of the given parity; per column tile
+            // there are ceil(tiles_r / 2) candidates, the surplus one of an odd count is skipped
+            const int per = (a.tiles_r + 1) / 2;
+            const int c = (int)(rest / per);
+            const int k = (int)(rest - (int64_t)c * per);
+            t.tb = ct0 + c;
+            t.ta = 2 * k + ((a.seg_parity[sgm] - (a.tile_b0 + t.tb)) & 1);
+            t.skip = t.ta >= a.tiles_r;
+        }
+        (void)cts;
+        t.mirror = true;
+        t.peer = blk;
+        return t;
+    }
     if (a.symmetric) {
         if (id < a.n_tri) {
             const int T = a.tiles_r, w = T + 1;
@@ -513,9 +560,17 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         cp_async16(colp + buf * (P_N * kTile) + f * kTile + 2 * part, a.soa + f * a.npad + j0 + 2 * part);
     };
 
-    int64_t id = blockIdx.x;
+    // next tile of this CTA at or after `from` (ids advance by gridDim.x; tiles that a peer computes are skipped)
+    auto next_tile = [&](int64_t from, TileId& tt) -> int64_t {
+        for (int64_t i = from; i < a.n_tiles; i += gridDim.x) {
+            tt = decode_tile(a, i);
+            if (!tt.skip) return i;
+        }
+        return a.n_tiles;
+    };
+    TileId t;
+    int64_t id = next_tile(blockIdx.x, t);
     if (id >= a.n_tiles) return;
-    TileId t = decode_tile(a, id);
     stage(0, t);
     cp_async_commit();
 
@@ -533,13 +588,10 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
 
     int buf = 0;
     for (;;) {
-        const int64_t id_next = id + gridDim.x;
-        const bool has_next = id_next < a.n_tiles;
         TileId tn = t;
-        if (has_next) {
-            tn = decode_tile(a, id_next);
-            stage(buf ^ 1, tn);
-        }
+        const int64_t id_next = next_tile(id + gridDim.x, tn);
+        const bool has_next = id_next < a.n_tiles;
+        if (has_next) stage(buf ^ 1, tn);
         cp_async_commit();
         cp_async_wait<1>();                           // this tile's records have landed (the next may be in flight)
         __syncthreads();
@@ -637,12 +689,21 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         if (mirror) {
             __syncthreads();
             // ---- transposed tile: rows j0.. of C, columns i0.. (inside the shard's square block) ------
+            // destination block of the mirrored tile: this rank's own rows, or - in the peer-to-peer mode - the
+            // row block of the rank that owns rows j0.. (stores go over NVLink into its memory)
+            OutT* mbase = out;
+            int64_t mrow0 = a.row0, mrow_end = row_end;
+            if (a.world > 1 && t.peer != a.rank) {
+                mbase = reinterpret_cast<OutT*>(a.peer_out[t.peer]);
+                mrow0 = a.blk_row0[t.peer];
+                mrow_end = a.blk_row0[t.peer + 1];
+            }
 #pragma unroll 2
             for (int r = 0; r < kTile / 8; ++r) {
                 const int jj = warp * (kTile / 8) + r;
                 const int64_t grow = j0 + jj;         // global row of the mirrored entry
-                if (grow >= row_end || grow >= a.N) continue;
-                OutT* dst = out + (grow - a.row0) * a.ld + i0;
+                if (grow >= mrow_end || grow >= a.N) continue;
+                OutT* dst = mbase + (grow - mrow0) * a.ld + i0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int ii = lane + 32 * h;
@@ -773,6 +834,16 @@ int launch_pairs(const double* params, const double* table, const GmgBesselConst
     return GMG_OK;
 }
 
+int launch_for_nu(const EllipseArgs& a, double nu, int matern_mode, int store_f32, cudaStream_t s) {
+    switch (resolve_mode(nu, matern_mode)) {
+        case MODE_NU05: return launch_tiles_mode<MODE_NU05>(a, a.n_tiles, store_f32, s);
+        case MODE_NU15: return launch_tiles_mode<MODE_NU15>(a, a.n_tiles, store_f32, s);
+        case MODE_NU25: return launch_tiles_mode<MODE_NU25>(a, a.n_tiles, store_f32, s);
+        case MODE_TABLE: return launch_tiles_mode<MODE_TABLE>(a, a.n_tiles, store_f32, s);
+        default: return launch_tiles_mode<MODE_DIRECT>(a, a.n_tiles, store_f32, s);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -839,17 +910,104 @@ int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, 
     const size_t elt = store_f32 ? sizeof(float) : sizeof(double);
     a.vec2 = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(C_rows) % (2 * elt)) == 0);
     a.bc = gmg_make_bessel_consts(nu);
+    a.world = 1; a.rank = 0; a.nseg = 0;
     const int64_t n_ctas = a.symmetric ? a.n_tri + (int64_t)a.tiles_r * (a.tiles_c - a.tiles_r)
                                        : (int64_t)a.tiles_r * a.tiles_c;
     a.n_tiles = n_ctas;
-    cudaStream_t s = (cudaStream_t)stream;
-    switch (resolve_mode(nu, matern_mode)) {
-        case MODE_NU05: return launch_tiles_mode<MODE_NU05>(a, n_ctas, store_f32, s);
-        case MODE_NU15: return launch_tiles_mode<MODE_NU15>(a, n_ctas, store_f32, s);
-        case MODE_NU25: return launch_tiles_mode<MODE_NU25>(a, n_ctas, store_f32, s);
-        case MODE_TABLE: return launch_tiles_mode<MODE_TABLE>(a, n_ctas, store_f32, s);
-        default: return launch_tiles_mode<MODE_DIRECT>(a, n_ctas, store_f32, s);
+    return launch_for_nu(a, nu, matern_mode, store_f32, (cudaStream_t)stream);
+}
+
+int gmg_ellipse_cov_p2p_f64(const void* ws, int64_t N, double nu, double max_dist_km, int matern_mode, int world,
+                            int rank, const int64_t* h_block_row0, void* const* h_block_rows, int64_t ld,
+                            int store_f32, gmg_stream_t stream) {
+    if (!ws) return -1;
+    if (N <= 0) return -2;
+    if (!(nu > 0.0)) return -3;
+    if (matern_mode < 0 || matern_mode > 2) return -5;
+    if (world < 2 || world > kMaxPeers) return -6;
+    if (rank < 0 || rank >= world) return -7;
+    if (!h_block_row0 || h_block_row0[0] != 0 || h_block_row0[world] != N) return -8;
+    if (!h_block_rows) return -9;
+    if (ld < N) return -10;
+    EllipseArgs a;
+    for (int g = 0; g < world; ++g) {
+        if (h_block_row0[g + 1] <= h_block_row0[g] || h_block_row0[g] % kTile != 0) return -8;   // tile-aligned blocks
+        if (!h_block_rows[g]) return -9;
+        a.blk_row0[g] = h_block_row0[g];
+        a.peer_out[g] = h_block_rows[g];
     }
+    a.blk_row0[world] = N;
+    a.aos = ws_aos(ws);
+    a.soa = ws_soa(ws, N);
+    a.npad = pad_points(N);
+    a.table = ws_table(ws);
+    a.out = h_block_rows[rank];
+    a.N = N; a.row0 = h_block_row0[rank]; a.nrows = h_block_row0[rank + 1] - h_block_row0[rank]; a.ld = ld;
+    a.tiles_r = (int)gmg_ceil_div(a.nrows, kTile);
+    a.tiles_c = (int)gmg_ceil_div(N, kTile);
+    a.symmetric = 1;
+    a.tile_b0 = (int)(a.row0 / kTile);
+    a.n_tri = (int64_t)a.tiles_r * (a.tiles_r + 1) / 2;
+    a.max_dist = (max_dist_km >= 0.0) ? max_dist_km : -1.0;
+    const size_t elt = store_f32 ? sizeof(float) : sizeof(double);
+    a.vec2 = (ld % 2 == 0);
+    for (int g = 0; g < world; ++g) a.vec2 = a.vec2 && ((reinterpret_cast<uintptr_t>(h_block_rows[g]) % (2 * elt)) == 0);
+    a.bc = gmg_make_bessel_consts(nu);
+    a.world = world; a.rank = rank;
+    // Every unordered pair of row blocks {r, c} is computed by exactly one of the two ranks: rank r takes the
+    // blocks at cyclic distance 1 .. (world-1)/2 to its right; at distance world/2 (even world) the two ranks
+    // split the block's tiles by the parity of (row tile + column tile), rank min(r, c) taking the even ones.
+    a.nseg = 0;
+    int64_t id0 = a.n_tri;
+    for (int dlt = 1; dlt <= world / 2; ++dlt) {
+        const int c = (rank + dlt) % world;
+        const bool half = (world % 2 == 0) && (dlt == world / 2);
+        if (a.nseg >= kMaxSeg) return GMG_ERR_UNSUPPORTED;
+        a.seg_id0[a.nseg] = id0;
+        a.seg_blk[a.nseg] = c;
+        a.seg_parity[a.nseg] = half ? (rank < c ? 0 : 1) : -1;
+        const int64_t cts = gmg_ceil_div(h_block_row0[c + 1] - h_block_row0[c], kTile);
+        id0 += (half ? (int64_t)(a.tiles_r + 1) / 2 : (int64_t)a.tiles_r) * cts;
+        ++a.nseg;
+    }
+    a.seg_id0[a.nseg] = id0;
+    a.n_tiles = id0;
+    return launch_for_nu(a, nu, matern_mode, store_f32, (cudaStream_t)stream);
+}
+
+// ---- CUDA IPC plumbing for the peer-to-peer mode (one process per GPU) -------------------------------------------
+// Torch's caching allocator sub-allocates cudaMalloc blocks, and an IPC handle always names a whole block, so the
+// row blocks that peers write into are allocated here (the one exception to "the library never allocates").
+int gmg_ipc_alloc_f64(size_t bytes, void** dev_ptr, void* handle64_out) {
+    if (bytes == 0) return -1;
+    if (!dev_ptr) return -2;
+    if (!handle64_out) return -3;
+    GMG_CUDA_CHECK(cudaMalloc(dev_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    GMG_CUDA_CHECK(cudaIpcGetMemHandle(&h, *dev_ptr));
+    memcpy(handle64_out, &h, sizeof(h));
+    return GMG_OK;
+}
+
+int gmg_ipc_free_f64(void* dev_ptr) {
+    if (!dev_ptr) return -1;
+    GMG_CUDA_CHECK(cudaFree(dev_ptr));
+    return GMG_OK;
+}
+
+int gmg_ipc_open_f64(const void* handle64, void** dev_ptr) {
+    if (!handle64) return -1;
+    if (!dev_ptr) return -2;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    GMG_CUDA_CHECK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GMG_OK;
+}
+
+int gmg_ipc_close_f64(void* dev_ptr) {
+    if (!dev_ptr) return -1;
+    GMG_CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+    return GMG_OK;
 }
 
 int gmg_ellipse_pairs_f64(const void* ws, int64_t N, const int64_t* i, const int64_t* j, int64_t npairs,

@@ -48,7 +48,9 @@ class EllipseCovarianceBuilder:
     `batch_size`.
 
     Extensions (keyword-only): `rows=(row0, nrows)` builds only that row block of the compressed
-    matrix; `matern_mode` in {"auto", "table", "direct"} selects how K_nu is evaluated.
+    matrix; `matern_mode` in {"auto", "table", "direct"} selects how K_nu is evaluated; `peer_blocks`
+    (`ellipse.p2p.PeerRowBlocks`) builds this rank's row block of a multi-GPU build in which every pair
+    is evaluated once across the box and mirrored into the owning peer over NVLink.
     """
 
     def __init__(
@@ -68,6 +70,7 @@ class EllipseCovarianceBuilder:
         *,
         rows: tuple[int, int] | None = None,
         matern_mode: str = "auto",
+        peer_blocks=None,
     ) -> None:
         if max_dist is not None and not isinstance(max_dist, (int, float)):
             raise ValueError("max_dist must be a number")  # reference :116-117
@@ -94,6 +97,9 @@ class EllipseCovarianceBuilder:
         self.n_elements = np.prod(self.xy_shape)
 
         self._get_mask()
+        self._peer_blocks = peer_blocks
+        if peer_blocks is not None:
+            rows = (peer_blocks.row0, peer_blocks.nrows)
         self._rows = rows
         self._calculate_covariance()
 
@@ -155,6 +161,20 @@ class EllipseCovarianceBuilder:
             raise ValueError(f"rows={self._rows} outside the {N} unmasked grid points")
         self.row0, self.nrows = row0, nrows
         f32 = self.precision == np.float32
+        pb = self._peer_blocks
+        if pb is not None:
+            # every pair once across the box: transposed tiles go straight into the owning peer's rows (NVLink)
+            if pb.N != N or pb.local.dtype != (torch.float32 if f32 else torch.float64):
+                raise ValueError("peer_blocks does not match the grid size / precision of this build")
+            pb.barrier()                      # peers may still be reading the previous contents
+            check(lib().gmg_ellipse_cov_p2p_f64(self._ws.data_ptr(), N, float(self.v),
+                                                -1.0 if self.max_dist is None else float(self.max_dist),
+                                                _MATERN[self.matern_mode], pb.world, pb.rank, pb.block_row0, pb.ptrs,
+                                                N, int(f32), dev.stream_ptr()), "gmg_ellipse_cov_p2p_f64")
+            pb.barrier()                      # this rank's block is complete once ALL ranks have finished
+            self.cov_ns_device = pb.local
+            self._cov_ns_host = None
+            return
         out = torch.empty((nrows, N), dtype=torch.float32 if f32 else torch.float64, device=self._ws.device)
         check(lib().gmg_ellipse_cov_f64(self._ws.data_ptr(), N, row0, nrows, float(self.v),
                                         -1.0 if self.max_dist is None else float(self.max_dist),

@@ -76,6 +76,27 @@ int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, 
                         double max_dist_km, int matern_mode, void* C_rows, int64_t ld,
                         int store_f32, gmg_stream_t stream);
 
+/* Multi-GPU build in which every pair of points is evaluated ONCE across the box: rank `rank` of `world`
+ * (one process per GPU) owns the tile-aligned row block [h_block_row0[rank], h_block_row0[rank + 1]) and
+ * computes its diagonal block plus the blocks at cyclic distance 1 .. world/2 to its right; each of those tiles
+ * is stored into its own rows and, transposed, straight into the owning peer's row block over NVLink
+ * (`h_block_rows[g]` = device pointer of rank g's row block, mapped into this process with gmg_ipc_open_f64).
+ * Both `h_*` arrays are HOST arrays.  The caller synchronises the ranks after the launch (every rank's block is
+ * complete when ALL ranks have finished).  Same replaced reference code as gmg_ellipse_cov_f64; the reference has
+ * no multi-device path. */
+int gmg_ellipse_cov_p2p_f64(const void* ws, int64_t N, double nu, double max_dist_km, int matern_mode,
+                            int world, int rank, const int64_t* h_block_row0, void* const* h_block_rows,
+                            int64_t ld, int store_f32, gmg_stream_t stream);
+
+/* CUDA IPC plumbing for the call above.  An IPC handle names a whole cudaMalloc block, which a caching allocator
+ * cannot promise, so the peer-visible row blocks are allocated by gmg_ipc_alloc_f64 (the one exception to "the
+ * library never allocates") and freed by gmg_ipc_free_f64; gmg_ipc_open_f64 / gmg_ipc_close_f64 map / unmap a
+ * peer's block (64-byte cudaIpcMemHandle_t obtained in the peer process) in this process. */
+int gmg_ipc_alloc_f64(size_t bytes, void** dev_ptr, void* handle64_out); /* cudaMalloc + cudaIpcGetMemHandle */
+int gmg_ipc_free_f64(void* dev_ptr);
+int gmg_ipc_open_f64(const void* handle64, void** dev_ptr);
+int gmg_ipc_close_f64(void* dev_ptr);
+
 /* Covariance of arbitrary index pairs (i[k], j[k]) - no diagonal term, no max_dist.
  * replaces `EllipseCovarianceBuilder.c_ij_anisotropic_array(i_s, j_s)` (:405-468). */
 int gmg_ellipse_pairs_f64(const void* ws, int64_t N, const int64_t* i, const int64_t* j,
