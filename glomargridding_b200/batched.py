@@ -13,6 +13,8 @@ data-path collective; `gather_results` collects the M-vectors on every rank with
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -44,13 +46,22 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
     cov = _as_device_cov(covariance)
     M = cov.shape[0]
     # the classes' constructor logic (subset E, drop NaN / zero-diagonal observations, warn) per problem
-    prepared = []
-    for idx, obs, E in problems:
+    def prepare(problem):
+        idx, obs, E = problem
         k = cls.__new__(cls)
         k.covariance, k.idx, k.obs, k.error_cov = covariance, np.asarray(idx), np.asarray(obs), E
         k._batch = k._user_weights = None
         k.subset_error_covariance()
-        prepared.append(k._problem())
+        return k._problem()
+
+    # the per-problem host work is an O(n^2) NaN scan of the error covariance: numpy releases the GIL for it
+    if len(problems) >= 8:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1))) as pool:
+            prepared = list(pool.map(prepare, problems))
+    else:
+        prepared = [prepare(p) for p in problems]
     if max_bytes is None:
         free, _ = torch.cuda.mem_get_info(cov.device)
         max_bytes = int(0.4 * free)

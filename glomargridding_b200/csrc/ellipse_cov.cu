@@ -628,8 +628,16 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         // from shared memory while this row is computed (ncu r01b: 12 % of the stall samples sat on its first use).
         const int row_off0 = kSmRow + buf * (P_N * kTile) + warp * (kTile / 8) * P_N;
         const int col_off = kSmCol + buf * (P_N * kTile) + jl;
-        auto rows = [&](auto fast_tag, auto mirror_tag) {
+        // SLOWALL = the cold re-run of the loop in which flagged lanes take the libm / Temme-CF2 path; it is taken
+        // after the hot loop when any lane of the thread was flagged (x >= 700, x outside the Matern table, NaN -
+        // in practice only the zero-distance lanes of diagonal tiles).  Keeping the call out of the hot loop
+        // matters: with a call inside it the table variant spilled and ran 12 % slower (profiles/r01_ellipse_summary.md).
+        bool slow_any = false;
+        OutT* const orow_start = orow;
+        auto rows = [&](auto fast_tag, auto mirror_tag, auto slowall_tag) {
             constexpr bool FAST = decltype(fast_tag)::value, MIRROR = decltype(mirror_tag)::value;
+            constexpr bool SLOWALL = decltype(slowall_tag)::value;
+            orow = orow_start;
             PointRegs pnext = load_point(smem + row_off0);
             constexpr int kRowUnroll = K1_UNROLL;
 #pragma unroll kRowUnroll
@@ -638,17 +646,25 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
                 const int row_off = row_off0 + r * P_N;
                 const PointRegs p = pnext;
                 if (r + 1 < kTile / 8) pnext = load_point(smem + row_off + P_N);
-                bool slow0, slow1;
-#if K1_EXPERIMENT == 2      // stores only: no pair arithmetic (kernel-experiment builds, never shipped)
-                double v0 = p.lat + c0.lat, v1 = p.lat + c1.lat;
-                slow0 = slow1 = false;
-#else
-                double v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
-                double v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
-#endif
-                if (slow0 | slow1) {                  // one cold branch for both pairs
+                bool slow0 = false, slow1 = false;
+                double v0, v1;
+                if (SLOWALL) {
+                    // same fast evaluation again (bit-identical), then only the flagged lanes take the cold path:
+                    // a value never depends on which tile or row block it was computed in
+                    v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
+                    v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
+                    if (!(slow0 | slow1)) { orow += a.ld; continue; }
                     if (slow0) v0 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off);
                     if (slow1) v1 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off + 1);
+                } else {
+#if K1_EXPERIMENT == 2      // stores only: no pair arithmetic (kernel-experiment builds, never shipped)
+                    v0 = p.lat + c0.lat;
+                    v1 = p.lat + c1.lat;
+#else
+                    v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
+                    v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
+#endif
+                    slow_any |= slow0 | slow1;
                 }
                 if (MAXDIST) {                        // :256-266 pairs beyond max_dist stay 0
                     if (tile_beyond_max_dist(row_off, col_off, a.max_dist)) v0 = 0.0;
@@ -682,9 +698,12 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         using T_ = std::true_type;
         using F_ = std::false_type;
         if (full && !diag) {
-            if (mirror) rows(T_{}, T_{}); else rows(T_{}, F_{});
+            if (mirror) rows(T_{}, T_{}, F_{}); else rows(T_{}, F_{}, F_{});
         } else {
-            if (mirror) rows(F_{}, T_{}); else rows(F_{}, F_{});
+            if (mirror) rows(F_{}, T_{}, F_{}); else rows(F_{}, F_{}, F_{});
+        }
+        if (slow_any) {                               // rare: redo this thread's 16 pairs on the cold path
+            if (mirror) rows(F_{}, T_{}, T_{}); else rows(F_{}, F_{}, T_{});
         }
         if (mirror) {
             __syncthreads();
