@@ -401,3 +401,96 @@ def test_batched_months_equal_per_month_classes(K):
             assert np.array_equal(res["field"][m], quiet(one.solve))
             assert np.array_equal(res["uncertainty"][m], quiet(one.get_uncertainty))
             assert np.array_equal(res["constraint_mask"][m], quiet(one.constraint_mask))
+
+
+# ---- stochastic ensemble (BASELINE.json config 5) -----------------------------------------------------------
+def test_stochastic_ensemble_distribution_and_consistency(K):
+    """200+ perturbed fields in one call: the ordinary-kriging part equals the class, the perturbations are
+    zero-mean with the covariance the two-stage construction implies (the simple-kriging posterior covariance
+    C - W_sk C_cross, Morice et al. 2021), and every member equals the class's formula on its own draws."""
+    from glomargridding_b200.batched import stochastic_ensemble
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(15.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office",
+                                   precision=np.float64).cov_ns
+    M = cov.shape[0]
+    idx, obs = synth.fixed_observations(8, M, 90)
+    E = synth.hadcrut_style_error_cov(idx, lons.size)
+    nm = 6000
+    res = stochastic_ensemble(cov, idx, obs, E.copy(), nm, seed=2014)
+    assert res["result"].shape == (nm, M) and res["epsilon"].shape == (nm, M)
+    ok = K.OrdinaryKriging(cov, idx, obs, E.copy())
+    assert max_norm_rel(res["gridded_field"], ok.solve()) <= 1e-12
+    assert var_rel(res["uncertainty"], ok.get_uncertainty()) <= 1e-12
+    assert np.allclose(res["result"], res["gridded_field"][None, :] + res["epsilon"])
+    eps = res["epsilon"]
+    S = cov[np.ix_(idx, idx)] + E
+    W = np.linalg.solve(S, cov[idx, :]).T                                   # simple kriging weights
+    # epsilon = W (x_obs + noise) - x: covariance W S W^T - W C_o. - C_.o W^T + C = C - W C_cross (posterior)
+    post = cov - W @ cov[idx, :]
+    se = np.sqrt(np.diag(post) / nm)
+    assert np.all(np.abs(eps.mean(0)) < 5 * se + 1e-12)
+    emp = np.cov(eps.T)
+    assert np.linalg.norm(emp - post) / np.linalg.norm(post) < 4 * np.sqrt(M / nm)
+    # same seed -> same members; different seed -> different members
+    again = stochastic_ensemble(cov, idx, obs, E.copy(), 5, seed=2014)
+    other = stochastic_ensemble(cov, idx, obs, E.copy(), 5, seed=2015)
+    assert again["result"].shape == (5, M) and not np.allclose(again["result"], other["result"])
+
+
+# ---- full-size properties (sizes of BASELINE.json configs[2] + [3]: 1-degree grid, 20 000 observations) ------
+def test_1deg_20000_obs_size_independent_properties(K):
+    """Too large for the oracle (minutes of LAPACK): checked through properties that do not depend on size.
+    (i) linearity of the kriged field in the observations, (ii) the solve residual S t = c on sampled grid columns
+    and S o = 1 for the Lagrange column, (iii) unbiasedness: ordinary-kriging weights of every sampled grid point
+    sum to one, (iv) the variance / mask identities between the forward-only results and the full weights."""
+    import torch
+
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(1.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    b = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office", precision=np.float64)
+    C = b.cov_ns_device
+    N, n = C.shape[0], 20000
+    idx, obs1 = synth.fixed_observations(4, N, n)
+    rng = np.random.default_rng(1)
+    obs2 = rng.standard_normal(n)
+    evar = rng.uniform(0.2, 0.4, n) ** 2
+    E = np.diag(evar)
+
+    def krige(y):
+        k = K.OrdinaryKriging(C, idx, y, E)
+        return k, k.solve(), k.get_uncertainty(), k.constraint_mask()
+
+    k1, z1, u1, m1 = krige(obs1)
+    assert k1._batch.lu_fallback == [] and np.isfinite(z1).all() and np.isfinite(u1).all()
+    _, z2, u2, _ = krige(obs2)
+    _, z3, u3, _ = krige(obs1 + 2.0 * obs2)
+    assert max_norm_rel(z3, z1 + 2.0 * z2) <= TOL                       # (i) linear in the observations
+    assert np.array_equal(u1, u2) and np.array_equal(u1, u3)            #     variance does not depend on them
+    assert (m1 > 0).all() and (m1 <= 1 + 1e-9).all() and (u1 >= 0).all()
+    # (ii) residuals with the full weights of the first system (runs the second triangular solve)
+    batch = k1._batch
+    T = batch.T(0)                                                      # (n, M + 2) = S^-1 [C_cross | 1 | y]
+    idx_t = torch.from_numpy(idx).cuda()
+    S = C[idx_t][:, idx_t] + torch.from_numpy(E).cuda()
+    cols = torch.tensor([0, 777, 32400, 64799, N, N + 1], device="cuda")          # four grid columns, ones, obs
+    rhs = torch.cat([C[idx_t][:, cols[:4]], torch.ones(n, 1, dtype=torch.float64, device="cuda"),
+                     torch.from_numpy(obs1).cuda()[:, None]], dim=1)
+    resid = S @ T[:, cols] - rhs
+    assert float(resid.abs().max() / rhs.abs().max()) <= 1e-9
+    # (iii) + (iv) on sampled grid points, from the materialised rows of the weights matrix
+    o = T[:, N]
+    alpha = batch.out[0, dn.OUT_ALPHA]
+    for m in (0, 777, 32400, 64799):
+        w = T[:, m] - o * alpha[m]                                      # ordinary-kriging weights of grid point m
+        assert abs(float(w.sum()) - 1.0) <= 1e-9
+        assert abs(float(w @ torch.from_numpy(obs1).cuda()) - z1[m]) <= TOL * np.abs(z1).max()
+        c_m = C[idx_t, m]
+        u2_m = float(C[m, m] - w @ c_m - 2 * alpha[m])
+        assert abs(u2_m - u1[m] ** 2) <= TOL * float(C[m, m])
+        assert abs(float(T[:, m] @ c_m / C[m, m]) - m1[m]) <= TOL
