@@ -30,6 +30,10 @@
 #include "bessel_k.cuh"
 #include "../../include/glomar_b200.h"
 
+#ifndef K1_EXPERIMENT
+#define K1_EXPERIMENT 0     // != 0: kernel-experiment builds that drop one component of the pair formula
+#endif
+
 namespace {
 
 constexpr double kEarthRadiusKm = 6371.0;           // reference constants.py:18
@@ -48,8 +52,8 @@ constexpr int kTabSub = 1 << kTabSubLog2;                   // linear sub-interv
 constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 336
 constexpr int kTabDeg = 7;
 constexpr int kTabCoef = kTabDeg + 1;
-constexpr int kTabDoubles = kTabNint * kTabCoef;            // 2688 (21.5 KB), layout [interval][coef]
-static_assert(kTabCoef == 8, "the table record is read as four 16-byte loads");
+constexpr int kTabDoubles = kTabNint * kTabCoef;            // 2688 (21.5 KB), layout [coef][interval]
+static_assert(kTabCoef == 8, "table_horner is written for degree 7");
 
 enum { MODE_NU05 = 0, MODE_NU15 = 1, MODE_NU25 = 2, MODE_TABLE = 3, MODE_DIRECT = 4 };
 
@@ -130,29 +134,25 @@ __global__ void __launch_bounds__(32) matern_table_kernel(GmgBesselConsts bc, do
             for (int j = 0; j < kTabCoef; ++j) tmp[j] = (j > 0 ? 2.0 * tn[j - 1] : 0.0) - tp[j];
             for (int j = 0; j < kTabCoef; ++j) { tp[j] = tn[j]; tn[j] = tmp[j]; mono[j] += cheb[n] * tmp[j]; }
         }
-        for (int j = 0; j < kTabCoef; ++j) table[interval * kTabCoef + j] = mono[j];   // [interval][coef]
+        for (int j = 0; j < kTabCoef; ++j) table[j * kTabNint + interval] = mono[j];   // [coef][interval]
     }
 }
 
 struct MaternCtx {
     GmgBesselConsts bc;
-    const double* table;   // shared-memory (tile kernel) or global (pairs kernel) pointer, [interval][coef]
+    const double* table;   // shared-memory (tile kernel) or global (pairs kernel) pointer, [coef][interval]
     double x_scale;        // 2 sqrt(nu) * R: inner = x_scale * sqrt(Q_rad / det)
 };
 
-// degree-7 Horner on one 64 B table record (four 16-byte loads)
+// degree-7 Horner; the table is coefficient-major, [coef][interval]: neighbouring lanes of a warp fall into the
+// same or adjacent intervals (x varies smoothly along a row of the tile), so each of the eight 8-byte loads touches
+// one or two 128-byte lines - one shared-memory wavefront - where a 64-byte-record layout read with LDS.128 needed
+// ~6 per load (ncu r01: 39 shared wavefronts per warp-pair, the LSU pipe 69 % busy, against 14 for the closed forms).
 __device__ __forceinline__ double table_horner(const double* c, double t) {
-    const double2 c01 = *reinterpret_cast<const double2*>(c);
-    const double2 c23 = *reinterpret_cast<const double2*>(c + 2);
-    const double2 c45 = *reinterpret_cast<const double2*>(c + 4);
-    const double2 c67 = *reinterpret_cast<const double2*>(c + 6);
-    double p = fma(c67.y, t, c67.x);
-    p = fma(p, t, c45.y);
-    p = fma(p, t, c45.x);
-    p = fma(p, t, c23.y);
-    p = fma(p, t, c23.x);
-    p = fma(p, t, c01.y);
-    return fma(p, t, c01.x);
+    double p = fma(c[7 * kTabNint], t, c[6 * kTabNint]);
+#pragma unroll
+    for (int k = 5; k >= 0; --k) p = fma(p, t, c[k * kTabNint]);
+    return p;
 }
 
 template <int MODE>
@@ -169,7 +169,7 @@ __device__ __forceinline__ double matern_scaled_eval(const MaternCtx& m, double 
             const int cbits = (hi & ((kTabSub - 1) << (20 - kTabSubLog2))) | (1 << (19 - kTabSubLog2));
             const double centre = __hiloint2double(0x3FF00000 | cbits, 0);
             const double t = (mant - centre) * (double)(2 * kTabSub);
-            return table_horner(m.table + idx * kTabCoef, t);
+            return table_horner(m.table + idx, t);
         }
     }
     return gmg_matern_scaled(m.bc, x);
@@ -304,7 +304,7 @@ __device__ __forceinline__ double matern_scaled_fast(const MaternCtx& m, double 
     // 1.(2 sub + 1) x 2^5, whose high word is 0x40400000 | sub << 16 | 1 << 15 - one LOP3 on hi
     const double c32 = __hiloint2double((hi & 0x000F0000) | 0x40408000, 0);
     const double t = fma(mant, kHot.tab_scale, -c32);
-    return table_horner(reinterpret_cast<const double*>(reinterpret_cast<const char*>(m.table) + idx * (kTabCoef * 8)), t);
+    return table_horner(m.table + idx, t);
 }
 
 // longitude wrap, reference ellipse/covariance.py:633-634:  dx > pi -> dx - 2 pi,  dx < -pi -> dx + 2 pi
@@ -340,7 +340,11 @@ __device__ __forceinline__ PairGeom pair_geom(const PointRegs& a, const PointReg
         dy = (double)__fsub_rn((float)a.lat, (float)b.lat);
     } else {
         dy = a.lat - b.lat;                                 // :631 orientation (i) - (j)
+#if K1_EXPERIMENT == 6      // cost of the longitude wrap
+        dx = a.lon - b.lon;
+#else
         dx = wrap_lon(a.lon - b.lon);                       // :632-634 exact IEEE subtract of host radians
+#endif
     }
     dx *= (a.hcos + b.hcos);                                // :636-637, after the wrap
     const double s0 = a.h00 + b.h00, s1 = a.h01 + b.h01, s3 = a.h11 + b.h11;   // :451
@@ -356,10 +360,24 @@ template <int MODE, bool GEOM_F32, int EXPSTRIDE>
 __device__ __forceinline__ double cov_pair(const PointRegs& a, const PointRegs& b, const MaternCtx& m,
                                            const double* __restrict__ sexp, bool& slow) {
     const PairGeom g = pair_geom<GEOM_F32>(a, b);
+#if K1_EXPERIMENT == 5      // cost of the two reciprocal square roots (kernel-experiment builds, never shipped)
+    const double r = g.det * 1e-12;
+    const double x = (m.x_scale * g.q) * (g.q * 1e-3) * r;
+#else
     const double r = rsqrt_pos(g.det);
     const double x = (m.x_scale * g.q) * rsqrt_pos(g.q) * r;                    // :457 inner
+#endif
+#if K1_EXPERIMENT == 7      // cost of the Matern factor
+    slow = false;
+    const double gm = 1.0;
+#else
     const double gm = matern_scaled_fast<MODE>(m, x, slow);
+#endif
+#if K1_EXPERIMENT == 4      // cost of exp(-x)
+    return ((a.w * b.w) * r) * gm * (1.0 - x * 1e-9);
+#else
     return ((a.w * b.w) * r) * gm * exp_neg<EXPSTRIDE>(x, sexp);                           // :447-455, :465-466
+#endif
 }
 
 // Cold path for flagged lanes: libm sqrt / exp, Temme-CF2 Bessel-K; any x (incl. underflow to 0 and NaN).
@@ -530,9 +548,11 @@ __device__ __forceinline__ TileId decode_tile(const EllipseArgs& a, int64_t id) 
 #ifndef K1_UNROLL
 #define K1_UNROLL 1
 #endif
-#ifndef K1_EXPERIMENT
-#define K1_EXPERIMENT 0
+#ifndef K1_NCOL
+#define K1_NCOL 2       // columns per thread: 2 (8 rows per warp) or 1 (two warps side by side, 16 rows per warp)
 #endif
+constexpr int kNC = K1_NCOL;
+constexpr int kRowsPerWarp = (kNC == 2) ? kTile / 8 : kTile / 4;
 
 // Persistent kernel: K1_MINB CTAs per SM, each looping over tiles id = blockIdx.x, += gridDim.x.  The exp and
 // Matern tables are staged once per CTA; the 2 x 4 KB of per-point records of the NEXT tile are fetched with
@@ -549,7 +569,8 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int jl = 2 * lane;
+    const int wr = (kNC == 2) ? warp : (warp >> 1);                 // warp-row: which strip of rows this warp owns
+    const int jl = (kNC == 2) ? 2 * lane : lane + 32 * (warp & 1);  // first (or only) column of this thread
     const int64_t row_end = a.row0 + a.nrows;
     OutT* out = reinterpret_cast<OutT*>(a.out);
 
@@ -602,7 +623,12 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         const bool mirror = t.mirror;
 
         PointRegs c0, c1;
-        {
+        if (kNC == 1) {
+            c0.lat = cp[P_LAT * kTile + jl];   c0.lon = cp[P_LON * kTile + jl];   c0.hcos = cp[P_HCOS * kTile + jl];
+            c0.h00 = cp[P_H00 * kTile + jl];   c0.h01 = cp[P_H01 * kTile + jl];   c0.h11 = cp[P_H11 * kTile + jl];
+            c0.w = cp[P_W * kTile + jl];
+            c1 = c0;
+        } else {
             auto ld2 = [&](int f, double& x0, double& x1) {
                 const double2 v = *reinterpret_cast<const double2*>(cp + f * kTile + jl);
                 x0 = v.x;
@@ -621,12 +647,12 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         const int dl = diag ? (int)dlt : (1 << 20);   // il == jl + dl  <=>  global row == global column
         const int rows_ok = (int)min((int64_t)kTile, row_end - i0);
         const int cols_ok = (int)min((int64_t)kTile, a.N - j0);
-        OutT* orow = out + (i0 - a.row0 + warp * (kTile / 8)) * a.ld + (j0 + jl);
+        OutT* orow = out + (i0 - a.row0 + wr * kRowsPerWarp) * a.ld + (j0 + jl);
 
         // Row loop.  FAST = the common tile (full, off the diagonal, no max_dist): the epilogue is one vector
         // store and there is no per-row branch besides the cold-path check.  The next row's record is fetched
         // from shared memory while this row is computed (ncu r01b: 12 % of the stall samples sat on its first use).
-        const int row_off0 = kSmRow + buf * (P_N * kTile) + warp * (kTile / 8) * P_N;
+        const int row_off0 = kSmRow + buf * (P_N * kTile) + wr * kRowsPerWarp * P_N;
         const int col_off = kSmCol + buf * (P_N * kTile) + jl;
         // SLOWALL = the cold re-run of the loop in which flagged lanes take the libm / Temme-CF2 path; it is taken
         // after the hot loop when any lane of the thread was flagged (x >= 700, x outside the Matern table, NaN -
@@ -641,39 +667,39 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
             PointRegs pnext = load_point(smem + row_off0);
             constexpr int kRowUnroll = K1_UNROLL;
 #pragma unroll kRowUnroll
-            for (int r = 0; r < kTile / 8; ++r) {
-                const int il = warp * (kTile / 8) + r;
+            for (int r = 0; r < kRowsPerWarp; ++r) {
+                const int il = wr * kRowsPerWarp + r;
                 const int row_off = row_off0 + r * P_N;
                 const PointRegs p = pnext;
-                if (r + 1 < kTile / 8) pnext = load_point(smem + row_off + P_N);
+                if (r + 1 < kRowsPerWarp) pnext = load_point(smem + row_off + P_N);
                 bool slow0 = false, slow1 = false;
                 double v0, v1;
                 if (SLOWALL) {
                     // same fast evaluation again (bit-identical), then only the flagged lanes take the cold path:
                     // a value never depends on which tile or row block it was computed in
                     v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
-                    v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
+                    v1 = (kNC == 2) ? cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1) : 0.0;
                     if (!(slow0 | slow1)) { orow += a.ld; continue; }
                     if (slow0) v0 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off);
-                    if (slow1) v1 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off + 1);
+                    if (kNC == 2 && slow1) v1 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off + 1);
                 } else {
 #if K1_EXPERIMENT == 2      // stores only: no pair arithmetic (kernel-experiment builds, never shipped)
                     v0 = p.lat + c0.lat;
                     v1 = p.lat + c1.lat;
 #else
                     v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
-                    v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
+                    v1 = (kNC == 2) ? cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1) : 0.0;
 #endif
                     slow_any |= slow0 | slow1;
                 }
                 if (MAXDIST) {                        // :256-266 pairs beyond max_dist stay 0
                     if (tile_beyond_max_dist(row_off, col_off, a.max_dist)) v0 = 0.0;
-                    if (tile_beyond_max_dist(row_off, col_off + 1, a.max_dist)) v1 = 0.0;
+                    if (kNC == 2 && tile_beyond_max_dist(row_off, col_off + 1, a.max_dist)) v1 = 0.0;
                 }
                 if (!FAST && diag) {                  // diagonal = stdev^2, :246
                     const double var = smem[row_off + P_VAR];
                     if (il == jl + dl) v0 = var;
-                    if (il == jl + 1 + dl) v1 = var;
+                    if (kNC == 2 && il == jl + 1 + dl) v1 = var;
                 }
 #if K1_EXPERIMENT == 1      // arithmetic only: the store is kept reachable but never taken
                 if (v0 == 123.456789 && v1 == 987.654321)
@@ -681,17 +707,21 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
                 if (FAST || full)
 #endif
                 {
-                    typename Vec2<OutT>::type v;
-                    v.x = (OutT)v0;
-                    v.y = (OutT)v1;
-                    *reinterpret_cast<typename Vec2<OutT>::type*>(orow) = v;
+                    if (kNC == 1) {
+                        *orow = (OutT)v0;
+                    } else {
+                        typename Vec2<OutT>::type v;
+                        v.x = (OutT)v0;
+                        v.y = (OutT)v1;
+                        *reinterpret_cast<typename Vec2<OutT>::type*>(orow) = v;
+                    }
                 } else if (il < rows_ok && jl < cols_ok) {
-                    store_pair<OutT>(orow, v0, v1, jl + 1 < cols_ok, a.vec2 != 0);
+                    store_pair<OutT>(orow, v0, v1, kNC == 2 && jl + 1 < cols_ok, a.vec2 != 0);
                 }
                 orow += a.ld;
                 if (MIRROR) {
                     tileT[il * kTileLd + jl] = v0;
-                    tileT[il * kTileLd + jl + 1] = v1;
+                    if (kNC == 2) tileT[il * kTileLd + jl + 1] = v1;
                 }
             }
         };
