@@ -42,7 +42,7 @@ def _declare(lib):
         "gmg_ipc_close_f64": (c_int, [p]),
         "gmg_bessel_kv_f64": (c_int, [dbl, p, i64, i32, p, p]),
         "gmg_matern_f64": (c_int, [p, dbl, i32, p, i64, p, p]),
-        "gmg_haversine_f64": (c_int, [p, p, i64, i64, i64, p, i64, p]),
+        "gmg_haversine_f64": (c_int, [p, p, i64, i64, i64, dbl, p, i64, p]),
     }
     u64 = c_uint64
     sigs.update({
@@ -56,6 +56,7 @@ def _declare(lib):
         "gmg_krige_weights_f64": (c_int, [p, i64, p, i64, p, i64, i64, p, i64, p]),
         "gmg_extended_inverse_f64": (c_int, [p, i64, i64, p, p, i64, p]),
         "gmg_normal_f64": (c_int, [p, i64, u64, u64, p]),
+        "gmg_variogram_f64": (c_int, [i32, p, i64, i64, i64, dbl, dbl, dbl, dbl, i32, i32, i32, dbl, p, i64, p]),
         "gmg_tril_f64": (c_int, [p, i64, i64, p]),
     })
     for name, (res, args) in sigs.items():

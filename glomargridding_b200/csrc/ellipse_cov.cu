@@ -816,15 +816,15 @@ __global__ void __launch_bounds__(256) matern_kernel(GmgBesselConsts bc, const d
 
 __global__ void __launch_bounds__(256) haversine_kernel(const double* __restrict__ lat,
                                                         const double* __restrict__ lon, int64_t N,
-                                                        int64_t row0, int64_t nrows, double* __restrict__ D,
-                                                        int64_t ld) {
+                                                        int64_t row0, int64_t nrows, double radius,
+                                                        double* __restrict__ D, int64_t ld) {
     // reference distances.py:191-218 (sklearn haversine_distances * 6371): asin form
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t i = row0 + blockIdx.y;
     if (j >= N || blockIdx.y >= nrows) return;
     const double sl = sin(0.5 * (lat[i] - lat[j])), so = sin(0.5 * (lon[i] - lon[j]));
     const double h = sl * sl + cos(lat[i]) * cos(lat[j]) * so * so;
-    D[(int64_t)blockIdx.y * ld + j] = kEarthRadiusKm * (2.0 * asin(sqrt(h)));
+    D[(int64_t)blockIdx.y * ld + j] = (2.0 * asin(sqrt(h))) * radius;    // sklearn: 2 asin(sqrt(h)), then "* radius"
 }
 
 int resolve_mode(double nu, int matern_mode) {
@@ -1121,16 +1121,16 @@ int gmg_matern_f64(const void* ws, double nu, int matern_mode, const double* x, 
 }
 
 int gmg_haversine_f64(const double* lat_rad, const double* lon_rad, int64_t N, int64_t row0, int64_t nrows,
-                      double* D_rows, int64_t ld, gmg_stream_t stream) {
+                      double radius, double* D_rows, int64_t ld, gmg_stream_t stream) {
     if (!lat_rad) return -1;
     if (!lon_rad) return -2;
     if (N <= 0) return -3;
     if (row0 < 0 || row0 >= N) return -4;
     if (nrows <= 0 || row0 + nrows > N || nrows > 65535) return -5;
-    if (!D_rows) return -6;
-    if (ld < N) return -7;
+    if (!D_rows) return -7;
+    if (ld < N) return -8;
     dim3 grid((unsigned)gmg_ceil_div(N, 256), (unsigned)nrows);
-    haversine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lat_rad, lon_rad, N, row0, nrows, D_rows, ld);
+    haversine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lat_rad, lon_rad, N, row0, nrows, radius, D_rows, ld);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
 }

@@ -113,10 +113,10 @@ int gmg_bessel_kv_f64(double nu, const double* x, int64_t n, int scaled, double*
 int gmg_matern_f64(const void* ws, double nu, int matern_mode, const double* x, int64_t n,
                    double* out, gmg_stream_t stream);
 
-/* Haversine (asin form) distance matrix rows in km, R = 6371.0.
- * replaces `distances.haversine_distance_from_frame` (distances.py:191-218). */
+/* Haversine (asin form) distance matrix rows on a sphere of the given radius (km), at most 65535 rows per call.
+ * replaces `distances.haversine_distance_from_frame` (distances.py:191-218: sklearn haversine_distances * radius). */
 int gmg_haversine_f64(const double* lat_rad, const double* lon_rad, int64_t N, int64_t row0,
-                      int64_t nrows, double* D_rows, int64_t ld, gmg_stream_t stream);
+                      int64_t nrows, double radius, double* D_rows, int64_t ld, gmg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense FP64 linear algebra of the kriging path (DMMA = mma.sync m8n8k4 f64 tiles)
@@ -229,6 +229,22 @@ int gmg_normal_f64(double* out, int64_t n, uint64_t seed, uint64_t offset, gmg_s
 
 /* Zero the strict upper triangle of the row-major n x n matrix A. */
 int gmg_tril_f64(double* A, int64_t n, int64_t ld, gmg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stationary variogram models on a distance matrix (the reference workflow's other covariance route)
+ * replaces glomar_gridding/variogram.py:96-138, :177-218, :257-289, :387-476 (the four `.fit`) and
+ * :479-504 (`variogram_to_covariance`, fused when to_covariance != 0: out = variance - variogram).
+ * matern_method: 0 "sklearn", 1 "gstat", 2 "karspeck".  fill_diag: set the diagonal to the nugget
+ * (MaternVariogram.fit does, :470-475).  Scalar parameters only.
+ * ------------------------------------------------------------------------------------------- */
+#define GMG_VARIOGRAM_SPHERICAL 0
+#define GMG_VARIOGRAM_GAUSSIAN 1
+#define GMG_VARIOGRAM_EXPONENTIAL 2
+#define GMG_VARIOGRAM_MATERN 3
+int gmg_variogram_f64(int model, const double* dist, int64_t rows, int64_t cols, int64_t ld,
+                      double psill, double nugget, double range, double nu, int matern_method,
+                      int fill_diag, int to_covariance, double variance, double* out, int64_t ldo,
+                      gmg_stream_t stream);
 
 #ifdef __cplusplus
 }

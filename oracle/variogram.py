@@ -35,3 +35,20 @@ def geostats_setup():
     idx = np.array([int((la - 1) * 20 + (lo - 1)) for la, lo in obs_latlon], dtype=np.int64)
     obs = np.array([1.0, 0.0, 1.0])
     return cov, idx, obs
+
+
+def spherical_variogram(dist, psill, nugget, range_):
+    """`SphericalVariogram.fit`, reference variogram.py:122-138."""
+    out = 0.5 * psill * (3 * dist / range_ - np.power(dist / range_, 3)) + nugget
+    out[dist >= range_] = nugget + psill
+    return out
+
+
+def gaussian_variogram(dist, psill, nugget, range_):
+    """`GaussianVariogram.fit`, reference variogram.py:203-215."""
+    return psill * (1.0 - np.exp(-(np.power(dist, 2.0) / np.power(range_, 2.0)))) + nugget
+
+
+def exponential_variogram(dist, psill, nugget, range_):
+    """`ExponentialVariogram.fit`, reference variogram.py:283-286."""
+    return psill * (1.0 - np.exp(-(dist / range_))) + nugget

@@ -21,6 +21,8 @@ import warnings
 
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
@@ -186,7 +188,31 @@ def make_kriging_small():
     np.savez_compressed(os.path.join(HERE, "kriging_small.npz"), **out)
 
 
+from variogram_cases import VARIOGRAM_CASES  # noqa: E402  (tests/golden/variogram_cases.py)
+
+
+def variogram_points():
+    """10 x 10 degree grid of reference test/test_variogram.py (lat 0..9, lon 0..9), row-major (lat, lon)."""
+    lat, lon = np.meshgrid(np.arange(10.0), np.arange(10.0), indexing="ij")
+    return lat.ravel(), lon.ravel()
+
+
+def make_variogram_small():
+    """The four variogram models of the reference on the haversine distance matrix of a 10 x 10 grid - the
+    parameter sets of reference test/test_variogram.py:22-110 plus one general-nu Matern."""
+    from sklearn.metrics.pairwise import haversine_distances
+
+    lat, lon = variogram_points()
+    dist = haversine_distances(np.radians(np.column_stack([lat, lon]))) * 6371.0   # reference distances.py:218
+    out = {"dist": dist}
+    for k, (cls, params) in enumerate(VARIOGRAM_CASES):
+        with np.errstate(all="ignore"):
+            out[f"case{k}"] = quiet(getattr(ref.variogram, cls)(**params).fit, dist.copy())
+    np.savez_compressed(os.path.join(HERE, "variogram_small.npz"), **out)
+
+
 if __name__ == "__main__":
+    make_variogram_small()
     make_geostats()
     make_ellipse_small()
     make_ellipse_pairs()

@@ -153,3 +153,21 @@ def test_api_errors_and_attributes(Builder):
     b.uncompress_cov()
     assert b.cov_ns.shape == (Lx.size, Lx.size)            # reference test/test_ellipse.py:387-388
     assert np.isnan(b.cov_ns).sum() > 0
+
+
+def test_haversine_distance_matrix_vs_oracle(Builder):
+    """reference test/test_distances.py:33-50 (Halifax - Southampton within 1 km) and the asin-form oracle"""
+    from glomargridding_b200.distances import haversine_distance_from_frame, radial_dist
+    from oracle.ellipse import haversine_km
+
+    rng = np.random.default_rng(5)
+    lat, lon = rng.uniform(-90, 90, 300), rng.uniform(-180, 180, 300)
+    got = haversine_distance_from_frame({"lat": lat, "lon": lon})
+    la, lo = np.radians(lat), np.radians(lon)
+    want = haversine_km(la[:, None], lo[:, None], la[None, :], lo[None, :])
+    assert got.shape == (300, 300) and np.max(np.abs(got - want)) <= 1e-9 and np.allclose(np.diag(got), 0)
+    d = haversine_distance_from_frame({"lat": [44.6476, 50.9097], "lon": [-63.5728, -1.4043]})
+    assert abs(d[0, 1] - 4557) < 1 and abs(radial_dist(44.6476, -63.5728, 50.9097, -1.4043) - d[0, 1]) < 1e-6
+    assert np.allclose(haversine_distance_from_frame({"lat": lat[:5], "lon": lon[:5]}, radius=1.0) * 6371, got[:5, :5])
+    with pytest.raises(ValueError, match="only contain 'lat' and 'lon'"):
+        haversine_distance_from_frame({"lon": lon, "lat": lat})

@@ -112,3 +112,32 @@ def test_extended_inverse(n):
     assert np.allclose(got, g[f"ext_inv_{n}"])
     S_ext = np.block([[S, np.ones((n, 1))], [np.ones((1, n)), 0]])
     assert np.allclose(got, np.linalg.inv(S_ext))
+
+
+def test_variogram_oracle_vs_reference_golden():
+    """oracle/variogram.py against the four reference variogram models (tests/golden/variogram_small.npz)."""
+    import importlib.util
+    import os
+
+    from oracle import variogram as ov
+
+    spec = importlib.util.spec_from_file_location("make_golden_cases", os.path.join(os.path.dirname(__file__), "golden",
+                                                                                   "variogram_cases.py"))
+    cases = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cases)
+    g = load_golden("variogram_small.npz")
+    dist = g["dist"]
+    for k, (cls, p) in enumerate(cases.VARIOGRAM_CASES):
+        rng = p.get("range")
+        if rng is None:
+            rng = p["effective_range"] / (2 if cls in ("GaussianVariogram", "MaternVariogram") else 3 if cls == "ExponentialVariogram" else 1)
+        with np.errstate(all="ignore"):
+            if cls == "MaternVariogram":
+                got = ov.matern_variogram(dist, p["psill"], p["nugget"], rng, p["nu"], p["method"])
+            elif cls == "GaussianVariogram":
+                got = ov.gaussian_variogram(dist, p["psill"], p["nugget"], rng)
+            elif cls == "ExponentialVariogram":
+                got = ov.exponential_variogram(dist, p["psill"], p["nugget"], rng)
+            else:
+                got = ov.spherical_variogram(dist, p["psill"], p["nugget"], rng)
+        assert np.allclose(got, g[f"case{k}"], rtol=1e-13, atol=1e-15), (k, cls)
