@@ -388,18 +388,85 @@ class KrigeBatch:
         return W
 
 
+def factor_inplace_distributed(S: torch.Tensor, n: int, group=None, what: str = "matrix") -> dict:
+    """The blocked Cholesky of `factor_inplace` spread over the ranks of `group` (one process per GPU).
+
+    S is REPLICATED (every rank holds the same n x n matrix) and ends up holding the complete factor on every rank,
+    which is what the column-sharded triangular solve needs.  Ownership is 1-D block-cyclic by tile row
+    (row block r belongs to rank r % world):  per block step the owner factors + inverts the 128 x 128 diagonal
+    block and broadcasts it (256 KB); every rank forms ITS rows of the panel L21 = S21 L11^-T; one NCCL all_reduce
+    of the zero-padded panel (<= (n - 128 k) x 128 doubles) gives everyone the whole panel - each element has
+    exactly one non-zero contributor, so the sum is exact; every rank then updates its own tile rows of the
+    trailing matrix.  Same kernels, same per-tile arithmetic as the single-GPU path: the factor is bit-identical."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    assert S.is_cuda and S.dtype == torch.float64 and S.stride(1) == 1 and S.stride(0) % 2 == 0
+    lin, pdb, ldp = solve_ws(n)
+    ws = {"Linv": torch.empty(lin, dtype=torch.float64, device=S.device),
+          "P": torch.empty(pdb, dtype=torch.float64, device=S.device),
+          "info": torch.zeros(1, dtype=torch.int32, device=S.device), "ldp": ldp}
+    d = np.zeros(1, dtype=SOLVE_DESC)
+    d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"], d["n"] = (
+        S.data_ptr(), S.stride(0), ws["Linv"].data_ptr(), ws["P"].data_ptr(), ldp, ws["info"].data_ptr(), n)
+    dt = _desc_tensor(d, S.device)
+    L, s = lib(), dev.stream_ptr()
+    nblk = (n + NB - 1) // NB
+    rows = torch.arange(n, device=S.device)
+    mine = ((rows // NB) % world == rank).to(torch.float64).unsqueeze(1)      # 1.0 on the tile rows this rank owns
+    blockbuf = torch.empty((2, NB, NB), dtype=torch.float64, device=S.device)
+    Linv = ws["Linv"].view(nblk, NB, NB)
+    for k in range(nblk):
+        k0 = k * NB
+        nb = min(NB, n - k0)
+        owner = k % world
+        if rank == owner:
+            check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 0, 1, 0, s), "gmg_potrf_step_f64")
+            blockbuf.zero_()
+            blockbuf[0, :nb, :nb] = S[k0:k0 + nb, k0:k0 + nb]
+            blockbuf[1] = Linv[k]
+        dist.broadcast(blockbuf, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        if rank != owner:
+            S[k0:k0 + nb, k0:k0 + nb] = blockbuf[0, :nb, :nb]
+            Linv[k] = blockbuf[1]
+        m = n - k0 - NB
+        if m <= 0:
+            break
+        check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 1, world, rank, s), "gmg_potrf_step_f64")
+        panel = S[k0 + NB:n, k0:k0 + NB]
+        buf = panel * mine[k0 + NB:n]                     # own rows, zeros elsewhere (contiguous copy)
+        dist.all_reduce(buf, group=group)
+        panel.copy_(buf)
+        check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 2, world, rank, s), "gmg_potrf_step_f64")
+    info = ws["info"].clone()
+    dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
+    code = int(info.item())
+    if code != 0:
+        raise np.linalg.LinAlgError(
+            f"{what} is not positive definite (Cholesky pivot {code} of {n} is not positive); "
+            "apply glomar_gridding.covariance_tools.eigenvalue_clip or use delta_x_method='Met_Office'")
+    return ws
+
+
 def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.Tensor, ldc: int, y: torch.Tensor,
-                   ordinary: bool) -> torch.Tensor:
+                   ordinary: bool, group=None) -> torch.Tensor:
     """Factor + forward solve + apply for ONE system whose operands are already assembled on this device:
     S (n, n) = C_obs + E (overwritten by its Cholesky factor), T (n, >= Mc + 2) = [C_cross columns | 1 | y]
     (overwritten by L^-1 T).  `diag_base` points at the element that holds C[m0, m0] for local column 0 and
     `ldc` is the stride to the next diagonal element minus one (the matrix leading dimension), so that local
     column m reads its prior variance at diag_base[m * ldc + m].  Used by the column-sharded multi-GPU path.
+    With an initialised process group of more than one rank the factorisation is the distributed one
+    (`factor_inplace_distributed`; `group=False` forces the local, replicated factorisation).
     Returns the (5, Mc) result rows.  Raises LinAlgError if S is not positive definite (no LU fallback here)."""
     n = S.shape[0]
     assert S.stride(1) == 1 and T.stride(1) == 1 and S.stride(0) % 2 == 0 and T.stride(0) % 2 == 0
     assert T.shape[1] >= Mc + 2
-    ws = factor_inplace(S, n, "observation covariance C[idx, idx] + E")
+    import torch.distributed as dist
+
+    if group is not False and dist.is_initialized() and dist.get_world_size(group) > 1:
+        ws = factor_inplace_distributed(S, n, group, "observation covariance C[idx, idx] + E")
+    else:
+        ws = factor_inplace(S, n, "observation covariance C[idx, idx] + E")
     slabs = (n + SLAB - 1) // SLAB
     partial = torch.empty(3 * slabs * Mc, dtype=torch.float64, device=S.device)
     out = torch.empty((5, Mc), dtype=torch.float64, device=S.device)

@@ -211,7 +211,11 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
 
 // ---- panel: L21 = S21 L11^-T  (in place; a CTA owns 128 full rows of the panel) ---------------------------
 // grid = (ceil((n_max - k0 - NB) / BM), 1, batch)
-__global__ void __launch_bounds__(GEMM_THREADS) potrf_panel_kernel(const GmgSolveDesc* __restrict__ descs, int kblk) {
+// (tr_mod, tr_rem): only tile rows with (global tile row) % tr_mod == tr_rem are processed - the 1-D block-cyclic
+// ownership of the multi-GPU factorisation (tr_mod = 1: every row).
+__global__ void __launch_bounds__(GEMM_THREADS) potrf_panel_kernel(const GmgSolveDesc* __restrict__ descs, int kblk,
+                                                                   int tr_mod, int tr_rem) {
+    if ((kblk + 1 + (int)blockIdx.x) % tr_mod != tr_rem) return;
     const GmgSolveDesc d = descs[blockIdx.z];
     const int k0 = kblk * NB;
     const int m = d.n - k0 - NB;                 // rows below the diagonal block
@@ -232,8 +236,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) potrf_panel_kernel(const GmgSolv
 
 // ---- trailing update: S22 -= L21 L21^T, lower tiles only ---------------------------------------------------
 // grid = (tiles, tiles, batch) with tiles = ceil((n_max - k0 - NB) / BM); tiles above the diagonal exit.
-__global__ void __launch_bounds__(GEMM_THREADS) potrf_update_kernel(const GmgSolveDesc* __restrict__ descs, int kblk) {
+__global__ void __launch_bounds__(GEMM_THREADS) potrf_update_kernel(const GmgSolveDesc* __restrict__ descs, int kblk,
+                                                                    int tr_mod, int tr_rem) {
     if (blockIdx.x > blockIdx.y) return;         // x = column tile, y = row tile: keep the lower triangle
+    if ((kblk + 1 + (int)blockIdx.y) % tr_mod != tr_rem) return;
     const GmgSolveDesc d = descs[blockIdx.z];
     const int k0 = kblk * NB;
     const int m = d.n - k0 - NB;
@@ -444,11 +450,37 @@ int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, g
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
         if (rem <= 0) break;
         const unsigned tiles = (unsigned)gmg_ceil_div(rem, BM);
-        potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
+        potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, 1, 0);
         GMG_LAUNCH_CHECK();
-        potrf_update_kernel<<<dim3(tiles, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
+        potrf_update_kernel<<<dim3(tiles, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, 1, 0);
         GMG_LAUNCH_CHECK();
     }
+    return GMG_OK;
+}
+
+int gmg_potrf_step_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int kblk, int phase, int tr_mod, int tr_rem,
+                       gmg_stream_t stream) {
+    if (!descs) return -1;
+    if (batch <= 0 || batch > 65535) return -2;
+    if (n_max <= 0 || n_max > 0x7fffffff) return -3;
+    if (kblk < 0 || (int64_t)kblk * NB >= n_max) return -4;
+    if (phase < GMG_POTRF_DIAG || phase > GMG_POTRF_UPDATE) return -5;
+    if (tr_mod < 1 || tr_rem < 0 || tr_rem >= tr_mod) return -6;
+    int rc = ensure_attrs();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t rem = n_max - (int64_t)(kblk + 1) * NB;
+    const unsigned tiles = rem > 0 ? (unsigned)gmg_ceil_div(rem, BM) : 0;
+    if (phase == GMG_POTRF_DIAG) {
+        potrf_diag_kernel<<<dim3(1, 1, batch), DIAG_THREADS, DIAG_SMEM, s>>>(descs, kblk);
+    } else if (tiles == 0) {
+        return GMG_OK;
+    } else if (phase == GMG_POTRF_PANEL) {
+        potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem);
+    } else {
+        potrf_update_kernel<<<dim3(tiles, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem);
+    }
+    GMG_LAUNCH_CHECK();
     return GMG_OK;
 }
 

@@ -152,6 +152,17 @@ int gmg_solve_ws_doubles(int64_t n, int64_t* linv_doubles, int64_t* p_doubles, i
  * Cholesky, trailing update on DMMA tiles.  *info must be zeroed by the caller. */
 int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, gmg_stream_t stream);
 
+/* One phase of block step `kblk` of the same factorisation, for callers that interleave communication:
+ * GMG_POTRF_DIAG factors and inverts the 128 x 128 diagonal block, GMG_POTRF_PANEL forms L21 = S21 L11^-T,
+ * GMG_POTRF_UPDATE applies S22 -= L21 L21^T; PANEL / UPDATE only touch tile rows r (in units of 128 rows from the
+ * top of the matrix) with r % tr_mod == tr_rem - the 1-D block-cyclic ownership of the multi-GPU factorisation
+ * (glomargridding_b200/distributed.py: the panel is exchanged between the phases with one NCCL all_reduce). */
+#define GMG_POTRF_DIAG 0
+#define GMG_POTRF_PANEL 1
+#define GMG_POTRF_UPDATE 2
+int gmg_potrf_step_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int kblk, int phase,
+                       int tr_mod, int tr_rem, gmg_stream_t stream);
+
 /* Triangular solves with the factored systems, each block step one GEMM (diagonal blocks were inverted
  * by gmg_potrf_batched_f64):  which = GMG_SOLVE_FORWARD: R <- L^-1 R;  GMG_SOLVE_BACKWARD: R <- L^-T R;
  * GMG_SOLVE_BOTH: R <- S^-1 R. */

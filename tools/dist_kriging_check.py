@@ -67,20 +67,25 @@ t_build = time.perf_counter() - t0
 idx, obs = synth.fixed_observations(4, N, a.nobs)
 Ediag = np.random.default_rng(7).uniform(0.2, 0.4, a.nobs) ** 2
 E = np.diag(Ediag)
-times = []
-for rep in range(2):
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res = krige_sharded(b.cov_ns_device, r0, idx, obs, E, "ordinary")
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    times.append(time.perf_counter() - t0)
+times, times_repl = [], []
+for rep in range(3):
+    for flag, acc in ((True, times), (False, times_repl)):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res_ = krige_sharded(b.cov_ns_device, r0, idx, obs, E, "ordinary", distributed_cholesky=flag)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        acc.append(time.perf_counter() - t0)
+        if flag:
+            res = res_
+        else:
+            assert np.array_equal(res["field"], res_["field"]) and np.array_equal(res["uncertainty"], res_["uncertainty"])
 if rank == 0:
     print(json.dumps({"world": world, "parity_5deg_max_norm_rel": errs, "res": a.res, "N": N, "n_obs": a.nobs,
-                      "cov_build_s (incl. host prep)": t_build, "krige_sharded_s": times,
+                      "cov_build_s (incl. host prep)": t_build, "krige_sharded_s": times, "krige_sharded_replicated_cholesky_s": times_repl,
                       "field_checksum": float(np.sum(res["field"])), "unc_mean": float(res["uncertainty"].mean())}))
 if world > 1:
     dist.destroy_process_group()
