@@ -30,15 +30,24 @@ from . import _dense as dn
 from .kriging import _finish_uncertainty
 
 
-def assemble_obs_system(cov_rows: torch.Tensor, r0: int, idx: torch.Tensor, error_cov: torch.Tensor | None,
-                        group=None) -> torch.Tensor:
+def assemble_obs_system(cov_rows: torch.Tensor, r0: int, idx: torch.Tensor, error_cov, group=None) -> torch.Tensor:
     """S = C[idx, idx] + E on every rank from row-block shards of C.  `idx` must be sorted ascending (then the
-    rows each rank contributes are contiguous in S).  Works on any device / backend (gloo test on CPU)."""
+    rows each rank contributes are contiguous in S).  `error_cov` (n x n, host numpy or tensor, identical on every
+    rank, or None): each rank adds - and, for a host array, uploads - only the rows of E that belong to the
+    observations it owns, so the host-to-device traffic of E is split across the ranks instead of repeated on each.
+    Works on any device / backend (gloo test on CPU)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n = idx.numel()
     nrows = cov_rows.shape[0]
     mine = (idx >= r0) & (idx < r0 + nrows)
     piece = cov_rows[idx[mine] - r0][:, idx]                       # (n_mine, n)
+    if error_cov is not None:
+        sel = mine.cpu().numpy() if isinstance(mine, torch.Tensor) else mine
+        if isinstance(error_cov, torch.Tensor):
+            e_rows = error_cov[torch.from_numpy(np.flatnonzero(sel)).to(error_cov.device)].to(piece.device)
+        else:
+            e_rows = torch.from_numpy(np.ascontiguousarray(np.asarray(error_cov, dtype=np.float64)[sel])).to(piece.device)
+        piece = piece + e_rows
     if world == 1:
         S = piece
     else:
@@ -54,8 +63,6 @@ def assemble_obs_system(cov_rows: torch.Tensor, r0: int, idx: torch.Tensor, erro
         S = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
     if S.shape[0] != n:
         raise ValueError("the row blocks of the ranks do not cover every observation index")
-    if error_cov is not None:
-        S = S + error_cov
     return S
 
 
@@ -82,8 +89,7 @@ def krige_sharded(cov_rows: torch.Tensor, r0: int, idx, obs, error_cov=None, met
         raise ValueError("idx must be sorted ascending and unique for the sharded path")
     idx_t = torch.from_numpy(idx_np).to(device)
     y = torch.from_numpy(np.asarray(obs, dtype=np.float64)).to(device)
-    E = None if error_cov is None else torch.from_numpy(np.asarray(error_cov, dtype=np.float64)).to(device)
-    S = dn.padded(assemble_obs_system(cov_rows, r0, idx_t, E, group))
+    S = dn.padded(assemble_obs_system(cov_rows, r0, idx_t, error_cov, group))
     T = local_rhs(cov_rows, idx_t, y)
     nrows, N = cov_rows.shape
     # local column j has its prior variance at cov_rows[j, r0 + j]

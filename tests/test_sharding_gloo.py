@@ -92,7 +92,7 @@ def _assemble_worker(rank, world, port, q):
     E = torch.from_numpy(np.diag(rng.uniform(0.1, 0.2, n)))
     bounds = [0, 20, N]                      # uneven row blocks
     r0, r1 = bounds[rank], bounds[rank + 1]
-    S = assemble_obs_system(C[r0:r1].contiguous(), r0, idx, E)
+    S = assemble_obs_system(C[r0:r1].contiguous(), r0, idx, E.numpy() if rank == 0 else E)
     T = local_rhs(C[r0:r1].contiguous(), idx, torch.arange(n, dtype=torch.float64))
     ok = bool(torch.equal(S, C[idx][:, idx] + E)) and bool(torch.equal(T[:, : r1 - r0], C[idx][:, r0:r1])) \
         and bool((T[:, r1 - r0] == 1).all()) and bool(torch.equal(T[:, r1 - r0 + 1], torch.arange(n, dtype=torch.float64)))
