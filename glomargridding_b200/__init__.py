@@ -13,7 +13,7 @@ import sys
 __version__ = "0.1.0"
 
 _SUBMODULES = ["ellipse", "ellipse.covariance", "kriging", "stochastic", "utils", "constants", "types",
-               "distances", "variogram", "batched", "distributed"]
+               "distances", "variogram", "covariance_tools", "batched", "distributed"]
 
 
 def install_as_glomar_gridding(name: str = "glomar_gridding") -> None:

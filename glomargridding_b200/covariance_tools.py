@@ -1,0 +1,169 @@
+"""`eigenvalue_clip` on the GPU: drop-in for `glomar_gridding.covariance_tools.eigenvalue_clip` /
+`explained_variance_clip` - the step that sits between the covariance build and kriging
+in the reference's workflow (notebook cell 20) and makes an indefinite ellipse covariance positive definite.
+
+Reference (`covariance_tools.py:633-785`): full `numpy.linalg.eigh`, keep the k largest eigenvalues whose sum
+first exceeds `target_variance_fraction * trace`, replace ALL others by their mean (so the trace is preserved),
+rebuild `V diag(lambda') V^T`.  Since the replaced eigenvalues all become one constant c,
+
+    out = c I + V_k (Lambda_k - c I) V_k^T ,      c = (trace - sum(Lambda_k)) / (n - k)
+
+needs only the k kept eigenpairs.  They are computed here by orthogonal (subspace) iteration with Rayleigh-Ritz:
+every step is a DMMA GEMM against C, a Cholesky-QR (Gram matrix, `gmg_potrf`, forward substitution) keeps the block
+orthonormal, and only the small m x m projected matrix is diagonalised (`gmg_jacobi_eigh_f64`).  No CPU fallback.
+
+Differences from the reference: `method="Laloux_2000"` is not implemented; the progress `print`s are dropped; the
+final "is it positive definite" check (`:779-784`, a second full eigendecomposition) is replaced by the sign of c
+and of the kept eigenvalues, which decide it.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Literal
+from warnings import warn
+
+import numpy as np
+import torch
+
+from . import _dense as dn
+from . import _device as dev
+from ._lib import check, lib
+
+
+def _jacobi_eigh(T: torch.Tensor, max_sweeps: int = 30, tol: float = 1e-15):
+    """Eigen-decomposition of a small symmetric device matrix: (eigenvalues descending, eigenvectors as columns)."""
+    m0 = T.shape[0]
+    m = m0 + (m0 & 1)
+    A = torch.zeros((m, m), dtype=torch.float64, device=T.device)
+    A[:m0, :m0] = T
+    U = torch.empty((m, m), dtype=torch.float64, device=T.device)
+    nbytes = ctypes.c_size_t()
+    check(lib().gmg_jacobi_eigh_ws_bytes(m, ctypes.byref(nbytes)), "gmg_jacobi_eigh_ws_bytes")
+    ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=T.device)
+    done = torch.zeros(1, dtype=torch.int32, device=T.device)
+    check(lib().gmg_jacobi_eigh_f64(A.data_ptr(), m, U.data_ptr(), m, m, max_sweeps, tol, ws.data_ptr(), nbytes.value,
+                                    done.data_ptr(), dev.stream_ptr()), "gmg_jacobi_eigh_f64")
+    w = torch.diagonal(A)[:m0].clone()
+    if m != m0:                                   # drop the padding eigenpair (exactly decoupled: zero row / column)
+        keep = torch.arange(m, device=T.device) != int(torch.argmax(U[m0].abs()))
+        w, U = torch.diagonal(A)[keep].clone(), U[:m0][:, keep]
+    order = torch.argsort(w, descending=True)     # plumbing: sort of m numbers
+    return w[order], U[:, order].contiguous()
+
+
+def top_eigenpairs(C: torch.Tensor, m: int, iters: int = 60, tol: float = 1e-13, seed: int = 0):
+    """The m algebraically largest eigenpairs of the symmetric device matrix C by orthogonal iteration.
+    Returns (theta (m,) descending, Vt (m, n) with the eigenvectors as ROWS, residual estimate per pair)."""
+    n = C.shape[0]
+    m = min(m, n)
+    ldn = n + (n & 1)
+    Cp = C if C.stride(0) % 2 == 0 else dn.padded(C)
+    g = torch.Generator(device=C.device)
+    g.manual_seed(seed)
+    Qt = torch.zeros((m, ldn), dtype=torch.float64, device=C.device)
+    Qt[:, :n] = torch.randn((m, n), dtype=torch.float64, device=C.device, generator=g)
+
+    def orthonormalise(Yt):
+        # Cholesky-QR twice: G = Y Y^T = L L^T, Q = L^-1 Y (forward substitution on DMMA tiles)
+        for _ in range(2):
+            G = dn.padded(dn.gemm(Yt[:, :n], Yt[:, :n], transb=True))
+            ws = dn.factor_inplace(G, m, "Gram matrix of the subspace iteration")
+            d = np.zeros(1, dtype=dn.SOLVE_DESC)
+            d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"] = (
+                G.data_ptr(), G.stride(0), ws["Linv"].data_ptr(), ws["P"].data_ptr(), ws["ldp"], ws["info"].data_ptr())
+            d["R"], d["ldr"], d["n"], d["nrhs"] = Yt.data_ptr(), Yt.stride(0), m, n
+            dt = dn._desc_tensor(d, C.device)
+            check(lib().gmg_potrs_batched_f64(dt.data_ptr(), 1, m, n, 1, dev.stream_ptr()), "gmg_potrs_batched_f64")
+            torch.cuda.current_stream().synchronize()
+        return Yt
+
+    Qt = orthonormalise(Qt)
+    theta_prev = None
+    for it in range(iters):
+        Yt = torch.zeros_like(Qt)
+        dn.gemm(Qt[:, :n], Cp[:, :n], out=Yt[:, :n])              # Y^T = Q^T C   (C symmetric)
+        if it % 4 == 3 or it == iters - 1:
+            T = dn.gemm(Yt[:, :n], Qt[:, :n], transb=True)        # Rayleigh-Ritz matrix Q^T C Q
+            T = 0.5 * (T + T.t())
+            theta, U = _jacobi_eigh(T)
+            Vt = torch.zeros_like(Qt)
+            dn.gemm(dn.padded(U), Qt[:, :n], transa=True, out=Vt[:, :n])   # Ritz vectors (rows) = U^T Q^T
+            if theta_prev is not None:
+                half = max(1, m // 2)
+                change = float(((theta[:half] - theta_prev[:half]).abs() / theta[:half].abs().clamp_min(1e-300)).max())
+                if change <= tol:
+                    Qt = Vt
+                    break
+            theta_prev = theta
+            Qt = Vt
+            Yt = torch.zeros_like(Qt)
+            dn.gemm(Qt[:, :n], Cp[:, :n], out=Yt[:, :n])
+        Qt = orthonormalise(Yt)
+    # final Rayleigh-Ritz on the converged basis + residuals ||C v - theta v||
+    Yt = torch.zeros_like(Qt)
+    dn.gemm(Qt[:, :n], Cp[:, :n], out=Yt[:, :n])
+    T = dn.gemm(Yt[:, :n], Qt[:, :n], transb=True)
+    theta, U = _jacobi_eigh(0.5 * (T + T.t()))
+    Vt = torch.zeros_like(Qt)
+    dn.gemm(dn.padded(U), Qt[:, :n], transa=True, out=Vt[:, :n])
+    CV = torch.zeros_like(Qt)
+    dn.gemm(Vt[:, :n], Cp[:, :n], out=CV[:, :n])
+    resid = (CV[:, :n] - theta[:, None] * Vt[:, :n]).norm(dim=1)
+    return theta, Vt, resid
+
+
+def explained_variance_clip(cov, target_variance_fraction: float = 0.95, return_device: bool = False):
+    """Clip all eigenvalues beyond `target_variance_fraction` of explained variance to their mean
+    (reference `covariance_tools.py:633-728`, `_eigenvalue_clip` `:731-785`)."""
+    if not 0.0 < target_variance_fraction <= 1.0:
+        raise ValueError("'target_variance_fraction' must be (0, 1.0]")
+    on_device = isinstance(cov, torch.Tensor)
+    C = cov.to(dev.require_cuda(), torch.float64) if on_device else dev.to_device(np.asarray(cov), torch.float64)
+    n = C.shape[0]
+    total = float(torch.diagonal(C).sum().item())            # trace = sum of all eigenvalues
+    target = target_variance_fraction * total
+    m = min(n, 256)
+    while True:
+        theta, Vt, resid = top_eigenpairs(C, m)
+        csum = torch.cumsum(theta, 0)
+        # only the better-converged leading half of the block is trusted for the cut (the rest is oversampling)
+        trusted = m if m == n else max(1, (2 * m) // 3)
+        over = torch.nonzero(csum[:trusted] > target)
+        if over.numel():
+            k = int(over[0].item()) + 1
+            break
+        if m == n:
+            raise ValueError("Target Explained Variance not exceeded")
+        m = min(n, 2 * m)
+    kept = float(csum[k - 1].item())
+    if total < kept:
+        raise ValueError("Variance explained by retained eigenvalues exceeds total variance. Resulting matrix will "
+                         "have negative eigenvalues. Try using a lower threshold.")
+    c = (total - kept) / (n - k) if n > k else 0.0
+    scale = float(theta[0].abs().item())
+    if float(resid[:k].max().item()) > 1e-9 * scale:
+        warn(f"eigenvalue_clip: kept eigenpairs converged to {float(resid[:k].max().item()) / scale:.1e} (relative "
+             "residual) only")
+    ld = Vt.stride(0)
+    W = torch.zeros((k, ld), dtype=torch.float64, device=C.device)
+    W[:, :n] = Vt[:k, :n] * (theta[:k, None] - c)             # (Lambda_k - c) V_k^T
+    out = torch.zeros((n, ld), dtype=torch.float64, device=C.device)
+    dn.gemm(Vt[:k, :n], W[:, :n], transa=True, out=out[:, :n])   # V_k (Lambda_k - c) V_k^T
+    res = out[:, :n]
+    res.diagonal().add_(c)
+    if not (c > 0 and float(theta[k - 1].item()) > 0):
+        warn("Resulting matrix is not positive-definite, and may not be a valid covariance matrix.")
+    res = 0.5 * (res + res.t())
+    return res.contiguous() if (on_device or return_device) else dev.to_host(res.contiguous())
+
+
+def eigenvalue_clip(cov, method: Literal["explained_variance", "Laloux_2000"] = "explained_variance", **kwargs):
+    """Denoise / repair a covariance matrix by eigenvalue clipping (reference `covariance_tools.py:788-847`)."""
+    match method:
+        case "explained_variance":
+            return explained_variance_clip(cov, **kwargs)
+        case "Laloux_2000":
+            raise NotImplementedError("method='Laloux_2000' is not available on the device path")
+        case _:
+            raise ValueError(f"Unknown clipping method: {method}")

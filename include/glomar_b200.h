@@ -257,6 +257,18 @@ int gmg_variogram_f64(int model, const double* dist, int64_t rows, int64_t cols,
                       int fill_diag, int to_covariance, double variance, double* out, int64_t ldo,
                       gmg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Small symmetric eigensolver (cyclic two-sided Jacobi, cooperative launch) for the device
+ * `eigenvalue_clip`: the reference takes a full numpy.linalg.eigh of the covariance
+ * (glomar_gridding/covariance_tools.py:616, :717); here only the m x m Rayleigh-Ritz matrix of a
+ * subspace iteration is diagonalised.  A (m x m symmetric, m even) is overwritten - its diagonal
+ * holds the eigenvalues (unsorted); U (m x m) receives the eigenvectors as columns.
+ * ------------------------------------------------------------------------------------------- */
+int gmg_jacobi_eigh_ws_bytes(int64_t m, size_t* bytes);
+int gmg_jacobi_eigh_f64(double* A, int64_t lda, double* U, int64_t ldu, int64_t m, int max_sweeps,
+                        double tol, void* ws, size_t ws_bytes, int* sweeps_done /* device */,
+                        gmg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

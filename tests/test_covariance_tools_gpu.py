@@ -1,0 +1,101 @@
+"""Device eigenvalue clipping (glomargridding_b200.covariance_tools) against the reference algorithm restated
+with numpy.linalg.eigh, and the properties the reference's own tests assert (test/test_covariance_tools.py:14-83:
+trace preserved, top eigenvalues unchanged, all eigenvalues positive afterwards)."""
+
+import warnings
+
+import numpy as np
+import pytest
+
+from glomargridding_b200 import synthetic as synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def CT():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import glomargridding_b200.covariance_tools as ct
+
+    return ct
+
+
+def reference_clip(cov, frac=0.95):
+    """`explained_variance_clip` + `_eigenvalue_clip` of the reference, restated (covariance_tools.py:633-785)."""
+    w, v = np.linalg.eigh(cov)
+    total, target = w.sum(), frac * w.sum()
+    csum = np.cumsum(w[::-1])
+    k = int(np.argmax(csum > target)) + 1
+    new = w.copy()
+    new[: len(w) - k] = (total - w[len(w) - k:].sum()) / (len(w) - k)
+    return (v * new) @ v.T, k, w
+
+
+@pytest.mark.parametrize("n", [7, 64, 301])
+def test_jacobi_eigh_vs_numpy(CT, n):
+    import torch
+
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    A = A + A.T
+    w, U = CT._jacobi_eigh(torch.from_numpy(A).cuda())
+    w, U = w.cpu().numpy(), U.cpu().numpy()
+    assert np.allclose(np.sort(w), np.linalg.eigvalsh(A), rtol=0, atol=1e-12 * np.abs(A).max() * n)
+    assert np.allclose(U.T @ U, np.eye(n), atol=1e-12)
+    assert np.allclose(U @ np.diag(w) @ U.T, A, atol=1e-11 * np.abs(A).max() * n)
+    assert np.all(np.diff(w) <= 0)
+
+
+@pytest.mark.parametrize("res,meth", [(10.0, "Modified_Met_Office"), (5.0, "Modified_Met_Office")])
+def test_eigenvalue_clip_vs_reference_algorithm(CT, res, meth):
+    from oracle import EllipseOracle
+
+    lats, lons = synth.global_grid(res)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5, meth).build()          # indefinite
+    assert np.linalg.eigvalsh(cov).min() < 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        got = CT.eigenvalue_clip(cov)
+    want, k, w = reference_clip(cov)
+    assert got.shape == cov.shape and got.dtype == np.float64
+    assert np.max(np.abs(got - want)) <= 1e-8 * np.max(np.abs(want))
+    ev = np.linalg.eigvalsh(got)
+    assert (ev > 0).all()                                                        # test_covariance_tools.py:80-83
+    assert abs(np.trace(got) - np.trace(cov)) <= 1e-9 * np.trace(cov)            # trace preserved
+    assert np.allclose(ev[-k:], w[-k:], rtol=1e-9)                               # kept eigenvalues unchanged
+    assert np.array_equal(got, got.T)
+
+
+def test_clip_then_krige_default_workflow(CT):
+    """Notebook cells 19-40 on the device: indefinite default covariance -> eigenvalue_clip -> ordinary kriging on
+    the Cholesky path (no LU fallback), against the oracle run on the reference-clipped matrix."""
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+    from glomargridding_b200.kriging import OrdinaryKriging
+    from oracle import ordinary_kriging
+
+    lats, lons = synth.global_grid(10.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    b = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, precision=np.float64)
+    clipped = CT.eigenvalue_clip(b.cov_ns_device)                 # device in -> device out
+    idx, obs = synth.fixed_observations(2, clipped.shape[0], 150)
+    E = synth.hadcrut_style_error_cov(idx, lons.size)
+    ok = OrdinaryKriging(clipped, idx, obs, E.copy())
+    z, u = ok.solve(), ok.get_uncertainty()
+    assert ok._batch.lu_fallback == []
+    want, _, _ = reference_clip(b.cov_ns)
+    ref = ordinary_kriging(want, idx, obs, E)
+    assert np.max(np.abs(z - ref["field"])) <= 1e-7 * np.max(np.abs(ref["field"]))
+    assert np.max(np.abs(u ** 2 - ref["uncertainty"] ** 2)) <= 1e-7 * np.max(ref["uncertainty"] ** 2)
+
+
+def test_clip_errors(CT):
+    with pytest.raises(ValueError, match="target_variance_fraction"):
+        CT.explained_variance_clip(np.eye(4), 1.5)
+    with pytest.raises(ValueError, match="Unknown clipping method"):
+        CT.eigenvalue_clip(np.eye(4), method="nope")
+    with pytest.raises(NotImplementedError):
+        CT.eigenvalue_clip(np.eye(4), method="Laloux_2000")
