@@ -31,6 +31,9 @@ from . import _device as dev
 from ._lib import check, lib
 
 
+FULL_JACOBI_MAX = 4096      # up to this order C is diagonalised directly; beyond it, subspace iteration
+
+
 def _jacobi_eigh(T: torch.Tensor, max_sweeps: int = 30, tol: float = 1e-15):
     """Eigen-decomposition of a small symmetric device matrix: (eigenvalues descending, eigenvectors as columns)."""
     m0 = T.shape[0]
@@ -83,7 +86,7 @@ def top_eigenpairs(C: torch.Tensor, m: int, iters: int = 60, tol: float = 1e-13,
     for it in range(iters):
         Yt = torch.zeros_like(Qt)
         dn.gemm(Qt[:, :n], Cp[:, :n], out=Yt[:, :n])              # Y^T = Q^T C   (C symmetric)
-        if it % 4 == 3 or it == iters - 1:
+        if it % 8 == 7 or it == iters - 1:
             T = dn.gemm(Yt[:, :n], Qt[:, :n], transb=True)        # Rayleigh-Ritz matrix Q^T C Q
             T = 0.5 * (T + T.t())
             theta, U = _jacobi_eigh(T)
@@ -123,19 +126,31 @@ def explained_variance_clip(cov, target_variance_fraction: float = 0.95, return_
     n = C.shape[0]
     total = float(torch.diagonal(C).sum().item())            # trace = sum of all eigenvalues
     target = target_variance_fraction * total
-    m = min(n, 256)
-    while True:
-        theta, Vt, resid = top_eigenpairs(C, m)
+    if n <= FULL_JACOBI_MAX:
+        # small enough for a full Jacobi diagonalisation of C itself (one cooperative kernel): cheaper than growing
+        # the subspace when many eigenvalues have to be kept (the synthetic 5-degree fields keep 780 of 2592)
+        theta, U = _jacobi_eigh(C)
+        Vt = dn.padded(U.t().contiguous())
+        resid = torch.zeros_like(theta)
         csum = torch.cumsum(theta, 0)
-        # only the better-converged leading half of the block is trusted for the cut (the rest is oversampling)
-        trusted = m if m == n else max(1, (2 * m) // 3)
-        over = torch.nonzero(csum[:trusted] > target)
-        if over.numel():
-            k = int(over[0].item()) + 1
-            break
-        if m == n:
+        over = torch.nonzero(csum > target)
+        if not over.numel():
             raise ValueError("Target Explained Variance not exceeded")
-        m = min(n, 2 * m)
+        k = int(over[0].item()) + 1
+    else:
+        m = min(n, 512)
+        while True:
+            theta, Vt, resid = top_eigenpairs(C, m)
+            csum = torch.cumsum(theta, 0)
+            # only the better-converged leading part of the block is trusted for the cut (the rest is oversampling)
+            trusted = m if m == n else max(1, (2 * m) // 3)
+            over = torch.nonzero(csum[:trusted] > target)
+            if over.numel():
+                k = int(over[0].item()) + 1
+                break
+            if m == n:
+                raise ValueError("Target Explained Variance not exceeded")
+            m = min(n, 2 * m)
     kept = float(csum[k - 1].item())
     if total < kept:
         raise ValueError("Variance explained by retained eigenvalues exceeds total variance. Resulting matrix will "

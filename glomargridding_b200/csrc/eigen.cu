@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) jacobi_eigh_kernel(double* __restrict__ A
                                                           double* __restrict__ stat /* [0] off, [1] diag */,
                                                           int* __restrict__ sweeps_done) {
     cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double rows[];     // 4 x m doubles
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     const int half = m / 2;
@@ -69,27 +70,43 @@ __global__ void __launch_bounds__(256) jacobi_eigh_kernel(double* __restrict__ A
                           (unsigned long long)__double_as_longlong(fmax(fabs(app), fabs(aqq))));
             }
             grid.sync();
-            // phase 1: A <- J^T A (rows p, q of every pair; column index fastest: coalesced)
-            for (int64_t e = tid; e < (int64_t)half * m; e += nthr) {
-                const int k = (int)(e / m), j = (int)(e % m);
-                const double c = cs[2 * k], s = cs[2 * k + 1];
+            // phase 1 (fused): every CTA takes pairs k = blockIdx.x, += gridDim.x.  Rows p, q of A and rows 2k, 2k+1 of
+            // U are staged in shared memory (coalesced), rows p, q get the row rotation of their own pair, then ALL
+            // column rotations of the round are applied inside shared memory (the scattered column pairs cost nothing
+            // there), and the four rows are written back coalesced:  A' = J^T A J and U' = U J with one read and one
+            // write of A and U per round.  (The first version rotated columns in global memory: 17 s for n = 2592.)
+            for (int k = blockIdx.x; k < half; k += gridDim.x) {
                 const int p = pq[2 * k], q = pq[2 * k + 1];
-                const double ap = A[p * lda + j], aq = A[q * lda + j];
-                A[p * lda + j] = c * ap - s * aq;
-                A[q * lda + j] = s * ap + c * aq;
-            }
-            grid.sync();
-            // phase 2: A <- A J, U <- U J (columns p, q; pair index fastest: one row of A / U per group of threads)
-            for (int64_t e = tid; e < (int64_t)half * m; e += nthr) {
-                const int i = (int)(e / half), k = (int)(e % half);
-                const double c = cs[2 * k], s = cs[2 * k + 1];
-                const int p = pq[2 * k], q = pq[2 * k + 1];
-                const double ap = A[i * lda + p], aq = A[i * lda + q];
-                A[i * lda + p] = c * ap - s * aq;
-                A[i * lda + q] = s * ap + c * aq;
-                const double up = U[i * ldu + p], uq = U[i * ldu + q];
-                U[i * ldu + p] = c * up - s * uq;
-                U[i * ldu + q] = s * up + c * uq;
+                double* rp = rows;
+                double* rq = rows + m;
+                double* u0 = rows + 2 * m;
+                double* u1 = rows + 3 * m;
+                for (int j = threadIdx.x; j < m; j += blockDim.x) {
+                    const double ap = A[p * lda + j], aq = A[q * lda + j];
+                    const double c = cs[2 * k], s = cs[2 * k + 1];
+                    rp[j] = c * ap - s * aq;                       // row rotation of this pair
+                    rq[j] = s * ap + c * aq;
+                    u0[j] = U[(int64_t)(2 * k) * ldu + j];
+                    u1[j] = U[(int64_t)(2 * k + 1) * ldu + j];
+                }
+                __syncthreads();
+                for (int k2 = threadIdx.x; k2 < half; k2 += blockDim.x) {
+                    const double c = cs[2 * k2], s = cs[2 * k2 + 1];
+                    const int p2 = pq[2 * k2], q2 = pq[2 * k2 + 1];
+                    double x, y;
+                    x = rp[p2]; y = rp[q2]; rp[p2] = c * x - s * y; rp[q2] = s * x + c * y;
+                    x = rq[p2]; y = rq[q2]; rq[p2] = c * x - s * y; rq[q2] = s * x + c * y;
+                    x = u0[p2]; y = u0[q2]; u0[p2] = c * x - s * y; u0[q2] = s * x + c * y;
+                    x = u1[p2]; y = u1[q2]; u1[p2] = c * x - s * y; u1[q2] = s * x + c * y;
+                }
+                __syncthreads();
+                for (int j = threadIdx.x; j < m; j += blockDim.x) {
+                    A[p * lda + j] = rp[j];
+                    A[q * lda + j] = rq[j];
+                    U[(int64_t)(2 * k) * ldu + j] = u0[j];
+                    U[(int64_t)(2 * k + 1) * ldu + j] = u1[j];
+                }
+                __syncthreads();
             }
             grid.sync();
         }
@@ -117,7 +134,7 @@ int gmg_jacobi_eigh_f64(double* A, int64_t lda, double* U, int64_t ldu, int64_t 
     if (lda < m) return -2;
     if (!U) return -3;
     if (ldu < m) return -4;
-    if (m < 2 || m > 8192 || (m & 1)) return -5;      // even order (the caller pads with an isolated row/column)
+    if (m < 2 || m > 6400 || (m & 1)) return -5;      // even order (the caller pads); 4 rows must fit shared memory
     if (max_sweeps < 1) return -6;
     if (!ws) return -8;
     size_t need;
@@ -134,14 +151,16 @@ int gmg_jacobi_eigh_f64(double* A, int64_t lda, double* U, int64_t ldu, int64_t 
     GMG_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) return GMG_ERR_UNSUPPORTED;
     GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_eigh_kernel, 256, 0));
-    int64_t want = gmg_ceil_div(m * (m / 2), 256 * 8);            // ~8 elements per thread per phase
-    int grid = (int)(want < 1 ? 1 : want);
+    const size_t smem = (size_t)4 * m * sizeof(double);
+    if (smem > 200 * 1024) return GMG_ERR_UNSUPPORTED;
+    GMG_CUDA_CHECK(cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_eigh_kernel, 256, smem));
+    if (per_sm < 1) return GMG_ERR_UNSUPPORTED;
+    int grid = (int)(m / 2);                                       // one pair per CTA and round, if they all fit
     if (grid > sms * per_sm) grid = sms * per_sm;
-    if (grid > 128) grid = 128;                                    // barrier cost grows with the grid
     int mi = (int)m;
     void* args[] = {&A, &lda, &U, &ldu, &mi, &max_sweeps, &tol, &cs, &pq, &stat, &sweeps_done};
-    GMG_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_eigh_kernel, dim3(grid), dim3(256), args, 0,
+    GMG_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_eigh_kernel, dim3(grid), dim3(256), args, smem,
                                                (cudaStream_t)stream));
     return GMG_OK;
 }

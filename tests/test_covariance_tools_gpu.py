@@ -99,3 +99,16 @@ def test_clip_errors(CT):
         CT.eigenvalue_clip(np.eye(4), method="nope")
     with pytest.raises(NotImplementedError):
         CT.eigenvalue_clip(np.eye(4), method="Laloux_2000")
+
+
+def test_subspace_iteration_path_matches_full_jacobi(CT, monkeypatch):
+    """Force the large-matrix route (orthogonal iteration + Rayleigh-Ritz) on a matrix the direct route can check."""
+    from oracle import EllipseOracle
+
+    lats, lons = synth.global_grid(10.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5).build()
+    want, k, _ = reference_clip(cov, 0.9)
+    monkeypatch.setattr(CT, "FULL_JACOBI_MAX", 0)
+    got = CT.explained_variance_clip(cov, 0.9)
+    assert np.max(np.abs(got - want)) <= 1e-8 * np.max(np.abs(want))
