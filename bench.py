@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ellipse-cov entries/s @1deg grid; kriged months/s"
 UNIT = "entries/s"
-TILE = 64
+TILE = 128                  # row blocks start on a macro-tile (2 x 2 tiles of 64) boundary
 DMMA_PEAK_TFLOPS = 37.1     # mma.sync m8n8k4 f64, measured on this pool's B200 (profiles/r01_microbench_fp64.json)
 DFMA_PEAK_TFLOPS = 34.2     # plain DFMA, same file
 
@@ -76,7 +76,7 @@ def month_problems(months, n_cells, nlon):
 
 
 def row_block(N, rank, world):
-    """Contiguous row block of rank `rank`, aligned to the 64-row tile so mirrored tiles stay inside it."""
+    """Contiguous row block of rank `rank`, aligned to the 128-row macro tile so mirrored tiles stay inside it."""
     tiles = (N + TILE - 1) // TILE
     t0 = tiles * rank // world
     t1 = tiles * (rank + 1) // world

@@ -41,8 +41,9 @@ constexpr double kPi = 3.141592653589793;           // np.pi
 constexpr double kTwoPi = 6.283185307179586;        // 2 * np.pi, reference ellipse/covariance.py:37
 
 constexpr int kTile = 64;
+constexpr int kMaxMT = 2;                           // largest macro tile: 2 x 2 tiles
+constexpr int kPadTail = kMaxMT * kTile;            // padding records after the (128-padded) points
 constexpr int kThreads = 256;
-constexpr int kTileLd = kTile + 1;                  // odd leading dimension: conflict-free transposed reads
 
 // Matern table geometry
 constexpr int kTabEmin = -12;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) ellipse_prepare_kernel(
     const double* __restrict__ stdev, const double* __restrict__ lat, const double* __restrict__ lon,
     int64_t N, int64_t npad, int disp_method, double* __restrict__ aos, double* __restrict__ soa) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= npad + kTile) return;
+    if (i >= npad + kPadTail) return;
     double rec[P_N];
     if (i < N) {
         // reference `_sigma_rot_func_multi`, ellipse/covariance.py:512-533
@@ -405,28 +406,34 @@ __device__ __forceinline__ bool beyond_max_dist(const double* pa, const double* 
 constexpr int kMaxPeers = 8;
 constexpr int kMaxSeg = 5;
 
-// dynamic shared-memory layout of the tile kernel, in doubles from the start of the extern array
-constexpr int kSmRow = 0;                                  // [2][kTile][P_N]  records (LDS.128 broadcast)
-constexpr int kSmCol = kSmRow + 2 * P_N * kTile;           // [2][P_N][kTile]  field-major (conflict-free LDS.128)
-constexpr int kSmExp = kSmCol + 2 * P_N * kTile;           // [kExpTab][kExpRep]
-constexpr int kSmCtx = kSmExp + kExpTab * kExpRep;         // MaternCtx for the cold path (16 doubles reserved)
-constexpr int kSmTileT = kSmCtx + 16;                      // [kTile][kTileLd]
-constexpr int kSmTab = kSmTileT + kTile * kTileLd;         // [kTabNint][kTabCoef] (MODE_TABLE only)
+// dynamic shared-memory layout of the tile kernel, in doubles from the start of the extern array.  MT = number of
+// 64-point tiles along each edge of the MACRO tile a CTA stages at once (1 or 2, see the kernel).
+constexpr int kWLd = kTile + 2;                            // leading dimension of a warp's 8 x 64 mirror strip
+template <int MT>
+struct SmLayout {
+    static constexpr int kMR = MT * kTile;                 // points along a macro-tile edge
+    static constexpr int kRow = 0;                         // [2][kMR][P_N]  records (LDS.128 broadcast)
+    static constexpr int kCol = kRow + 2 * P_N * kMR;      // [2][P_N][kMR]  field-major (conflict-free LDS.128)
+    static constexpr int kExp = kCol + 2 * P_N * kMR;      // [kExpTab][kExpRep]
+    static constexpr int kCtx = kExp + kExpTab * kExpRep;  // MaternCtx for the cold path (16 doubles reserved)
+    static constexpr int kW = kCtx + 16;                   // [8 warps][8 rows][kWLd]  warp-private mirror strips
+    static constexpr int kTab = kW + 8 * 8 * kWLd;         // [kTabCoef][kTabNint] (MODE_TABLE only)
+};
 static_assert(sizeof(MaternCtx) <= 16 * sizeof(double), "MaternCtx must fit its shared-memory slot");
 
 // Cold paths of the tile kernel.  They take OFFSETS into the dynamic shared memory, not pointers: a generic
 // pointer to shared memory costs an S2UR SR_CgaCtaId + address arithmetic where it is formed, which the compiler
 // otherwise re-materialises inside the hot loop (ncu r01: 5.6 % of the stall samples).
 template <int MODE, bool GEOM_F32>
-__device__ __noinline__ double tile_pair_slow(int row_off, int col_off) {
+__device__ __noinline__ double tile_pair_slow(int row_off, int col_off, int col_stride, int ctx_off) {
     extern __shared__ __align__(16) double smem[];
-    const MaternCtx* m = reinterpret_cast<const MaternCtx*>(smem + kSmCtx);
-    return cov_pair_slow<MODE, GEOM_F32>(smem + row_off, smem + col_off, kTile, m);
+    const MaternCtx* m = reinterpret_cast<const MaternCtx*>(smem + ctx_off);
+    return cov_pair_slow<MODE, GEOM_F32>(smem + row_off, smem + col_off, col_stride, m);
 }
 
-__device__ __noinline__ bool tile_beyond_max_dist(int row_off, int col_off, double max_dist) {
+__device__ __noinline__ bool tile_beyond_max_dist(int row_off, int col_off, int col_stride, double max_dist) {
     extern __shared__ __align__(16) double smem[];
-    return beyond_max_dist(smem + row_off, smem + col_off, kTile, max_dist);
+    return beyond_max_dist(smem + row_off, smem + col_off, col_stride, max_dist);
 }
 
 struct EllipseArgs {
@@ -437,6 +444,8 @@ struct EllipseArgs {
     int64_t N, npad, row0, nrows, ld;
     int tiles_r, tiles_c, tile_b0, symmetric;
     int64_t n_tri, n_tiles;
+    // macro-tile enumeration of the MT = 2 kernel (128 x 128 blocks of 2 x 2 tiles)
+    int mt_r, mt_c, mt_b0, m_tri;
     double max_dist;
     int vec2;
     GmgBesselConsts bc;
@@ -548,50 +557,111 @@ __device__ __forceinline__ TileId decode_tile(const EllipseArgs& a, int64_t id) 
 #ifndef K1_UNROLL
 #define K1_UNROLL 1
 #endif
-#ifndef K1_NCOL
-#define K1_NCOL 2       // columns per thread: 2 (8 rows per warp) or 1 (two warps side by side, 16 rows per warp)
-#endif
-constexpr int kNC = K1_NCOL;
-constexpr int kRowsPerWarp = (kNC == 2) ? kTile / 8 : kTile / 4;
+constexpr int kRowsPerWarp = kTile / 8;
 
-// Persistent kernel: K1_MINB CTAs per SM, each looping over tiles id = blockIdx.x, += gridDim.x.  The exp and
-// Matern tables are staged once per CTA; the 2 x 4 KB of per-point records of the NEXT tile are fetched with
-// cp.async into the other half of a double buffer while the current tile is computed.
-template <int MODE, bool MAXDIST, typename OutT>
+// What a CTA works on between two barriers: a macro tile of MT x MT 64-point tiles.
+struct MacroId {
+    int ta, tb;        // macro row (relative to the row block) and macro column (global), in units of MT tiles
+    bool mirror;       // the tiles are also written transposed (inside the square block / into a peer's block)
+    bool tri_diag;     // macro tile on the diagonal of the symmetric block: sub-tiles below the diagonal are skipped
+    bool skip;
+    int peer;
+};
+
+template <int MT>
+__device__ __forceinline__ MacroId decode_macro(const EllipseArgs& a, int id) {
+    MacroId t;
+    t.mirror = false;
+    t.tri_diag = false;
+    t.skip = false;
+    t.peer = a.rank;
+    if (MT == 1) {
+        const TileId s = decode_tile(a, id);
+        t.ta = s.ta; t.tb = s.tb; t.mirror = s.mirror; t.skip = s.skip; t.peer = s.peer;
+        return t;
+    }
+    // 32-bit arithmetic throughout (the host rejects launches with 2^31 or more tiles)
+    if (a.symmetric) {
+        if (id < a.m_tri) {
+            // upper triangle of the mt_r x mt_r macro block on the diagonal; rows r and T-1-r share a strip of T+1
+            const unsigned T = (unsigned)a.mt_r, w = T + 1;
+            const unsigned pr = (unsigned)id / w, k = (unsigned)id - pr * w;
+            unsigned r, off;
+            if (k < T - pr) { r = pr; off = k; } else { r = T - 1 - pr; off = k - (T - pr); }
+            t.ta = (int)r;
+            t.tb = a.mt_b0 + (int)(r + off);
+            t.mirror = true;
+            t.tri_diag = off == 0;
+        } else {
+            const unsigned rest = (unsigned)(id - a.m_tri), wide = (unsigned)(a.mt_c - a.mt_r);
+            const unsigned r = rest / wide, c = rest - r * wide;
+            t.ta = (int)r;
+            t.tb = (int)c < a.mt_b0 ? (int)c : (int)c + a.mt_r;
+        }
+    } else {
+        const unsigned r = (unsigned)id / (unsigned)a.mt_c;
+        t.ta = (int)r;
+        t.tb = id - (int)r * a.mt_c;
+    }
+    return t;
+}
+
+// Persistent kernel: K1_MINB CTAs per SM, each looping over macro tiles id = blockIdx.x, += gridDim.x.
+//
+// A macro tile is MT x MT tiles of 64 x 64 entries (MT = 2 wherever the row block is 128-aligned; MT = 1 keeps the
+// per-tile enumeration for 64-aligned blocks and for the peer-to-peer mode).  Per macro tile there is ONE barrier,
+// ONE tile-id decode and ONE cp.async stage of the 2 x MT x 4 KB of per-point records of the NEXT macro tile into
+// the other half of a double buffer (ncu r01, per-tile version: 21 % of the stall samples sat in the per-tile
+// preamble and 16 % in the mirrored stores, with the FP64 pipe idle; the row loop itself ran the pipe at 80 %).
+// The exp and Matern tables are staged once per CTA.
+//
+// Mirrored (transposed) stores are warp-private: a warp owns 8 rows x 64 columns of the tile, parks them in its own
+// 8 x 66 strip of shared memory with one STS.128 per row, and writes the transposed 64 x 8 block as 64 B row pieces
+// (four lanes x 16 B per mirrored row, two full 32 B sectors) - no CTA barrier, 5 instructions per store.
+template <int MODE, bool MAXDIST, typename OutT, int MT>
 __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(const EllipseArgs a) {
+    using SL = SmLayout<MT>;
+    constexpr int kMR = SL::kMR;
     constexpr bool GEOM_F32 = sizeof(OutT) == 4;
+    using V2 = typename Vec2<OutT>::type;
     extern __shared__ __align__(16) double smem[];
-    double* rowp = smem + kSmRow;
-    double* colp = smem + kSmCol;
-    double* sexp = smem + kSmExp;
-    double* tileT = smem + kSmTileT;
-    double* stab = smem + kSmTab;
+    double* sexp = smem + SL::kExp;
+    double* stab = smem + SL::kTab;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int wr = (kNC == 2) ? warp : (warp >> 1);                 // warp-row: which strip of rows this warp owns
-    const int jl = (kNC == 2) ? 2 * lane : lane + 32 * (warp & 1);  // first (or only) column of this thread
-    const int64_t row_end = a.row0 + a.nrows;
+    const int jl = 2 * lane;                                        // first of this thread's two columns
+    const int N = (int)a.N, row0 = (int)a.row0;                     // N < 2^31 - 256 (checked by the host)
+    const int row_end = row0 + (int)a.nrows;
+    const int n_ids = (int)a.n_tiles;
     OutT* out = reinterpret_cast<OutT*>(a.out);
+    double* Ww = smem + SL::kW + warp * (8 * kWLd);                 // this warp's mirror strip
 
-    auto stage = [&](int buf, const TileId& t) {      // 2 x 16 B per thread
-        const int64_t i0 = a.row0 + (int64_t)t.ta * kTile, j0 = (int64_t)t.tb * kTile;
-        cp_async16(rowp + buf * (P_N * kTile) + 2 * tid, a.aos + i0 * P_N + 2 * tid);
-        const int f = tid >> 5, part = tid & 31;       // field f, points 2 part, 2 part + 1
-        cp_async16(colp + buf * (P_N * kTile) + f * kTile + 2 * part, a.soa + f * a.npad + j0 + 2 * part);
+    auto stage = [&](int buf, const MacroId& t) {                  // 2 x MT x 16 B per thread
+        const double* rsrc = a.aos + (a.row0 + (int64_t)t.ta * kMR) * P_N;
+        const double* csrc = a.soa + (int64_t)t.tb * kMR;
+        double* rdst = smem + SL::kRow + buf * (P_N * kMR);
+        double* cdst = smem + SL::kCol + buf * (P_N * kMR);
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+            const int e = tid + h * kThreads;                       // 16-byte chunk, 4 * kMR of them per side
+            cp_async16(rdst + 2 * e, rsrc + 2 * e);
+            const int f = e / (kMR / 2), part = e % (kMR / 2);      // field f, points 2 part, 2 part + 1
+            cp_async16(cdst + f * kMR + 2 * part, csrc + f * a.npad + 2 * part);
+        }
     };
 
-    // next tile of this CTA at or after `from` (ids advance by gridDim.x; tiles that a peer computes are skipped)
-    auto next_tile = [&](int64_t from, TileId& tt) -> int64_t {
-        for (int64_t i = from; i < a.n_tiles; i += gridDim.x) {
-            tt = decode_tile(a, i);
+    // next macro tile of this CTA at or after `from` (ids advance by gridDim.x; tiles that a peer computes are skipped)
+    auto next_tile = [&](int from, MacroId& tt) -> int {
+        for (int i = from; i < n_ids; i += gridDim.x) {
+            tt = decode_macro<MT>(a, i);
             if (!tt.skip) return i;
         }
-        return a.n_tiles;
+        return n_ids;
     };
-    TileId t;
-    int64_t id = next_tile(blockIdx.x, t);
-    if (id >= a.n_tiles) return;
+    MacroId t;
+    int id = next_tile(blockIdx.x, t);
+    if (id >= n_ids) return;
     stage(0, t);
     cp_async_commit();
 
@@ -604,164 +674,172 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         for (int e = tid; e < kTabDoubles / 2; e += kThreads)
             reinterpret_cast<double2*>(stab)[e] = reinterpret_cast<const double2*>(a.table)[e];
     }
-    if (tid == 0) *reinterpret_cast<MaternCtx*>(smem + kSmCtx) = m;
+    if (tid == 0) *reinterpret_cast<MaternCtx*>(smem + SL::kCtx) = m;
     const double* sexp_lane = sexp + (lane & (kExpRep - 1));
 
     int buf = 0;
     for (;;) {
-        TileId tn = t;
-        const int64_t id_next = next_tile(id + gridDim.x, tn);
-        const bool has_next = id_next < a.n_tiles;
-        if (has_next) stage(buf ^ 1, tn);
+        cp_async_wait<0>();                           // this macro tile's records have landed ...
+        __syncthreads();                              // ... for every thread, and everybody left the previous one
+        MacroId tn = t;
+        const int id_next = next_tile(id + gridDim.x, tn);
+        const bool has_next = id_next < n_ids;
+        if (has_next) stage(buf ^ 1, tn);             // in flight while this macro tile is computed
         cp_async_commit();
-        cp_async_wait<1>();                           // this tile's records have landed (the next may be in flight)
-        __syncthreads();
 
-        const double* cp = colp + buf * (P_N * kTile);
-        const int64_t i0 = a.row0 + (int64_t)t.ta * kTile;   // global index of the tile's first row point
-        const int64_t j0 = (int64_t)t.tb * kTile;            // global index of the tile's first column point
-        const bool mirror = t.mirror;
+        const int I0 = row0 + t.ta * kMR;             // global index of the macro tile's first row point
+        const int J0 = t.tb * kMR;                    // global index of the macro tile's first column point
+        // destination block of mirrored tiles: this rank's own rows, or - in the peer-to-peer mode - the row block
+        // of the rank that owns those rows (stores go over NVLink into its memory)
+        OutT* mbase = out;
+        int mrow0 = row0, mlim = row_end;
+        if (a.world > 1 && t.peer != a.rank) {
+            mbase = reinterpret_cast<OutT*>(a.peer_out[t.peer]);
+            mrow0 = (int)a.blk_row0[t.peer];
+            mlim = (int)a.blk_row0[t.peer + 1];
+        }
+        mlim = min(mlim, N);
 
-        PointRegs c0, c1;
-        if (kNC == 1) {
-            c0.lat = cp[P_LAT * kTile + jl];   c0.lon = cp[P_LON * kTile + jl];   c0.hcos = cp[P_HCOS * kTile + jl];
-            c0.h00 = cp[P_H00 * kTile + jl];   c0.h01 = cp[P_H01 * kTile + jl];   c0.h11 = cp[P_H11 * kTile + jl];
-            c0.w = cp[P_W * kTile + jl];
-            c1 = c0;
-        } else {
+#pragma unroll 1
+        for (int s = 0; s < MT * MT; ++s) {
+            const int sa = s / MT, sb = s % MT;       // sub-tile (row, column) inside the macro tile
+            if (t.tri_diag && sa > sb) continue;      // below the diagonal: produced by mirroring
+            const int i0 = I0 + sa * kTile, j0 = J0 + sb * kTile;
+            if (i0 >= row_end || j0 >= N) continue;   // outside the row block / matrix (ragged edge)
+            const bool mirror = t.mirror && !(t.tri_diag && sa == sb);
+
+            const double* cp = smem + SL::kCol + buf * (P_N * kMR) + sb * kTile;
+            PointRegs c0, c1;
             auto ld2 = [&](int f, double& x0, double& x1) {
-                const double2 v = *reinterpret_cast<const double2*>(cp + f * kTile + jl);
+                const double2 v = *reinterpret_cast<const double2*>(cp + f * kMR + jl);
                 x0 = v.x;
                 x1 = v.y;
             };
             ld2(P_LAT, c0.lat, c1.lat);   ld2(P_LON, c0.lon, c1.lon);   ld2(P_HCOS, c0.hcos, c1.hcos);
             ld2(P_H00, c0.h00, c1.h00);   ld2(P_H01, c0.h01, c1.h01);   ld2(P_H11, c0.h11, c1.h11);
             ld2(P_W, c0.w, c1.w);
-        }
-        // CTA-uniform tile classification, so that the per-row epilogue of the common case (a full tile off the
-        // diagonal) is one vector store: `diag` = the tile touches the matrix diagonal, `full` = all 64 x 64
-        // entries are inside the row block / matrix and the output admits 16 B (8 B for float) vector stores.
-        const int64_t dlt = j0 - i0;                  // column index - row index at the tile origin
-        const bool diag = dlt > -(int64_t)kTile && dlt < (int64_t)kTile;
-        const bool full = (i0 + kTile <= row_end) && (j0 + kTile <= a.N) && a.vec2;
-        const int dl = diag ? (int)dlt : (1 << 20);   // il == jl + dl  <=>  global row == global column
-        const int rows_ok = (int)min((int64_t)kTile, row_end - i0);
-        const int cols_ok = (int)min((int64_t)kTile, a.N - j0);
-        OutT* orow = out + (i0 - a.row0 + wr * kRowsPerWarp) * a.ld + (j0 + jl);
+            // CTA-uniform tile classification, so that the per-row epilogue of the common case (a full tile off the
+            // diagonal) is one vector store: `diag` = the tile touches the matrix diagonal, `full` = all 64 x 64
+            // entries are inside the row block / matrix and the output admits 16 B (8 B for float) vector stores.
+            const int dlt = j0 - i0;                  // column index - row index at the tile origin
+            const bool diag = dlt > -kTile && dlt < kTile;
+            const bool full = (i0 + kTile <= row_end) && (j0 + kTile <= N) && a.vec2;
+            const int dl = diag ? dlt : (1 << 20);    // il == jl + dl  <=>  global row == global column
+            const int rows_ok = min(kTile, row_end - i0);
+            const int cols_ok = min(kTile, N - j0);
+            OutT* const orow_start = out + (int64_t)(i0 - row0 + warp * kRowsPerWarp) * a.ld + (j0 + jl);
 
-        // Row loop.  FAST = the common tile (full, off the diagonal, no max_dist): the epilogue is one vector
-        // store and there is no per-row branch besides the cold-path check.  The next row's record is fetched
-        // from shared memory while this row is computed (ncu r01b: 12 % of the stall samples sat on its first use).
-        const int row_off0 = kSmRow + buf * (P_N * kTile) + wr * kRowsPerWarp * P_N;
-        const int col_off = kSmCol + buf * (P_N * kTile) + jl;
-        // SLOWALL = the cold re-run of the loop in which flagged lanes take the libm / Temme-CF2 path; it is taken
-        // after the hot loop when any lane of the thread was flagged (x >= 700, x outside the Matern table, NaN -
-        // in practice only the zero-distance lanes of diagonal tiles).  Keeping the call out of the hot loop
-        // matters: with a call inside it the table variant spilled and ran 12 % slower (profiles/r01_ellipse_summary.md).
-        bool slow_any = false;
-        OutT* const orow_start = orow;
-        auto rows = [&](auto fast_tag, auto mirror_tag, auto slowall_tag) {
-            constexpr bool FAST = decltype(fast_tag)::value, MIRROR = decltype(mirror_tag)::value;
-            constexpr bool SLOWALL = decltype(slowall_tag)::value;
-            orow = orow_start;
-            PointRegs pnext = load_point(smem + row_off0);
-            constexpr int kRowUnroll = K1_UNROLL;
+            // Row loop.  FAST = the common tile (full, off the diagonal, no max_dist): the epilogue is one vector
+            // store and there is no per-row branch besides the cold-path check.  The next row's record is fetched
+            // from shared memory while this row is computed (ncu r01b: 12 % of the stall samples sat on its first use).
+            const int row_off0 = SL::kRow + buf * (P_N * kMR) + (sa * kTile + warp * kRowsPerWarp) * P_N;
+            const int col_off = SL::kCol + buf * (P_N * kMR) + sb * kTile + jl;
+            // SLOWALL = the cold re-run of the loop in which flagged lanes take the libm / Temme-CF2 path; it is taken
+            // after the hot loop when any lane of the thread was flagged (x >= 700, x outside the Matern table, NaN -
+            // in practice only the zero-distance lanes of diagonal tiles).  Keeping the call out of the hot loop
+            // matters: with a call inside it the table variant spilled and ran 12 % slower (profiles/r01_ellipse_summary.md).
+            bool slow_any = false;
+            auto rows = [&](auto fast_tag, auto mirror_tag, auto slowall_tag) {
+                constexpr bool FAST = decltype(fast_tag)::value, MIRROR = decltype(mirror_tag)::value;
+                constexpr bool SLOWALL = decltype(slowall_tag)::value;
+                OutT* orow = orow_start;
+                PointRegs pnext = load_point(smem + row_off0);
+                constexpr int kRowUnroll = K1_UNROLL;
 #pragma unroll kRowUnroll
-            for (int r = 0; r < kRowsPerWarp; ++r) {
-                const int il = wr * kRowsPerWarp + r;
-                const int row_off = row_off0 + r * P_N;
-                const PointRegs p = pnext;
-                if (r + 1 < kRowsPerWarp) pnext = load_point(smem + row_off + P_N);
-                bool slow0 = false, slow1 = false;
-                double v0, v1;
-                if (SLOWALL) {
-                    // same fast evaluation again (bit-identical), then only the flagged lanes take the cold path:
-                    // a value never depends on which tile or row block it was computed in
-                    v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
-                    v1 = (kNC == 2) ? cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1) : 0.0;
-                    if (!(slow0 | slow1)) { orow += a.ld; continue; }
-                    if (slow0) v0 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off);
-                    if (kNC == 2 && slow1) v1 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off + 1);
-                } else {
-#if K1_EXPERIMENT == 2      // stores only: no pair arithmetic (kernel-experiment builds, never shipped)
-                    v0 = p.lat + c0.lat;
-                    v1 = p.lat + c1.lat;
-#else
-                    v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
-                    v1 = (kNC == 2) ? cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1) : 0.0;
-#endif
-                    slow_any |= slow0 | slow1;
-                }
-                if (MAXDIST) {                        // :256-266 pairs beyond max_dist stay 0
-                    if (tile_beyond_max_dist(row_off, col_off, a.max_dist)) v0 = 0.0;
-                    if (kNC == 2 && tile_beyond_max_dist(row_off, col_off + 1, a.max_dist)) v1 = 0.0;
-                }
-                if (!FAST && diag) {                  // diagonal = stdev^2, :246
-                    const double var = smem[row_off + P_VAR];
-                    if (il == jl + dl) v0 = var;
-                    if (kNC == 2 && il == jl + 1 + dl) v1 = var;
-                }
-#if K1_EXPERIMENT == 1      // arithmetic only: the store is kept reachable but never taken
-                if (v0 == 123.456789 && v1 == 987.654321)
-#else
-                if (FAST || full)
-#endif
-                {
-                    if (kNC == 1) {
-                        *orow = (OutT)v0;
+                for (int r = 0; r < kRowsPerWarp; ++r) {
+                    const int il = warp * kRowsPerWarp + r;
+                    const int row_off = row_off0 + r * P_N;
+                    const PointRegs p = pnext;
+                    if (r + 1 < kRowsPerWarp) pnext = load_point(smem + row_off + P_N);
+                    bool slow0 = false, slow1 = false;
+                    double v0, v1;
+                    if (SLOWALL) {
+                        // same fast evaluation again (bit-identical), then only the flagged lanes take the cold path:
+                        // a value never depends on which tile or row block it was computed in
+                        v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
+                        v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
+                        if (!(slow0 | slow1)) { orow += a.ld; continue; }
+                        if (slow0) v0 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off, kMR, SL::kCtx);
+                        if (slow1) v1 = tile_pair_slow<MODE, GEOM_F32>(row_off, col_off + 1, kMR, SL::kCtx);
                     } else {
-                        typename Vec2<OutT>::type v;
+#if K1_EXPERIMENT == 2      // stores only: no pair arithmetic (kernel-experiment builds, never shipped)
+                        v0 = p.lat + c0.lat;
+                        v1 = p.lat + c1.lat;
+#else
+                        v0 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c0, m, sexp_lane, slow0);
+                        v1 = cov_pair<MODE, GEOM_F32, kExpRep>(p, c1, m, sexp_lane, slow1);
+#endif
+                        slow_any |= slow0 | slow1;
+                    }
+                    if (MAXDIST) {                        // :256-266 pairs beyond max_dist stay 0
+                        if (tile_beyond_max_dist(row_off, col_off, kMR, a.max_dist)) v0 = 0.0;
+                        if (tile_beyond_max_dist(row_off, col_off + 1, kMR, a.max_dist)) v1 = 0.0;
+                    }
+                    if (!FAST && diag) {                  // diagonal = stdev^2, :246
+                        const double var = smem[row_off + P_VAR];
+                        if (il == jl + dl) v0 = var;
+                        if (il == jl + 1 + dl) v1 = var;
+                    }
+#if K1_EXPERIMENT == 1      // arithmetic only: the store is kept reachable but never taken
+                    if (v0 == 123.456789 && v1 == 987.654321)
+#else
+                    if (FAST || full)
+#endif
+                    {
+                        V2 v;
                         v.x = (OutT)v0;
                         v.y = (OutT)v1;
-                        *reinterpret_cast<typename Vec2<OutT>::type*>(orow) = v;
+                        *reinterpret_cast<V2*>(orow) = v;
+                    } else if (il < rows_ok && jl < cols_ok) {
+                        store_pair<OutT>(orow, v0, v1, jl + 1 < cols_ok, a.vec2 != 0);
                     }
-                } else if (il < rows_ok && jl < cols_ok) {
-                    store_pair<OutT>(orow, v0, v1, kNC == 2 && jl + 1 < cols_ok, a.vec2 != 0);
+                    orow += a.ld;
+                    if (MIRROR) *reinterpret_cast<double2*>(Ww + r * kWLd + jl) = make_double2(v0, v1);
                 }
-                orow += a.ld;
-                if (MIRROR) {
-                    tileT[il * kTileLd + jl] = v0;
-                    if (kNC == 2) tileT[il * kTileLd + jl + 1] = v1;
-                }
+            };
+            using T_ = std::true_type;
+            using F_ = std::false_type;
+            if (full && !diag) {
+                if (mirror) rows(T_{}, T_{}, F_{}); else rows(T_{}, F_{}, F_{});
+            } else {
+                if (mirror) rows(F_{}, T_{}, F_{}); else rows(F_{}, F_{}, F_{});
             }
-        };
-        using T_ = std::true_type;
-        using F_ = std::false_type;
-        if (full && !diag) {
-            if (mirror) rows(T_{}, T_{}, F_{}); else rows(T_{}, F_{}, F_{});
-        } else {
-            if (mirror) rows(F_{}, T_{}, F_{}); else rows(F_{}, F_{}, F_{});
-        }
-        if (slow_any) {                               // rare: redo this thread's 16 pairs on the cold path
-            if (mirror) rows(F_{}, T_{}, T_{}); else rows(F_{}, F_{}, T_{});
-        }
-        if (mirror) {
-            __syncthreads();
-            // ---- transposed tile: rows j0.. of C, columns i0.. (inside the shard's square block) ------
-            // destination block of the mirrored tile: this rank's own rows, or - in the peer-to-peer mode - the
-            // row block of the rank that owns rows j0.. (stores go over NVLink into its memory)
-            OutT* mbase = out;
-            int64_t mrow0 = a.row0, mrow_end = row_end;
-            if (a.world > 1 && t.peer != a.rank) {
-                mbase = reinterpret_cast<OutT*>(a.peer_out[t.peer]);
-                mrow0 = a.blk_row0[t.peer];
-                mrow_end = a.blk_row0[t.peer + 1];
+            if (slow_any) {                               // rare: redo this thread's 16 pairs on the cold path
+                if (mirror) rows(F_{}, T_{}, T_{}); else rows(F_{}, F_{}, T_{});
             }
-#pragma unroll 2
-            for (int r = 0; r < kTile / 8; ++r) {
-                const int jj = warp * (kTile / 8) + r;
-                const int64_t grow = j0 + jj;         // global row of the mirrored entry
-                if (grow >= mrow_end || grow >= a.N) continue;
-                OutT* dst = mbase + (grow - mrow0) * a.ld + i0;
+            if (mirror) {
+                // ---- transposed block of this warp: rows j0 + 0..63 of C, columns i0 + 8 warp + 0..7 ------------
+                // lane = 4 k + q stores entries 2q, 2q + 1 of mirrored row 8 it + k; the strip is read with a
+                // leading dimension of 66 doubles, so a half warp hits 16 different 8-byte banks
+                __syncwarp();
+                const int k = lane >> 2, q = lane & 3;
+                const double* wsrc = Ww + (2 * q) * kWLd + k;
+                const int c0g = i0 + warp * kRowsPerWarp + 2 * q;     // global column of the first entry
+                OutT* dst = mbase + (int64_t)(j0 + k - mrow0) * a.ld + c0g;
+                const int64_t step = 8 * a.ld;
+                if (full && j0 + kTile <= mlim) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int ii = lane + 32 * h;
-                    if (i0 + ii < row_end) dst[ii] = (OutT)tileT[ii * kTileLd + jj];
+                    for (int it = 0; it < 8; ++it) {
+                        V2 v;
+                        v.x = (OutT)wsrc[8 * it];
+                        v.y = (OutT)wsrc[kWLd + 8 * it];
+                        *reinterpret_cast<V2*>(dst) = v;
+                        dst += step;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int it = 0; it < 8; ++it) {
+                        if (j0 + 8 * it + k < mlim) {
+                            if (c0g < row_end) dst[0] = (OutT)wsrc[8 * it];
+                            if (c0g + 1 < row_end) dst[1] = (OutT)wsrc[kWLd + 8 * it];
+                        }
+                        dst += step;
+                    }
                 }
+                __syncwarp();                             // strip free for the next sub-tile
             }
         }
         if (!has_next) break;
-        __syncthreads();                              // all reads of buf / tileT done before they are refilled
         id = id_next;
         t = tn;
         buf ^= 1;
@@ -836,10 +914,10 @@ int resolve_mode(double nu, int matern_mode) {
     return (nu <= 10.0) ? MODE_TABLE : MODE_DIRECT;   // table accuracy degrades for large nu
 }
 
-// workspace layout: [Matern table, padded to 256 B][records (npad + kTile) x 8 doubles][fields 8 x npad doubles]
+// workspace layout: [Matern table, padded to 256 B][records (npad + 128) x 8 doubles][fields 8 x npad doubles]
 constexpr size_t kTableBytes = ((size_t)kTabDoubles * sizeof(double) + 255) / 256 * 256;
-inline int64_t pad_points(int64_t N) { return gmg_ceil_div(N, kTile) * kTile; }
-inline size_t aos_bytes(int64_t N) { return gmg_align_up((size_t)(pad_points(N) + kTile) * P_N * sizeof(double), 256); }
+inline int64_t pad_points(int64_t N) { return gmg_ceil_div(N, kPadTail) * kPadTail; }
+inline size_t aos_bytes(int64_t N) { return gmg_align_up((size_t)(pad_points(N) + kPadTail) * P_N * sizeof(double), 256); }
 inline size_t soa_bytes(int64_t N) { return gmg_align_up((size_t)pad_points(N) * P_N * sizeof(double), 256); }
 inline const double* ws_table(const void* ws) { return reinterpret_cast<const double*>(ws); }
 inline const double* ws_aos(const void* ws) {
@@ -849,11 +927,11 @@ inline const double* ws_soa(const void* ws, int64_t N) {
     return reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + kTableBytes + aos_bytes(N));
 }
 
-template <int MODE, bool MAXDIST, typename OutT>
+template <int MODE, bool MAXDIST, typename OutT, int MT>
 int launch_tiles(const EllipseArgs& a, int64_t n_ctas, cudaStream_t s) {
-    size_t smem = (size_t)kSmTab * sizeof(double);
+    size_t smem = (size_t)SmLayout<MT>::kTab * sizeof(double);
     if (MODE == MODE_TABLE) smem += (size_t)kTabDoubles * sizeof(double);
-    auto kern = ellipse_cov_tile_kernel<MODE, MAXDIST, OutT>;
+    auto kern = ellipse_cov_tile_kernel<MODE, MAXDIST, OutT, MT>;
     GMG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid: K1_MINB resident CTAs per SM (cached per device)
     static int sm_count[64] = {0};
@@ -868,11 +946,37 @@ int launch_tiles(const EllipseArgs& a, int64_t n_ctas, cudaStream_t s) {
     return GMG_OK;
 }
 
+// Chooses the enumeration: macro tiles of 2 x 2 tiles wherever the row block allows it (single-rank launches whose
+// block starts on a 128-row boundary, or that do not use symmetry at all); per-tile otherwise.
+template <int MODE, bool MAXDIST, typename OutT>
+int launch_tiles_mt(EllipseArgs a, cudaStream_t s) {
+    if (a.N >= (int64_t)2147483647 - 4 * kPadTail) return GMG_ERR_UNSUPPORTED;
+#ifdef K1_FORCE_MT1         // kernel-experiment builds: per-tile enumeration everywhere
+    const bool macro = false;
+#else
+    const bool macro = a.world == 1 && (!a.symmetric || a.row0 % (2 * kTile) == 0);
+#endif
+    if (macro) {
+        a.mt_r = (a.tiles_r + 1) / 2;
+        a.mt_c = (a.tiles_c + 1) / 2;
+        a.mt_b0 = a.tile_b0 / 2;
+        const int64_t m_tri = (int64_t)a.mt_r * (a.mt_r + 1) / 2;
+        const int64_t n = a.symmetric ? m_tri + (int64_t)a.mt_r * (a.mt_c - a.mt_r) : (int64_t)a.mt_r * a.mt_c;
+        if (n >= 2147483647) return GMG_ERR_UNSUPPORTED;
+        a.m_tri = (int)m_tri;
+        a.n_tiles = n;
+        return launch_tiles<MODE, MAXDIST, OutT, 2>(a, n, s);
+    }
+    if (a.n_tiles >= 2147483647) return GMG_ERR_UNSUPPORTED;
+    return launch_tiles<MODE, MAXDIST, OutT, 1>(a, a.n_tiles, s);
+}
+
 template <int MODE>
 int launch_tiles_mode(const EllipseArgs& a, int64_t n, int f32, cudaStream_t s) {
+    (void)n;
     const bool md = a.max_dist >= 0.0;
-    if (f32) return md ? launch_tiles<MODE, true, float>(a, n, s) : launch_tiles<MODE, false, float>(a, n, s);
-    return md ? launch_tiles<MODE, true, double>(a, n, s) : launch_tiles<MODE, false, double>(a, n, s);
+    if (f32) return md ? launch_tiles_mt<MODE, true, float>(a, s) : launch_tiles_mt<MODE, false, float>(a, s);
+    return md ? launch_tiles_mt<MODE, true, double>(a, s) : launch_tiles_mt<MODE, false, double>(a, s);
 }
 
 template <int MODE>
@@ -923,7 +1027,7 @@ int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* th
     cudaStream_t s = (cudaStream_t)stream;
     double* table = const_cast<double*>(ws_table(ws));
     const int64_t npad = pad_points(N);
-    ellipse_prepare_kernel<<<(unsigned)gmg_ceil_div(npad + kTile, 256), 256, 0, s>>>(
+    ellipse_prepare_kernel<<<(unsigned)gmg_ceil_div(npad + kPadTail, 256), 256, 0, s>>>(
         Lx, Ly, theta, stdev, lat_rad, lon_rad, N, npad, disp_method, const_cast<double*>(ws_aos(ws)),
         const_cast<double*>(ws_soa(ws, N)));
     GMG_LAUNCH_CHECK();
@@ -960,6 +1064,7 @@ int gmg_ellipse_cov_f64(const void* ws, int64_t N, int64_t row0, int64_t nrows, 
     a.vec2 = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(C_rows) % (2 * elt)) == 0);
     a.bc = gmg_make_bessel_consts(nu);
     a.world = 1; a.rank = 0; a.nseg = 0;
+    a.mt_r = a.mt_c = a.mt_b0 = a.m_tri = 0;
     const int64_t n_ctas = a.symmetric ? a.n_tri + (int64_t)a.tiles_r * (a.tiles_c - a.tiles_r)
                                        : (int64_t)a.tiles_r * a.tiles_c;
     a.n_tiles = n_ctas;
@@ -1003,6 +1108,7 @@ int gmg_ellipse_cov_p2p_f64(const void* ws, int64_t N, double nu, double max_dis
     for (int g = 0; g < world; ++g) a.vec2 = a.vec2 && ((reinterpret_cast<uintptr_t>(h_block_rows[g]) % (2 * elt)) == 0);
     a.bc = gmg_make_bessel_consts(nu);
     a.world = world; a.rank = rank;
+    a.mt_r = a.mt_c = a.mt_b0 = a.m_tri = 0;
     // Every unordered pair of row blocks {r, c} is computed by exactly one of the two ranks: rank r takes the
     // blocks at cyclic distance 1 .. (world-1)/2 to its right; at distance world/2 (even world) the two ranks
     // split the block's tiles by the parity of (row tile + column tile), rank min(r, c) taking the even ones.

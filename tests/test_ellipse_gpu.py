@@ -127,7 +127,8 @@ def test_row_block_equals_full_build(Builder):
     Lx, Ly, th, sd = synth.ellipse_fields(lats, lons, land_mask=True)
     full = Builder(Lx, Ly, th, sd, lats, lons, v=2.2, precision=np.float64).cov_ns
     N = full.shape[0]
-    for row0, nrows in [(0, 64), (64, 100), (128, N - 128), (70, 33), (N - 1, 1)]:
+    for row0, nrows in [(0, 64), (64, 100), (128, N - 128), (70, 33), (N - 1, 1), (128, 192), (0, 200), (256, 100),
+                        (192, 130)]:
         blk = Builder(Lx, Ly, th, sd, lats, lons, v=2.2, precision=np.float64, rows=(row0, nrows)).cov_ns
         assert np.array_equal(blk, full[row0:row0 + nrows])
 
