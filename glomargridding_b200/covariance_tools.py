@@ -8,9 +8,17 @@ rebuild `V diag(lambda') V^T`.  Since the replaced eigenvalues all become one co
 
     out = c I + V_k (Lambda_k - c I) V_k^T ,      c = (trace - sum(Lambda_k)) / (n - k)
 
-needs only the k kept eigenpairs.  They are computed here by orthogonal (subspace) iteration with Rayleigh-Ritz:
-every step is a DMMA GEMM against C, a Cholesky-QR (Gram matrix, `gmg_potrf`, forward substitution) keeps the block
-orthonormal, and only the small m x m projected matrix is diagonalised (`gmg_jacobi_eigh_f64`).  No CPU fallback.
+needs only the k kept eigenpairs - or, equivalently, the spectral PROJECTOR P onto their span:
+
+    out = c I + P (C - c I) ,      P = (I + sign(C - tau I)) / 2 ,   lambda_{k+1} < tau < lambda_k .
+
+Default route (n <= 8192): all eigenVALUES from a Householder tridiagonalisation + Sturm bisection on the device
+(`gmg_sym_eigvals_f64`, csrc/spectrum.cu) give k, c and tau; sign(C - tau I) is a Newton-Schulz iteration
+X <- (mu/2) X (3 I - mu^2 X^2) - two DMMA GEMMs per step - whose scaling mu is chosen each step from the KNOWN
+spectrum (the scalar recurrence is run on the eigenvalues alongside), which cuts the ~25 unscaled steps to ~12.
+Larger matrices: orthogonal (subspace) iteration with Rayleigh-Ritz for the kept eigenpairs - every step a DMMA GEMM
+against C, Cholesky-QR (Gram matrix, `gmg_potrf`, forward substitution) keeps the block orthonormal, and only the
+small m x m projected matrix is diagonalised (`gmg_jacobi_eigh_f64`).  No CPU fallback.
 
 Differences from the reference: `method="Laloux_2000"` is not implemented; the progress `print`s are dropped; the
 final "is it positive definite" check (`:779-784`, a second full eigendecomposition) is replaced by the sign of c
@@ -31,7 +39,56 @@ from . import _device as dev
 from ._lib import check, lib
 
 
-FULL_JACOBI_MAX = 4096      # up to this order C is diagonalised directly; beyond it, subspace iteration
+FULL_JACOBI_MAX = 4096      # up to this order C can be diagonalised directly (Jacobi); beyond it, subspace iteration
+SPECTRAL_MAX = 8192         # up to this order: tridiagonal eigenvalues + sign-function projector (the default route)
+MIN_REL_GAP = 1e-9          # below this relative gap at the cut the projector is ill-conditioned: use eigenvectors
+
+
+def sym_eigvals(C: torch.Tensor) -> torch.Tensor:
+    """All eigenvalues (ascending) of a symmetric device matrix: `gmg_sym_eigvals_f64` on a padded copy."""
+    n = C.shape[0]
+    A = dn.padded(C)                                          # the kernel destroys its input
+    w = torch.empty(n, dtype=torch.float64, device=C.device)
+    nbytes = ctypes.c_size_t()
+    check(lib().gmg_sym_eigvals_ws_bytes(n, ctypes.byref(nbytes)), "gmg_sym_eigvals_ws_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=C.device)
+    check(lib().gmg_sym_eigvals_f64(A.data_ptr(), A.stride(0), n, w.data_ptr(), ws.data_ptr(), nbytes.value,
+                                    dev.stream_ptr()), "gmg_sym_eigvals_f64")
+    return w
+
+
+def _projector_clip(C: torch.Tensor, lam: torch.Tensor, tau: float, c: float, max_steps: int = 80):
+    """c I + P (C - c I) with P the spectral projector of C for the eigenvalues above tau; `lam` = all eigenvalues.
+    Returns (matrix (n, n) view of an even-ld buffer, Newton-Schulz steps taken)."""
+    n = C.shape[0]
+    X = dn.padded(C)
+    X[:, :n].diagonal().sub_(tau)
+    x = lam - tau                                             # the spectrum of X, iterated alongside
+    s = float(x.abs().max().item()) * (1.0 + 1e-12)
+    X.div_(s)
+    x = x / s
+    steps = 0
+    for steps in range(max_steps + 1):
+        ax = x.abs()
+        a, b = float(ax.min().item()), float(ax.max().item())
+        if 1.0 - a <= 4e-16 and b - 1.0 <= 4e-16:
+            break
+        if steps == max_steps:
+            raise np.linalg.LinAlgError("sign-function iteration of eigenvalue_clip did not converge")
+        mu = (3.0 / (a * a + a * b + b * b)) ** 0.5
+        Y = torch.zeros_like(X)
+        dn.gemm(X[:, :n], X[:, :n], out=Y[:, :n])             # X^2
+        Xn = X.clone()
+        dn.gemm(X[:, :n], Y[:, :n], out=Xn[:, :n], alpha=-0.5 * mu ** 3, beta=1.5 * mu)
+        x = 0.5 * mu * x * (3.0 - (mu * x) ** 2)
+        X = Xn
+    Cc = dn.padded(C)
+    Cc[:, :n].diagonal().sub_(c)
+    out = Cc.clone()
+    dn.gemm(X[:, :n], Cc[:, :n], out=out[:, :n], alpha=0.5, beta=0.5)   # (C - cI)/2 + sign (C - cI)/2 = P (C - cI)
+    res = out[:, :n]
+    res.diagonal().add_(c)
+    return res, steps
 
 
 def _jacobi_eigh(T: torch.Tensor, max_sweeps: int = 30, tol: float = 1e-15):
@@ -126,6 +183,31 @@ def explained_variance_clip(cov, target_variance_fraction: float = 0.95, return_
     n = C.shape[0]
     total = float(torch.diagonal(C).sum().item())            # trace = sum of all eigenvalues
     target = target_variance_fraction * total
+    if n <= SPECTRAL_MAX and n >= 2:
+        lam = sym_eigvals(C)                                  # ascending
+        theta = lam.flip(0)
+        csum = torch.cumsum(theta, 0)
+        over = torch.nonzero(csum > target)
+        if not over.numel():
+            raise ValueError("Target Explained Variance not exceeded")
+        k = int(over[0].item()) + 1
+        kept = float(csum[k - 1].item())
+        if total < kept:
+            raise ValueError("Variance explained by retained eigenvalues exceeds total variance. Resulting matrix "
+                             "will have negative eigenvalues. Try using a lower threshold.")
+        scale = float(theta.abs().max().item())
+        gap = float((theta[k - 1] - theta[k]).item()) if k < n else float("inf")
+        if k == n or gap > MIN_REL_GAP * scale:
+            c = (total - kept) / (n - k) if n > k else 0.0
+            if k == n:
+                res = C.clone()
+            else:
+                res, _ = _projector_clip(C, lam, float((0.5 * (theta[k - 1] + theta[k])).item()), c)
+            if not (c > 0 and float(theta[k - 1].item()) > 0):
+                warn("Resulting matrix is not positive-definite, and may not be a valid covariance matrix.")
+            res = 0.5 * (res + res.t())
+            return res.contiguous() if (on_device or return_device) else dev.to_host(res.contiguous())
+        # (nearly) degenerate eigenvalues at the cut: fall through to the eigenvector routes below
     if n <= FULL_JACOBI_MAX:
         # small enough for a full Jacobi diagonalisation of C itself (one cooperative kernel): cheaper than growing
         # the subspace when many eigenvalues have to be kept (the synthetic 5-degree fields keep 780 of 2592)

@@ -700,30 +700,40 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         }
         mlim = min(mlim, N);
 
+        // `interior` = every sub-tile of the macro tile is a full 64 x 64 tile off the matrix diagonal (all but the
+        // O(N / 128) macro tiles on the diagonal and on the ragged edge): its sub-tiles skip the classification
+        // below, and vertically adjacent sub-tiles share the column registers (ncu s3a: the per-sub-tile preamble -
+        // flag reloads, 7 LDS.128, pointer arithmetic - held 7 - 14 % of the stall samples with the FP64 pipe idle).
+        const bool interior = !t.tri_diag && a.vec2 && (I0 + kMR <= row_end) && (J0 + kMR <= N) &&
+                              (J0 - I0 >= kMR || I0 - J0 >= kMR) && (!t.mirror || J0 + kMR <= mlim);
+        PointRegs c0, c1;
 #pragma unroll 1
         for (int s = 0; s < MT * MT; ++s) {
-            const int sa = s / MT, sb = s % MT;       // sub-tile (row, column) inside the macro tile
-            if (t.tri_diag && sa > sb) continue;      // below the diagonal: produced by mirroring
+            const int sb = s / MT, sa = s % MT;       // sub-tile (row, column) inside the macro tile, column-major
             const int i0 = I0 + sa * kTile, j0 = J0 + sb * kTile;
-            if (i0 >= row_end || j0 >= N) continue;   // outside the row block / matrix (ragged edge)
+            if (!interior) {
+                if (t.tri_diag && sa > sb) continue;      // below the diagonal: produced by mirroring
+                if (i0 >= row_end || j0 >= N) continue;   // outside the row block / matrix (ragged edge)
+            }
             const bool mirror = t.mirror && !(t.tri_diag && sa == sb);
 
-            const double* cp = smem + SL::kCol + buf * (P_N * kMR) + sb * kTile;
-            PointRegs c0, c1;
-            auto ld2 = [&](int f, double& x0, double& x1) {
-                const double2 v = *reinterpret_cast<const double2*>(cp + f * kMR + jl);
-                x0 = v.x;
-                x1 = v.y;
-            };
-            ld2(P_LAT, c0.lat, c1.lat);   ld2(P_LON, c0.lon, c1.lon);   ld2(P_HCOS, c0.hcos, c1.hcos);
-            ld2(P_H00, c0.h00, c1.h00);   ld2(P_H01, c0.h01, c1.h01);   ld2(P_H11, c0.h11, c1.h11);
-            ld2(P_W, c0.w, c1.w);
+            if (!interior || sa == 0) {
+                const double* cp = smem + SL::kCol + buf * (P_N * kMR) + sb * kTile;
+                auto ld2 = [&](int f, double& x0, double& x1) {
+                    const double2 v = *reinterpret_cast<const double2*>(cp + f * kMR + jl);
+                    x0 = v.x;
+                    x1 = v.y;
+                };
+                ld2(P_LAT, c0.lat, c1.lat);   ld2(P_LON, c0.lon, c1.lon);   ld2(P_HCOS, c0.hcos, c1.hcos);
+                ld2(P_H00, c0.h00, c1.h00);   ld2(P_H01, c0.h01, c1.h01);   ld2(P_H11, c0.h11, c1.h11);
+                ld2(P_W, c0.w, c1.w);
+            }
             // CTA-uniform tile classification, so that the per-row epilogue of the common case (a full tile off the
             // diagonal) is one vector store: `diag` = the tile touches the matrix diagonal, `full` = all 64 x 64
             // entries are inside the row block / matrix and the output admits 16 B (8 B for float) vector stores.
             const int dlt = j0 - i0;                  // column index - row index at the tile origin
-            const bool diag = dlt > -kTile && dlt < kTile;
-            const bool full = (i0 + kTile <= row_end) && (j0 + kTile <= N) && a.vec2;
+            const bool diag = !interior && dlt > -kTile && dlt < kTile;
+            const bool full = interior || ((i0 + kTile <= row_end) && (j0 + kTile <= N) && a.vec2);
             const int dl = diag ? dlt : (1 << 20);    // il == jl + dl  <=>  global row == global column
             const int rows_ok = min(kTile, row_end - i0);
             const int cols_ok = min(kTile, N - j0);
@@ -799,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
             };
             using T_ = std::true_type;
             using F_ = std::false_type;
-            if (full && !diag) {
+            if (interior) {
                 if (mirror) rows(T_{}, T_{}, F_{}); else rows(T_{}, F_{}, F_{});
             } else {
                 if (mirror) rows(F_{}, T_{}, F_{}); else rows(F_{}, F_{}, F_{});
@@ -817,7 +827,7 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
                 const int c0g = i0 + warp * kRowsPerWarp + 2 * q;     // global column of the first entry
                 OutT* dst = mbase + (int64_t)(j0 + k - mrow0) * a.ld + c0g;
                 const int64_t step = 8 * a.ld;
-                if (full && j0 + kTile <= mlim) {
+                if (interior || (full && j0 + kTile <= mlim)) {
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         V2 v;

@@ -269,6 +269,17 @@ int gmg_jacobi_eigh_f64(double* A, int64_t lda, double* U, int64_t ldu, int64_t 
                         double tol, void* ws, size_t ws_bytes, int* sweeps_done /* device */,
                         gmg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * All eigenvalues of a dense symmetric matrix (ascending) - the spectrum `explained_variance_clip`
+ * needs to find its cut (glomar_gridding/covariance_tools.py:616, :717 take them from a full
+ * numpy.linalg.eigh).  Householder tridiagonalisation in one cooperative kernel (rank-2 update fused
+ * with the next matrix-vector product), then Sturm-count bisection.  A (n x n, full symmetric
+ * storage, row-major) is DESTROYED; w receives n eigenvalues.  n <= 8192.
+ * ------------------------------------------------------------------------------------------- */
+int gmg_sym_eigvals_ws_bytes(int64_t n, size_t* bytes);
+int gmg_sym_eigvals_f64(double* A, int64_t lda, int64_t n, double* w, void* ws, size_t ws_bytes,
+                        gmg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,3 +51,13 @@ def reference():
     if not reference_available():
         pytest.skip("reference sources not present (GPU box)")
     return load_reference()
+
+
+def load_notebook_case():
+    """configs[0] fixture (tests/golden/make_golden_notebook.py): the HadSST.4.0.1.0 2014-03 field of the reference's
+    notebook with the HadCRUT.5 error covariance of that month, plus the unmodified reference's kriging outputs.
+    Returns (golden npz, full-grid float32 error covariance rebuilt from its non-zero entries)."""
+    g = load_golden("notebook_2014_03.npz")
+    E = np.zeros((2592, 2592), dtype=np.float32)
+    E[g["E_rows"], g["E_cols"]] = g["E_vals"]
+    return g, E

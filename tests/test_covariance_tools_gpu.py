@@ -24,14 +24,10 @@ def CT():
 
 
 def reference_clip(cov, frac=0.95):
-    """`explained_variance_clip` + `_eigenvalue_clip` of the reference, restated (covariance_tools.py:633-785)."""
-    w, v = np.linalg.eigh(cov)
-    total, target = w.sum(), frac * w.sum()
-    csum = np.cumsum(w[::-1])
-    k = int(np.argmax(csum > target)) + 1
-    new = w.copy()
-    new[: len(w) - k] = (total - w[len(w) - k:].sum()) / (len(w) - k)
-    return (v * new) @ v.T, k, w
+    """`explained_variance_clip` + `_eigenvalue_clip` of the reference, restated (oracle/covariance_tools.py)."""
+    from oracle.covariance_tools import explained_variance_clip
+
+    return explained_variance_clip(cov, frac)
 
 
 @pytest.mark.parametrize("n", [7, 64, 301])

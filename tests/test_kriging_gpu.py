@@ -494,3 +494,38 @@ def test_1deg_20000_obs_size_independent_properties(K):
         u2_m = float(C[m, m] - w @ c_m - 2 * alpha[m])
         assert abs(u2_m - u1[m] ** 2) <= TOL * float(C[m, m])
         assert abs(float(T[:, m] @ c_m / C[m, m]) - m1[m]) <= TOL
+
+
+def test_notebook_2014_03_field_configs0():
+    """BASELINE configs[0] on the device: 5-degree ellipse covariance build -> eigenvalue clip -> simple and ordinary
+    kriging of the real HadSST.4.0.1.0 2014-03 ensemble-member field with the real HadCRUT.5 error covariance
+    (`notebooks/Ellipse_to_grid.ipynb` cells 17-34), against the UNMODIFIED reference's outputs
+    (`tests/golden/make_golden_notebook.py`).  Tolerance: 1e-8 max-norm relative."""
+    import torch
+    from conftest import load_notebook_case
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import glomargridding_b200.covariance_tools as ct
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+    from glomargridding_b200.kriging import OrdinaryKriging, SimpleKriging
+
+    g, E = load_notebook_case()
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    b = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, precision=np.float64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cov = ct.eigenvalue_clip(b.cov_ns_device)                     # notebook cell 20, device in -> device out
+        assert max_norm_rel(torch.diagonal(cov).cpu().numpy(), g["cov_diag_clipped"]) <= 1e-8
+        idx, obs = g["idx"], g["obs"]
+        sk = SimpleKriging(cov, idx.copy(), obs.copy(), E.copy())
+        ok = OrdinaryKriging(cov, idx.copy(), obs.copy(), E.copy())
+        for k, tag in ((sk, "sk"), (ok, "ok")):
+            z, u, m = k.solve(), k.get_uncertainty(), k.constraint_mask()
+            assert k._batch.lu_fallback == []                         # Cholesky path, no LU fallback
+            assert z.shape == (2592,)
+            assert max_norm_rel(z, g[f"{tag}_field"]) <= 1e-8
+            assert max_norm_rel(u ** 2, g[f"{tag}_unc"] ** 2) <= 1e-8
+            assert max_norm_rel(m, g[f"{tag}_mask"]) <= 1e-8
+    assert np.array_equal(ok.idx, g["kept_idx"])

@@ -141,3 +141,27 @@ def test_variogram_oracle_vs_reference_golden():
             else:
                 got = ov.spherical_variogram(dist, p["psill"], p["nugget"], rng)
         assert np.allclose(got, g[f"case{k}"], rtol=1e-13, atol=1e-15), (k, cls)
+
+
+def test_notebook_2014_03_field_chain():
+    """BASELINE configs[0]: 5-degree ellipse covariance -> eigenvalue clip -> simple / ordinary kriging of the real
+    HadSST.4 2014-03 field with the real HadCRUT.5 error covariance; golden = the unmodified reference's outputs."""
+    from conftest import load_notebook_case
+    from oracle.covariance_tools import explained_variance_clip
+
+    g, E = load_notebook_case()
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    raw = EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5, "Modified_Met_Office").build()
+    cov, kept, w = explained_variance_clip(raw)
+    assert abs(w.min() - float(g["cov_min_eig_raw"])) < 1e-9          # indefinite before the clip (SURVEY.md H3)
+    assert max_norm_rel(np.diag(cov), g["cov_diag_clipped"]) <= 1e-10
+    idx, obs = g["idx"], g["obs"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sk = simple_kriging(cov, idx, obs, E)
+        ok = ordinary_kriging(cov, idx, obs, E)
+    for got, tag in ((sk, "sk"), (ok, "ok")):
+        assert max_norm_rel(got["field"], g[f"{tag}_field"]) <= 1e-8
+        assert max_norm_rel(got["uncertainty"] ** 2, g[f"{tag}_unc"] ** 2) <= 1e-8
+        assert max_norm_rel(got["constraint_mask"], g[f"{tag}_mask"]) <= 1e-8

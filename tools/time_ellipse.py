@@ -10,13 +10,14 @@ from glomargridding_b200.ellipse import EllipseCovarianceBuilder
 ap = argparse.ArgumentParser()
 ap.add_argument("--res", type=float, default=1.0)
 ap.add_argument("--rows", type=int, default=0)
+ap.add_argument("--row0", type=int, default=0, help="first row; not a multiple of 64 -> no symmetry, every entry computed")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--nus", default="1.5,2.2")
 a = ap.parse_args()
 lats, lons = synth.global_grid(a.res)
 Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
 N = lats.size * lons.size
-rows = a.rows or N
+rows = a.rows or (N - a.row0)
 out = torch.empty((rows, N), dtype=torch.float64, device="cuda")
 L = lib()
 res = {}
@@ -27,7 +28,7 @@ for nu in [float(x) for x in a.nus.split(",")]:
     for i in range(a.reps + 2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        check(L.gmg_ellipse_cov_f64(b._ws.data_ptr(), N, 0, rows, nu, -1.0, 0, out.data_ptr(), N, 0, s), "cov")
+        check(L.gmg_ellipse_cov_f64(b._ws.data_ptr(), N, a.row0, rows, nu, -1.0, 0, out.data_ptr(), N, 0, s), "cov")
         e1.record(); e1.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = float(np.median(ts[2:]))
