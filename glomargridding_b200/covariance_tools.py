@@ -20,7 +20,7 @@ Larger matrices: orthogonal (subspace) iteration with Rayleigh-Ritz for the kept
 against C, Cholesky-QR (Gram matrix, `gmg_potrf`, forward substitution) keeps the block orthonormal, and only the
 small m x m projected matrix is diagonalised (`gmg_jacobi_eigh_f64`).  No CPU fallback.
 
-Differences from the reference: `method="Laloux_2000"` is not implemented; the progress `print`s are dropped; the
+Differences from the reference: `method="Laloux_2000"` is limited to n <= 8192; the progress `print`s are dropped; the
 final "is it positive definite" check (`:779-784`, a second full eigendecomposition) is replaced by the sign of c
 and of the kept eigenvalues, which decide it.
 """
@@ -173,6 +173,70 @@ def top_eigenpairs(C: torch.Tensor, m: int, iters: int = 60, tol: float = 1e-13,
     return theta, Vt, resid
 
 
+def _clip_keep_top(C: torch.Tensor, lam: torch.Tensor, k: int, total: float):
+    """`_eigenvalue_clip` (reference `covariance_tools.py:731-785`) from the spectrum alone: keep the k largest
+    eigenvalues of C, replace the others by their mean.  `lam` = all eigenvalues ascending, `total` = their sum.
+    Returns the clipped matrix, or None when the eigenvalues at the cut are too close for the projector route."""
+    n = C.shape[0]
+    theta = lam.flip(0)
+    kept = float(theta[:k].sum().item())
+    if total < kept:
+        raise ValueError("Variance explained by retained eigenvalues exceeds total variance. Resulting matrix will "
+                         "have negative eigenvalues. Try using a lower threshold.")
+    if k <= 0 or k >= n:                                      # nothing is clipped (reference: `new_eigvals[:0] = ...`)
+        res, pd = C.clone(), float(lam[0].item()) > 0
+    else:
+        scale = float(theta.abs().max().item())
+        if float((theta[k - 1] - theta[k]).item()) <= MIN_REL_GAP * scale:
+            return None
+        c = (total - kept) / (n - k)
+        res, _ = _projector_clip(C, lam, float((0.5 * (theta[k - 1] + theta[k])).item()), c)
+        pd = c > 0 and float(theta[k - 1].item()) > 0
+    if not pd:
+        warn("Resulting matrix is not positive-definite, and may not be a valid covariance matrix.")
+    return 0.5 * (res + res.t())
+
+
+def laloux_clip(cov, num_grid_pts: int | None = None, num_time_pts: int = 40, return_device: bool = False):
+    """Clip the eigenvalues of the CORRELATION matrix below the Marchenko-Pastur noise level (1 + sqrt(q))^2,
+    q = num_grid_pts / num_time_pts (inverted if < 1), to their mean and scale back to a covariance
+    (reference `covariance_tools.py:488-630`; `cov_2_cor` / `cor_2_cov` `utils.py:611-671`)."""
+    on_device = isinstance(cov, torch.Tensor)
+    C = cov.to(dev.require_cuda(), torch.float64) if on_device else dev.to_device(np.asarray(cov), torch.float64)
+    n = C.shape[0]
+    if n > SPECTRAL_MAX:
+        raise NotImplementedError(f"method='Laloux_2000' is limited to matrices of order <= {SPECTRAL_MAX} on the device")
+    num_grid_pts = num_grid_pts or n
+    sd = torch.sqrt(torch.diagonal(C))
+    norm = sd[:, None] * sd[None, :]
+    cor = C / norm                                            # elementwise plumbing (utils.cov_2_cor)
+    dg = torch.diagonal(cor)
+    if not bool((dg == 1.0).all()):
+        bad = float((dg - 1.0).abs().max().item())
+        if not bad <= 1e-6:                                   # also catches NaN (zero / negative variances)
+            raise ValueError(f"Correlation Diagonal contains values not close to 1. With difference to 1: {bad}")
+        dg.fill_(1.0)
+    cor[C == 0] = 0.0
+    q = num_grid_pts / num_time_pts
+    if q < 1.0:
+        q = 1.0 / q
+    lam = sym_eigvals(cor)
+    k = int((lam > (1.0 + np.sqrt(q)) ** 2.0).sum().item())
+    res = _clip_keep_top(cor, lam, k, float(lam.sum().item()))
+    if res is None:
+        if n > FULL_JACOBI_MAX:
+            raise np.linalg.LinAlgError("degenerate eigenvalues at the Laloux cut")
+        theta, U = _jacobi_eigh(cor)
+        c = float((theta[k:].sum() / (n - k)).item())
+        new = theta.clone()
+        new[k:] = c
+        res = dn.gemm(dn.padded(U * new[None, :]), dn.padded(U), transb=True)[:, :n]
+        res = 0.5 * (res + res.t())
+    out = res * norm                                          # utils.cor_2_cov
+    out[res == 0] = 0.0
+    return out.contiguous() if (on_device or return_device) else dev.to_host(out.contiguous())
+
+
 def explained_variance_clip(cov, target_variance_fraction: float = 0.95, return_device: bool = False):
     """Clip all eigenvalues beyond `target_variance_fraction` of explained variance to their mean
     (reference `covariance_tools.py:633-728`, `_eigenvalue_clip` `:731-785`)."""
@@ -185,27 +249,12 @@ def explained_variance_clip(cov, target_variance_fraction: float = 0.95, return_
     target = target_variance_fraction * total
     if n <= SPECTRAL_MAX and n >= 2:
         lam = sym_eigvals(C)                                  # ascending
-        theta = lam.flip(0)
-        csum = torch.cumsum(theta, 0)
+        csum = torch.cumsum(lam.flip(0), 0)
         over = torch.nonzero(csum > target)
         if not over.numel():
             raise ValueError("Target Explained Variance not exceeded")
-        k = int(over[0].item()) + 1
-        kept = float(csum[k - 1].item())
-        if total < kept:
-            raise ValueError("Variance explained by retained eigenvalues exceeds total variance. Resulting matrix "
-                             "will have negative eigenvalues. Try using a lower threshold.")
-        scale = float(theta.abs().max().item())
-        gap = float((theta[k - 1] - theta[k]).item()) if k < n else float("inf")
-        if k == n or gap > MIN_REL_GAP * scale:
-            c = (total - kept) / (n - k) if n > k else 0.0
-            if k == n:
-                res = C.clone()
-            else:
-                res, _ = _projector_clip(C, lam, float((0.5 * (theta[k - 1] + theta[k])).item()), c)
-            if not (c > 0 and float(theta[k - 1].item()) > 0):
-                warn("Resulting matrix is not positive-definite, and may not be a valid covariance matrix.")
-            res = 0.5 * (res + res.t())
+        res = _clip_keep_top(C, lam, int(over[0].item()) + 1, total)
+        if res is not None:
             return res.contiguous() if (on_device or return_device) else dev.to_host(res.contiguous())
         # (nearly) degenerate eigenvalues at the cut: fall through to the eigenvector routes below
     if n <= FULL_JACOBI_MAX:
@@ -261,6 +310,6 @@ def eigenvalue_clip(cov, method: Literal["explained_variance", "Laloux_2000"] = 
         case "explained_variance":
             return explained_variance_clip(cov, **kwargs)
         case "Laloux_2000":
-            raise NotImplementedError("method='Laloux_2000' is not available on the device path")
+            return laloux_clip(cov, **kwargs)
         case _:
             raise ValueError(f"Unknown clipping method: {method}")

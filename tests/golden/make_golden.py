@@ -188,6 +188,22 @@ def make_kriging_small():
     np.savez_compressed(os.path.join(HERE, "kriging_small.npz"), **out)
 
 
+def make_clip_small():
+    """`eigenvalue_clip` of the reference (both methods) on the indefinite default-method 20-degree covariance."""
+    lats, lons = synth.global_grid(20.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = quiet(ref.EllipseCovarianceBuilder, Lx, Ly, th, sd, lats, lons, v=1.5, precision=np.float64).cov_ns
+    out = {"cov": triu(cov), "min_eig": np.linalg.eigvalsh(cov).min()}
+    clip = ref.covariance_tools.eigenvalue_clip
+    out["ev95"] = triu(quiet(clip, cov))
+    out["ev80"] = triu(quiet(clip, cov, method="explained_variance", target_variance_fraction=0.8))
+    out["laloux_t40"] = triu(quiet(clip, cov, method="Laloux_2000", num_time_pts=40))
+    out["laloux_t400"] = triu(quiet(clip, cov, method="Laloux_2000", num_time_pts=400, num_grid_pts=cov.shape[0]))
+    w = np.linalg.eigvalsh(cov / np.sqrt(np.outer(np.diag(cov), np.diag(cov))))
+    out["laloux_kept"] = np.array([int((w > (1 + np.sqrt(cov.shape[0] / t)) ** 2).sum()) for t in (40, 400)])
+    np.savez_compressed(os.path.join(HERE, "clip_small.npz"), **out)
+
+
 from variogram_cases import VARIOGRAM_CASES  # noqa: E402  (tests/golden/variogram_cases.py)
 
 
@@ -212,6 +228,11 @@ def make_variogram_small():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                      # e.g. `make_golden.py make_clip_small`: regenerate single fixtures
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
+    make_clip_small()
     make_variogram_small()
     make_geostats()
     make_ellipse_small()

@@ -45,6 +45,44 @@ def test_jacobi_eigh_vs_numpy(CT, n):
     assert np.all(np.diff(w) <= 0)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 64, 301, 1000])
+def test_sym_eigvals_vs_numpy(CT, n):
+    """Householder tridiagonalisation + Sturm bisection on the device (csrc/spectrum.cu) against numpy eigvalsh."""
+    import torch
+
+    rng = np.random.default_rng(100 + n)
+    A = rng.standard_normal((n, n))
+    A = A + A.T
+    if n == 64:
+        A[:, 10:20] = 0.0                     # already-tridiagonal columns: zero Householder tails
+        A[10:20, :] = 0.0
+    w = CT.sym_eigvals(torch.from_numpy(A).cuda()).cpu().numpy()
+    want = np.linalg.eigvalsh(A)
+    assert w.shape == (n,) and np.all(np.diff(w) >= 0)
+    assert np.max(np.abs(w - want)) <= 1e-13 * max(1.0, np.abs(want).max()) * max(n, 8)
+
+
+def test_projector_route_vs_eigenvector_routes(CT, monkeypatch):
+    """The default route (eigenvalues + sign-function projector) and the Jacobi eigenvector route agree."""
+    from oracle import EllipseOracle
+
+    lats, lons = synth.global_grid(10.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5).build()
+    want, k, _ = reference_clip(cov, 0.9)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = CT.explained_variance_clip(cov, 0.9)
+        monkeypatch.setattr(CT, "SPECTRAL_MAX", 0)
+        jac = CT.explained_variance_clip(cov, 0.9)
+    assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want))
+    assert np.max(np.abs(jac - want)) <= 1e-9 * np.max(np.abs(want))
+    assert np.array_equal(got, got.T)
+    # nothing to clip: every eigenvalue is kept
+    eye = CT.explained_variance_clip(np.diag([3.0, 2.0, 1.0]), 1.0 - 1e-12)
+    assert np.allclose(eye, np.diag([3.0, 2.0, 1.0]), atol=1e-14)
+
+
 @pytest.mark.parametrize("res,meth", [(10.0, "Modified_Met_Office"), (5.0, "Modified_Met_Office")])
 def test_eigenvalue_clip_vs_reference_algorithm(CT, res, meth):
     from oracle import EllipseOracle
@@ -88,13 +126,31 @@ def test_clip_then_krige_default_workflow(CT):
     assert np.max(np.abs(u ** 2 - ref["uncertainty"] ** 2)) <= 1e-7 * np.max(ref["uncertainty"] ** 2)
 
 
+def test_clip_vs_reference_golden(CT):
+    """Both clipping methods against the unmodified reference's outputs (tests/golden/clip_small.npz)."""
+    from conftest import from_triu, load_golden
+
+    g = load_golden("clip_small.npz")
+    cov = from_triu(g["cov"])
+    scale = np.abs(cov).max()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cases = [(dict(), "ev95"), (dict(method="explained_variance", target_variance_fraction=0.8), "ev80"),
+                 (dict(method="Laloux_2000", num_time_pts=40), "laloux_t40"),
+                 (dict(method="Laloux_2000", num_time_pts=400, num_grid_pts=cov.shape[0]), "laloux_t400")]
+        for kw, tag in cases:
+            got = CT.eigenvalue_clip(cov, **kw)
+            assert got.shape == cov.shape and got.dtype == np.float64
+            assert np.max(np.abs(got - from_triu(g[tag]))) <= 1e-9 * scale, tag
+
+
 def test_clip_errors(CT):
     with pytest.raises(ValueError, match="target_variance_fraction"):
         CT.explained_variance_clip(np.eye(4), 1.5)
     with pytest.raises(ValueError, match="Unknown clipping method"):
         CT.eigenvalue_clip(np.eye(4), method="nope")
-    with pytest.raises(NotImplementedError):
-        CT.eigenvalue_clip(np.eye(4), method="Laloux_2000")
+    with pytest.raises(ValueError, match="Correlation Diagonal"):
+        CT.eigenvalue_clip(np.diag([1.0, 0.0, 2.0]), method="Laloux_2000")
 
 
 def test_subspace_iteration_path_matches_full_jacobi(CT, monkeypatch):
@@ -106,5 +162,6 @@ def test_subspace_iteration_path_matches_full_jacobi(CT, monkeypatch):
     cov = EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5).build()
     want, k, _ = reference_clip(cov, 0.9)
     monkeypatch.setattr(CT, "FULL_JACOBI_MAX", 0)
+    monkeypatch.setattr(CT, "SPECTRAL_MAX", 0)
     got = CT.explained_variance_clip(cov, 0.9)
     assert np.max(np.abs(got - want)) <= 1e-8 * np.max(np.abs(want))

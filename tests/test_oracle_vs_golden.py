@@ -165,3 +165,16 @@ def test_notebook_2014_03_field_chain():
         assert max_norm_rel(got["field"], g[f"{tag}_field"]) <= 1e-8
         assert max_norm_rel(got["uncertainty"] ** 2, g[f"{tag}_unc"] ** 2) <= 1e-8
         assert max_norm_rel(got["constraint_mask"], g[f"{tag}_mask"]) <= 1e-8
+
+
+def test_eigenvalue_clip_oracle_vs_reference_golden():
+    """oracle/covariance_tools.py against the reference's `eigenvalue_clip` outputs (tests/golden/clip_small.npz)."""
+    from oracle.covariance_tools import explained_variance_clip, laloux_clip
+
+    g = load_golden("clip_small.npz")
+    cov = from_triu(g["cov"])
+    scale = np.abs(cov).max()
+    assert np.max(np.abs(explained_variance_clip(cov)[0] - from_triu(g["ev95"]))) <= 1e-11 * scale
+    assert np.max(np.abs(explained_variance_clip(cov, 0.8)[0] - from_triu(g["ev80"]))) <= 1e-11 * scale
+    assert np.max(np.abs(laloux_clip(cov, None, 40) - from_triu(g["laloux_t40"]))) <= 1e-11 * scale
+    assert np.max(np.abs(laloux_clip(cov, cov.shape[0], 400) - from_triu(g["laloux_t400"]))) <= 1e-11 * scale

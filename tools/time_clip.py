@@ -25,3 +25,20 @@ _ = np.linalg.eigvalsh(ref)          # the reference's positive-definiteness che
 t_ref = time.perf_counter() - t0
 print(json.dumps({"n": int(C.shape[0]), "kept": k, "device_s": ts, "reference_algorithm_host_s": t_ref,
                   "max_abs_diff": float(np.max(np.abs(out.cpu().numpy() - ref)))}))
+# phase breakdown of the spectral route
+import glomargridding_b200.covariance_tools as ct
+def timed(fn, reps=3):
+    best = 1e9
+    for _ in range(reps):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return r, best
+lam, t_eig = timed(lambda: ct.sym_eigvals(C))
+we = np.linalg.eigvalsh(covh)
+theta = lam.flip(0); csum = torch.cumsum(theta, 0); total = float(torch.diagonal(C).sum())
+kk = int(torch.nonzero(csum > 0.95 * total)[0]) + 1
+tau = float(0.5 * (theta[kk - 1] + theta[kk])); c = (total - float(csum[kk - 1])) / (C.shape[0] - kk)
+(res, steps), t_proj = timed(lambda: ct._projector_clip(C, lam, tau, c))
+print(json.dumps({"eigvals_s": t_eig, "eigvals_max_abs_err": float(np.max(np.abs(lam.cpu().numpy() - we))),
+                  "k": kk, "rel_gap": float((theta[kk - 1] - theta[kk]) / theta[0]), "newton_schulz_steps": steps,
+                  "projector_s": t_proj}))
