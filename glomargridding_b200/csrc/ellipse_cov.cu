@@ -64,7 +64,7 @@ enum { P_LAT = 0, P_LON = 1, P_HCOS = 2, P_H00 = 3, P_H01 = 4, P_H11 = 5, P_W = 
 __global__ void __launch_bounds__(256) ellipse_prepare_kernel(
     const double* __restrict__ Lx, const double* __restrict__ Ly, const double* __restrict__ theta,
     const double* __restrict__ stdev, const double* __restrict__ lat, const double* __restrict__ lon,
-    int64_t N, int64_t npad, int disp_method, double* __restrict__ aos, double* __restrict__ soa) {
+    int64_t N, int64_t npad, int disp_method, double x_scale, double* __restrict__ aos, double* __restrict__ soa) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= npad + kPadTail) return;
     double rec[P_N];
@@ -84,10 +84,16 @@ __global__ void __launch_bounds__(256) ellipse_prepare_kernel(
         // 0.5*(cos a + cos b) == 0.5 cos a + 0.5 cos b exactly; "Met_Office" has no cos-latitude factor
         // (0.5 + 0.5 == 1)
         rec[P_HCOS] = disp_method == GMG_DISP_MODIFIED_MET_OFFICE ? 0.5 * cos(lat[i]) : 0.5;
-        rec[P_H00] = 0.5 * s00;                 // 0.5*(S_i + S_j)   == 0.5 S_i + 0.5 S_j     exactly
-        rec[P_H01] = 0.5 * s01;
-        rec[P_H11] = 0.5 * s11;
-        rec[P_W] = sd * sqrt(sqrt(det));        // stdev_i * det_i^(1/4): sqrt(sqrt_det_i sqrt_det_j) = q_i q_j
+        // 0.5*(S_i + S_j) == 0.5 S_i + 0.5 S_j exactly.  The constant of the Matern argument, inner = x_scale *
+        // sqrt(Q / det) with x_scale = 2 sqrt(nu) R (:224, :457, :639), is folded into the records: with S' = S /
+        // x_scale^2 the quadratic form and determinant become Q / x_scale^2 and det / x_scale^4, so that
+        // sqrt(Q' / det') = inner and rsqrt(det') = x_scale^2 rsqrt(det) - the latter absorbed by w' = w / x_scale.
+        // One FP64 multiply less per pair; the extra rounding is half an ulp per record entry.
+        const double lam = x_scale * x_scale;
+        rec[P_H00] = (0.5 * s00) / lam;
+        rec[P_H01] = (0.5 * s01) / lam;
+        rec[P_H11] = (0.5 * s11) / lam;
+        rec[P_W] = sd * sqrt(sqrt(det)) / x_scale;   // stdev_i det_i^(1/4): sqrt(sqrt_det_i sqrt_det_j) = w_i w_j
         rec[P_VAR] = sd * sd;                   // diagonal, :246
     } else {
         // padding points of partial tiles: benign values (det = 1 > 0, q = 0 -> cold path), never stored
@@ -142,7 +148,6 @@ __global__ void __launch_bounds__(32) matern_table_kernel(GmgBesselConsts bc, do
 struct MaternCtx {
     GmgBesselConsts bc;
     const double* table;   // shared-memory (tile kernel) or global (pairs kernel) pointer, [coef][interval]
-    double x_scale;        // 2 sqrt(nu) * R: inner = x_scale * sqrt(Q_rad / det)
 };
 
 // degree-7 Horner; the table is coefficient-major, [coef][interval]: neighbouring lanes of a warp fall into the
@@ -248,8 +253,11 @@ __constant__ HotConsts kHot = {6755399441055744.0,        // 1.5 * 2^52
                                4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5, 1.0, 0.375,
                                3.141592653589793, 1.0 / 3.0, (double)(2 * kTabSub)};
 
-// 1/sqrt(a), a > 0 normal: MUFU seed (rel. error < 2^-22) and one cubically convergent step
-//   e = 1 - a r^2,  r <- r + r e (1/2 + 3/8 e)      (error ~ 5/16 e^3 < 2^-64)       5 FP64 instructions
+// 1/sqrt(a), a > 0 normal: MUFU.RSQ64H seed and one cubically convergent step
+//   e = 1 - a r^2,  r <- r + r e (1/2 + 3/8 e)      (error ~ 5/16 e^3)       5 FP64 instructions
+// The quadratic step r <- r + r e / 2 (4 instructions) is NOT enough: measured on B200 it leaves 1.2e-10 relative
+// on covariance entries (the seed is good to ~2^-18 only, and the error of rsqrt(Q) is amplified by the Matern
+// argument), against 5e-14 with the cubic step.
 __device__ __forceinline__ double rsqrt_pos(double a) {
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
@@ -321,9 +329,9 @@ __device__ __forceinline__ double wrap_lon(double dx) {
 
 // Geometry shared by the fast and slow paths: reference `c_ij_anisotropic_array`,
 // ellipse/covariance.py:441-463, with
-//   sqrt(sqrt_det_i sqrt_det_j / det) = q_i q_j rsqrt(det)   and   inner = 2 sqrt(nu) R sqrt(Q) rsqrt(det)
-// where Q is the quadratic form of the displacements in RADIANS (the Earth radius of :639 is folded into the
-// constant).  For "Met_Office" the prepare kernel stores hcos = 0.5, so (a.hcos + b.hcos) == 1.0 exactly and
+//   sqrt(sqrt_det_i sqrt_det_j / det) = w_i w_j rsqrt(det)   and   inner = 2 sqrt(nu) R sqrt(Q) rsqrt(det)
+// where Q is the quadratic form of the displacements in RADIANS (the Earth radius of :639 and 2 sqrt(nu) are
+// folded into the per-point records by the prepare kernel).  For "Met_Office" the prepare kernel stores hcos = 0.5, so (a.hcos + b.hcos) == 1.0 exactly and
 // the mean-cos-latitude factor of "Modified_Met_Office" (:636-637) drops out without a second code path.
 struct PairGeom { double det, q, dx, dy; };
 
@@ -363,10 +371,10 @@ __device__ __forceinline__ double cov_pair(const PointRegs& a, const PointRegs& 
     const PairGeom g = pair_geom<GEOM_F32>(a, b);
 #if K1_EXPERIMENT == 5      // cost of the two reciprocal square roots (kernel-experiment builds, never shipped)
     const double r = g.det * 1e-12;
-    const double x = (m.x_scale * g.q) * (g.q * 1e-3) * r;
+    const double x = g.q * (g.q * 1e-3) * r;
 #else
     const double r = rsqrt_pos(g.det);
-    const double x = (m.x_scale * g.q) * rsqrt_pos(g.q) * r;                    // :457 inner
+    const double x = g.q * rsqrt_pos(g.q) * r;                                  // :457 inner (x_scale is in the records)
 #endif
 #if K1_EXPERIMENT == 7      // cost of the Matern factor
     slow = false;
@@ -391,7 +399,7 @@ __device__ __forceinline__ double cov_pair_slow(const double* pa, const double* 
     b.lat = pb[P_LAT * sb]; b.lon = pb[P_LON * sb]; b.hcos = pb[P_HCOS * sb]; b.h00 = pb[P_H00 * sb];
     b.h01 = pb[P_H01 * sb]; b.h11 = pb[P_H11 * sb]; b.w = pb[P_W * sb];
     const PairGeom g = pair_geom<GEOM_F32>(a, b);
-    const double x = m->x_scale * sqrt(g.q / g.det);
+    const double x = sqrt(g.q / g.det);
     return (a.w * b.w) * rsqrt(g.det) * matern_scaled_eval<MODE>(*m, x) * exp(-x);
 }
 
@@ -659,17 +667,19 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         }
         return n_ids;
     };
-    MacroId t;
-    int id = next_tile(blockIdx.x, t);
-    if (id >= n_ids) return;
-    stage(0, t);
-    cp_async_commit();
+    int id;
+    {
+        MacroId t0;
+        id = next_tile(blockIdx.x, t0);
+        if (id >= n_ids) return;
+        stage(0, t0);
+        cp_async_commit();
+    }
 
     for (int e = tid; e < kExpTab * kExpRep; e += kThreads) sexp[e] = kExp2Neg[e / kExpRep];
     MaternCtx m;
     m.bc = a.bc;
     m.table = stab;
-    m.x_scale = a.bc.two_sqrt_nu * kEarthRadiusKm;
     if (MODE == MODE_TABLE) {
         for (int e = tid; e < kTabDoubles / 2; e += kThreads)
             reinterpret_cast<double2*>(stab)[e] = reinterpret_cast<const double2*>(a.table)[e];
@@ -681,11 +691,19 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
     for (;;) {
         cp_async_wait<0>();                           // this macro tile's records have landed ...
         __syncthreads();                              // ... for every thread, and everybody left the previous one
-        MacroId tn = t;
-        const int id_next = next_tile(id + gridDim.x, tn);
+        // The descriptor of the NEXT macro tile is only needed to issue its loads: it is decoded here and dropped
+        // again, and this tile's own descriptor is re-decoded below (a 32-bit division) instead of being carried in
+        // registers across the row loops (ncu s3a: the table variant spilled both descriptors and stalled on the
+        // reloads at the head of every sub-tile).
+        int id_next;
+        {
+            MacroId tn;
+            id_next = next_tile(id + gridDim.x, tn);
+            if (id_next < n_ids) stage(buf ^ 1, tn);      // in flight while this macro tile is computed
+            cp_async_commit();
+        }
         const bool has_next = id_next < n_ids;
-        if (has_next) stage(buf ^ 1, tn);             // in flight while this macro tile is computed
-        cp_async_commit();
+        const MacroId t = decode_macro<MT>(a, id);
 
         const int I0 = row0 + t.ta * kMR;             // global index of the macro tile's first row point
         const int J0 = t.tb * kMR;                    // global index of the macro tile's first column point
@@ -851,7 +869,6 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         }
         if (!has_next) break;
         id = id_next;
-        t = tn;
         buf ^= 1;
     }
     cp_async_wait<0>();
@@ -873,7 +890,6 @@ __global__ void __launch_bounds__(256) ellipse_pairs_kernel(const double* __rest
     MaternCtx m;
     m.bc = bc;
     m.table = table;
-    m.x_scale = bc.two_sqrt_nu * kEarthRadiusKm;
     const double* pa = params + is[k] * P_N;
     const double* pb = params + js[k] * P_N;
     bool slow;
@@ -898,7 +914,6 @@ __global__ void __launch_bounds__(256) matern_kernel(GmgBesselConsts bc, const d
     MaternCtx m;
     m.bc = bc;
     m.table = table;
-    m.x_scale = 0.0;
     out[k] = matern_scaled_eval<MODE>(m, x[k]) * exp(-x[k]);
 }
 
@@ -1037,11 +1052,11 @@ int gmg_ellipse_prepare_f64(const double* Lx, const double* Ly, const double* th
     cudaStream_t s = (cudaStream_t)stream;
     double* table = const_cast<double*>(ws_table(ws));
     const int64_t npad = pad_points(N);
-    ellipse_prepare_kernel<<<(unsigned)gmg_ceil_div(npad + kPadTail, 256), 256, 0, s>>>(
-        Lx, Ly, theta, stdev, lat_rad, lon_rad, N, npad, disp_method, const_cast<double*>(ws_aos(ws)),
-        const_cast<double*>(ws_soa(ws, N)));
-    GMG_LAUNCH_CHECK();
     const GmgBesselConsts bc = gmg_make_bessel_consts(nu);
+    ellipse_prepare_kernel<<<(unsigned)gmg_ceil_div(npad + kPadTail, 256), 256, 0, s>>>(
+        Lx, Ly, theta, stdev, lat_rad, lon_rad, N, npad, disp_method, bc.two_sqrt_nu * kEarthRadiusKm,
+        const_cast<double*>(ws_aos(ws)), const_cast<double*>(ws_soa(ws, N)));
+    GMG_LAUNCH_CHECK();
     matern_table_kernel<<<kTabNint, 32, 0, s>>>(bc, table);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
