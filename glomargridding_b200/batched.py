@@ -54,37 +54,98 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
         k.subset_error_covariance()
         return k._problem()
 
-    # the per-problem host work is an O(n^2) NaN scan of the error covariance: numpy releases the GIL for it
-    if len(problems) >= 8:
-        from concurrent.futures import ThreadPoolExecutor
-
-        with ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1))) as pool:
-            prepared = list(pool.map(prepare, problems))
-    else:
-        prepared = [prepare(p) for p in problems]
     if max_bytes is None:
         free, _ = torch.cuda.mem_get_info(cov.device)
         max_bytes = int(0.4 * free)
-    out = torch.empty((len(prepared), 5, M), dtype=torch.float64, device=cov.device)
-    start = 0
-    while start < len(prepared):
+    # Chunks of problems: bounded by `max_bytes` of device memory (sized from the unfiltered observation counts, an
+    # upper bound) and - for large batches - at most an eighth of the batch, so that there is something to overlap:
+    # while chunk i runs on the device, a background thread does the host work of chunk i+1 (the classes'
+    # constructor logic - an O(n^2) NaN scan per error covariance, numpy releases the GIL for it -, the packing into
+    # pinned staging buffers and the H2D copies, on a side stream).  End to end the three stages cost about the
+    # same (profiles/: 480 months, 5 GB of error covariances), so the pipeline is worth ~2x.
+    n_all = len(problems)
+    if n_all == 0:
+        empty = np.empty((0, M)) if not return_device else torch.empty((0, M), dtype=torch.float64, device=cov.device)
+        return {"field": empty, ("variance" if return_device else "uncertainty"): empty, "constraint_mask": empty}
+    cap = n_all if n_all < 32 else max(8, (n_all + 7) // 8)
+    bounds, start = [], 0
+    while start < n_all:
         used, stop = 0, start
-        while stop < len(prepared):
-            need = _bytes_per_problem(len(prepared[stop][0]), M)
-            if stop > start and used + need > max_bytes:
+        while stop < n_all and stop - start < cap:
+            need = _bytes_per_problem(len(problems[stop][0]), M)
+            if stop > start and used + need > max_bytes // 2:      # two chunks are alive at a time
                 break
             used += need
             stop += 1
-        batch = dn.KrigeBatch(cov, prepared[start:stop], ordinary=method == "ordinary").run()
-        out[start:stop] = batch.out
-        del batch
+        bounds.append((start, stop))
         start = stop
+    from concurrent.futures import ThreadPoolExecutor
+
+    main_stream = torch.cuda.current_stream(cov.device)
+    side = torch.cuda.Stream(cov.device) if len(bounds) > 1 else main_stream
+    workers = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1))) if n_all >= 8 else None
+
+    timing = os.environ.get("GLOMAR_B200_TIMING")
+    import time as _time
+
+    def prep(lo, hi):
+        chunk = problems[lo:hi]
+        return list(workers.map(prepare, chunk)) if workers is not None else [prepare(p) for p in chunk]
+
+    def upload(prepared_or_future, lo, hi):
+        torch.cuda.set_device(cov.device)
+        t0 = _time.perf_counter()
+        prepared = prepared_or_future.result() if hasattr(prepared_or_future, "result") else prepared_or_future
+        t1 = _time.perf_counter()
+        with torch.cuda.stream(side):
+            kb = dn.KrigeBatch(cov, prepared, ordinary=method == "ordinary")
+            side.synchronize()                                     # uploads complete before the main stream reads them
+        if timing:
+            print(f"[krige_batch] upload {lo}:{hi} waited {1e3 * (t1 - t0):.1f} ms for prepare, pack + H2D "
+                  f"{1e3 * (_time.perf_counter() - t1):.1f} ms", flush=True)
+        return kb
+
+    out = torch.empty((n_all, 5, M), dtype=torch.float64, device=cov.device)
+    try:
+        if len(bounds) == 1:
+            batch = upload(prep(*bounds[0]), *bounds[0]).run()
+            out[:] = batch.out
+            main_stream.synchronize()
+            del batch
+        else:
+            # three stages in flight: constructor logic of chunk i+2.. (one thread feeding the worker pool), packing +
+            # H2D of chunk i+1 (one thread, side stream), device work of chunk i (this thread, current stream)
+            with ThreadPoolExecutor(max_workers=1) as prepper, ThreadPoolExecutor(max_workers=1) as uploader:
+                prepped = [prepper.submit(prep, lo, hi) for lo, hi in bounds]
+                fut = uploader.submit(upload, prepped[0], *bounds[0])
+                for i, (lo, hi) in enumerate(bounds):
+                    tw = _time.perf_counter()
+                    batch = fut.result()
+                    prepped[i] = None
+                    tr = _time.perf_counter()
+                    if i + 1 < len(bounds):
+                        fut = uploader.submit(upload, prepped[i + 1], *bounds[i + 1])
+                    batch.run()
+                    out[lo:hi] = batch.out
+                    main_stream.synchronize()                      # its memory was allocated on the side stream
+                    del batch
+                    if timing:
+                        print(f"[krige_batch] chunk {i}: waited {1e3 * (tr - tw):.1f} ms for its inputs, device "
+                              f"{1e3 * (_time.perf_counter() - tr):.1f} ms", flush=True)
+    finally:
+        if workers is not None:
+            workers.shutdown(wait=True)
+    t_out = _time.perf_counter()
     if return_device:
         field = out[:, dn.OUT_FIELD] + (mean if method == "simple" else 0.0)
         return {"field": field, "variance": out[:, dn.OUT_U2], "constraint_mask": out[:, dn.OUT_MASK]}
-    o = out.cpu().numpy()
+    from . import _device as dev
+
+    o = dev.to_host(out)
     field = o[:, dn.OUT_FIELD] + (mean if method == "simple" else 0.0)
-    unc = np.stack([_finish_uncertainty(o[b, dn.OUT_U2], np.float64) for b in range(o.shape[0])]) if len(o) else o[:, 0]
+    unc = _finish_uncertainty(np.ascontiguousarray(o[:, dn.OUT_U2]), np.float64)     # elementwise: all problems at once
+    if timing:
+        print(f"[krige_batch] results to host + uncertainty clamp {1e3 * (_time.perf_counter() - t_out):.1f} ms", flush=True)
     return {"field": field, "uncertainty": unc, "constraint_mask": o[:, dn.OUT_MASK]}
 
 

@@ -102,7 +102,11 @@ class Kriging(ABC):
                 self.idx = self.idx[idx_keep]
                 self.obs = self.obs[idx_keep]
                 self.error_cov = self.error_cov[idx_keep[:, None], idx_keep[None, :]]
-            self.error_cov[np.isnan(self.error_cov)] = 0.0
+            # NaN -> 0 (reference :120).  A sum is NaN whenever any entry is (or +inf meets -inf), and costs a tenth of
+            # the boolean-mask assignment, which is therefore only run when there is something to replace
+            ec = self.error_cov
+            if not (isinstance(ec, np.ndarray) and ec.dtype.kind == "f") or np.isnan(ec.sum()):
+                ec[np.isnan(ec)] = 0.0
         return None
 
     # -- weights attribute: computed lazily from the device factorisation --------------------------------
