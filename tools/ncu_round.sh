@@ -16,3 +16,5 @@ ncu --set full --clock-control none --import-source on -k regex:trsm_step_fwd -c
     -o gpurun_out/${TAG}_trsm_step python tools/time_kriging.py --months 60 --reps 1 > gpurun_out/${TAG}_trsm_step.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:potrf_diag -c 1 -s 3 -f \
     -o gpurun_out/${TAG}_potrf_diag python tools/time_kriging.py --months 60 --reps 1 > gpurun_out/${TAG}_potrf_diag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:sytrd_kernel -c 1 -s 1 -f \
+    -o gpurun_out/${TAG}_sytrd python tools/time_clip.py > gpurun_out/${TAG}_sytrd.log 2>&1
