@@ -67,7 +67,7 @@ def _h2d_concat(arrays, total: int, device, chunk_bytes: int = 512 << 20) -> tor
     if _STAGE is None or _STAGE[0].numel() < cap:       # pinned allocations are slow (~0.3 s): keep them
         _STAGE = [torch.empty(cap, dtype=torch.float64, pin_memory=True) for _ in range(2)]
     if _POOL is None:
-        _POOL = ThreadPoolExecutor(max_workers=max(1, min(14, (os.cpu_count() or 2) - 2)))   # memcpy-bound packing
+        _POOL = ThreadPoolExecutor(max_workers=dev.host_threads(14))   # memcpy-bound packing
     stage = [t.numpy() for t in _STAGE]
     done = [torch.cuda.Event(), torch.cuda.Event()]
     used = [False, False]

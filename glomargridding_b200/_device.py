@@ -14,6 +14,18 @@ def require_cuda() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def host_threads(cap: int) -> int:
+    """Worker threads for host-side packing / bookkeeping: the cores of the box divided by the ranks that share
+    it (`LOCAL_WORLD_SIZE`, set by torchrun - one process per GPU), one left free, at most `cap`."""
+    import os
+
+    try:
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:
+        ranks = 1
+    return max(1, min(cap, (os.cpu_count() or 2) // ranks - 1))
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 

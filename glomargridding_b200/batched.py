@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from . import _dense as dn
+from . import _device as _dev
 from .kriging import OrdinaryKriging, SimpleKriging, _as_device_cov, _finish_uncertainty
 
 
@@ -58,7 +59,7 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
         free, _ = torch.cuda.mem_get_info(cov.device)
         max_bytes = int(0.4 * free)
     # Chunks of problems: bounded by `max_bytes` of device memory (sized from the unfiltered observation counts, an
-    # upper bound) and - for large batches - at most an eighth of the batch, so that there is something to overlap:
+    # upper bound) and - for large batches - at most an eighth of the batch (but 24 problems or more), so that there is something to overlap:
     # while chunk i runs on the device, a background thread does the host work of chunk i+1 (the classes'
     # constructor logic - an O(n^2) NaN scan per error covariance, numpy releases the GIL for it -, the packing into
     # pinned staging buffers and the H2D copies, on a side stream).  End to end the three stages cost about the
@@ -67,7 +68,7 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
     if n_all == 0:
         empty = np.empty((0, M)) if not return_device else torch.empty((0, M), dtype=torch.float64, device=cov.device)
         return {"field": empty, ("variance" if return_device else "uncertainty"): empty, "constraint_mask": empty}
-    cap = n_all if n_all < 32 else max(8, (n_all + 7) // 8)
+    cap = n_all if n_all < 32 else max(24, (n_all + 7) // 8)
     bounds, start = [], 0
     while start < n_all:
         used, stop = 0, start
@@ -83,7 +84,7 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
 
     main_stream = torch.cuda.current_stream(cov.device)
     side = torch.cuda.Stream(cov.device) if len(bounds) > 1 else main_stream
-    workers = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1))) if n_all >= 8 else None
+    workers = ThreadPoolExecutor(max_workers=_dev.host_threads(8)) if n_all >= 8 else None
 
     timing = os.environ.get("GLOMAR_B200_TIMING")
     import time as _time
