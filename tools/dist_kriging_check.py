@@ -26,9 +26,9 @@ if world > 1:
 
 
 def block(N):
-    tiles = (N + 63) // 64
+    tiles = (N + 127) // 128           # 128-row macro-tile alignment: the symmetric 2 x 2-tile enumeration applies
     t0, t1 = tiles * rank // world, tiles * (rank + 1) // world
-    return t0 * 64, min(N, t1 * 64) - t0 * 64
+    return t0 * 128, min(N, t1 * 128) - t0 * 128
 
 
 def build(res):
