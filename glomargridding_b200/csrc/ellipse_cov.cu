@@ -494,6 +494,34 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- bulk-copy (TMA) + mbarrier helpers for the barrier-free record pipeline (K1_PIPE) ------------------------
+#ifndef K1_PIPE
+#define K1_PIPE 1
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "K1_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra K1_DONE;\n\t"
+        "bra K1_WAIT;\n\t"
+        "K1_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct TileId { int ta, tb; bool mirror; int peer; bool skip; };   // peer: block that receives the mirrored tile
 
 // Tile `id` of the launch -> (row tile, column tile).  In symmetric mode (row0 aligned to the tile size) the
@@ -667,13 +695,47 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         }
         return n_ids;
     };
+    // ---- record pipeline -------------------------------------------------------------------------------------
+    // K1_PIPE: no CTA barrier in the steady state.  The records of macro tile i live in buffer i & 1 and are brought
+    // in by bulk copies (cp.async.bulk, one 8 KB row block + 8 x 1 KB column fields) that complete on an mbarrier;
+    // every warp walks the CTA's tile sequence on its own, waits on that mbarrier, and counts itself out of the
+    // buffer when it is done with the tile - the LAST warp to leave refills the buffer with tile i + 2.  Warps drift
+    // apart by up to a macro tile, so one warp's mirrored stores and sub-tile preambles overlap the other warps' FP64
+    // work (ncu r01: with a CTA barrier per macro tile 6-8 % of the stall samples sat at the barrier).
+    __shared__ __align__(8) unsigned long long full_bar[2];
+    __shared__ int done_cnt[2];
+    constexpr unsigned kStageBytes = 2u * P_N * kMR * sizeof(double);
+    auto issue = [&](int buf, const MacroId& t) {                  // one thread
+        const unsigned bar = smem_u32(&full_bar[buf]);
+        const double* rsrc = a.aos + (a.row0 + (int64_t)t.ta * kMR) * P_N;
+        const double* csrc = a.soa + (int64_t)t.tb * kMR;
+        const unsigned rdst = smem_u32(smem + SL::kRow + buf * (P_N * kMR));
+        const unsigned cdst = smem_u32(smem + SL::kCol + buf * (P_N * kMR));
+        mbar_arrive_expect_tx(bar, kStageBytes);
+        bulk_g2s(rdst, rsrc, P_N * kMR * (unsigned)sizeof(double), bar);
+#pragma unroll
+        for (int f = 0; f < P_N; ++f)
+            bulk_g2s(cdst + f * kMR * (unsigned)sizeof(double), csrc + f * a.npad, kMR * (unsigned)sizeof(double), bar);
+    };
     int id;
     {
         MacroId t0;
         id = next_tile(blockIdx.x, t0);
         if (id >= n_ids) return;
+#if K1_PIPE
+        if (tid == 0) {
+            mbar_init(smem_u32(&full_bar[0]), 1);
+            mbar_init(smem_u32(&full_bar[1]), 1);
+            done_cnt[0] = done_cnt[1] = 0;
+            fence_proxy_async();                                    // the barriers are visible to the copy engine
+            issue(0, t0);
+            MacroId t1;
+            if (next_tile(id + gridDim.x, t1) < n_ids) issue(1, t1);
+        }
+#else
         stage(0, t0);
         cp_async_commit();
+#endif
     }
 
     for (int e = tid; e < kExpTab * kExpRep; e += kThreads) sexp[e] = kExp2Neg[e / kExpRep];
@@ -686,22 +748,33 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
     }
     if (tid == 0) *reinterpret_cast<MaternCtx*>(smem + SL::kCtx) = m;
     const double* sexp_lane = sexp + (lane & (kExpRep - 1));
+#if K1_PIPE
+    __syncthreads();                                  // tables, context and mbarriers are set up
+#endif
 
     int buf = 0;
-    for (;;) {
+    for (int it = 0;; ++it) {
+        int id_next;
+#if K1_PIPE
+        {
+            MacroId tn;
+            id_next = next_tile(id + gridDim.x, tn);
+        }
+        mbar_wait(smem_u32(&full_bar[buf]), (unsigned)(it >> 1) & 1u);   // this macro tile's records have landed
+#else
         cp_async_wait<0>();                           // this macro tile's records have landed ...
         __syncthreads();                              // ... for every thread, and everybody left the previous one
         // The descriptor of the NEXT macro tile is only needed to issue its loads: it is decoded here and dropped
         // again, and this tile's own descriptor is re-decoded below (a 32-bit division) instead of being carried in
         // registers across the row loops (ncu s3a: the table variant spilled both descriptors and stalled on the
         // reloads at the head of every sub-tile).
-        int id_next;
         {
             MacroId tn;
             id_next = next_tile(id + gridDim.x, tn);
             if (id_next < n_ids) stage(buf ^ 1, tn);      // in flight while this macro tile is computed
             cp_async_commit();
         }
+#endif
         const bool has_next = id_next < n_ids;
         const MacroId t = decode_macro<MT>(a, id);
 
@@ -867,11 +940,30 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
                 __syncwarp();                             // strip free for the next sub-tile
             }
         }
+#if K1_PIPE
+        // leave the buffer; the last warp out refills it with the tile after next
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();                    // this warp's reads of the buffer are done
+            if (atomicAdd(&done_cnt[buf], 1) == kThreads / 32 - 1) {
+                done_cnt[buf] = 0;
+                __threadfence_block();
+                MacroId t2;
+                if (has_next && next_tile(id_next + gridDim.x, t2) < n_ids) {
+                    fence_proxy_async();              // generic-proxy reads before the async-proxy overwrite
+                    issue(buf, t2);
+                }
+            }
+        }
+        __syncwarp();
+#endif
         if (!has_next) break;
         id = id_next;
         buf ^= 1;
     }
+#if !K1_PIPE
     cp_async_wait<0>();
+#endif
 }
 
 template <int MODE>
