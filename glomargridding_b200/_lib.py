@@ -59,6 +59,9 @@ def _declare(lib):
         "gmg_normal_f64": (c_int, [p, i64, u64, u64, p]),
         "gmg_jacobi_eigh_ws_bytes": (c_int, [i64, POINTER(c_size_t)]),
         "gmg_jacobi_eigh_f64": (c_int, [p, i64, p, i64, i64, i32, dbl, p, c_size_t, p, p]),
+        "gmg_cov2cor": (c_int, [p, i64, i64, i32, p, p, i64, p, p]),
+        "gmg_cor2cov": (c_int, [p, i64, i64, i32, p, p, i64, p]),
+        "gmg_uncompress": (c_int, [p, i64, p, i64, i32, dbl, dbl, p, i64, p]),
         "gmg_sym_eigvals_ws_bytes": (c_int, [i64, POINTER(c_size_t)]),
         "gmg_sym_eigvals_f64": (c_int, [p, i64, i64, p, p, c_size_t, p]),
         "gmg_variogram_f64": (c_int, [i32, p, i64, i64, i64, dbl, dbl, dbl, dbl, i32, i32, i32, dbl, p, i64, p]),

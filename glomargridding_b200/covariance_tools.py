@@ -37,6 +37,7 @@ import torch
 from . import _dense as dn
 from . import _device as dev
 from ._lib import check, lib
+from .utils import cor_2_cov, cov_2_cor
 
 
 FULL_JACOBI_MAX = 4096      # up to this order C can be diagonalised directly (Jacobi); beyond it, subspace iteration
@@ -207,16 +208,8 @@ def laloux_clip(cov, num_grid_pts: int | None = None, num_time_pts: int = 40, re
     if n > SPECTRAL_MAX:
         raise NotImplementedError(f"method='Laloux_2000' is limited to matrices of order <= {SPECTRAL_MAX} on the device")
     num_grid_pts = num_grid_pts or n
-    sd = torch.sqrt(torch.diagonal(C))
-    norm = sd[:, None] * sd[None, :]
-    cor = C / norm                                            # elementwise plumbing (utils.cov_2_cor)
-    dg = torch.diagonal(cor)
-    if not bool((dg == 1.0).all()):
-        bad = float((dg - 1.0).abs().max().item())
-        if not bad <= 1e-6:                                   # also catches NaN (zero / negative variances)
-            raise ValueError(f"Correlation Diagonal contains values not close to 1. With difference to 1: {bad}")
-        dg.fill_(1.0)
-    cor[C == 0] = 0.0
+    variances = torch.diagonal(C).clone()
+    cor = cov_2_cor(C)                                        # gmg_cov2cor; raises like the reference on a bad diagonal
     q = num_grid_pts / num_time_pts
     if q < 1.0:
         q = 1.0 / q
@@ -232,9 +225,8 @@ def laloux_clip(cov, num_grid_pts: int | None = None, num_time_pts: int = 40, re
         new[k:] = c
         res = dn.gemm(dn.padded(U * new[None, :]), dn.padded(U), transb=True)[:, :n]
         res = 0.5 * (res + res.t())
-    out = res * norm                                          # utils.cor_2_cov
-    out[res == 0] = 0.0
-    return out.contiguous() if (on_device or return_device) else dev.to_host(out.contiguous())
+    out = cor_2_cov(res.contiguous(), variances)              # gmg_cor2cov
+    return out if (on_device or return_device) else dev.to_host(out)
 
 
 def explained_variance_clip(cov, target_variance_fraction: float = 0.95, return_device: bool = False):

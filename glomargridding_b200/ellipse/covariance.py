@@ -234,18 +234,41 @@ class EllipseCovarianceBuilder:
         return out.cpu().numpy().astype(self.precision)
 
     def calculate_cor(self) -> None:
-        """Correlation matrix from the covariance matrix (reference `:470-473`)."""
-        self.cor_ns = cov_2_cor(self.cov_ns)
+        """Correlation matrix from the covariance matrix (reference `:470-473`), on the device; `cor_ns` is copied to
+        the host on first use, `cor_ns_device` is the CUDA tensor."""
+        if self.cov_ns_device is None:
+            self.cov_ns_device = dev.to_device(self._cov_ns_host,
+                                               torch.float32 if self.precision == np.float32 else torch.float64)
+        if self.cov_ns_device.shape[0] != self.cov_ns_device.shape[1]:
+            raise ValueError("calculate_cor needs the full matrix (this builder holds a row block)")
+        self.cor_ns_device = cov_2_cor(self.cov_ns_device)
+        self._cor_ns_host = None
+
+    @property
+    def cor_ns(self) -> np.ndarray:
+        if getattr(self, "cor_ns_device", None) is None:
+            raise AttributeError("cor_ns")                       # reference: the attribute exists after calculate_cor()
+        if self._cor_ns_host is None:
+            self._cor_ns_host = dev.to_host(self.cor_ns_device)
+        return self._cor_ns_host
 
     def uncompress_cov(self, diag_fill_value: Any = np.nan, fill_value: Any = np.nan) -> None:
-        """Scatter the compressed matrix into full-grid size (reference `:475-509`); overwrites `cov_ns`."""
-        cov = self.cov_ns
+        """Scatter the compressed matrix into full-grid size (reference `:475-509`) on the device; overwrites
+        `cov_ns` / `cov_ns_device`."""
+        if self.cov_ns_device is None:
+            self.cov_ns_device = dev.to_device(self._cov_ns_host,
+                                               torch.float32 if self.precision == np.float32 else torch.float64)
+        cov = self.cov_ns_device
         flat = np.asarray(self.data_mask).flatten()
-        if not np.sum(~flat) == cov.shape[0]:
+        if cov.shape[0] != cov.shape[1] or not np.sum(~flat) == cov.shape[0]:
             raise ValueError("Data mask and coordinates cannot be aligned")
         M = flat.size
-        out = np.full((M, M), fill_value, dtype=self.precision)
-        out[np.arange(M), np.arange(M)] = diag_fill_value
-        keep = np.flatnonzero(~flat)
-        out[np.ix_(keep, keep)] = cov
-        self.cov_ns = out
+        inv = np.full(M, -1, dtype=np.int32)
+        inv[~flat] = np.arange(cov.shape[0], dtype=np.int32)
+        inv_t = dev.to_device(inv, torch.int32)
+        out = torch.empty((M, M), dtype=cov.dtype, device=cov.device)
+        check(lib().gmg_uncompress(cov.data_ptr(), cov.stride(0), inv_t.data_ptr(), M,
+                                   int(cov.dtype == torch.float32), float(fill_value), float(diag_fill_value),
+                                   out.data_ptr(), M, dev.stream_ptr()), "gmg_uncompress")
+        torch.cuda.current_stream().synchronize()                # inv_t dies with this frame
+        self.cov_ns_device, self._cov_ns_host = out, None

@@ -1,7 +1,7 @@
 """Host-side helpers of the hot path, mirroring the reference's `glomar_gridding/utils.py`.
 
-Only the helpers the ellipse / kriging classes use are provided: they act on
-O(N)-sized vectors or are pure bookkeeping; the N x N arithmetic lives in the CUDA library.
+Only the helpers the ellipse / kriging classes use are provided.  The N x N ones (`cov_2_cor`,
+`cor_2_cov`) run on the GPU through the C ABI; the rest act on O(N)-sized vectors or are pure bookkeeping.
 """
 
 from __future__ import annotations
@@ -28,33 +28,71 @@ def adjust_small_negative(mat: np.ndarray, atol: float = 1e-8) -> np.ndarray:
     return ret.astype(mat.dtype)
 
 
-def cor_2_cov(cor: np.ndarray, variances: np.ndarray, rounding: int | None = None) -> np.ndarray:
-    """Covariance from correlation and variances (reference `utils.py:611-634`)."""
-    stdevs = np.sqrt(variances)
-    cov = cor * np.outer(stdevs, stdevs)
-    cov[cor == 0] = 0
+def _as_matrix(a):
+    """numpy / torch matrix -> (CUDA tensor float32|float64 with unit column stride, was_tensor, numpy dtype)."""
+    import torch
+
+    from . import _device as dev
+
+    if isinstance(a, torch.Tensor):
+        dt = a.dtype if a.dtype in (torch.float32, torch.float64) else torch.float64
+        t = a.to(dev.require_cuda(), dt)
+        return (t if t.stride(1) == 1 else t.contiguous()), True, (np.float32 if dt == torch.float32 else np.float64)
+    arr = np.asarray(a)
+    npdt = np.float32 if arr.dtype == np.float32 else np.float64
+    return dev.to_device(arr, torch.float32 if npdt == np.float32 else torch.float64), False, npdt
+
+
+def cor_2_cov(cor, variances, rounding: int | None = None, return_device: bool = False):
+    """Covariance from correlation and variances (reference `utils.py:611-634`): `cor * outer(sd, sd)` with the
+    exact zeros of `cor` kept, evaluated on the GPU (`gmg_cor2cov`) in the matrix' own precision.
+    numpy in -> numpy out; CUDA tensor in (or `return_device`) -> CUDA tensor out."""
+    import torch
+
+    from . import _device as dev
+    from ._lib import check, lib
+
+    C, was_tensor, npdt = _as_matrix(cor)
+    n = C.shape[0]
+    var = variances if isinstance(variances, torch.Tensor) else torch.from_numpy(np.array(variances, copy=True))
+    sd = torch.sqrt(var.to(C.device, C.dtype)).contiguous()                  # O(n) plumbing
+    out = torch.empty((n, n), dtype=C.dtype, device=C.device)
+    check(lib().gmg_cor2cov(C.data_ptr(), C.stride(0), n, int(npdt == np.float32), sd.data_ptr(), out.data_ptr(), n,
+                            dev.stream_ptr()), "gmg_cor2cov")
     if rounding is not None:
-        cov = np.round(cov, rounding)
-    return cov
+        out = torch.round(out, decimals=rounding)
+    return out if (was_tensor or return_device) else dev.to_host(out)
 
 
-def cov_2_cor(cov: np.ndarray, rounding: int | None = None) -> np.ndarray:
-    """Correlation from covariance, unit diagonal enforced, exact zeros kept (reference `utils.py:637-671`)."""
-    stdevs = np.sqrt(np.diag(cov))
-    cor = cov / np.outer(stdevs, stdevs)
-    if not np.all(np.diag(cor) == 1.0):
-        bad_val = np.max(np.abs(np.diag(cor) - 1.0))
-        if bad_val > 1e-6:
+def cov_2_cor(cov, rounding: int | None = None, return_device: bool = False):
+    """Correlation from covariance, unit diagonal enforced, exact zeros kept (reference `utils.py:637-671`),
+    evaluated on the GPU (`gmg_cov2cor`) in the matrix' own precision.
+    numpy in -> numpy out; CUDA tensor in (or `return_device`) -> CUDA tensor out."""
+    import torch
+
+    from . import _device as dev
+    from ._lib import check, lib
+
+    C, was_tensor, npdt = _as_matrix(cov)
+    n = C.shape[0]
+    sd = torch.empty(n, dtype=C.dtype, device=C.device)
+    stat = torch.zeros(2, dtype=torch.int64, device=C.device)
+    cor = torch.empty((n, n), dtype=C.dtype, device=C.device)
+    check(lib().gmg_cov2cor(C.data_ptr(), C.stride(0), n, int(npdt == np.float32), sd.data_ptr(), cor.data_ptr(), n,
+                            stat.data_ptr(), dev.stream_ptr()), "gmg_cov2cor")
+    n_bad, dev_bits = (int(x) for x in stat.cpu().numpy())
+    if n_bad:
+        bad_val = float(np.array([dev_bits], dtype=np.int64).view(np.float64)[0])
+        if not bad_val <= 1e-6:
             raise ValueError(
                 "Correlation Diagonal contains values not close to 1. " + f"With difference to 1: {bad_val}"
             )
         print("Numerical error correction applied to correlation matrix diagonal "
               + f"With difference to 1: {bad_val}")
-        np.fill_diagonal(cor, 1.0)
-    cor[cov == 0] = 0
+        cor.fill_diagonal_(1.0)
     if rounding is not None:
-        cor = np.round(cor, rounding)
-    return cor
+        cor = torch.round(cor, decimals=rounding)
+    return cor if (was_tensor or return_device) else dev.to_host(cor)
 
 
 def mask_array(arr: np.ndarray) -> np.ma.MaskedArray:

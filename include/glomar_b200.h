@@ -270,6 +270,25 @@ int gmg_jacobi_eigh_f64(double* A, int64_t lda, double* U, int64_t ldu, int64_t 
                         gmg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N x N bookkeeping of the covariance path, arithmetic in the matrix' own precision (is_f32).
+ *   gmg_cov2cor     utils.cov_2_cor, glomar_gridding/utils.py:637-671 (EllipseCovarianceBuilder.calculate_cor,
+ *                   ellipse/covariance.py:470-473): cor = cov / outer(sd, sd), sd = sqrt(diag(cov)) (written to
+ *                   sd_ws, n elements), zeros kept.  stat (device, 2 x u64): [0] = number of diagonal entries
+ *                   != 1, [1] = bit pattern of the largest |diag - 1| as a double - the caller resets the diagonal
+ *                   or raises like the reference (:655-668).
+ *   gmg_cor2cov     utils.cor_2_cov, utils.py:611-634: cov = cor * outer(sd, sd), zeros kept.
+ *   gmg_uncompress  EllipseCovarianceBuilder.uncompress_cov, ellipse/covariance.py:475-509: out (M x M) gets
+ *                   cov[inv[r], inv[c]] where both points are unmasked (inv >= 0), diag_fill on the rest of the
+ *                   diagonal, fill elsewhere.
+ * ------------------------------------------------------------------------------------------- */
+int gmg_cov2cor(const void* cov, int64_t ld, int64_t n, int is_f32, void* sd_ws, void* cor, int64_t ldo,
+                unsigned long long* stat, gmg_stream_t stream);
+int gmg_cor2cov(const void* cor, int64_t ld, int64_t n, int is_f32, const void* sd, void* cov, int64_t ldo,
+                gmg_stream_t stream);
+int gmg_uncompress(const void* cov, int64_t ld, const int* inv, int64_t M, int is_f32, double fill,
+                   double diag_fill, void* out, int64_t ldo, gmg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * All eigenvalues of a dense symmetric matrix (ascending) - the spectrum `explained_variance_clip`
  * needs to find its cut (glomar_gridding/covariance_tools.py:616, :717 take them from a full
  * numpy.linalg.eigh).  Householder tridiagonalisation in one cooperative kernel (rank-2 update fused

@@ -172,3 +172,43 @@ def test_haversine_distance_matrix_vs_oracle(Builder):
     assert np.allclose(haversine_distance_from_frame({"lat": lat[:5], "lon": lon[:5]}, radius=1.0) * 6371, got[:5, :5])
     with pytest.raises(ValueError, match="only contain 'lat' and 'lon'"):
         haversine_distance_from_frame({"lon": lon, "lat": lat})
+
+
+@pytest.mark.parametrize("prec", [np.float64, np.float32])
+def test_calculate_cor_and_uncompress_on_device_vs_oracle(Builder, prec):
+    """`calculate_cor` (utils.cov_2_cor, reference utils.py:637-671) and `uncompress_cov` (ellipse/covariance.py:475-509)
+    run as CUDA kernels: bit-equal to the numpy restatement (same IEEE operations in the matrix' own precision)."""
+    import torch
+
+    from glomargridding_b200.utils import cor_2_cov, cov_2_cor
+    from oracle.ellipse import cov_2_cor as cor_oracle
+    from oracle.ellipse import uncompress_cov as unc_oracle
+
+    lats, lons = synth.global_grid(20.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons, land_mask=True)
+    b = Builder(Lx, Ly, th, sd, lats, lons, v=1.5, precision=prec, max_dist=9000.0)     # max_dist: exact zeros
+    cov = b.cov_ns.copy()
+    assert cov.dtype == prec and (cov == 0).sum() > 0
+    b.calculate_cor()
+    want = cor_oracle(cov)
+    assert b.cor_ns.dtype == prec and b.cor_ns_device.is_cuda
+    assert np.array_equal(b.cor_ns, want)
+    assert np.all(np.diag(b.cor_ns) == 1) and ((b.cor_ns == 0) == (cov == 0)).all()
+    # round trip through the functional forms, numpy in / numpy out and tensor in / tensor out
+    back = cor_2_cov(b.cor_ns, np.diag(cov))
+    assert back.dtype == prec and np.array_equal(back, want * np.outer(np.sqrt(np.diag(cov)), np.sqrt(np.diag(cov))))
+    t = cov_2_cor(torch.from_numpy(cov).cuda())
+    assert isinstance(t, torch.Tensor) and t.is_cuda and np.array_equal(t.cpu().numpy(), want)
+    for fills in ((np.nan, np.nan), (1.0, 0.0)):
+        b2 = Builder(Lx, Ly, th, sd, lats, lons, v=1.5, precision=prec, max_dist=9000.0)
+        b2.uncompress_cov(*fills)
+        got = b2.cov_ns
+        ref = unc_oracle(cov, b2.data_mask, *fills)
+        assert got.shape == (Lx.size, Lx.size) and got.dtype == prec
+        assert np.array_equal(got, ref, equal_nan=True)
+    with pytest.raises(ValueError, match="Correlation Diagonal"):
+        cov_2_cor(np.diag([1.0, 0.0, 4.0]))
+    bad = Builder(Lx, Ly, th, sd, lats, lons, v=1.5, precision=prec)
+    bad.data_mask = np.zeros_like(np.asarray(bad.data_mask))
+    with pytest.raises(ValueError, match="cannot be aligned"):
+        bad.uncompress_cov()
