@@ -58,24 +58,32 @@ def sym_eigvals(C: torch.Tensor) -> torch.Tensor:
     return w
 
 
-def _projector_clip(C: torch.Tensor, lam: torch.Tensor, tau: float, c: float, max_steps: int = 80):
-    """c I + P (C - c I) with P the spectral projector of C for the eigenvalues above tau; `lam` = all eigenvalues.
-    Returns (matrix (n, n) view of an even-ld buffer, Newton-Schulz steps taken)."""
+def matrix_sign(C: torch.Tensor, lam: torch.Tensor, tau: float = 0.0, max_steps: int = 80, zero_tol: float = 1e-13):
+    """sign(C - tau I) of a symmetric device matrix by the scaled Newton-Schulz iteration X <- (mu/2) X (3 I - mu^2 X^2)
+    (two DMMA GEMMs per step).  `lam` = all eigenvalues of C (`sym_eigvals`): the scalar recurrence is run on them
+    alongside the matrix one, which gives the optimal scaling mu = sqrt(3 / (a^2 + a b + b^2)) of every step from the
+    current extreme moduli a, b, and the step count.  Eigenvalues within `zero_tol` (relative) of tau are treated as
+    zeros of the sign function.  Returns (X as an (n, even ld) buffer, steps)."""
     n = C.shape[0]
     X = dn.padded(C)
     X[:, :n].diagonal().sub_(tau)
     x = lam - tau                                             # the spectrum of X, iterated alongside
     s = float(x.abs().max().item()) * (1.0 + 1e-12)
+    if s == 0.0:
+        return torch.zeros_like(X), 0
     X.div_(s)
     x = x / s
+    x = x[x.abs() > zero_tol]
     steps = 0
     for steps in range(max_steps + 1):
+        if x.numel() == 0:
+            break
         ax = x.abs()
         a, b = float(ax.min().item()), float(ax.max().item())
         if 1.0 - a <= 4e-16 and b - 1.0 <= 4e-16:
             break
         if steps == max_steps:
-            raise np.linalg.LinAlgError("sign-function iteration of eigenvalue_clip did not converge")
+            raise np.linalg.LinAlgError("sign-function iteration did not converge")
         mu = (3.0 / (a * a + a * b + b * b)) ** 0.5
         Y = torch.zeros_like(X)
         dn.gemm(X[:, :n], X[:, :n], out=Y[:, :n])             # X^2
@@ -83,6 +91,27 @@ def _projector_clip(C: torch.Tensor, lam: torch.Tensor, tau: float, c: float, ma
         dn.gemm(X[:, :n], Y[:, :n], out=Xn[:, :n], alpha=-0.5 * mu ** 3, beta=1.5 * mu)
         x = 0.5 * mu * x * (3.0 - (mu * x) ** 2)
         X = Xn
+    return X, steps
+
+
+def matrix_abs(C: torch.Tensor, lam: torch.Tensor | None = None) -> torch.Tensor:
+    """|C| = V |Lambda| V^T = C sign(C) of a symmetric device matrix - the covariance `numpy.random.multivariate_normal`
+    actually draws from when it is handed an indefinite matrix (its SVD factor uses the singular values)."""
+    n = C.shape[0]
+    lam = sym_eigvals(C) if lam is None else lam
+    X, _ = matrix_sign(C, lam)
+    Cp = dn.padded(C)
+    out = torch.zeros_like(Cp)
+    dn.gemm(Cp[:, :n], X[:, :n], out=out[:, :n])
+    res = out[:, :n]
+    return (0.5 * (res + res.t())).contiguous()
+
+
+def _projector_clip(C: torch.Tensor, lam: torch.Tensor, tau: float, c: float, max_steps: int = 80):
+    """c I + P (C - c I) with P the spectral projector of C for the eigenvalues above tau; `lam` = all eigenvalues.
+    Returns (matrix (n, n) view of an even-ld buffer, Newton-Schulz steps taken)."""
+    n = C.shape[0]
+    X, steps = matrix_sign(C, lam, tau, max_steps, zero_tol=0.0)
     Cc = dn.padded(C)
     Cc[:, :n].diagonal().sub_(c)
     out = Cc.clone()

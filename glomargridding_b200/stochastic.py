@@ -9,8 +9,9 @@ state and simulated observations.  Both sets of weights come from ONE device Cho
 Draw parity with the reference is impossible by construction: `np.random.multivariate_normal`
 uses numpy's legacy MT19937 stream and an SVD factor.  What is kept: shapes, dtypes, the deterministic
 sub-results, reproducibility under `np.random.seed` (the Philox key is drawn from numpy's global state), and the
-distribution N(loc, cov).  A covariance that is not positive definite is retried with a diagonal jitter
-(warning), which plays the role of the reference's eigenvalue-clipping fallback (`:469-500`).
+distribution N(loc, cov).  For an INDEFINITE covariance numpy's SVD factor draws from V |Lambda| V^T (with a
+RuntimeWarning); so does this implementation, through |C| = C sign(C) on the device; a merely singular matrix gets a
+small diagonal lift (warning) before its Cholesky factorisation.
 """
 
 from __future__ import annotations
@@ -186,18 +187,34 @@ class StochasticKriging(Kriging):
 
 
 def _chol_with_jitter(cov_t: torch.Tensor, n: int) -> torch.Tensor:
-    """Lower Cholesky factor (upper triangle zeroed) of an n x n device matrix; on a non-positive pivot the
-    diagonal is lifted by 1e-10, 1e-8, 1e-6 x mean(diag) (warning), then the error is raised."""
-    mean_diag = float(torch.diagonal(cov_t[:, :n]).mean().item())
+    """Lower Cholesky factor (upper triangle zeroed) of the covariance the draws come from.
+
+    A positive definite matrix is factored as it is.  Otherwise the reference's `np.random.multivariate_normal`
+    (`stochastic.py:460`) does not fail: it warns and draws from its SVD factor, i.e. from V |Lambda| V^T.  The same
+    here: an indefinite matrix (n <= covariance_tools.SPECTRAL_MAX) is replaced by |C| = C sign(C) (device
+    eigenvalues + sign-function iteration on DMMA GEMMs) with numpy's warning; what is then still singular gets a
+    diagonal lift of 1e-10, 1e-8, 1e-6 x mean(diag) (warning), after which the reference's error is raised."""
+    from . import covariance_tools as ct
+
+    src = cov_t[:, :n]
+    mean_diag = float(torch.diagonal(src).mean().item())
     last = None
-    for jitter in (0.0, 1e-10, 1e-8, 1e-6):
-        L = dn.padded(cov_t[:, :n])
+    tried_abs = False
+    for jitter in (0.0, 0.0, 1e-10, 1e-8, 1e-6):
+        L = dn.padded(src)
         if jitter:
             L[:, :n].diagonal().add_(jitter * mean_diag)
         try:
             dn.factor_inplace(L, n, "cov")
         except np.linalg.LinAlgError as e:
             last = e
+            if not tried_abs:
+                tried_abs = True
+                if 2 <= n <= ct.SPECTRAL_MAX:
+                    lam = ct.sym_eigvals(src.contiguous())
+                    if float(lam[0].item()) < -1e-12 * float(lam.abs().max().item()):
+                        warn("covariance is not symmetric positive-semidefinite.", RuntimeWarning)   # numpy's text
+                        src = ct.matrix_abs(src.contiguous(), lam)
             continue
         if jitter:
             warn(f"covariance is not positive definite; drew from cov + {jitter:g} * mean(diag) * I")

@@ -361,6 +361,39 @@ def test_mv_normal_draw_shapes_seed_and_distribution(K):
         K.scipy_mv_normal_draw(loc, np.ones((3, 4)))
 
 
+def test_mv_normal_draw_from_indefinite_covariance_like_numpy(K):
+    """`np.random.multivariate_normal` (reference stochastic.py:460) draws from its SVD factor, i.e. from V |Lambda| V^T,
+    when the covariance is indefinite (and warns).  Same distribution here, through |C| = C sign(C) on the device;
+    a StochasticKriging solve on the un-clipped default covariance therefore runs like the reference's does."""
+    import torch
+
+    import glomargridding_b200.covariance_tools as ct
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(20.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, precision=np.float64).cov_ns
+    w, v = np.linalg.eigh(cov)
+    assert w.min() < -1e-4                                           # indefinite (SURVEY.md H3)
+    want = (v * np.abs(w)) @ v.T
+    got = ct.matrix_abs(torch.from_numpy(cov).cuda()).cpu().numpy()
+    assert np.max(np.abs(got - want)) <= 1e-11 * np.abs(want).max()
+    n, nd = cov.shape[0], 60000
+    with pytest.warns(RuntimeWarning, match="not symmetric positive-semidefinite"):
+        X = K.scipy_mv_normal_draw(np.zeros(n), cov, nd, seed=7)
+    emp = np.cov(X.T)
+    assert np.linalg.norm(emp - want) / np.linalg.norm(want) < 4 * np.sqrt(n / nd)
+    assert np.linalg.norm(emp - want) < np.linalg.norm(emp - cov)       # |C|, not C
+    idx, obs = synth.fixed_observations(5, n, 60)
+    E = synth.hadcrut_style_error_cov(idx, lons.size)
+    np.random.seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        st = K.StochasticKriging(cov, idx, obs, E)
+        res = st.solve()
+    assert res.shape == (n,) and np.isfinite(res).all()
+
+
 def test_normal_generator_moments(K):
     import torch
 
