@@ -463,10 +463,20 @@ def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.T
     assert T.shape[1] >= Mc + 2
     import torch.distributed as dist
 
+    import time
+
+    timing = bool(os.environ.get("GLOMAR_B200_TIMING"))
+    if timing:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
     if group is not False and dist.is_initialized() and dist.get_world_size(group) > 1:
         ws = factor_inplace_distributed(S, n, group, "observation covariance C[idx, idx] + E")
     else:
         ws = factor_inplace(S, n, "observation covariance C[idx, idx] + E")
+    if timing:
+        torch.cuda.synchronize()
+        if not dist.is_initialized() or dist.get_rank() == 0:
+            print(f"[solve_prepared] Cholesky n = {n}: {1e3 * (time.perf_counter() - t0):.1f} ms", flush=True)
     slabs = (n + SLAB - 1) // SLAB
     partial = torch.empty(3 * slabs * Mc, dtype=torch.float64, device=S.device)
     out = torch.empty((5, Mc), dtype=torch.float64, device=S.device)

@@ -67,12 +67,13 @@ __device__ __forceinline__ void load_rowk(double* s, const double* G, int64_t ld
     }
 }
 
-// Fetch one [BK][cols] k-slab of a matrix stored k x cols (row-major) into a [k][col] tile (ld = LDN).
+// Fetch one [BK][cols] k-slab of a matrix stored k x cols (row-major) into a [k][col] tile (ld = LDN); NC = columns.
+template <int NC = BN>
 __device__ __forceinline__ void load_kcol(double* s, const double* G, int64_t ld, int col0, int cols_total, int k0,
                                           int k_total, int tid) {
 #pragma unroll
-    for (int c = tid; c < BK * (BN / 2); c += GEMM_THREADS) {
-        const int r = c / (BN / 2), c2 = c % (BN / 2);
+    for (int c = tid; c < BK * (NC / 2); c += GEMM_THREADS) {
+        const int r = c / (NC / 2), c2 = c % (NC / 2);
         const int gk = k0 + r, gc = col0 + 2 * c2;
         int bytes = (gk < k_total) ? (cols_total - gc) * 8 : 0;
         bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
@@ -81,22 +82,29 @@ __device__ __forceinline__ void load_kcol(double* s, const double* G, int64_t ld
     }
 }
 
-// D[m0.., n0..] = alpha op(A) op(B) + beta C for one BM x BN tile.  `smem` = GEMM_SMEM_BYTES, 16 B aligned.
+// D[m0.., n0..] = alpha op(A) op(B) + beta C for one BM x BNT tile.  `smem` = GEMM_SMEM_BYTES, 16 B aligned.
+// BNT = 128 (default) or 64: the narrow tile halves the work per CTA (warp tile 32 x 16) and is used by the
+// triangular-solve steps when the right-hand sides give fewer 128-column strips than the GPU has SMs (a column-sharded
+// solve on 8 GPUs has 64 of them for 148 SMs).  Every output element is accumulated over k in the same order either
+// way, so the two tile shapes give bit-identical results.
 // Every thread of the 512-thread CTA must call this (it contains __syncthreads).
 // In-place note: a CTA reads all of its A / B slabs before the epilogue writes D, so D may alias rows of A
 // or B that only THIS tile reads (used by the panel solve and the triangular solves).
-template <bool TA, bool TB>
+template <bool TA, bool TB, int BNT = BN>
 __device__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
+    static_assert(BNT == 128 || BNT == 64, "tile widths: 128 or 64 columns");
+    constexpr int NJ = BNT / 32;          // 8-column DMMA tiles per warp along n
+    constexpr int WN = BNT / 4;           // columns per warp
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 2, wn = warp & 3;
     const int grp = lane >> 2, t4 = lane & 3;
 
-    double acc[4][4][2];
+    double acc[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int nk = (g.k + BK - 1) / BK;
     auto load_stage = [&](int kt) {
@@ -105,7 +113,7 @@ __device__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
         if (TA) load_kcol(sA, g.A, g.lda, m0, g.m, kt * BK, g.k, tid);
         else    load_rowk(sA, g.A, g.lda, m0, g.m, kt * BK, g.k, tid);
         if (TB) load_rowk(sB, g.B, g.ldb, n0, g.n, kt * BK, g.k, tid);
-        else    load_kcol(sB, g.B, g.ldb, n0, g.n, kt * BK, g.k, tid);
+        else    load_kcol<BNT>(sB, g.B, g.ldb, n0, g.n, kt * BK, g.k, tid);
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -121,19 +129,19 @@ __device__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
         const double* sB = sA + TILE_DOUBLES;
 #pragma unroll
         for (int k4 = 0; k4 < BK / 4; ++k4) {
-            double a[4], b[4];
+            double a[4], b[NJ];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 a[i] = TA ? sA[(k4 * 4 + t4) * LDN + wm * 32 + i * 8 + grp]
                           : sA[(wm * 32 + i * 8 + grp) * LDK + k4 * 4 + t4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                b[j] = TB ? sB[(wn * 32 + j * 8 + grp) * LDK + k4 * 4 + t4]
-                          : sB[(k4 * 4 + t4) * LDN + wn * 32 + j * 8 + grp];
+            for (int j = 0; j < NJ; ++j)
+                b[j] = TB ? sB[(wn * WN + j * 8 + grp) * LDK + k4 * 4 + t4]
+                          : sB[(k4 * 4 + t4) * LDN + wn * WN + j * 8 + grp];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     cp_wait<0>();
@@ -146,8 +154,8 @@ __device__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
         const int row = m0 + wm * 32 + i * 8 + grp;
         if (row >= g.m) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = n0 + wn * 32 + j * 8 + 2 * t4;
+        for (int j = 0; j < NJ; ++j) {
+            const int col = n0 + wn * WN + j * 8 + 2 * t4;
             if (col >= g.n) continue;
             double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
             double* d = g.D + (int64_t)row * g.ldd + col;

@@ -436,6 +436,28 @@ def test_batched_months_equal_per_month_classes(K):
             assert np.array_equal(res["constraint_mask"][m], quiet(one.constraint_mask))
 
 
+def test_narrow_and_wide_solve_tiles_are_bit_identical(K):
+    """The triangular-solve steps use 64-column strips when 128-column ones would leave SMs idle (one 5-degree month:
+    21 strips) and 128-column strips otherwise (eight copies of it: 168); every output element is accumulated over k
+    in the same order, so the results must be bit-equal."""
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office",
+                                   precision=np.float64).cov_ns_device
+    idx, obs = synth.month_observations(3, cov.shape[0], n_min=700, n_max=701)
+    E = synth.hadcrut_style_error_cov(idx, lons.size, seed=3)
+    prob = (idx.astype(np.int64), obs.astype(np.float64), E)
+    one = dn.KrigeBatch(cov, [prob], ordinary=True).run()
+    many = dn.KrigeBatch(cov, [prob] * 8, ordinary=True).run()
+    a, b = one.out[0].cpu().numpy(), many.out.cpu().numpy()
+    for k in range(8):
+        assert np.array_equal(a, b[k])
+    assert np.array_equal(one.weights(0).cpu().numpy(), many.weights(5).cpu().numpy())   # backward solve as well
+
+
 # ---- stochastic ensemble (BASELINE.json config 5) -----------------------------------------------------------
 def test_stochastic_ensemble_distribution_and_consistency(K):
     """200+ perturbed fields in one call: the ordinary-kriging part equals the class, the perturbations are
