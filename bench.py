@@ -456,10 +456,11 @@ def run_months(args, rank, world, device, barrier, max_over_ranks, local):
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
         e2e = {"value": args.months / dt, "unit": "months/s",
-               "h2d_bytes_per_step": int(sum(8 * (len(p[0]) ** 2 + 2 * len(p[0])) for p in probs)),
+               "h2d_bytes_per_step": int(sum(8 * (dn.packed_error_cov_doubles(len(p[0])) + 2 * len(p[0])) for p in probs)),
                "d2h_bytes_per_step": int(len(probs) * 5 * M * 8), "steps": args.e2e_steps,
                "note": "krige_batch(cov on device, host idx/obs/error_cov per month) -> numpy field, uncertainty, "
-                       "constraint mask; per-rank share of the months"}
+                       "constraint mask; per-rank share of the months; symmetric error covariances are uploaded "
+                       "as their lower block trapezoid (about half of n^2)"}
     return {"metric": "kriged months/s", "value": args.months / (ms * 1e-3), "unit": "months/s",
             "ms_per_step": ms, "steps": args.month_steps, "months": args.months,
             "config": {"workload": f"5deg grid (M={M}) ordinary kriging, {args.months} synthetic months, n~U(600,1600) "

@@ -90,7 +90,7 @@ def _h2d_concat(arrays, total: int, device, chunk_bytes: int = 512 << 20) -> tor
 
         def pack(item, buf=buf):
             off, a = item
-            buf[off:off + a.size] = np.asarray(a, dtype=np.float64).reshape(-1)
+            np.copyto(buf[off:off + a.size].reshape(a.shape), a, casting="unsafe")   # one (strided) copy, any dtype
 
         list(_POOL.map(pack, chunk))
         n = chunk[-1][0] + chunk[-1][1].size
@@ -103,6 +103,26 @@ def _h2d_concat(arrays, total: int, device, chunk_bytes: int = 512 << 20) -> tor
 
 
 _POOL = None
+_SYM_PAIRS: dict[int, tuple[np.ndarray, np.ndarray]] = {}
+
+
+def _looks_symmetric(E: np.ndarray, samples: int = 1024) -> bool:
+    """E[i, j] == E[j, i] on a fixed pseudo-random sample of index pairs (O(samples), not O(n^2): a full scan of
+    480 monthly matrices would cost more host time than the upload it saves).  Any asymmetry that is not confined
+    to a handful of entries is caught; the caller then uploads the whole matrix like the reference adds it."""
+    n = E.shape[0]
+    if n not in _SYM_PAIRS:
+        rng = np.random.default_rng(n)
+        _SYM_PAIRS[n] = (rng.integers(0, n, samples), rng.integers(0, n, samples))
+    i, j = _SYM_PAIRS[n]
+    return bool(np.array_equal(E[i, j], E[j, i]))
+
+
+def packed_error_cov_doubles(n: int) -> int:
+    """Doubles uploaded for one symmetric n x n error covariance (block trapezoid, see `KrigeBatch`)."""
+    if n <= NB:
+        return n * n
+    return sum((min(n, r0 + NB) - r0) * min(n, r0 + NB) for r0 in range(0, n, NB))
 
 
 def factor_inplace(S: torch.Tensor, n: int, what: str = "matrix") -> dict:
@@ -244,9 +264,33 @@ class KrigeBatch:
         offs_n = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
         self._idx = _h2d(np.concatenate([np.asarray(p[0], dtype=np.int64) for p in problems]), device)
         self._y = _h2d(np.concatenate([np.asarray(p[1], dtype=np.float64) for p in problems]), device)
+        # A symmetric error covariance (what a covariance is; checked on a fixed sample of mirrored entry pairs, an
+        # asymmetric one is uploaded whole) travels as the block trapezoid below and on its 128 x 128 diagonal
+        # blocks - row block b of 128 rows with its first 128 (b + 1) columns, a strided VIEW of the host array.
+        # That is everything the Cholesky path reads and halves the H2D bytes of the kriging path
+        # (GmgKrigeDesc.lde < 0; the LU fallback reads the mirrored entries).
         has_E = [p[2] is not None for p in problems]
-        offs_E = np.concatenate([[0], np.cumsum([n * n if h else 0 for n, h in zip(ns, has_E)])]).astype(np.int64)
-        self._E = _h2d_concat([p[2] for p in problems if p[2] is not None], int(offs_E[-1]), device) if any(has_E) else None
+        blocks, sizes_E, ldes = [], [], []
+        for p, n, h in zip(problems, ns, has_E):
+            size, lde = 0, n
+            if h:
+                E = np.asarray(p[2])
+                if E.shape != (n, n):
+                    raise ValueError(f"error covariance of shape {E.shape} does not match {n} observations")
+                if n > NB and _looks_symmetric(E):
+                    lde = -NB
+                    for r0 in range(0, n, NB):
+                        blk = E[r0:min(n, r0 + NB), :min(n, r0 + NB)]
+                        blocks.append(blk)
+                        size += blk.size
+                else:
+                    blocks.append(E)
+                    size = E.size
+            sizes_E.append(size)
+            ldes.append(lde)
+        offs_E = np.concatenate([[0], np.cumsum(sizes_E)]).astype(np.int64)
+        self._E = _h2d_concat(blocks, int(offs_E[-1]), device) if any(has_E) else None
+        self.h2d_bytes = 8 * int(offs_E[-1]) + 16 * int(offs_n[-1])
 
         kd = np.zeros(B, dtype=KRIGE_DESC)
         sd = np.zeros(B, dtype=SOLVE_DESC)
@@ -256,7 +300,7 @@ class KrigeBatch:
             S_ptr = self._S.data_ptr() + f8 * int(oS[b])
             T_ptr = self._T.data_ptr() + f8 * int(oT[b])
             kd[b] = (self._idx.data_ptr() + f8 * int(offs_n[b]),
-                     (self._E.data_ptr() + f8 * int(offs_E[b])) if has_E[b] else 0, n,
+                     (self._E.data_ptr() + f8 * int(offs_E[b])) if has_E[b] else 0, ldes[b],
                      self._y.data_ptr() + f8 * int(offs_n[b]), S_ptr, lds[b], 0, self.ldx, T_ptr, self.ldt,
                      self._partial.data_ptr() + f8 * int(oPa[b]), self.out.data_ptr() + f8 * 5 * M * b, n,
                      int(self.ordinary))

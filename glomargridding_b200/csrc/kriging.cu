@@ -41,7 +41,26 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
     // S row: the first ceil(n / 256) column blocks also fill S[a, :]
     if (m < d.n) {
         double s = crow[d.idx[m]];
-        if (d.E) s += d.E[(int64_t)a * d.lde + m];   // :342, :576
+        if (d.E) {                                   // :342, :576
+            if (d.lde > 0) {
+                s += d.E[(int64_t)a * d.lde + m];
+            } else {
+                // block-trapezoid packed lower triangle of a SYMMETRIC E (see GmgKrigeDesc): row i of row block
+                // b = i / hb holds its first L_b = min(n, hb (b + 1)) entries.  The Cholesky path only reads the
+                // lower triangle and the diagonal tiles of S, all inside the trapezoid; the full-solve (LU) path,
+                // recognisable by Cx != NULL, gets the mirrored entries as well.
+                const int hb = (int)(-d.lde);
+                int i = a, j = (int)m;
+                const int La = min(d.n, hb * (a / hb + 1));
+                bool have = j < La;
+                if (!have && d.Cx) { i = (int)m; j = a; have = true; }
+                if (have) {
+                    const int b = i / hb;
+                    const int Lb = min(d.n, hb * (b + 1));
+                    s += d.E[(int64_t)hb * hb * ((int64_t)b * (b + 1) / 2) + (int64_t)(i - hb * b) * Lb + j];
+                }
+            }
+        }
         d.S[(int64_t)a * d.lds + m] = s;
     }
 }

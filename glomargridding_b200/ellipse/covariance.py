@@ -30,6 +30,7 @@ import torch
 
 from .. import _device as dev
 from .._lib import check, lib
+from ..constants import RADIUS_OF_EARTH_KM
 from ..types import CovarianceMethod, DeltaXMethod
 from ..utils import cov_2_cor, mask_array
 
@@ -183,6 +184,38 @@ class EllipseCovarianceBuilder:
         self.cov_ns_device = out
         self._cov_ns_host = None
 
+    # -- the reference's three execution strategies (`:250-403`) -------------------------------------
+    # Each fills `cov_ns` with the off-diagonal covariances and a ZERO diagonal (the reference adds diag(stdev^2)
+    # afterwards, `:246`); here all three are the same tile kernel - there is no pair-index array to batch and no
+    # Python loop to fall back to - followed by a reset of the diagonal.
+    def _off_diagonal_build(self) -> None:
+        self._calculate_covariance()
+        self.cov_ns_device.diagonal(offset=self.row0).zero_()      # (r, row0 + r) for a row block
+
+    def calculate_covariance_array(self) -> None:
+        """Reference `:250-279` (all pairs at once)."""
+        self._off_diagonal_build()
+
+    def calculate_covariance_loop(self) -> None:
+        """Reference `:281-354` (scalar loop over pairs)."""
+        self._off_diagonal_build()
+
+    def calculate_covariance_batched(self) -> None:
+        """Reference `:356-403` (`batch_size` pairs at a time)."""
+        if self.batch_size is None:
+            raise ValueError("batch_size must be set if using 'batched' method")   # :375-376
+        self._off_diagonal_build()
+
+    def _get_disp_fn(self) -> None:
+        """Reference `:182-203`: `disp_fn` is the displacement helper the chosen strategy would call."""
+        single = self.covariance_method == "low_memory"
+        if self.delta_x_method == "Modified_Met_Office":
+            self.disp_fn = _mod_mo_disp_single if single else _mod_mo_disp_multi
+        elif self.delta_x_method == "Met_Office":
+            self.disp_fn = _mo_disp_single if single else _mo_disp_multi
+        else:
+            raise ValueError(f"Unknown 'delta_x_method' value: {self.delta_x_method}")
+
     # -- results ---------------------------------------------------------------------------------
     @property
     def cov_ns(self) -> np.ndarray:
@@ -272,3 +305,97 @@ class EllipseCovarianceBuilder:
                                    out.data_ptr(), M, dev.stream_ptr()), "gmg_uncompress")
         torch.cuda.current_stream().synchronize()                # inv_t dies with this frame
         self.cov_ns_device, self._cov_ns_host = out, None
+
+
+# -- module-level geometry helpers (reference `:512-654`), evaluated on the GPU ------------------------------------
+def _dtype_of(*arrays):
+    """float32 only if every array input is float32 (numpy's promotion for the reference expressions)."""
+    kinds = [np.asarray(a).dtype for a in arrays]
+    return np.float32 if all(k == np.float32 for k in kinds) else np.float64
+
+
+def _dev_vec(a) -> torch.Tensor:
+    return dev.to_device(np.atleast_1d(np.asarray(a, dtype=np.float64)).reshape(-1), torch.float64)
+
+
+def _sigma_rot_func_multi(Lx: np.ndarray, Ly: np.ndarray, theta: np.ndarray) -> np.ndarray:
+    """Flattened Sigma matrices (n x 4) for Lx, Ly, theta triplets; reference `:512-533` (`gmg_sigma_rot_f64`)."""
+    lx, ly, th = _dev_vec(Lx), _dev_vec(Ly), _dev_vec(theta)
+    if not lx.numel() == ly.numel() == th.numel():
+        raise ValueError("Lx, Ly and theta must have the same length")
+    out = torch.empty((lx.numel(), 4), dtype=torch.float64, device=lx.device)
+    check(lib().gmg_sigma_rot_f64(lx.data_ptr(), ly.data_ptr(), th.data_ptr(), lx.numel(), out.data_ptr(),
+                                  dev.stream_ptr()), "gmg_sigma_rot_f64")
+    return out.cpu().numpy().astype(_dtype_of(Lx, Ly, theta), copy=False)
+
+
+def _det_22_multi(mats: np.ndarray) -> np.ndarray:
+    """Determinants of an array of flattened 2 x 2 matrices; reference `:543-547` (`gmg_det22_f64`)."""
+    m = np.asarray(mats)
+    if m.ndim != 2 or m.shape[1] != 4:
+        raise ValueError("mats must have shape (n, 4)")
+    t = dev.to_device(m, torch.float64)
+    out = torch.empty(t.shape[0], dtype=torch.float64, device=t.device)
+    check(lib().gmg_det22_f64(t.data_ptr(), t.shape[0], out.data_ptr(), dev.stream_ptr()), "gmg_det22_f64")
+    return out.cpu().numpy().astype(_dtype_of(m), copy=False)
+
+
+def _det_22_single(mat: np.ndarray):
+    """Determinant of one flattened 2 x 2 matrix; reference `:536-540`."""
+    return _det_22_multi(np.asarray(mat).reshape(1, 4))[0]
+
+
+def _pairs(lat0, lon0, lat1, lon1):
+    ts = [_dev_vec(a) for a in (lat0, lon0, lat1, lon1)]
+    if len({t.numel() for t in ts}) != 1:
+        raise ValueError("lat0, lon0, lat1, lon1 must have the same length")
+    return ts
+
+
+def _haversine_multi(lat0: np.ndarray, lon0: np.ndarray, lat1: np.ndarray, lon1: np.ndarray) -> np.ndarray:
+    """Haversine distance (km) for a list of pairs of points in radians; reference `:572-588`
+    (`gmg_pair_haversine_f64`)."""
+    ts = _pairs(lat0, lon0, lat1, lon1)
+    out = torch.empty(ts[0].numel(), dtype=torch.float64, device=ts[0].device)
+    check(lib().gmg_pair_haversine_f64(*[t.data_ptr() for t in ts], out.numel(), RADIUS_OF_EARTH_KM, out.data_ptr(),
+                                       dev.stream_ptr()), "gmg_pair_haversine_f64")
+    return out.cpu().numpy().astype(_dtype_of(lat0, lon0, lat1, lon1), copy=False)
+
+
+def _haversine_single(lat0: float, lon0: float, lat1: float, lon1: float) -> float:
+    """Haversine distance between a pair of points; reference `:550-569` (exactly 0 below 1e-6 rad)."""
+    if abs(lon0 - lon1) < 1e-6 and abs(lat0 - lat1) < 1e-6:
+        return 0
+    return float(_haversine_multi([lat0], [lon0], [lat1], [lon1])[0])
+
+
+def _disp(lat0, lon0, lat1, lon1, modified: int):
+    ts = _pairs(lat0, lon0, lat1, lon1)
+    out = torch.empty((2, ts[0].numel()), dtype=torch.float64, device=ts[0].device)
+    check(lib().gmg_pair_displacement_f64(*[t.data_ptr() for t in ts], out.shape[1], modified, RADIUS_OF_EARTH_KM,
+                                          out[0].data_ptr(), out[1].data_ptr(), dev.stream_ptr()),
+          "gmg_pair_displacement_f64")
+    o = out.cpu().numpy().astype(_dtype_of(lat0, lon0, lat1, lon1), copy=False)
+    return o[0], o[1]
+
+
+def _mod_mo_disp_multi(lat0, lon0, lat1, lon1) -> tuple[np.ndarray, np.ndarray]:
+    """Modified Met Office displacements (dy, dx) in km between pairs of points; reference `:624-639`."""
+    return _disp(lat0, lon0, lat1, lon1, 1)
+
+
+def _mo_disp_multi(lat0, lon0, lat1, lon1) -> tuple[np.ndarray, np.ndarray]:
+    """Met Office displacements (dy, dx) in km between pairs of points; reference `:642-654`."""
+    return _disp(lat0, lon0, lat1, lon1, 0)
+
+
+def _mod_mo_disp_single(lat0: float, lon0: float, lat1: float, lon1: float) -> tuple[float, float]:
+    """Reference `:591-606`."""
+    dy, dx = _disp([lat0], [lon0], [lat1], [lon1], 1)
+    return float(dy[0]), float(dx[0])
+
+
+def _mo_disp_single(lat0: float, lon0: float, lat1: float, lon1: float) -> tuple[float, float]:
+    """Reference `:609-621`."""
+    dy, dx = _disp([lat0], [lon0], [lat1], [lon1], 0)
+    return float(dy[0]), float(dx[0])

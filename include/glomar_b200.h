@@ -189,7 +189,9 @@ int gmg_gesv_batched_f64(const GmgSolveDesc* descs, int batch, int64_t nrhs_max,
 typedef struct GmgKrigeDesc {
     const int64_t* idx;  /* n observation cells                                                    */
     const double* E;     /* n x n error covariance or NULL                                         */
-    int64_t lde;
+    int64_t lde;         /* > 0: row-major, leading dimension lde.  < 0: E is SYMMETRIC and packed as a block
+                          * trapezoid with row blocks of hb = -lde rows: row i of block b = i / hb stores its first
+                          * min(n, hb (b + 1)) entries, blocks one after the other (half the bytes to upload)    */
     const double* y;     /* n observations                                                         */
     double* S;           /* n x n  out: C[idx, idx] + E                                            */
     int64_t lds;
@@ -298,6 +300,26 @@ int gmg_uncompress(const void* cov, int64_t ld, const int* inv, int64_t M, int i
 int gmg_sym_eigvals_ws_bytes(int64_t n, size_t* bytes);
 int gmg_sym_eigvals_f64(double* A, int64_t lda, int64_t n, double* w, void* ws, size_t ws_bytes,
                         gmg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Elementwise geometry helpers of the ellipse covariance path (the module-level functions next to the
+ * reference's builder; its tests call them directly, test/test_matrix.py:74-140).  Device pointers,
+ * n elements, radians.
+ *   gmg_sigma_rot_f64          _sigma_rot_func_multi, glomar_gridding/ellipse/covariance.py:512-533:
+ *                              sigmas (n x 4, 16-byte aligned) = [c2 Lx2 + s2 Ly2, cs (Lx2 - Ly2), same, s2 Lx2 + c2 Ly2]
+ *   gmg_det22_f64              _det_22_single / _det_22_multi, :536-547: m0 m3 - m1 m2 of n flattened 2 x 2 matrices
+ *   gmg_pair_haversine_f64     _haversine_single / _haversine_multi, :550-588: asin-form haversine of n point pairs
+ *   gmg_pair_displacement_f64  _mo_disp_* (modified = 0) / _mod_mo_disp_* (modified = 1), :591-654: (dy, dx) in km,
+ *                              longitude difference wrapped into [-pi, pi] with strict comparisons
+ * ------------------------------------------------------------------------------------------- */
+int gmg_sigma_rot_f64(const double* Lx, const double* Ly, const double* theta, int64_t n, double* sigmas,
+                      gmg_stream_t stream);
+int gmg_det22_f64(const double* mats, int64_t n, double* dets, gmg_stream_t stream);
+int gmg_pair_haversine_f64(const double* lat0, const double* lon0, const double* lat1, const double* lon1,
+                           int64_t n, double radius_km, double* dist, gmg_stream_t stream);
+int gmg_pair_displacement_f64(const double* lat0, const double* lon0, const double* lat1, const double* lon1,
+                              int64_t n, int modified, double radius_km, double* dy, double* dx,
+                              gmg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -89,3 +89,27 @@ def test_install_as_glomar_gridding_aliases_import_paths():
             "from glomar_gridding.stochastic import StochasticKriging, scipy_mv_normal_draw; "
             "from glomar_gridding.utils import adjust_small_negative, cov_2_cor" % ROOT)
     subprocess.run([sys.executable, "-c", code], check=True)
+
+
+@pytest.mark.parametrize("n", [129, 256, 300, 1341])
+def test_block_trapezoid_layout_of_symmetric_error_covariances(n):
+    """Host packing (`KrigeBatch`: row block b of 128 rows with its first min(n, 128 (b + 1)) columns) against the
+    index formula of `gather_kernel` (`csrc/kriging.cu`, `GmgKrigeDesc.lde < 0`), restated here in numpy: every
+    entry (i, j) with j inside row i's trapezoid - in particular the whole lower triangle and the whole diagonal
+    blocks - is found at offset hb^2 b (b + 1) / 2 + (i - hb b) L_b + j."""
+    from glomargridding_b200 import _dense as dn
+
+    hb = dn.NB
+    rng = np.random.default_rng(n)
+    E = rng.standard_normal((n, n))
+    E = E + E.T
+    assert dn._looks_symmetric(E) and not dn._looks_symmetric(np.triu(E) + 0.5 * np.tril(E, -1))
+    packed = np.concatenate([E[r0:min(n, r0 + hb), :min(n, r0 + hb)].reshape(-1) for r0 in range(0, n, hb)])
+    assert packed.size == dn.packed_error_cov_doubles(n)
+    i, j = np.tril_indices(n)
+    extra = (np.arange(n)[:, None] // hb == np.arange(n)[None, :] // hb).nonzero()      # diagonal blocks, both halves
+    i, j = np.concatenate([i, extra[0]]), np.concatenate([j, extra[1]])
+    b = i // hb
+    Lb = np.minimum(n, hb * (b + 1))
+    off = hb * hb * (b * (b + 1) // 2) + (i - hb * b) * Lb + j
+    assert np.array_equal(packed[off], E[i, j])

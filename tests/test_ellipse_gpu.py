@@ -212,3 +212,58 @@ def test_calculate_cor_and_uncompress_on_device_vs_oracle(Builder, prec):
     bad.data_mask = np.zeros_like(np.asarray(bad.data_mask))
     with pytest.raises(ValueError, match="cannot be aligned"):
         bad.uncompress_cov()
+
+
+def test_geometry_helpers_vs_reference_golden(Builder):
+    """`_sigma_rot_func_multi`, `_det_22_*`, `_haversine_*`, `_mo_disp_*`, `_mod_mo_disp_*` (reference
+    `ellipse/covariance.py:512-654`; its own checks: `test/test_matrix.py:74-140`) as device kernels against the
+    unmodified reference's outputs.  Products and sums are rounded like numpy's; sin / cos / asin are CUDA's (1-2 ulp),
+    hence 1e-13 relative; the wrap of the longitude difference at exactly +-pi must fall on the same side."""
+    import glomargridding_b200.ellipse.covariance as ec
+
+    g = load_golden("geometry_small.npz")
+    sig = ec._sigma_rot_func_multi(g["Lx"], g["Ly"], g["theta"])
+    assert sig.shape == g["sigmas"].shape and sig.dtype == np.float64
+    assert np.max(np.abs(sig - g["sigmas"])) <= 1e-13 * np.max(np.abs(g["sigmas"]))
+    assert np.array_equal(sig[:, 1], sig[:, 2])
+    assert np.array_equal(ec._det_22_multi(g["sigmas"]), g["dets"])                    # exact: two products, one difference
+    assert np.array_equal([ec._det_22_single(g["sigmas"][i]) for i in range(8)], g["single_det"])
+    pts = (g["lat0"], g["lon0"], g["lat1"], g["lon1"])
+    hav = ec._haversine_multi(*pts)
+    assert np.allclose(hav, g["haversine"], rtol=1e-12, atol=1e-9)
+    for fn, key in ((ec._mo_disp_multi, "mo"), (ec._mod_mo_disp_multi, "mod_mo")):
+        dy, dx = fn(*pts)
+        assert np.array_equal(dy, g[key][0])                                           # one subtraction, one product
+        assert np.allclose(dx, g[key][1], rtol=1e-14, atol=1e-11)
+        assert np.array_equal(np.sign(dx), np.sign(g[key][1]))                         # same side of the wrap
+    assert np.array_equal(ec._mo_disp_multi(*pts)[1], g["mo"][1])                      # no transcendental: exact
+    for k in range(8):
+        args = tuple(float(p[k - 8]) for p in pts)
+        assert np.isclose(ec._haversine_single(*args), g["single_haversine"][k], rtol=1e-12, atol=1e-9)
+        assert np.allclose(ec._mod_mo_disp_single(*args), g["single_mod_mo"][k], rtol=1e-14, atol=1e-11)
+        assert np.array_equal(ec._mo_disp_single(*args), g["single_mo"][k])
+    # float32 inputs give float32 results like the numpy expressions do
+    assert ec._haversine_multi(*[p.astype(np.float32) for p in pts]).dtype == np.float32
+
+
+def test_strategy_methods_leave_the_off_diagonal_matrix(Builder):
+    """`calculate_covariance_array / _loop / _batched` (reference `:250-403`) fill `cov_ns` WITHOUT the diagonal
+    (`_calculate_covariance` adds diag(stdev^2) afterwards, `:246`); the three strategies agree exactly (reference
+    test/test_ellipse.py:300-353 allows rtol 1e-5 between them)."""
+    lats, lons = synth.global_grid(20.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons, land_mask=True)
+    b = Builder(Lx, Ly, th, sd, lats, lons, v=1.5, precision=np.float64, batch_size=100)
+    full = b.cov_ns.copy()
+    off = full - np.diag(np.diag(full))
+    assert np.array_equal(np.diag(full), b.stdev_compressed ** 2)
+    for name in ("calculate_covariance_array", "calculate_covariance_loop", "calculate_covariance_batched"):
+        getattr(b, name)()
+        assert np.array_equal(b.cov_ns, off), name
+    b.batch_size = None
+    with pytest.raises(ValueError, match="batch_size must be set"):
+        b.calculate_covariance_batched()
+    b._get_disp_fn()
+    assert b.disp_fn.__name__ == "_mod_mo_disp_multi"
+    b.covariance_method, b.delta_x_method = "low_memory", "Met_Office"
+    b._get_disp_fn()
+    assert b.disp_fn.__name__ == "_mo_disp_single"

@@ -436,6 +436,43 @@ def test_batched_months_equal_per_month_classes(K):
             assert np.array_equal(res["constraint_mask"][m], quiet(one.constraint_mask))
 
 
+def test_packed_symmetric_error_cov_upload_is_bit_identical_and_asymmetric_falls_back(K, monkeypatch):
+    """A symmetric error covariance is uploaded as its lower block trapezoid (`GmgKrigeDesc.lde < 0`), an asymmetric
+    one whole.  The packed path must give the same bits as the full upload - on the Cholesky path (SPD covariance)
+    and on the LU fallback (indefinite covariance, which reads the mirrored entries) - and an asymmetric E must be
+    added as it is, like the reference's `S += error_cov` (`kriging.py:342,576`)."""
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+    from oracle import kriging as ok
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    for method in ("Met_Office", "Modified_Met_Office"):          # SPD -> Cholesky; indefinite -> LU fallback
+        cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method=method,
+                                       precision=np.float64).cov_ns_device
+        probs = []
+        for m, n in enumerate((129, 300, 517)):                   # ragged last blocks, one block boundary + 1
+            idx, obs = synth.month_observations(m, cov.shape[0], n_min=n, n_max=n + 1)
+            probs.append((idx.astype(np.int64), obs.astype(np.float64),
+                          synth.hadcrut_style_error_cov(idx, lons.size, seed=m)))
+        packed = quiet(lambda: dn.KrigeBatch(cov, probs, ordinary=True).run())
+        assert packed.h2d_bytes < 0.7 * sum(8 * len(p[0]) ** 2 for p in probs)
+        assert bool(packed.lu_fallback) == (method == "Modified_Met_Office")
+        with monkeypatch.context() as mp:
+            mp.setattr(dn, "_looks_symmetric", lambda E, samples=0: False)
+            full = quiet(lambda: dn.KrigeBatch(cov, probs, ordinary=True).run())
+        assert np.array_equal(packed.out.cpu().numpy(), full.out.cpu().numpy())
+    # asymmetric E: detected, uploaded whole, result = LU solve with the asymmetric matrix (oracle)
+    idx, obs, E = probs[1]
+    E = E.copy()
+    E[np.triu_indices_from(E, 1)] *= 0.5
+    assert not dn._looks_symmetric(E)
+    C = cov.cpu().numpy()
+    got = quiet(lambda: K.OrdinaryKriging(cov, idx.copy(), obs.copy(), E.copy()).solve())
+    want = ok.ordinary_kriging(C, idx, obs, E, big_temporaries=False)["field"]
+    assert max_norm_rel(got, want) < 1e-8
+
+
 def test_narrow_and_wide_solve_tiles_are_bit_identical(K):
     """The triangular-solve steps use 64-column strips when 128-column ones would leave SMs idle (one 5-degree month:
     21 strips) and 128-column strips otherwise (eight copies of it: 168); every output element is accumulated over k

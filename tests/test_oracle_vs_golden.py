@@ -178,3 +178,21 @@ def test_eigenvalue_clip_oracle_vs_reference_golden():
     assert np.max(np.abs(explained_variance_clip(cov, 0.8)[0] - from_triu(g["ev80"]))) <= 1e-11 * scale
     assert np.max(np.abs(laloux_clip(cov, None, 40) - from_triu(g["laloux_t40"]))) <= 1e-11 * scale
     assert np.max(np.abs(laloux_clip(cov, cov.shape[0], 400) - from_triu(g["laloux_t400"]))) <= 1e-11 * scale
+
+
+def test_geometry_helpers_oracle_vs_reference_golden():
+    """Module-level geometry helpers (`ellipse/covariance.py:512-654`): the oracle's restatements are the same numpy
+    expressions, so they must reproduce the reference's outputs bit for bit - including the strict +-pi wrap."""
+    from oracle import ellipse as oe
+
+    g = load_golden("geometry_small.npz")
+    sig = oe.sigma_rot(g["Lx"], g["Ly"], g["theta"])
+    assert np.array_equal(sig, g["sigmas"])
+    assert np.array_equal(oe.det22(sig), g["dets"])
+    pts = (g["lat0"], g["lon0"], g["lat1"], g["lon1"])
+    assert np.array_equal(oe.haversine_km(*pts), g["haversine"])
+    assert np.array_equal(np.stack(oe.displacements_km(*pts, "Met_Office")), g["mo"])
+    assert np.array_equal(np.stack(oe.displacements_km(*pts, "Modified_Met_Office")), g["mod_mo"])
+    # the scalar variants agree with the vector ones except for the coincident-point shortcut (`:561-562`)
+    assert np.array_equal(g["single_mo"], g["mo"][:, -8:].T) and np.array_equal(g["single_mod_mo"], g["mod_mo"][:, -8:].T)
+    assert np.allclose(g["single_haversine"], g["haversine"][-8:], rtol=1e-15, atol=0)
