@@ -54,15 +54,18 @@ def _h2d(a: np.ndarray, device) -> torch.Tensor:
 _STAGE = None
 
 
-def _h2d_concat(arrays, total: int, device, chunk_bytes: int = 512 << 20) -> torch.Tensor:
-    """Flattened concatenation of host float64 arrays on the device.  The arrays are packed into one of two
-    pinned staging buffers by a small thread pool (numpy copies release the GIL; a single thread packs at
-    ~6 GB/s, far below PCIe) while the previous buffer is in flight, so packing overlaps the H2D copy.  The
-    per-month n x n error covariances are the bulk of the kriging path's host-to-device traffic."""
+def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20) -> torch.Tensor:
+    """Flattened concatenation of host floating-point arrays on the device, as float64.  `groups` is a list of
+    lists of arrays (one list per kriging problem: the row blocks of its error covariance); every group is ONE task
+    of a small thread pool that packs it into one of two pinned staging buffers (numpy copies release the GIL; a
+    single thread packs at ~6 GB/s, far below PCIe) while the previous buffer is in flight, so packing overlaps the
+    H2D copy - also inside one call, which is why the staging buffers are much smaller (128 MB) than a chunk of months
+    (~500 MB).  The per-month error covariances are the bulk of the kriging path's host-to-device traffic."""
     from concurrent.futures import ThreadPoolExecutor
 
     out = torch.empty(total, dtype=torch.float64, device=device)
-    cap = max(chunk_bytes // 8, max(int(a.size) for a in arrays))
+    sizes = [sum(int(a.size) for a in g) for g in groups]
+    cap = max(chunk_bytes // 8, max(sizes))
     global _STAGE, _POOL
     if _STAGE is None or _STAGE[0].numel() < cap:       # pinned allocations are slow (~0.3 s): keep them
         _STAGE = [torch.empty(cap, dtype=torch.float64, pin_memory=True) for _ in range(2)]
@@ -71,29 +74,30 @@ def _h2d_concat(arrays, total: int, device, chunk_bytes: int = 512 << 20) -> tor
     stage = [t.numpy() for t in _STAGE]
     done = [torch.cuda.Event(), torch.cuda.Event()]
     used = [False, False]
-    # chunks of whole arrays that fit one staging buffer
+    # chunks of whole groups that fit one staging buffer
     chunks, cur, fill = [], [], 0
-    for a in arrays:
-        if fill + a.size > cap and cur:
-            chunks.append(cur)
+    for g, size in zip(groups, sizes):
+        if fill + size > cap and cur:
+            chunks.append((cur, fill))
             cur, fill = [], 0
-        cur.append((fill, a))
-        fill += a.size
+        cur.append((fill, g))
+        fill += size
     if cur:
-        chunks.append(cur)
+        chunks.append((cur, fill))
     pos = 0
-    for ci, chunk in enumerate(chunks):
+    for ci, (chunk, n) in enumerate(chunks):
         which = ci & 1
         if used[which]:
             done[which].synchronize()                    # the copy that last read this buffer has finished
         buf = stage[which]
 
         def pack(item, buf=buf):
-            off, a = item
-            np.copyto(buf[off:off + a.size].reshape(a.shape), a, casting="unsafe")   # one (strided) copy, any dtype
+            off, g = item
+            for a in g:                                  # one (strided) copy per block, any float dtype
+                np.copyto(buf[off:off + a.size].reshape(a.shape), a, casting="unsafe")
+                off += a.size
 
         list(_POOL.map(pack, chunk))
-        n = chunk[-1][0] + chunk[-1][1].size
         out[pos:pos + n].copy_(_STAGE[which][:n], non_blocking=True)
         done[which].record()
         used[which] = True
@@ -103,6 +107,7 @@ def _h2d_concat(arrays, total: int, device, chunk_bytes: int = 512 << 20) -> tor
 
 
 _POOL = None
+PACK_SYMMETRIC_ERROR_COV = True     # tests switch the trapezoid packing off to compare it with whole uploads
 _SYM_PAIRS: dict[int, tuple[np.ndarray, np.ndarray]] = {}
 
 
@@ -115,7 +120,7 @@ def _looks_symmetric(E: np.ndarray, samples: int = 1024) -> bool:
         rng = np.random.default_rng(n)
         _SYM_PAIRS[n] = (rng.integers(0, n, samples), rng.integers(0, n, samples))
     i, j = _SYM_PAIRS[n]
-    return bool(np.array_equal(E[i, j], E[j, i]))
+    return bool(np.array_equal(E[i, j], E[j, i], equal_nan=True))
 
 
 def packed_error_cov_doubles(n: int) -> int:
@@ -200,7 +205,7 @@ def apply_reduce(cov: torch.Tensor, Cx: torch.Tensor, T: torch.Tensor, y: torch.
     M, n = cov.shape[0], T.shape[0]
     assert Cx.stride(1) == 1 and T.stride(1) == 1 and y.is_contiguous()
     slabs = (n + SLAB - 1) // SLAB
-    partial = torch.empty(3 * slabs * M, dtype=torch.float64, device=cov.device)
+    partial = torch.empty(4 * slabs * M, dtype=torch.float64, device=cov.device)
     out = torch.empty((5, M), dtype=torch.float64, device=cov.device)
     kd = np.zeros(1, dtype=KRIGE_DESC)
     kd[0] = (0, 0, n, y.data_ptr(), 0, 0, Cx.data_ptr(), Cx.stride(0), T.data_ptr(), T.stride(0),
@@ -257,7 +262,7 @@ class KrigeBatch:
         self._T, oT = pool([n * self.ldt for n in ns])
         self._Linv, oL = pool([w[0] for w in ws])
         self._P, oP = pool([w[1] for w in ws])
-        self._partial, oPa = pool([3 * s * M for s in slabs])
+        self._partial, oPa = pool([4 * s * M for s in slabs])
         self.out = torch.empty((B, 5, M), dtype=torch.float64, device=device)
         self.info = torch.zeros(B, dtype=torch.int32, device=device)
         # inputs: one H2D copy each (idx, obs, error covariances)
@@ -270,26 +275,29 @@ class KrigeBatch:
         # That is everything the Cholesky path reads and halves the H2D bytes of the kriging path
         # (GmgKrigeDesc.lde < 0; the LU fallback reads the mirrored entries).
         has_E = [p[2] is not None for p in problems]
-        blocks, sizes_E, ldes = [], [], []
-        for p, n, h in zip(problems, ns, has_E):
+        groups, sizes_E, ldes, self._asym = [], [], [], []
+        for b, (p, n, h) in enumerate(zip(problems, ns, has_E)):
             size, lde = 0, n
             if h:
                 E = np.asarray(p[2])
                 if E.shape != (n, n):
                     raise ValueError(f"error covariance of shape {E.shape} does not match {n} observations")
-                if n > NB and _looks_symmetric(E):
+                if E.dtype.kind != "f":
+                    E = E.astype(np.float64)
+                sym = _looks_symmetric(E)
+                if not sym:
+                    self._asym.append(b)                 # no Cholesky for this system: LU like the reference
+                if sym and n > NB and PACK_SYMMETRIC_ERROR_COV:
                     lde = -NB
-                    for r0 in range(0, n, NB):
-                        blk = E[r0:min(n, r0 + NB), :min(n, r0 + NB)]
-                        blocks.append(blk)
-                        size += blk.size
+                    blocks = [E[r0:min(n, r0 + NB), :min(n, r0 + NB)] for r0 in range(0, n, NB)]
                 else:
-                    blocks.append(E)
-                    size = E.size
+                    blocks = [E]
+                groups.append(blocks)
+                size = sum(blk.size for blk in blocks)
             sizes_E.append(size)
             ldes.append(lde)
         offs_E = np.concatenate([[0], np.cumsum(sizes_E)]).astype(np.int64)
-        self._E = _h2d_concat(blocks, int(offs_E[-1]), device) if any(has_E) else None
+        self._E = _h2d_concat(groups, int(offs_E[-1]), device) if any(has_E) else None
         self.h2d_bytes = 8 * int(offs_E[-1]) + 16 * int(offs_n[-1])
 
         kd = np.zeros(B, dtype=KRIGE_DESC)
@@ -345,20 +353,26 @@ class KrigeBatch:
         check(L.gmg_krige_gather_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, s), "gather")
         check(L.gmg_potrf_batched_f64(self._sd.data_ptr(), self.B, self.n_max, s), "gmg_potrf_batched_f64")
         info = self.info.cpu().numpy()               # synchronises: the factorisation outcome decides the path
-        bad = np.flatnonzero(info)
+        asym = np.asarray(self._asym, dtype=np.int64)
+        if asym.size:
+            warn(f"the error covariance of {asym.size} of {self.B} kriging system(s) is not symmetric (first: system "
+                 f"{int(asym[0])}); solving those by LU with partial pivoting like the reference does - slow path")
+        not_spd = np.setdiff1d(np.flatnonzero(info), asym)
+        bad = np.union1d(not_spd, asym)
         self.lu_fallback = bad.tolist()
         if bad.size == 0:
             check(L.gmg_potrs_batched_f64(self._sd.data_ptr(), self.B, self.n_max, self.nrhs, 1, s),
                   "gmg_potrs_batched_f64")
             check(L.gmg_krige_apply_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, 1, s), "apply")
             return self
-        if not allow_lu_fallback:
+        if not allow_lu_fallback and not_spd.size:
             self.raise_if_not_spd(info)
-        warn(f"C[idx, idx] + E is not positive definite for {bad.size} of {self.B} kriging system(s) "
-             f"(first: system {int(bad[0])}, Cholesky pivot {int(info[bad[0]])}); solving those by LU with "
-             "partial pivoting like the reference does - slow path, consider "
-             "glomar_gridding.covariance_tools.eigenvalue_clip or delta_x_method='Met_Office'")
-        good = np.flatnonzero(info == 0)
+        if not_spd.size:
+            warn(f"C[idx, idx] + E is not positive definite for {not_spd.size} of {self.B} kriging system(s) "
+                 f"(first: system {int(not_spd[0])}, Cholesky pivot {int(info[not_spd[0]])}); solving those by LU "
+                 "with partial pivoting like the reference does - slow path, consider "
+                 "glomar_gridding.covariance_tools.eigenvalue_clip or delta_x_method='Met_Office'")
+        good = np.setdiff1d(np.arange(self.B), bad)
         self.info.zero_()
         kd_bad_np = self._kd_np[bad].copy()
         for i, b in enumerate(bad):
@@ -522,7 +536,7 @@ def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.T
         if not dist.is_initialized() or dist.get_rank() == 0:
             print(f"[solve_prepared] Cholesky n = {n}: {1e3 * (time.perf_counter() - t0):.1f} ms", flush=True)
     slabs = (n + SLAB - 1) // SLAB
-    partial = torch.empty(3 * slabs * Mc, dtype=torch.float64, device=S.device)
+    partial = torch.empty(4 * slabs * Mc, dtype=torch.float64, device=S.device)
     out = torch.empty((5, Mc), dtype=torch.float64, device=S.device)
     sd = np.zeros(1, dtype=SOLVE_DESC)
     sd[0] = (S.data_ptr(), S.stride(0), ws["Linv"].data_ptr(), T.data_ptr(), T.stride(0), ws["P"].data_ptr(),

@@ -31,7 +31,19 @@ def shard(n_items: int, rank: int, world: int) -> list[int]:
 def _bytes_per_problem(n: int, M: int) -> int:
     lin, pdb, _ = dn.solve_ws(n)
     slabs = (n + dn.SLAB - 1) // dn.SLAB
-    return 8 * (n * (n + 2) + 2 * n * (M + 2) + lin + pdb + 3 * slabs * M + 5 * M + n * n)
+    return 8 * (n * (n + 2) + 2 * n * (M + 2) + lin + pdb + 4 * slabs * M + 5 * M + n * n)
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    """One upload stream per device for the life of the process: the caching allocator keeps a pool per stream, so a
+    fresh stream per call would cudaMalloc every buffer of every call anew (~50 ms on the first chunk)."""
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
 
 
 def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_bytes: int | None = None,
@@ -52,6 +64,7 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
         k = cls.__new__(cls)
         k.covariance, k.idx, k.obs, k.error_cov = covariance, np.asarray(idx), np.asarray(obs), E
         k._batch = k._user_weights = None
+        k._nan_to_zero_on_device = True
         k.subset_error_covariance()
         return k._problem()
 
@@ -72,7 +85,9 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
     bounds, start = [], 0
     while start < n_all:
         used, stop = 0, start
-        while stop < n_all and stop - start < cap:
+        # the first chunk has nothing to hide behind: a quarter-size one, then a half-size one, fill the pipeline
+        cap_now = cap if n_all < 32 else max(8, cap >> max(0, 2 - len(bounds)))
+        while stop < n_all and stop - start < cap_now:
             need = _bytes_per_problem(len(problems[stop][0]), M)
             if stop > start and used + need > max_bytes // 2:      # two chunks are alive at a time
                 break
@@ -83,7 +98,7 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
     from concurrent.futures import ThreadPoolExecutor
 
     main_stream = torch.cuda.current_stream(cov.device)
-    side = torch.cuda.Stream(cov.device) if len(bounds) > 1 else main_stream
+    side = _side_stream(cov.device) if len(bounds) > 1 else main_stream
     workers = ThreadPoolExecutor(max_workers=_dev.host_threads(8)) if n_all >= 8 else None
 
     timing = os.environ.get("GLOMAR_B200_TIMING")
@@ -142,12 +157,13 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
         return {"field": field, "variance": out[:, dn.OUT_U2], "constraint_mask": out[:, dn.OUT_MASK]}
     from . import _device as dev
 
-    o = dev.to_host(out)
-    field = o[:, dn.OUT_FIELD] + (mean if method == "simple" else 0.0)
-    unc = _finish_uncertainty(np.ascontiguousarray(o[:, dn.OUT_U2]), np.float64)     # elementwise: all problems at once
+    o = dev.to_host(out[:, :3].permute(1, 0, 2).contiguous())      # field, variance, mask planes: 3 of the 5 result rows
+    assert (dn.OUT_FIELD, dn.OUT_U2, dn.OUT_MASK) == (0, 1, 2)
+    field = o[dn.OUT_FIELD] + mean if method == "simple" else o[dn.OUT_FIELD]
+    unc = _finish_uncertainty(o[dn.OUT_U2], np.float64)            # elementwise: all problems at once
     if timing:
         print(f"[krige_batch] results to host + uncertainty clamp {1e3 * (_time.perf_counter() - t_out):.1f} ms", flush=True)
-    return {"field": field, "uncertainty": unc, "constraint_mask": o[:, dn.OUT_MASK]}
+    return {"field": field, "uncertainty": unc, "constraint_mask": o[dn.OUT_MASK]}
 
 
 def gather_results(local: np.ndarray, n_items: int, rank: int, world: int) -> np.ndarray:

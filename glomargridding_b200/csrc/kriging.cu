@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
         double s = crow[d.idx[m]];
         if (d.E) {                                   // :342, :576
             if (d.lde > 0) {
-                s += d.E[(int64_t)a * d.lde + m];
+                const double e = d.E[(int64_t)a * d.lde + m];
+                s += e != e ? 0.0 : e;               // NaN -> 0.0, kriging.py:120
             } else {
                 // block-trapezoid packed lower triangle of a SYMMETRIC E (see GmgKrigeDesc): row i of row block
                 // b = i / hb holds its first L_b = min(n, hb (b + 1)) entries.  The Cholesky path only reads the
@@ -57,7 +58,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
                 if (have) {
                     const int b = i / hb;
                     const int Lb = min(d.n, hb * (b + 1));
-                    s += d.E[(int64_t)hb * hb * ((int64_t)b * (b + 1) / 2) + (int64_t)(i - hb * b) * Lb + j];
+                    const double e = d.E[(int64_t)hb * hb * ((int64_t)b * (b + 1) / 2) + (int64_t)(i - hb * b) * Lb + j];
+                    s += e != e ? 0.0 : e;
                 }
             }
         }
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kColsPerBlock) reduce_kernel(int64_t M, const 
     }
     __syncthreads();
     if (m >= M) return;
-    double yT = 0.0, dd = 0.0, oc = 0.0;
+    double yT = 0.0, dd = 0.0, oc = 0.0, st = 0.0;
     const double* t = d.T + (int64_t)a0 * d.ldt + m;
     const double* x = d.Cx + (int64_t)a0 * d.ldx + m;
 #pragma unroll 4
@@ -125,12 +127,14 @@ __global__ void __launch_bounds__(kColsPerBlock) reduce_kernel(int64_t M, const 
         yT = fma(sy[a], tv, yT);
         dd = fma(tv, xv, dd);
         oc = fma(so[a], xv, oc);
+        st += tv;                                // 1^T S^-1 c: equals o^T c only for a symmetric S
     }
     const int64_t slabs = (d.n + kSlab - 1) / kSlab;
     double* p = d.partial + (int64_t)blockIdx.y * M + m;
     p[0] = yT;
     p[slabs * M] = dd;
     p[2 * slabs * M] = oc;
+    p[3 * slabs * M] = st;
 }
 
 // grid = (ceil(M / 256), 1, batch)
@@ -168,16 +172,20 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (m >= M) return;
     const int64_t slabs = (d.n + kSlab - 1) / kSlab;
-    double yT = 0.0, dd = 0.0, oc = 0.0;
+    double yT = 0.0, dd = 0.0, oc = 0.0, st = 0.0;
     for (int64_t s = 0; s < slabs; ++s) {
         yT += d.partial[s * M + m];
         dd += d.partial[(slabs + s) * M + m];
         oc += d.partial[(2 * slabs + s) * M + m];
+        if (!fwd_only) st += d.partial[(3 * slabs + s) * M + m];
     }
     const double cmm = C[m * ldc + m];
     double field = yT, rowdot = dd, alpha = 0.0, u2 = cmm - dd;
     if (d.ordinary) {
-        alpha = (oc - 1.0) / sum_o;              // Schur complement of the bordered system (:579-586)
+        // Schur complement of the bordered system (:579-586): alpha = (1^T S^-1 c - 1) / (1^T S^-1 1).  On the
+        // Cholesky path S is symmetric and 1^T S^-1 c = o^T c; the full-solve path (LU: indefinite or asymmetric S,
+        // user-supplied weights) sums the solved column itself
+        alpha = ((fwd_only ? oc : st) - 1.0) / sum_o;
         field = yT - alpha * o_dot_y;            // W_ext @ [y; 0]                              (:677-679)
         rowdot = dd - alpha * oc;                // rowdot(W, Cx^T)
         u2 = cmm - rowdot - alpha - alpha;       // diag(C - W_ext @ Cx_ext) - alpha            (:699-701)

@@ -104,7 +104,11 @@ class Kriging(ABC):
                 self.error_cov = self.error_cov[idx_keep[:, None], idx_keep[None, :]]
             # NaN -> 0 (reference :120).  A sum is NaN whenever any entry is (or +inf meets -inf), and costs a tenth of
             # the boolean-mask assignment, which is therefore only run when there is something to replace
+            # The batched driver skips this O(n^2) host scan altogether: the gather kernel reads NaN entries of E as
+            # 0 (`csrc/kriging.cu`), and nobody sees the per-problem `error_cov` attribute there.
             ec = self.error_cov
+            if getattr(self, "_nan_to_zero_on_device", False) and isinstance(ec, np.ndarray) and ec.dtype.kind == "f":
+                return None
             if not (isinstance(ec, np.ndarray) and ec.dtype.kind == "f") or np.isnan(ec.sum()):
                 ec[np.isnan(ec)] = 0.0
         return None
@@ -165,7 +169,7 @@ class Kriging(ABC):
         return self._cov_dev
 
     def _problem(self):
-        E = None if self.error_cov is None else np.asarray(self.error_cov, dtype=np.float64)
+        E = None if self.error_cov is None else np.asarray(self.error_cov)     # cast to float64 while packing
         return (np.asarray(self.idx, dtype=np.int64), np.asarray(self.obs, dtype=np.float64), E)
 
     def _factorise(self, ordinary: bool) -> dn.KrigeBatch:

@@ -199,7 +199,7 @@ typedef struct GmgKrigeDesc {
     int64_t ldx;
     double* T;           /* n x (M + 2)  out: [Cx | 1 | y] = right-hand sides                      */
     int64_t ldt;
-    double* partial;     /* workspace: 3 * ceil(n/256) * M doubles                                 */
+    double* partial;     /* workspace: 4 * ceil(n/256) * M doubles                                 */
     double* out;         /* 5 x M: field, u2 (variance before clamping), mask, alpha, rowdot       */
     int32_t n;
     int32_t ordinary;    /* 0 simple kriging, 1 ordinary kriging (Lagrange-extended system)        */

@@ -427,6 +427,13 @@ def test_batched_months_equal_per_month_classes(K):
     E_full = synth.full_grid_error_cov(idx, M, lons.size)
     E_full[idx[3], idx[3]] = 0.0
     problems.append((idx, obs, E_full))
+    # NaN entries off the diagonal (reference `kriging.py:120`: NaN -> 0): the classes replace them on the host, the
+    # batched driver leaves that to the gather kernel; a float32 error covariance is cast while it is packed
+    idx, obs = synth.month_observations(100, M, n_min=200, n_max=260)
+    E_nan = synth.hadcrut_style_error_cov(idx, lons.size, seed=100)
+    E_nan[3, 150] = E_nan[150, 3] = E_nan[199, 0] = E_nan[0, 199] = np.nan
+    problems.append((idx, obs, E_nan))
+    problems.append((idx, obs, synth.hadcrut_style_error_cov(idx, lons.size, seed=101).astype(np.float32)))
     for method, cls in (("ordinary", K.OrdinaryKriging), ("simple", K.SimpleKriging)):
         res = quiet(krige_batch, b.cov_ns_device, problems, method, max_bytes=40 << 20)   # forces several chunks
         for m, (idx, obs, E) in enumerate(problems):
@@ -459,8 +466,9 @@ def test_packed_symmetric_error_cov_upload_is_bit_identical_and_asymmetric_falls
         assert packed.h2d_bytes < 0.7 * sum(8 * len(p[0]) ** 2 for p in probs)
         assert bool(packed.lu_fallback) == (method == "Modified_Met_Office")
         with monkeypatch.context() as mp:
-            mp.setattr(dn, "_looks_symmetric", lambda E, samples=0: False)
+            mp.setattr(dn, "PACK_SYMMETRIC_ERROR_COV", False)
             full = quiet(lambda: dn.KrigeBatch(cov, probs, ordinary=True).run())
+        assert full.h2d_bytes > 1.4 * packed.h2d_bytes
         assert np.array_equal(packed.out.cpu().numpy(), full.out.cpu().numpy())
     # asymmetric E: detected, uploaded whole, result = LU solve with the asymmetric matrix (oracle)
     idx, obs, E = probs[1]
