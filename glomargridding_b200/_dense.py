@@ -44,17 +44,33 @@ def solve_ws(n: int) -> tuple[int, int, int]:
 
 
 def _desc_tensor(arr: np.ndarray, device) -> torch.Tensor:
-    return torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(device)
+    return _h2d(np.ascontiguousarray(arr).view(np.uint8).reshape(-1), device)
 
 
 def _h2d(a: np.ndarray, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(a)).to(device)
 
 
+_INFO_HOST = None
+
+
+def _d2h_info(t: torch.Tensor) -> np.ndarray:
+    """Factorisation status words -> numpy through a persistent pinned buffer, waiting on the stream only: a pageable
+    cudaMemcpy is synchronous inside the driver and stalls the CUDA calls of the other pipeline thread
+    (`batched.krige_batch`) for as long as the factorisation runs."""
+    global _INFO_HOST
+    if _INFO_HOST is None or _INFO_HOST.numel() < t.numel():
+        _INFO_HOST = torch.empty(max(4096, t.numel()), dtype=torch.int32, pin_memory=True)
+    host = _INFO_HOST[: t.numel()]
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy().copy()
+
+
 _STAGE = None
 
 
-def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20) -> torch.Tensor:
+def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=None) -> torch.Tensor:
     """Flattened concatenation of host floating-point arrays on the device, as float64.  `groups` is a list of
     lists of arrays (one list per kriging problem: the row blocks of its error covariance); every group is ONE task
     of a small thread pool that packs it into one of two pinned staging buffers (numpy copies release the GIL; a
@@ -63,14 +79,14 @@ def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20) -> tor
     (~500 MB).  The per-month error covariances are the bulk of the kriging path's host-to-device traffic."""
     from concurrent.futures import ThreadPoolExecutor
 
-    out = torch.empty(total, dtype=torch.float64, device=device)
+    if out is None:
+        out = torch.empty(total, dtype=torch.float64, device=device)
     sizes = [sum(int(a.size) for a in g) for g in groups]
     cap = max(chunk_bytes // 8, max(sizes))
     global _STAGE, _POOL
     if _STAGE is None or _STAGE[0].numel() < cap:       # pinned allocations are slow (~0.3 s): keep them
         _STAGE = [torch.empty(cap, dtype=torch.float64, pin_memory=True) for _ in range(2)]
-    if _POOL is None:
-        _POOL = ThreadPoolExecutor(max_workers=dev.host_threads(14))   # memcpy-bound packing
+    _pool()
     stage = [t.numpy() for t in _STAGE]
     done = [torch.cuda.Event(), torch.cuda.Event()]
     used = [False, False]
@@ -107,13 +123,25 @@ def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20) -> tor
 
 
 _POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _POOL = ThreadPoolExecutor(max_workers=dev.host_threads(14))   # memcpy-bound packing
+    return _POOL
+
+
 PACK_SYMMETRIC_ERROR_COV = True     # tests switch the trapezoid packing off to compare it with whole uploads
 _SYM_PAIRS: dict[int, tuple[np.ndarray, np.ndarray]] = {}
 
 
-def _looks_symmetric(E: np.ndarray, samples: int = 1024) -> bool:
+def _looks_symmetric(E: np.ndarray, samples: int = 96) -> bool:
     """E[i, j] == E[j, i] on a fixed pseudo-random sample of index pairs (O(samples), not O(n^2): a full scan of
-    480 monthly matrices would cost more host time than the upload it saves).  Any asymmetry that is not confined
+    480 monthly matrices would cost more host time than the upload it saves; every sample is two cache misses,
+    1024 of them cost 0.17 ms per matrix - 10 ms per chunk of 60 months - and hold the GIL).  Any asymmetry that is not confined
     to a handful of entries is caught; the caller then uploads the whole matrix like the reference adds it."""
     n = E.shape[0]
     if n not in _SYM_PAIRS:
@@ -226,6 +254,38 @@ def padded(a, rows: int | None = None, cols: int | None = None) -> torch.Tensor:
     return out
 
 
+class Arena:
+    """Bump allocator over one float64 device buffer: `KrigeBatch` carves its pools (S, T, inverted blocks, error
+    covariances ...) out of it instead of asking the caching allocator for five multi-hundred-MB blocks per chunk of
+    months (5-6 ms of cudaMalloc per chunk in the pipelined driver, `batched.krige_batch`).  256-byte granularity."""
+
+    def __init__(self, numel: int, device):
+        self.buf = torch.empty(max(int(numel), 32), dtype=torch.float64, device=device)
+        self.off = 0
+
+    def reset(self) -> "Arena":
+        self.off = 0
+        return self
+
+    def __call__(self, numel: int) -> torch.Tensor:
+        numel = int(numel)
+        if self.off + numel > self.buf.numel():
+            return torch.empty(numel, dtype=torch.float64, device=self.buf.device)    # does not fit: ordinary allocation
+        out = self.buf[self.off:self.off + numel]
+        self.off += (numel + 31) // 32 * 32
+        return out
+
+
+def krige_batch_doubles(ns, M: int, has_E=True) -> int:
+    """Upper bound of the doubles a `KrigeBatch` of problems with `ns` observations takes from its allocator."""
+    total = 0
+    for n in ns:
+        lin, pdb, _ = solve_ws(n)
+        slabs = (n + SLAB - 1) // SLAB
+        total += n * _even(n) + n * _even(M + 2) + lin + pdb + 4 * slabs * M + (n * n if has_E else 0)
+    return total + sum(2 * n + 5 * M for n in ns) + 32 * len(ns) + 32 * 8     # + idx, y, results, descriptors, alignment
+
+
 class KrigeBatch:
     """`B` kriging problems against one covariance matrix, solved together on the current device.
 
@@ -238,8 +298,11 @@ class KrigeBatch:
       T(b)    (n, ldt) tensor: S^-1 [C_cross | 1 | y]: simple-kriging weights transposed, column M = S^-1 1
     """
 
-    def __init__(self, cov: torch.Tensor, problems, ordinary: bool):
+    def __init__(self, cov: torch.Tensor, problems, ordinary: bool, alloc=None):
         assert cov.is_cuda and cov.dtype == torch.float64 and cov.dim() == 2 and cov.stride(1) == 1
+        import time
+
+        marks = [("start", time.perf_counter())]
         self.cov, self.ordinary = cov, bool(ordinary)
         self.M = M = cov.shape[0]
         device = cov.device
@@ -254,36 +317,38 @@ class KrigeBatch:
         ws = [solve_ws(n) for n in ns]
         slabs = [(n + SLAB - 1) // SLAB for n in ns]
 
+        if alloc is None:
+            def alloc(numel):
+                return torch.empty(int(numel), dtype=torch.float64, device=device)
+
         def pool(sizes):
             offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-            return torch.empty(int(offs[-1]), dtype=torch.float64, device=device), offs
+            return alloc(int(offs[-1])), offs
 
         self._S, oS = pool([n * l for n, l in zip(ns, lds)])
         self._T, oT = pool([n * self.ldt for n in ns])
         self._Linv, oL = pool([w[0] for w in ws])
         self._P, oP = pool([w[1] for w in ws])
         self._partial, oPa = pool([4 * s * M for s in slabs])
-        self.out = torch.empty((B, 5, M), dtype=torch.float64, device=device)
-        self.info = torch.zeros(B, dtype=torch.int32, device=device)
-        # inputs: one H2D copy each (idx, obs, error covariances)
+        self.out = alloc(B * 5 * M).view(B, 5, M)
+        marks.append(("pools", time.perf_counter()))
         offs_n = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
-        self._idx = _h2d(np.concatenate([np.asarray(p[0], dtype=np.int64) for p in problems]), device)
-        self._y = _h2d(np.concatenate([np.asarray(p[1], dtype=np.float64) for p in problems]), device)
+        has_E = [p[2] is not None for p in problems]
+        Es = []
+        for p, n, h in zip(problems, ns, has_E):
+            E = np.asarray(p[2]) if h else None
+            if h and E.shape != (n, n):
+                raise ValueError(f"error covariance of shape {E.shape} does not match {n} observations")
+            Es.append(E.astype(np.float64) if h and E.dtype.kind != "f" else E)
         # A symmetric error covariance (what a covariance is; checked on a fixed sample of mirrored entry pairs, an
         # asymmetric one is uploaded whole) travels as the block trapezoid below and on its 128 x 128 diagonal
         # blocks - row block b of 128 rows with its first 128 (b + 1) columns, a strided VIEW of the host array.
         # That is everything the Cholesky path reads and halves the H2D bytes of the kriging path
         # (GmgKrigeDesc.lde < 0; the LU fallback reads the mirrored entries).
-        has_E = [p[2] is not None for p in problems]
         groups, sizes_E, ldes, self._asym = [], [], [], []
-        for b, (p, n, h) in enumerate(zip(problems, ns, has_E)):
+        for b, (E, n) in enumerate(zip(Es, ns)):
             size, lde = 0, n
-            if h:
-                E = np.asarray(p[2])
-                if E.shape != (n, n):
-                    raise ValueError(f"error covariance of shape {E.shape} does not match {n} observations")
-                if E.dtype.kind != "f":
-                    E = E.astype(np.float64)
+            if E is not None:
                 sym = _looks_symmetric(E)
                 if not sym:
                     self._asym.append(b)                 # no Cholesky for this system: LU like the reference
@@ -297,8 +362,21 @@ class KrigeBatch:
             sizes_E.append(size)
             ldes.append(lde)
         offs_E = np.concatenate([[0], np.cumsum(sizes_E)]).astype(np.int64)
-        self._E = _h2d_concat(groups, int(offs_E[-1]), device) if any(has_E) else None
-        self.h2d_bytes = 8 * int(offs_E[-1]) + 16 * int(offs_n[-1])
+        marks.append(("symmetry + blocks", time.perf_counter()))
+        # ALL inputs - error covariances, observation cells, observations and the two descriptor arrays - go up as one
+        # blob through the pinned, pipelined staging of `_h2d_concat`: [E | idx | y | krige descs | solve descs].
+        # (Separate small pageable copies stall against the CUDA calls of the other pipeline thread, ~5 ms per chunk.)
+        nE, nn = int(offs_E[-1]), int(offs_n[-1])
+        o_idx, o_y, o_kd = nE, nE + nn, nE + 2 * nn
+        o_sd = o_kd + B * KRIGE_DESC.itemsize // 8
+        o_info = o_sd + B * SOLVE_DESC.itemsize // 8
+        blob = alloc(o_info + (B + 1) // 2)
+        self.info = blob[o_info:].view(torch.int32)[:B]       # zeroed by the upload
+        self._E = blob[:nE] if nE else None
+        self._idx = blob[o_idx:o_y].view(torch.int64)
+        self._y = blob[o_y:o_kd]
+        self._kd, self._sd = blob[o_kd:o_sd], blob[o_sd:o_info]
+        self.h2d_bytes = 8 * blob.numel()
 
         kd = np.zeros(B, dtype=KRIGE_DESC)
         sd = np.zeros(B, dtype=SOLVE_DESC)
@@ -308,13 +386,22 @@ class KrigeBatch:
             S_ptr = self._S.data_ptr() + f8 * int(oS[b])
             T_ptr = self._T.data_ptr() + f8 * int(oT[b])
             kd[b] = (self._idx.data_ptr() + f8 * int(offs_n[b]),
-                     (self._E.data_ptr() + f8 * int(offs_E[b])) if has_E[b] else 0, ldes[b],
+                     (blob.data_ptr() + f8 * int(offs_E[b])) if has_E[b] else 0, ldes[b],
                      self._y.data_ptr() + f8 * int(offs_n[b]), S_ptr, lds[b], 0, self.ldx, T_ptr, self.ldt,
                      self._partial.data_ptr() + f8 * int(oPa[b]), self.out.data_ptr() + f8 * 5 * M * b, n,
                      int(self.ordinary))
             sd[b] = (S_ptr, lds[b], self._Linv.data_ptr() + f8 * int(oL[b]), T_ptr, self.ldt,
                      self._P.data_ptr() + f8 * int(oP[b]), ws[b][2], self.info.data_ptr() + 4 * b, n, self.nrhs)
-        self._kd, self._sd = _desc_tensor(kd, device), _desc_tensor(sd, device)
+        marks.append(("descriptors", time.perf_counter()))
+        idx_all = np.concatenate([np.asarray(p[0], dtype=np.int64) for p in problems])
+        y_all = np.concatenate([np.asarray(p[1], dtype=np.float64) for p in problems])
+        groups += [[idx_all.view(np.float64)], [y_all], [kd.view(np.uint8).view(np.float64)],
+                   [sd.view(np.uint8).view(np.float64)], [np.zeros((B + 1) // 2)]]
+        _h2d_concat(groups, blob.numel(), device, out=blob)
+        marks.append(("pack + H2D of all inputs", time.perf_counter()))
+        if os.environ.get("GLOMAR_B200_TIMING") and B > 1:
+            print(f"[KrigeBatch] {B} problems: " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.1f} ms"
+                                                              for a, b in zip(marks, marks[1:])), flush=True)
         self._kd_np, self._sd_np = kd, sd
         self._oS, self._oT, self._lds, self._offs_n = oS, oT, lds, offs_n
         self._Cx = {}                       # C_cross copies, made on demand (LU fallback, weights from outside)
@@ -352,7 +439,7 @@ class KrigeBatch:
         self.full[:] = False
         check(L.gmg_krige_gather_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, s), "gather")
         check(L.gmg_potrf_batched_f64(self._sd.data_ptr(), self.B, self.n_max, s), "gmg_potrf_batched_f64")
-        info = self.info.cpu().numpy()               # synchronises: the factorisation outcome decides the path
+        info = _d2h_info(self.info)                  # synchronises: the factorisation outcome decides the path
         asym = np.asarray(self._asym, dtype=np.int64)
         if asym.size:
             warn(f"the error covariance of {asym.size} of {self.B} kriging system(s) is not symmetric (first: system "
@@ -391,7 +478,7 @@ class KrigeBatch:
             check(L.gmg_potrs_batched_f64(sd_good.data_ptr(), int(good.size), n_good, self.nrhs, 1, s),
                   "gmg_potrs_batched_f64")
             check(L.gmg_krige_apply_batched_f64(C, M, ldc, kd_good.data_ptr(), int(good.size), n_good, 1, s), "apply")
-        if np.any(self.info.cpu().numpy()):          # also synchronises before the temporaries die
+        if np.any(_d2h_info(self.info)):             # also synchronises before the temporaries die
             raise np.linalg.LinAlgError("Singular matrix")
         return self
 

@@ -35,6 +35,12 @@ def _bytes_per_problem(n: int, M: int) -> int:
 
 
 _SIDE_STREAMS: dict = {}
+_ARENAS: dict = {}
+
+
+def release_workspaces() -> None:
+    """Give the device arenas of the pipelined driver back to the allocator (they are kept between calls)."""
+    _ARENAS.clear()
 
 
 def _side_stream(device) -> torch.cuda.Stream:
@@ -104,6 +110,22 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
     timing = os.environ.get("GLOMAR_B200_TIMING")
     import time as _time
 
+    # Two arenas, used alternately by consecutive chunks (chunk i + 1 is uploaded while chunk i runs; chunk i is dead
+    # before the upload of chunk i + 2 starts), kept for the life of the process like the pinned staging buffers.
+    chunk_no = {lo: i for i, (lo, hi) in enumerate(bounds)}
+
+    def arena_for(lo, prepared):
+        if len(bounds) == 1:
+            return None
+        need = dn.krige_batch_doubles([len(p[0]) for p in prepared], M, any(p[2] is not None for p in prepared))
+        key = (cov.device.index, chunk_no[lo] & 1)
+        arena = _ARENAS.get(key)
+        if arena is None or arena.buf.numel() < need:
+            _ARENAS.pop(key, None)
+            arena = None                                               # free the old one before asking for more
+            _ARENAS[key] = arena = dn.Arena(int(1.15 * need), cov.device)
+        return arena.reset()
+
     def prep(lo, hi):
         chunk = problems[lo:hi]
         return list(workers.map(prepare, chunk)) if workers is not None else [prepare(p) for p in chunk]
@@ -114,7 +136,7 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
         prepared = prepared_or_future.result() if hasattr(prepared_or_future, "result") else prepared_or_future
         t1 = _time.perf_counter()
         with torch.cuda.stream(side):
-            kb = dn.KrigeBatch(cov, prepared, ordinary=method == "ordinary")
+            kb = dn.KrigeBatch(cov, prepared, ordinary=method == "ordinary", alloc=arena_for(lo, prepared))
             side.synchronize()                                     # uploads complete before the main stream reads them
         if timing:
             print(f"[krige_batch] upload {lo}:{hi} waited {1e3 * (t1 - t0):.1f} ms for prepare, pack + H2D "
