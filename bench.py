@@ -44,10 +44,10 @@ def parse_args():
     ap.add_argument("--res", type=float, default=1.0, help="grid resolution in degrees (1.0 = headline config)")
     ap.add_argument("--nu", type=float, default=2.2)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-rows", type=int, default=192, help="rows of the 1-degree matrix the CPU baseline evaluates")
+    ap.add_argument("--cpu-rows", type=int, default=768, help="rows of the 1-degree matrix the CPU baseline evaluates")
     ap.add_argument("--months", type=int, default=480)
     ap.add_argument("--month-steps", type=int, default=3)
-    ap.add_argument("--cpu-months", type=int, default=4)
+    ap.add_argument("--cpu-months", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kriging", action="store_true")

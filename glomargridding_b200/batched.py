@@ -143,11 +143,25 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
                   f"{1e3 * (_time.perf_counter() - t1):.1f} ms", flush=True)
         return kb
 
-    out = torch.empty((n_all, 5, M), dtype=torch.float64, device=cov.device)
+    assert (dn.OUT_FIELD, dn.OUT_U2, dn.OUT_MASK) == (0, 1, 2)
+    if return_device:
+        out = torch.empty((n_all, 5, M), dtype=torch.float64, device=cov.device)
+    else:
+        # field, variance and mask planes of every chunk go home as soon as the chunk is done (pinned, asynchronous)
+        host = torch.empty((3, n_all, M), dtype=torch.float64, pin_memory=True)
+
+    def collect(batch, lo, hi):
+        if return_device:
+            out[lo:hi] = batch.out
+        else:
+            planes = batch.out[:, :3].permute(1, 0, 2).contiguous()
+            for p in range(3):
+                host[p, lo:hi].copy_(planes[p], non_blocking=True)
+
     try:
         if len(bounds) == 1:
             batch = upload(prep(*bounds[0]), *bounds[0]).run()
-            out[:] = batch.out
+            collect(batch, 0, n_all)
             main_stream.synchronize()
             del batch
         else:
@@ -164,7 +178,7 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
                     if i + 1 < len(bounds):
                         fut = uploader.submit(upload, prepped[i + 1], *bounds[i + 1])
                     batch.run()
-                    out[lo:hi] = batch.out
+                    collect(batch, lo, hi)
                     main_stream.synchronize()                      # its memory was allocated on the side stream
                     del batch
                     if timing:
@@ -177,14 +191,11 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
     if return_device:
         field = out[:, dn.OUT_FIELD] + (mean if method == "simple" else 0.0)
         return {"field": field, "variance": out[:, dn.OUT_U2], "constraint_mask": out[:, dn.OUT_MASK]}
-    from . import _device as dev
-
-    o = dev.to_host(out[:, :3].permute(1, 0, 2).contiguous())      # field, variance, mask planes: 3 of the 5 result rows
-    assert (dn.OUT_FIELD, dn.OUT_U2, dn.OUT_MASK) == (0, 1, 2)
+    o = host.numpy()
     field = o[dn.OUT_FIELD] + mean if method == "simple" else o[dn.OUT_FIELD]
     unc = _finish_uncertainty(o[dn.OUT_U2], np.float64)            # elementwise: all problems at once
     if timing:
-        print(f"[krige_batch] results to host + uncertainty clamp {1e3 * (_time.perf_counter() - t_out):.1f} ms", flush=True)
+        print(f"[krige_batch] uncertainty clamp {1e3 * (_time.perf_counter() - t_out):.1f} ms", flush=True)
     return {"field": field, "uncertainty": unc, "constraint_mask": o[dn.OUT_MASK]}
 
 
