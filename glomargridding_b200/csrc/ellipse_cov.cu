@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(kThreads, K1_MINB) ellipse_cov_tile_kernel(con
         // of the rank that owns those rows (stores go over NVLink into its memory)
         OutT* mbase = out;
         int mrow0 = row0, mlim = row_end;
-        if (a.world > 1 && t.peer != a.rank) {
+        if (MT == 1 && a.world > 1 && t.peer != a.rank) {        // macro tiles (MT = 2) never leave the rank
             mbase = reinterpret_cast<OutT*>(a.peer_out[t.peer]);
             mrow0 = (int)a.blk_row0[t.peer];
             mlim = (int)a.blk_row0[t.peer + 1];
