@@ -87,7 +87,8 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
     if n_all == 0:
         empty = np.empty((0, M)) if not return_device else torch.empty((0, M), dtype=torch.float64, device=cov.device)
         return {"field": empty, ("variance" if return_device else "uncertainty"): empty, "constraint_mask": empty}
-    cap = n_all if n_all < 32 else max(24, (n_all + 7) // 8)
+    n_chunks = max(1, int(os.environ.get("GLOMAR_B200_CHUNKS", "8")))
+    cap = n_all if n_all < 32 else max(24, (n_all + n_chunks - 1) // n_chunks)
     bounds, start = [], 0
     while start < n_all:
         used, stop = 0, start

@@ -205,7 +205,9 @@ typedef struct GmgKrigeDesc {
     int32_t ordinary;    /* 0 simple kriging, 1 ordinary kriging (Lagrange-extended system)        */
 } GmgKrigeDesc;
 
-/* S = C[idx, idx] + E, Cx = C[idx, :], T = [Cx | 1 | y]   (reference kriging.py:337-342, :571-583) */
+/* S = C[idx, idx] + E, Cx = C[idx, :], T = [Cx | 1 | y]   (reference kriging.py:337-342, :571-583).
+ * NaN entries of E are read as 0.0 (kriging.py:120).  With even leading dimensions and 16-byte aligned base
+ * pointers the rows move as 16-byte vectors; anything else takes the scalar path of the same kernel. */
 int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs,
                                  int batch, int64_t n_max, gmg_stream_t stream);
 
