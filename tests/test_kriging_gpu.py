@@ -481,6 +481,44 @@ def test_packed_symmetric_error_cov_upload_is_bit_identical_and_asymmetric_falls
     assert max_norm_rel(got, want) < 1e-8
 
 
+def test_pipelined_driver_many_small_months(K):
+    """40 problems take the pipelined route of `krige_batch` (ramped chunks, uploads on the side stream into the two
+    persistent arenas, everything of a chunk in one blob, result planes copied home per chunk); a second call reuses
+    arenas, staging buffers and the upload stream.  Results must not depend on the chunking: bit-equal to one
+    `KrigeBatch` over all problems and to the per-month class."""
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200.batched import krige_batch, release_workspaces
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(10.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office",
+                                   precision=np.float64).cov_ns_device
+    M = cov.shape[0]
+    problems = []
+    for m in range(40):
+        idx, obs = synth.month_observations(m, M, n_min=100 + 5 * m, n_max=140 + 5 * m)   # some above 128: packed E
+        problems.append((idx.astype(np.int64), obs.astype(np.float64), synth.hadcrut_style_error_cov(idx, lons.size, seed=m)))
+    problems[7] = (problems[7][0], problems[7][1], None)                                  # no error covariance at all
+    first = quiet(krige_batch, cov, problems, "ordinary")
+    again = quiet(krige_batch, cov, problems, "ordinary")
+    for key in ("field", "uncertainty", "constraint_mask"):
+        assert first[key].shape == (40, M) and np.array_equal(first[key], again[key])
+    whole = quiet(lambda: dn.KrigeBatch(cov, problems, ordinary=True).run()).out.cpu().numpy()
+    assert np.array_equal(first["field"], whole[:, dn.OUT_FIELD])
+    assert np.array_equal(first["constraint_mask"], whole[:, dn.OUT_MASK])
+    for m in (0, 7, 39):
+        idx, obs, E = problems[m]
+        one = quiet(K.OrdinaryKriging, cov, idx.copy(), obs.copy(), None if E is None else E.copy())
+        assert np.array_equal(first["field"][m], quiet(one.solve))
+        assert np.array_equal(first["uncertainty"][m], quiet(one.get_uncertainty))
+    dev = quiet(krige_batch, cov, problems, "simple", mean=0.5, return_device=True)
+    host = quiet(krige_batch, cov, problems, "simple", mean=0.5)
+    assert np.array_equal(dev["field"].cpu().numpy(), host["field"])
+    assert np.array_equal(dev["constraint_mask"].cpu().numpy(), host["constraint_mask"])
+    release_workspaces()
+
+
 def test_narrow_and_wide_solve_tiles_are_bit_identical(K):
     """The triangular-solve steps use 64-column strips when 128-column ones would leave SMs idle (one 5-degree month:
     21 strips) and 128-column strips otherwise (eight copies of it: 168); every output element is accumulated over k
