@@ -267,3 +267,23 @@ def test_strategy_methods_leave_the_off_diagonal_matrix(Builder):
     b.covariance_method, b.delta_x_method = "low_memory", "Met_Office"
     b._get_disp_fn()
     assert b.disp_fn.__name__ == "_mo_disp_single"
+
+
+def test_reference_own_golden_atlantic_window(Builder):
+    """The reference's own known-answer test for this path, `test/test_ellipse.py:177-217`: fitted ellipse parameters
+    of an Atlantic window, nu = 0.5, DEFAULT precision (float32), expected covariance from `test/data/cov_no_hfix.nc`
+    (fixture: tests/golden/make_golden_atlantic.py) - with the reference's own tolerance, then the correlation check
+    of `:213-217` and the uncompress check of `test_ellipse_covariance_rescale` (`:356-388`)."""
+    g = load_golden("ellipse_atlantic.npz")
+    expected = from_triu(g["cov_triu"])
+    mask = g["Lx"] > 1e5
+    fields = [np.ma.masked_where(mask, g[k]) for k in ("Lx", "Ly", "theta", "stdev")]
+    b = Builder(*fields, g["lats"], g["lons"], v=0.5)
+    assert b.cov_ns.dtype == np.float32 and b.cov_ns.shape == expected.shape
+    assert np.allclose(b.cov_ns, expected, rtol=1e-5)
+    b64 = Builder(*fields, g["lats"], g["lons"], v=0.5, precision=np.float64)
+    assert np.allclose(b64.cov_ns, expected, rtol=1e-5)
+    b.calculate_cor()
+    assert hasattr(b, "cor_ns") and np.isclose(1, np.max(np.diag(b.cor_ns)))
+    b.uncompress_cov()
+    assert b.cov_ns.shape[0] == b.cov_ns.shape[1] == g["Lx"].shape[0] ** 2

@@ -196,3 +196,30 @@ def test_geometry_helpers_oracle_vs_reference_golden():
     # the scalar variants agree with the vector ones except for the coincident-point shortcut (`:561-562`)
     assert np.array_equal(g["single_mo"], g["mo"][:, -8:].T) and np.array_equal(g["single_mod_mo"], g["mod_mo"][:, -8:].T)
     assert np.allclose(g["single_haversine"], g["haversine"][-8:], rtol=1e-15, atol=0)
+
+
+def _atlantic_case():
+    from conftest import from_triu
+
+    g = load_golden("ellipse_atlantic.npz")
+    mask = g["Lx"] > 1e5                                       # test/test_ellipse.py:196
+    fields = [np.ma.masked_where(mask, g[k]) for k in ("Lx", "Ly", "theta", "stdev")]
+    return g, fields, from_triu(g["cov_triu"])
+
+
+def test_reference_own_ellipse_golden_atlantic():
+    """The reference's own known-answer test for the covariance path (`test/test_ellipse.py:177-217`): fitted ellipse
+    parameters of an Atlantic window (`test/data/Atlantic_Ocean_07.nc`), nu = 0.5, default float32 precision, expected
+    covariance `test/data/cov_no_hfix.nc` - same tolerance as the reference (`np.allclose(rtol=1e-5)`), in float32 like
+    the reference's default and in float64."""
+    from oracle.ellipse import cov_2_cor, ellipse_covariance
+
+    g, fields, expected = _atlantic_case()
+    assert float(g["matern_nu"]) == 0.5 and expected.shape == (262, 262)
+    for precision in (np.float32, np.float64):
+        cov = ellipse_covariance(*fields, g["lats"], g["lons"], 0.5, precision=precision)
+        assert cov.shape == expected.shape and cov.dtype == precision
+        assert np.allclose(cov, expected, rtol=1e-5)
+        cor = cov_2_cor(np.asarray(cov, dtype=np.float64))
+        assert np.isclose(1, np.max(np.diag(cor)))              # :215-217
+    assert np.allclose(g["cor_diag"], 1.0)
