@@ -232,19 +232,15 @@ class EllipseCovarianceBuilder:
             self._cov_ns_host = np.asarray(value)
             self.cov_ns_device = None
 
-    # reference computes these on the host at :219-224; kept as cheap O(N) attributes for users
+    # reference computes these at :219-224 and keeps them as attributes; here they are evaluated on demand by the
+    # same device helpers the module exports (`gmg_sigma_rot_f64`, `gmg_det22_f64`)
     @property
     def sigmas(self) -> np.ndarray:
-        ct, st = np.cos(self.theta_compressed), np.sin(self.theta_compressed)
-        c2, s2, cs = ct ** 2, st ** 2, ct * st
-        lx2, ly2 = self.Lx_compressed ** 2, self.Ly_compressed ** 2
-        off = cs * (lx2 - ly2)
-        return np.column_stack([c2 * lx2 + s2 * ly2, off, off, s2 * lx2 + c2 * ly2]).astype(self.precision)
+        return _sigma_rot_func_multi(self.Lx_compressed, self.Ly_compressed, self.theta_compressed).astype(self.precision)
 
     @property
     def sqrt_dets(self) -> np.ndarray:
-        s = self.sigmas
-        return np.sqrt(s[:, 0] * s[:, 3] - s[:, 1] * s[:, 2])
+        return np.sqrt(_det_22_multi(self.sigmas))
 
     @property
     def gamma_v_term(self) -> float:
