@@ -58,7 +58,12 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
 
     Returns a dict of (len(problems), M) arrays: "field", "uncertainty", "constraint_mask" (numpy, or CUDA
     tensors "field", "variance", "constraint_mask" if `return_device`).  `max_bytes` bounds the device
-    memory of one chunk of problems (default: 40 % of the free memory)."""
+    memory of one chunk of problems (default: 40 % of the free memory).
+
+    Batches of 32 or more problems run as a three-stage pipeline over chunks (an eighth of the batch each, the first
+    two smaller; `GLOMAR_B200_CHUNKS` overrides the eighth): constructor logic, packing + H2D on a side stream, device
+    work.  The two device arenas the chunks live in, the pinned staging buffers and the side stream are kept between
+    calls (a second call allocates nothing); `release_workspaces()` returns the arenas to the allocator."""
     if method not in ("ordinary", "simple"):
         raise ValueError(f"Unknown kriging method: {method}")
     cls = OrdinaryKriging if method == "ordinary" else SimpleKriging
