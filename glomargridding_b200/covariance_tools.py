@@ -334,3 +334,62 @@ def eigenvalue_clip(cov, method: Literal["explained_variance", "Laloux_2000"] = 
             return laloux_clip(cov, **kwargs)
         case _:
             raise ValueError(f"Unknown clipping method: {method}")
+
+
+# -- scalar helpers of the clipping path (reference `covariance_tools.py:393-517`): O(n) logic on a spectrum, host side --
+def csum_up_to_val(vals: np.ndarray, target: float, reverse: bool = True, niter: int = 0, csum: float = 0.0):
+    """Cumulative sum and index at which `target` is surpassed (reference `:393-460`; its own checks:
+    `test/test_covariance_tools.py:140-170`).  With `reverse` the vector is summed from its end and the returned index
+    is negative, i.e. valid for the un-reversed vector.  Warns when `vals` is empty or the target is never exceeded."""
+    vals = np.asarray(vals)
+    if vals.size == 0:
+        warn("`vals` is empty")
+        return csum, niter
+    if len(vals) != vals.size:
+        raise ValueError("`vals` must be a vector")
+    vals = vals[::-1] if reverse else vals
+    i = 0
+    for v in vals:                                     # accumulate(vals, initial=csum): the initial value is entry 0
+        if csum > target:
+            return csum, niter + (-i if reverse else i)
+        csum = csum + v
+        i += 1
+    if csum > target:
+        return csum, niter + (-i if reverse else i)
+    warn("Out of `vals`, target not exceeded.")
+    return csum, niter + (-i if reverse else i)
+
+
+def clean_small(matrix: np.ndarray, atol: float = 1e-5) -> np.ndarray:
+    """Set entries with abs(x) < atol to 0 (reference `:463-470`)."""
+    cleaned = np.array(matrix, copy=True)
+    cleaned[np.abs(cleaned) < atol] = 0.0
+    return cleaned
+
+
+def check_symmetric(a: np.ndarray, rtol: float = 1e-5, atol: float = 1e-8) -> bool:
+    """`np.allclose(a, a.T)` (reference `:108-114`)."""
+    a = np.asarray(a)
+    return bool(np.allclose(a, a.T, rtol=rtol, atol=atol))
+
+
+def _find_index_explained_variance(eigvals, target: float = 0.95) -> int:
+    """(Negative) index of the eigenvalue - ascending spectrum - at which the cumulative sum from the top exceeds
+    `target` of the total variance (reference `:473-485`)."""
+    eigvals = np.asarray(eigvals)
+    total_variance = np.sum(eigvals)
+    target_explained_variance = target * total_variance
+    csum, i2goal = csum_up_to_val(eigvals, target_explained_variance)
+    if csum <= target_explained_variance:
+        raise ValueError("Target Explained Variance not exceeded")
+    return i2goal
+
+
+def _find_index_aspect_ratio(eigvals: np.ndarray, num_grid_pts: int = 180 * 360, num_times: int = 41 * 6) -> int:
+    """(Negative) number of eigenvalues above the Marchenko-Pastur edge (1 + sqrt(q))^2, q = grid points / times
+    (reference `:488-516`, 7.2.2 in Bun et al.)."""
+    q = num_grid_pts / num_times
+    if q < 1.0:
+        q = 1.0 / q
+    threshold = (1.0 + np.sqrt(q)) ** 2.0
+    return -int(np.sum(np.asarray(eigvals) > threshold))

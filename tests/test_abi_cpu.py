@@ -113,3 +113,62 @@ def test_block_trapezoid_layout_of_symmetric_error_covariances(n):
     Lb = np.minimum(n, hb * (b + 1))
     off = hb * hb * (b * (b + 1) // 2) + (i - hb * b) * Lb + j
     assert np.array_equal(packed[off], E[i, j])
+
+
+# ---- scalar helpers of the clipping path (host logic; reference covariance_tools.py:393-517) ----------------------
+@pytest.mark.parametrize("n, expected_i", [(10, 7), (25, 24), (100, 100), (15, 1)])
+def test_cumsum(n, expected_i):
+    """reference test/test_covariance_tools.py:140-157"""
+    from glomargridding_b200.covariance_tools import csum_up_to_val
+
+    vals = np.arange(n + 1)
+    target_sum = expected_i * (expected_i + 1) / 2
+    csum, i = csum_up_to_val(vals, target_sum - 1, reverse=False)      # cumulatively sum to just under the target
+    assert expected_i == i - 1
+    assert target_sum == csum
+
+
+def test_cumsum_exceeds_target_and_clip_indices(reference):
+    """reference test/test_covariance_tools.py:160-169, then the helpers against the live reference on random spectra
+    (skipped where the reference sources are absent)."""
+    import contextlib
+    import importlib
+    import io
+    import warnings
+
+    import glomargridding_b200.covariance_tools as mine
+
+    rng = np.random.default_rng(50)
+    vals = np.sort(rng.random(50))
+    target_csum = 0.9 * vals.sum()
+    csum, _ = mine.csum_up_to_val(vals, target_csum, reverse=True)
+    assert csum >= target_csum
+    ct = importlib.import_module("glomar_gridding.covariance_tools")
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        for _ in range(100):
+            n = int(rng.integers(0, 30))
+            v = rng.random(n)
+            target = rng.random() * max(v.sum(), 0.1) * 1.2
+            for rev in (True, False):
+                assert ct.csum_up_to_val(v, target, reverse=rev, niter=2, csum=0.5) == \
+                    mine.csum_up_to_val(v, target, reverse=rev, niter=2, csum=0.5)
+        ev = np.sort(rng.random(60))
+        assert ct._find_index_explained_variance(ev, 0.9) == mine._find_index_explained_variance(ev, 0.9)
+        assert ct._find_index_aspect_ratio(ev * 300, 2592, 40) == mine._find_index_aspect_ratio(ev * 300, 2592, 40)
+    m = rng.standard_normal((6, 6))
+    assert np.array_equal(ct.clean_small(m * 1e-5), mine.clean_small(m * 1e-5))
+    assert mine.check_symmetric(m + m.T) and not mine.check_symmetric(m)
+
+
+def test_cumsum_warnings():
+    from glomargridding_b200.covariance_tools import _find_index_explained_variance, csum_up_to_val
+
+    with pytest.warns(UserWarning, match="empty"):
+        assert csum_up_to_val(np.array([]), 1.0) == (0.0, 0)
+    with pytest.warns(UserWarning, match="target not exceeded"):
+        csum_up_to_val(np.ones(4), 10.0)
+    with pytest.raises(ValueError, match="must be a vector"):
+        csum_up_to_val(np.ones((2, 2)), 1.0)
+    with pytest.raises(ValueError, match="not exceeded"), pytest.warns(UserWarning):
+        _find_index_explained_variance(np.ones(4), 1.0)
