@@ -1,0 +1,103 @@
+"""Host-side helpers of the hot path (`utils.py`, the observation-preparation helpers of `kriging.py`): pure numpy
+logic that runs without a GPU.  Fixed expectations first (they hold on the GPU box too), then a comparison with the
+live reference on random inputs (skipped where `/root/reference` is absent)."""
+
+import contextlib
+import importlib
+import io
+import warnings
+
+import numpy as np
+import pytest
+
+
+def test_adjust_small_negative_texts_and_values(capsys):
+    """reference utils.py:132-175: (-1e-8, 0) -> 0 with a warning and a print of the values; other negatives only warn."""
+    from glomargridding_b200.utils import adjust_small_negative
+
+    a = np.array([1.0, -5e-9, 0.0, 2.0])
+    with pytest.warns(UserWarning, match="Small negative vals are detected. Setting to 0."):
+        out = adjust_small_negative(a)
+    assert np.array_equal(out, [1.0, 0.0, 0.0, 2.0]) and a[1] == -5e-9            # input untouched
+    assert "-5.e-09" in capsys.readouterr().out
+    with pytest.warns(UserWarning, match="Negative values are detected"):
+        out = adjust_small_negative(np.array([1.0, -0.5]))
+    assert np.array_equal(out, [1.0, -0.5])
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert np.array_equal(adjust_small_negative(np.array([0.0, 3.0], dtype=np.float32)), [0.0, 3.0])
+
+
+def test_mask_array_and_uncompress_masked():
+    """reference utils.py:674-694 (mask_array) and :550-608 (uncompress_masked)."""
+    from glomargridding_b200.utils import mask_array, uncompress_masked
+
+    m = mask_array(np.array([[1.0, np.nan], [3.0, 4.0]]))
+    assert isinstance(m, np.ma.MaskedArray)
+    already = np.ma.masked_greater(np.arange(4.0), 2)
+    assert np.array_equal(np.ma.getmaskarray(mask_array(already)), [False, False, False, True])
+    mask = np.array([False, True, False, True, False])
+    full = uncompress_masked(np.array([1.0, 2.0, 3.0]), mask, fill_value=-9.0)
+    assert np.array_equal(np.asarray(full), [1.0, -9.0, 2.0, -9.0, 3.0])
+    masked = uncompress_masked(np.array([1.0, 2.0, 3.0]), mask, apply_mask=True)
+    assert isinstance(masked, np.ma.MaskedArray) and np.array_equal(np.ma.getmaskarray(masked), mask)
+    with pytest.raises(ValueError):
+        uncompress_masked(np.array([1.0, 2.0]), mask)
+
+
+def test_batched_and_intersect():
+    """reference utils.py:697-712 (batched), :246-279 (intersect_mtlb)."""
+    from glomargridding_b200.utils import batched, intersect_mtlb
+
+    assert [tuple(b) for b in batched(range(7), 3)] == [(0, 1, 2), (3, 4, 5), (6,)]
+    with pytest.raises(ValueError):
+        list(batched(range(3), 0))
+    c, ia, ib = intersect_mtlb(np.array([5, 1, 3, 3, 9]), np.array([3, 9, 7, 5]))
+    assert np.array_equal(c, [3, 5, 9]) and np.array_equal(np.array([5, 1, 3, 3, 9])[ia], c)
+    assert np.array_equal(np.array([3, 9, 7, 5])[ib], c)
+
+
+@pytest.mark.gpu
+def test_get_spatial_mean_on_device():
+    """reference utils.py:766-793: the BLUE of a constant mean, 1^T S^-1 y / 1^T S^-1 1 (the solve runs on the GPU)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from glomargridding_b200.utils import get_spatial_mean
+
+    rng = np.random.default_rng(3)
+    for n in (2, 7, 150):
+        A = rng.standard_normal((n, n))
+        covx = A @ A.T + n * np.eye(n)
+        obs = rng.standard_normal(n)
+        ones = np.ones(n)
+        want = (ones @ np.linalg.solve(covx, obs)) / (ones @ np.linalg.solve(covx, ones))
+        assert np.isclose(get_spatial_mean(obs, covx), want, rtol=1e-10)
+
+
+def test_host_helpers_against_the_live_reference(reference):
+    import glomargridding_b200.kriging as mk
+    import glomargridding_b200.utils as mu
+
+    ru = importlib.import_module("glomar_gridding.utils")
+    rk = importlib.import_module("glomar_gridding.kriging")
+    rng = np.random.default_rng(11)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        for _ in range(20):
+            v = rng.standard_normal(30) * 10.0 ** rng.integers(-10, 1, 30)
+            assert np.array_equal(ru.adjust_small_negative(v), mu.adjust_small_negative(v))
+            a, b = rng.integers(0, 40, 25), rng.integers(0, 40, 18)
+            for x, y in zip(ru.intersect_mtlb(a, b), mu.intersect_mtlb(a, b)):
+                assert np.array_equal(x, y)
+            mask = rng.random(50) < 0.4
+            comp = rng.standard_normal(int((~mask).sum()))
+            for apply_mask in (False, True):
+                x = ru.uncompress_masked(comp, mask, fill_value=1.5, apply_mask=apply_mask)
+                y = mu.uncompress_masked(comp, mask, fill_value=1.5, apply_mask=apply_mask)
+                assert np.array_equal(np.ma.getmaskarray(x), np.ma.getmaskarray(y))
+                assert np.array_equal(np.ma.filled(x, 0.0), np.ma.filled(y, 0.0))   # data under the mask is np.empty
+            unmask = np.sort(rng.choice(60, 30, replace=False))
+            uniq = np.sort(rng.choice(unmask, 12, replace=False))
+            assert np.array_equal(rk.get_unmasked_obs_indices(unmask, uniq), mk.get_unmasked_obs_indices(unmask, uniq))
