@@ -356,8 +356,17 @@ class KrigeBatch:
                     lde = -NB
                     blocks = [E[r0:min(n, r0 + NB), :min(n, r0 + NB)] for r0 in range(0, n, NB)]
                 else:
-                    blocks = [E]
-                groups.append(blocks)
+                    blocks = [E[r0:r0 + NB] for r0 in range(0, n, NB)]       # whole matrix, in row slabs
+                # packing tasks of at most ~32 MB: one per 5-degree month, many for one large system (whose 1.6 - 3.2 GB
+                # would otherwise be ONE task and need staging buffers of that size)
+                task, fill = [], 0
+                for blk in blocks:
+                    if task and fill + blk.size > (4 << 20):
+                        groups.append(task)
+                        task, fill = [], 0
+                    task.append(blk)
+                    fill += blk.size
+                groups.append(task)
                 size = sum(blk.size for blk in blocks)
             sizes_E.append(size)
             ldes.append(lde)
