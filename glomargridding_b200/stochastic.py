@@ -44,6 +44,11 @@ class StochasticKriging(Kriging):
         super().__init__(covariance=covariance, idx=idx, obs=obs, error_cov=error_cov)
 
     # -- simple kriging weights of the second stage --------------------------------------------------------
+    def _has_simple_weights(self) -> bool:
+        """`hasattr(self, "simple_kriging_weights")` without evaluating the property (see `Kriging._has_weights`)."""
+        return self._user_simple_weights is not None or (self._batch is not None
+                                                          and not getattr(self, "_simple_deleted", False))
+
     @property
     def simple_kriging_weights(self) -> np.ndarray:
         if self._user_simple_weights is not None:
@@ -121,7 +126,7 @@ class StochasticKriging(Kriging):
 
     def get_uncertainty(self) -> np.ndarray:
         """As `OrdinaryKriging.get_uncertainty` (reference `:220-243`)."""
-        if not hasattr(self, "kriging_weights"):
+        if not self._has_weights():
             raise KeyError("Please compute Kriging Weights first")
         if self._batch is not None:
             u2 = self._out_host[dn.OUT_U2]
@@ -134,7 +139,7 @@ class StochasticKriging(Kriging):
 
     def constraint_mask(self) -> np.ndarray:
         """Constraint mask from the simple kriging weights (reference `:245-297`)."""
-        if not hasattr(self, "simple_kriging_weights"):
+        if not self._has_simple_weights():
             raise KeyError("Please set kriging weights")
         if self._user_simple_weights is not None:
             _, _, mask = self._apply_user_weights(self._user_simple_weights, len(self.idx))
@@ -144,7 +149,7 @@ class StochasticKriging(Kriging):
 
     def solve(self, simulated_state: np.ndarray | None = None) -> np.ndarray:
         """Ordinary-kriging field + simple-kriging perturbation (reference `:299-392`)."""
-        if not hasattr(self, "kriging_weights"):
+        if not self._has_weights():
             self.get_kriging_weights()
         if self.error_cov is None:
             raise ValueError("Error Covariance must be set to draw simulated observations")
