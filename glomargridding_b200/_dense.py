@@ -346,6 +346,7 @@ class KrigeBatch:
         # That is everything the Cholesky path reads and halves the H2D bytes of the kriging path
         # (GmgKrigeDesc.lde < 0; the LU fallback reads the mirrored entries).
         groups, sizes_E, ldes, self._asym = [], [], [], []
+        task_cap = (4 << 20) if B >= 8 else (1 << 17)          # doubles per packing task: a lone problem still uses the pool
         for b, (E, n) in enumerate(zip(Es, ns)):
             size, lde = 0, n
             if E is not None:
@@ -357,11 +358,12 @@ class KrigeBatch:
                     blocks = [E[r0:min(n, r0 + NB), :min(n, r0 + NB)] for r0 in range(0, n, NB)]
                 else:
                     blocks = [E[r0:r0 + NB] for r0 in range(0, n, NB)]       # whole matrix, in row slabs
-                # packing tasks of at most ~32 MB: one per 5-degree month, many for one large system (whose 1.6 - 3.2 GB
-                # would otherwise be ONE task and need staging buffers of that size)
+                # packing tasks of at most ~32 MB (1 MB when there are few problems): one per 5-degree month of a batch,
+                # many for one large system (whose 1.6 - 3.2 GB would otherwise be ONE task and need staging buffers of
+                # that size)
                 task, fill = [], 0
                 for blk in blocks:
-                    if task and fill + blk.size > (4 << 20):
+                    if task and fill + blk.size > task_cap:
                         groups.append(task)
                         task, fill = [], 0
                     task.append(blk)
