@@ -223,3 +223,64 @@ def test_reference_own_ellipse_golden_atlantic():
         cor = cov_2_cor(np.asarray(cov, dtype=np.float64))
         assert np.isclose(1, np.max(np.diag(cor)))              # :215-217
     assert np.allclose(g["cor_diag"], 1.0)
+
+
+# ---- SURVEY 8f row N4 (ellipse-parameter fit): the oracle is in place and pinned; the device port is the next step ----
+def _fit_cases():
+    from oracle.ellipse_fit import EllipseModelOracle
+
+    g = load_golden("ellipse_fit.npz")
+    for c in range(int(g["n_cases"])):
+        aniso, rot, pd, unit = (bool(x) for x in g[f"c{c}_meta"])
+        yield c, g, EllipseModelOracle(aniso, rot, pd, float(g[f"c{c}_v"]), unit_sigma=unit)
+
+
+def test_ellipse_fit_correlation_and_likelihood_vs_reference_golden():
+    """`cov_ij_anisotropic` / `cov_ij_isotropic` (model.py:582-686) and `negative_log_likelihood` (model.py:266-384)
+    against the unmodified reference's outputs on the same displacements / correlations."""
+    for c, g, m in _fit_cases():
+        X, y, true = g[f"c{c}_X"], g[f"c{c}_y"], list(g[f"c{c}_true"])
+        assert np.allclose(m.cov_ij(X, true), g[f"c{c}_cov"], rtol=1e-13, atol=0)
+        p_true = true + ([] if m.unit_sigma else [0.05])
+        p_guess = list(m.default_guesses) + ([] if m.unit_sigma else [0.1])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = [m.negative_log_likelihood(X, y.copy(), p_true), m.negative_log_likelihood(X, y.copy(), p_guess)]
+        assert np.allclose(got, g[f"c{c}_nll"], rtol=1e-12, atol=0), (c, got, g[f"c{c}_nll"])
+
+
+def test_ellipse_fit_nelder_mead_vs_reference_golden():
+    """`EllipseModel.fit(estimate_SE=None)` (model.py:402-500): same optimiser, same likelihood - same optimum."""
+    for c, g, m in _fit_cases():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res, se, bounds = m.fit(g[f"c{c}_X"], g[f"c{c}_y"].copy())
+        assert se is None and np.array_equal(np.array(bounds), g[f"c{c}_bounds"])
+        assert np.allclose(res.x, g[f"c{c}_fit_x"], rtol=1e-6, atol=1e-9), (c, res.x, g[f"c{c}_fit_x"])
+        assert np.isclose(res.fun, g[f"c{c}_fit"][0], rtol=1e-9)
+        assert bool(res.success) == bool(g[f"c{c}_fit"][3])
+
+
+def test_ellipse_fit_oracle_vs_live_reference(reference):
+    """Random parameters and displacements against the live reference (skipped where its sources are absent)."""
+    import importlib
+
+    from oracle import ellipse_fit as ef
+
+    model = importlib.import_module("glomar_gridding.ellipse.model")
+    dist = importlib.import_module("glomar_gridding.distances")
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        v = float(rng.choice([0.5, 1.5, 2.2, 3.7]))
+        Lx, Ly, th = rng.uniform(300, 3000), rng.uniform(300, 3000), rng.uniform(-np.pi, np.pi)
+        dx, dy = rng.uniform(-2000, 2000, 40), rng.uniform(-2000, 2000, 40)
+        for theta in (th, None):
+            assert np.array_equal(ef.mahalanobis(dx, dy, Lx, Ly, theta), dist.mahal_dist_func(dx, dy, Lx, Ly, theta=theta))
+            assert np.array_equal(ef.cov_ij_anisotropic(v, 1, dx, dy, Lx, Ly, theta=theta),
+                                  model.cov_ij_anisotropic(v, 1, dx, dy, Lx, Ly, theta=theta))
+        assert np.array_equal(ef.cov_ij_isotropic(v, 1, np.hypot(dx, dy), Lx), model.cov_ij_isotropic(v, 1, np.hypot(dx, dy), Lx))
+        assert np.array_equal(ef.sigma_rot(Lx, Ly, th), dist.sigma_rot_func(Lx, Ly, th))
+    with pytest.raises(ValueError, match="isotropic rotated"):
+        ef.EllipseModelOracle(False, True, True, 1.5)
+    with pytest.raises(ValueError, match="must be > 0"):
+        ef.EllipseModelOracle(True, True, True, 0.0)
