@@ -5,7 +5,11 @@ Primary line value: 1-degree global (N = 64 800) non-stationary ellipse Matern c
 Bessel-K (BASELINE.json configs[2], the configuration "ellipse-cov entries/s @1deg grid" is quoted on), row-block
 sharded across the GPUs of one box.  The second half of the metric, "kriged months/s" (configs[1]: 480 synthetic
 months of 5-degree ordinary kriging, sharded by month), is measured in the same run and reported under
-`"kriging"` in the same JSON line, with its own roofline, e2e and cpu_baseline objects.
+`"kriging"` in the same JSON line, with its own roofline, e2e and cpu_baseline objects.  So are configs[3] -
+1-degree ordinary kriging of 20 000 observations against the row-block sharded covariance (`"kriging_1deg"`:
+distributed Cholesky + column-sharded forward solve) - and configs[4] - the 200-member 5-degree stochastic
+ensemble (`"stochastic"`).  The FP64 peaks the fractions are taken against (DFMA pipe, DMMA) are measured in the
+run by `gmg_microbench_fp64` (`"fp64_peaks"`).
 
     python bench.py --gpus N --steps K --warmup W            # this implementation
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port)
@@ -31,8 +35,14 @@ sys.path.insert(0, ROOT)
 METRIC = "ellipse-cov entries/s @1deg grid; kriged months/s"
 UNIT = "entries/s"
 TILE = 128                  # row blocks start on a macro-tile (2 x 2 tiles of 64) boundary
+# Fallbacks only: the run measures both with gmg_microbench_fp64 ("fp64_peaks" in the line) and divides by those.
 DMMA_PEAK_TFLOPS = 37.1     # mma.sync m8n8k4 f64, measured on this pool's B200 (profiles/r01_microbench_fp64.json)
 DFMA_PEAK_TFLOPS = 34.2     # plain DFMA, same file
+# FP64-pipe instructions per evaluated pair of the general-nu tile kernel (SASS of the shipped row loop, two pairs
+# per iteration: 48 DFMA + 32 DMUL + 16 DADD + 2 DSETP; frozen, re-counted when the kernel changes - see
+# profiles/r02_k1_instruction_mix.md).  Every one of them holds an FP64 issue slot, so the pipe-bound figure counts
+# each as one FMA slot (2 flop) against the measured DFMA rate.
+K1_FP64_INSTR_PER_PAIR = {"table": 49.0, "closed": 43.0}
 
 
 def parse_args():
@@ -51,6 +61,15 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kriging", action="store_true")
+    ap.add_argument("--no-kriging-1deg", action="store_true")
+    ap.add_argument("--no-stochastic", action="store_true")
+    ap.add_argument("--nobs-1deg", type=int, default=20000)
+    ap.add_argument("--krige-1deg-steps", type=int, default=3)
+    ap.add_argument("--members", type=int, default=200)
+    ap.add_argument("--stochastic-steps", type=int, default=5)
+    ap.add_argument("--cpu-cols-1deg", type=int, default=1024,
+                    help="grid columns the CPU arm of the 1-degree kriging solves for (scaled to 64 800)")
+    ap.add_argument("--ref-batches", type=int, default=2, help="2M-pair batches of the reference's own batched loop per step")
     return ap.parse_args()
 
 
@@ -86,7 +105,9 @@ def row_block(N, rank, world):
 def config_dict(args, wl, world):
     return {"workload": f"{args.res:g}deg global grid ({wl['N']} cells) ellipse Matern covariance, nu={args.nu:g} "
                         f"(general nu via Bessel-K), Modified_Met_Office, FP64 [BASELINE configs[2]]; secondary: "
-                        f"5deg grid ordinary kriging of {args.months} synthetic months [configs[1]]",
+                        f"5deg grid ordinary kriging of {args.months} synthetic months [configs[1]]; 1deg ordinary "
+                        f"kriging of {args.nobs_1deg} observations against the sharded covariance [configs[3]]; "
+                        f"5deg stochastic kriging, {args.members} members [configs[4]]",
             "N": wl["N"], "nu": args.nu, "sharding": f"row blocks x{world}; months round-robin x{world}",
             "l2": "output (8*N^2/world bytes per GPU) is far larger than the 126 MB L2; no flush needed"}
 
@@ -115,9 +136,68 @@ def cpu_cov_sample(wl, n_rows):
     return 2.0 * pairs / dt, pairs, dt
 
 
-def cpu_kriging_sample(n_months):
-    """The reference's per-month workflow (oracle port, M x M temporaries included like the reference):
-    OrdinaryKriging construct + solve + get_uncertainty on the first `n_months` synthetic months."""
+def reference_ns():
+    """The UNMODIFIED reference package (staged under oracle/_ref by __graft_entry__.build(), or /root/reference in
+    the build container) imported through the stub shim - or None, in which case the CPU legs time the oracle port."""
+    try:
+        from oracle.reference_shim import load_reference, reference_available
+
+        return load_reference() if reference_available() else None
+    except Exception:
+        return None
+
+
+_REF_BUILDER = {}
+
+
+def ref_cov_sample(ref, wl, n_batches, batch_size=2_000_000):
+    """The reference's OWN covariance build, bounded: the statements of `calculate_covariance_batched`
+    (ellipse/covariance.py:382-401) on the unmodified class - `itertools.batched(combinations(range(N), 2),
+    batch_size)` pair generation, `np.asarray(batch).T`, `c_ij_anisotropic_array`, scatter - for the first
+    `n_batches` batches.  (The method itself cannot be called at 1 degree: it allocates the 33.6 GB matrix and mirrors
+    it with a second one.)  `combinations` yields rows 0, 1, ... first, so the sample is the leading rows of the
+    matrix and the scatter goes into a buffer of just those rows.  entries/s = 2 * pairs/s like the port."""
+    import contextlib
+    import io
+    from itertools import combinations, islice
+
+    cov_mod = ref.ellipse_covariance
+    key = (wl["N"], wl["nu"])
+    if key not in _REF_BUILDER:
+        class PreTermsOnly(ref.EllipseCovarianceBuilder):
+            def _calculate_covariance(self):              # pre-terms of :218-224, nothing else
+                self._get_disp_fn()
+                self.sigmas = cov_mod._sigma_rot_func_multi(
+                    self.Lx_compressed, self.Ly_compressed, self.theta_compressed).astype(self.precision)
+                self.sqrt_dets = np.sqrt(cov_mod._det_22_multi(self.sigmas))
+                self.gamma_v_term = cov_mod.gamma(self.v) * (2 ** (self.v - 1))
+                self.sqrt_v_term = np.sqrt(self.v) * 2
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            _REF_BUILDER[key] = PreTermsOnly(wl["Lx"], wl["Ly"], wl["theta"], wl["stdev"], wl["lats"], wl["lons"],
+                                             v=wl["nu"], precision=np.float64, covariance_method="batched",
+                                             batch_size=batch_size)
+    b = _REF_BUILDER[key]
+    N = wl["N"]
+    want = n_batches * batch_size
+    per_row = N - 1 - np.arange(N)
+    rows = int(np.searchsorted(np.cumsum(per_row), want) + 1)
+    block = np.zeros((rows, N), dtype=b.precision)
+    pairs = 0
+    t0 = time.perf_counter()
+    for batch in islice(cov_mod.batched(combinations(range(N), 2), b.batch_size), n_batches):
+        i_s, j_s = np.asarray(batch).T
+        loop_c_ij = b.c_ij_anisotropic_array(i_s, j_s)
+        block[i_s, j_s] = loop_c_ij.astype(b.precision)
+        pairs += i_s.size
+    dt = time.perf_counter() - t0
+    return 2.0 * pairs / dt, pairs, dt
+
+
+def cpu_kriging_sample(n_months, ref=None):
+    """The reference's per-month workflow: OrdinaryKriging construct + solve + get_uncertainty on the first `n_months`
+    synthetic months - the unmodified classes when `ref` is given, the oracle port (M x M temporaries included like
+    the reference) otherwise."""
     from glomargridding_b200 import synthetic as synth
     from oracle import EllipseOracle, ordinary_kriging
 
@@ -130,9 +210,119 @@ def cpu_kriging_sample(n_months):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         for idx, obs, E in probs:
-            ordinary_kriging(cov, idx, obs, E, big_temporaries=True)
+            if ref is not None:
+                k = ref.OrdinaryKriging(cov, idx, obs, E)
+                k.solve()
+                k.get_uncertainty()
+            else:
+                ordinary_kriging(cov, idx, obs, E, big_temporaries=True)
     dt = time.perf_counter() - t0
     return n_months / dt, dt
+
+
+def kriging_1deg_inputs(n_obs):
+    from glomargridding_b200 import synthetic as synth
+
+    lats, lons = synth.global_grid(1.0)
+    N = lats.size * lons.size
+    idx, obs = synth.fixed_observations(4, N, n_obs)
+    return lats, lons, N, idx, obs
+
+
+def cpu_kriging_1deg_sample(n_obs, n_cols):
+    """configs[3] on the host cores, bounded.  The reference solves the (n+1) x (n+1)
+    Lagrange-extended system for all 64 800 grid columns with LAPACK dgesv (kriging.py:571-586): ~5.3e12 flop of LU
+    and ~5.2e13 flop of triangular solves.  Timed here: the SAME two LAPACK stages - dgetrf on the full extended
+    matrix, dgetrs on `n_cols` of the grid columns - the second scaled by 64 800 / n_cols, plus the field and a
+    DIAGONAL-ONLY variance on those columns (the reference's `get_uncertainty` forms two 64 800 x 64 800 temporaries,
+    67 GB, and cannot run at this size).  The matrix is assembled (untimed) from the oracle's pair formula."""
+    import scipy.linalg as sla
+    from concurrent.futures import ThreadPoolExecutor
+
+    from glomargridding_b200 import synthetic as synth
+    from oracle import EllipseOracle
+
+    use_all_host_threads()
+    lats, lons, N, idx, obs = kriging_1deg_inputs(n_obs)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    o = EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5, "Met_Office")
+    n = idx.size
+    t_setup = time.perf_counter()
+    S_ext = np.zeros((n + 1, n + 1))
+    S_ext[:n, :n] = synth.hadcrut_style_error_cov(idx, lons.size)
+
+    def strip(a0):
+        a1 = min(n, a0 + 64)
+        ii, jj = np.meshgrid(np.arange(a0, a1), np.arange(n), indexing="ij")
+        up = jj > ii
+        vals = o.pairs(idx[ii[up]], idx[jj[up]])
+        blk = np.zeros((a1 - a0, n))
+        blk[up] = vals
+        return a0, a1, blk
+
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        for a0, a1, blk in ex.map(strip, range(0, n, 64)):
+            S_ext[a0:a1, :n] += blk
+            S_ext[:n, a0:a1] += blk.T
+    S_ext[np.arange(n), np.arange(n)] += o.stdev[idx] ** 2
+    S_ext[n, :n] = 1.0
+    S_ext[:n, n] = 1.0
+    cols = np.linspace(0, N - 1, n_cols).astype(np.int64)
+    rhs = np.ones((n + 1, n_cols))
+    lo, hi = np.minimum(idx[:, None], cols[None, :]), np.maximum(idx[:, None], cols[None, :])
+    same = lo == hi
+    vals = o.pairs(np.where(same, 0, lo).ravel(), np.where(same, 1, hi).ravel()).reshape(n, n_cols)
+    rhs[:n] = np.where(same, (o.stdev[idx] ** 2)[:, None], vals)
+    t_setup = time.perf_counter() - t_setup
+    t0 = time.perf_counter()
+    lu, piv = sla.lu_factor(S_ext, overwrite_a=True, check_finite=False)
+    t_factor = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    W = sla.lu_solve((lu, piv), rhs, check_finite=False)                  # (n + 1, n_cols): weights^T incl. multiplier
+    field = W[:n].T @ obs
+    u2 = o.stdev[cols] ** 2 - np.einsum("ak,ak->k", W, rhs) - W[n]       # diag(C - W Cx_ext) - alpha, diagonal only
+    t_solve = time.perf_counter() - t0
+    total = t_factor + t_solve * (N / n_cols)
+    assert np.isfinite(field).all() and np.isfinite(u2).all()
+    return {"seconds_scaled": total, "t_factor": t_factor, "t_solve_sample": t_solve, "t_setup": t_setup,
+            "n_cols": n_cols}
+
+
+def cpu_stochastic_sample(n_members, ref=None):
+    """configs[4] on the host cores: StochasticKriging weights, 200 states from the
+    covariance and 200 observation-noise vectors (numpy's SVD-based multivariate normal, stochastic.py:460), the
+    epsilon GEMM and the ordinary-kriging field - unmodified reference classes when `ref` is given."""
+    from glomargridding_b200 import synthetic as synth
+    from oracle import EllipseOracle, mv_normal_draw, stochastic_kriging
+
+    use_all_host_threads()
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5, "Met_Office").build()
+    M = cov.shape[0]
+    idx, obs = synth.fixed_observations(201403, M, 1341)
+    E = synth.hadcrut_style_error_cov(idx, lons.size)
+    np.random.seed(20140371)
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if ref is not None:
+            sk = ref.StochasticKriging(cov, idx, obs, E)
+            sk.get_kriging_weights()
+            W_ok, W_sk = sk.kriging_weights, sk.simple_kriging_weights
+            X = ref.scipy_mv_normal_draw(np.zeros(M), cov, ndraws=n_members)
+            noise = ref.scipy_mv_normal_draw(np.zeros(idx.size), E, ndraws=n_members)
+        else:
+            r = stochastic_kriging(cov, idx, obs, E, simulated_state=np.zeros(M), simulated_obs_noise=np.zeros(idx.size),
+                                   big_temporaries=False)
+            W_ok, W_sk = r["weights"], r["simple_weights"]
+            X = mv_normal_draw(np.zeros(M), cov, n_members)
+            noise = mv_normal_draw(np.zeros(idx.size), E, n_members)
+        eps = (X[:, idx] + noise) @ W_sk.T - X
+        result = (W_ok @ np.append(obs, 0.0))[None, :] + eps
+    dt = time.perf_counter() - t0
+    assert result.shape == (n_members, M)
+    return n_members / dt, dt
 
 
 def host_threads():
@@ -154,39 +344,79 @@ def use_all_host_threads():
         pass
 
 
+def cpu_sub_baselines(args, ref):
+    """cpu_baseline objects of the three secondary workloads (rank 0, N = 1 / the reference arm)."""
+    kind = "reference" if ref is not None else "port"
+    out = {}
+    if not args.no_kriging:
+        mps, dt = cpu_kriging_sample(args.cpu_months, ref)
+        out["kriging"] = {"value": mps, "unit": "months/s", "cores": host_threads(), "kind": kind,
+                          "sample": f"{args.cpu_months} of the {args.months} months ({dt:.1f} s): OrdinaryKriging "
+                                    "construct + solve + get_uncertainty, numpy LAPACK/BLAS on all host threads"}
+    if not args.no_kriging_1deg:
+        r = cpu_kriging_1deg_sample(args.nobs_1deg, args.cpu_cols_1deg)
+        out["kriging_1deg"] = {
+            "value": 1.0 / r["seconds_scaled"], "unit": "solves/s", "cores": host_threads(), "kind": "port",
+            "seconds_scaled": r["seconds_scaled"],
+            "sample": f"LAPACK dgetrf of the full ({args.nobs_1deg}+1)-extended system ({r['t_factor']:.1f} s) + dgetrs, "
+                      f"field and DIAGONAL-ONLY variance on {r['n_cols']} of the 64800 grid columns "
+                      f"({r['t_solve_sample']:.2f} s, scaled x{64800 / r['n_cols']:.1f}); what np.linalg.solve does "
+                      "at kriging.py:584-586; the reference's get_uncertainty needs two 64800^2 temporaries (67 GB) "
+                      f"and cannot run; matrix assembly by the oracle untimed ({r['t_setup']:.0f} s)"}
+    if not args.no_stochastic:
+        mps, dt = cpu_stochastic_sample(args.members, ref)
+        out["stochastic"] = {"value": mps, "unit": "members/s", "cores": host_threads(), "kind": kind,
+                             "sample": f"all {args.members} members once ({dt:.1f} s): StochasticKriging weights "
+                                       "(explicit inverse), SVD-based draws of 200 states and 200 noise vectors "
+                                       "(np.random.multivariate_normal), epsilon GEMM, ordinary-kriging field"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = workload(args.res, args.nu)
+    ref = reference_ns()
+    kind = "reference" if ref is not None else "port"
+
+    def sample(full):
+        if ref is not None:
+            return ref_cov_sample(ref, wl, args.ref_batches if full else 1, 2_000_000 if full else 100_000)
+        return cpu_cov_sample(wl, args.cpu_rows if full else 8)
+
     for _ in range(min(args.warmup, 1)):
-        cpu_cov_sample(wl, 8)
+        sample(False)
     vals, times = [], []
     for _ in range(args.steps):
-        v, pairs, dt = cpu_cov_sample(wl, args.cpu_rows)
+        v, pairs, dt = sample(True)
         vals.append(v)
         times.append(dt)
     value = float(np.mean(vals))
-    sample = (f"all i<j pairs with i in a {args.cpu_rows}-row block of the {wl['N']}-cell matrix per step "
-              f"({pairs} pairs), numpy/scipy (the reference's covariance build is single-threaded); "
-              f"entries/s = 2*pairs/s")
+    if ref is not None:
+        what = (f"the unmodified reference's batched build (ellipse/covariance.py:382-401: itertools pair generation, "
+                f"np.asarray(batch), c_ij_anisotropic_array, scatter) for its first {args.ref_batches} batches of "
+                f"2 000 000 pairs per step ({pairs} pairs), precision float64; single-threaded like the reference; "
+                f"entries/s = 2*pairs/s")
+    else:
+        what = (f"all i<j pairs with i in a {args.cpu_rows}-row block of the {wl['N']}-cell matrix per step "
+                f"({pairs} pairs), numpy/scipy oracle port (the reference's covariance build is single-threaded); "
+                f"entries/s = 2*pairs/s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, wl, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": what},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    if not args.no_kriging:
-        mps, dt = cpu_kriging_sample(args.cpu_months)
-        line["kriging"] = {"metric": "kriged months/s", "value": mps, "unit": "months/s",
-                           "cpu_baseline": {"value": mps, "unit": "months/s", "cores": host_threads(), "kind": "port",
-                                            "sample": f"{args.cpu_months} of the {args.months} months ({dt:.1f} s): "
-                                                      "OrdinaryKriging construct + solve + get_uncertainty, numpy "
-                                                      "LAPACK/BLAS on all host threads"},
-                           "e2e": {"value": mps, "unit": "months/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    names = {"kriging": "kriged months/s", "kriging_1deg": "1deg ordinary kriging solves/s (n=20000)",
+             "stochastic": "stochastic kriging members/s"}
+    for key, cb in cpu_sub_baselines(args, ref).items():
+        line[key] = {"metric": names[key], "value": cb["value"], "unit": cb["unit"], "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0,
+                             "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -333,6 +563,7 @@ def run_b200(args):
             kernel_ms.append(k0.elapsed_time(k1))
     ms_per_step = max_over_ranks(total_ms) / args.steps
     value = float(N) * float(N) / (ms_per_step * 1e-3)
+    fp64_peaks = measure_fp64_peaks(L, device, local) if rank == 0 else None
 
     # ---- end to end through the public API: host inputs -> numpy cov_ns (pinned) ------------------
     e2e = None
@@ -357,9 +588,17 @@ def run_b200(args):
     del out
     torch.cuda.empty_cache()
 
+    # the DMMA rate the secondary workloads divide by: measured by rank 0 in this run, shared with every rank
+    dmma_peak = max_over_ranks(fp64_peaks["dmma_tflops"] if fp64_peaks else 0.0) or DMMA_PEAK_TFLOPS
     kriging = None
     if not args.no_kriging:
-        kriging = run_months(args, rank, world, device, barrier, max_over_ranks, local)
+        kriging = run_months(args, rank, world, device, barrier, max_over_ranks, local, dmma_peak)
+    kriging_1deg = None
+    if not args.no_kriging_1deg:
+        kriging_1deg = run_kriging_1deg(args, rank, world, device, barrier, max_over_ranks, local, dmma_peak)
+    stochastic = None
+    if not args.no_stochastic:
+        stochastic = run_stochastic(args, rank, world, device, barrier, max_over_ranks, local, dmma_peak)
 
     if rank != 0:
         if world > 1:
@@ -369,42 +608,92 @@ def run_b200(args):
     peaks = load_json("MEASURED_PEAKS.json", {})
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     k_ms = float(np.mean(kernel_ms))
-    achieved = 8.0 * nrows * N / (k_ms * 1e-3) / 1e9
-    prof = load_json("profiles/r01_ellipse_full_traffic.json", {})
-    traffic = prof.get("dram_bytes_per_launch") if world == 1 and abs(args.nu - prof.get("nu", -1)) < 1e-12 else None
-    roofline = {"bound": "hbm", "kernel": "ellipse_cov_tile_kernel<TABLE, f64> (persistent, 2 CTAs/SM)",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                "traffic": traffic, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": 8 * int(nrows) * N,
-                "note": "8 B written per entry (SURVEY 8d).  The general-nu kernel is FP64-pipe bound, not HBM "
-                        "bound: ~53 FP64 instructions per evaluated pair (profiles/r01_ellipse_summary.md) against "
-                        f"a {DFMA_PEAK_TFLOPS} TFLOP/s DFMA pipe; see fp64_pipe_frac",
-                "fp64_pipe_frac": prof.get("fp64_pipe_pct_of_peak")}
+    hbm_achieved = 8.0 * nrows * N / (k_ms * 1e-3) / 1e9
+    general_nu = args.nu not in (0.5, 1.5, 2.5)
+    # pairs this rank's launch evaluates: 64 x 64 tiles, upper triangle only inside the square block on the diagonal
+    tr, tc = -(-nrows // 64), -(-N // 64)
+    pairs_eval = 4096.0 * (tr * (tr + 1) // 2 + tr * (tc - tr))
+    fp64_instr = K1_FP64_INSTR_PER_PAIR["table" if general_nu else "closed"] * pairs_eval
+    dfma_peak = fp64_peaks["dfma_tflops"] if fp64_peaks else DFMA_PEAK_TFLOPS
+    fp64_achieved = 2.0 * fp64_instr / (k_ms * 1e-3) / 1e12
+    prof = load_json("profiles/r02_ellipse_full_traffic.json", None) or load_json("profiles/r01_ellipse_full_traffic.json", {})
+    replay = world == 1 and abs(args.nu - prof.get("nu", -1)) < 1e-12
+    common = {"kernel": "ellipse_cov_tile_kernel<%s, f64> (persistent, 2 CTAs/SM)" % ("TABLE" if general_nu else "closed form"),
+              "kernel_ms": k_ms, "traffic": prof.get("dram_bytes_per_launch") if replay else None,
+              "traffic_replayed_from": prof.get("source") if replay else None,
+              "algorithmic_bytes_per_launch": 8 * int(nrows) * N, "pairs_evaluated_per_launch": pairs_eval,
+              "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"},
+              "fp64": {"achieved": fp64_achieved, "peak": dfma_peak, "unit": "TFLOP/s", "frac": fp64_achieved / dfma_peak,
+                       "fp64_instructions_per_pair": fp64_instr / pairs_eval,
+                       "peak_source": "gmg_microbench_fp64 DFMA burst in this run" if fp64_peaks else "fallback constant",
+                       "ncu_fp64_pipe_active_replayed": prof.get("fp64_pipe_pct_of_peak") if replay else None}}
+    if general_nu:
+        roofline = dict(bound="fp64", achieved=fp64_achieved, peak=dfma_peak, unit="TFLOP/s", frac=fp64_achieved / dfma_peak,
+                        note="general nu (SURVEY 8d): FP64-pipe bound.  achieved = FP64 pipe instructions per launch "
+                             "(frozen SASS count x evaluated pairs), each counted as one FMA slot = 2 flop, / kernel "
+                             "time; peak = DFMA rate measured in this run.  The HBM-write view of the same launch (8 B "
+                             "per entry against the measured copy bandwidth) is under 'hbm'.", **common)
+    else:
+        roofline = dict(bound="hbm", achieved=hbm_achieved, peak=hbm_peak, unit="GB/s", frac=hbm_achieved / hbm_peak,
+                        note="closed-form nu (SURVEY 8d): HBM-write bound, 8 B per entry", **common)
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (the reference arm covers N > 1)
-        v, pairs, dt = cpu_cov_sample(wl, args.cpu_rows)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"all i<j pairs with i in a {args.cpu_rows}-row block ({pairs} pairs, {dt:.1f} s), "
-                         f"numpy/scipy oracle port (the reference's build is single-threaded); entries/s = 2*pairs/s"}
-        if kriging is not None:
-            mps, dtk = cpu_kriging_sample(args.cpu_months)
-            kriging["cpu_baseline"] = {"value": mps, "unit": "months/s", "cores": host_threads(), "kind": "port",
-                                       "sample": f"{args.cpu_months} of the {args.months} months ({dtk:.1f} s): "
-                                                 "OrdinaryKriging construct + solve + get_uncertainty, numpy "
-                                                 "LAPACK/BLAS on all host threads"}
+        ref = reference_ns()
+        if ref is not None:
+            v, pairs, dt = ref_cov_sample(ref, wl, args.ref_batches)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"the unmodified reference's batched build loop (ellipse/covariance.py:382-401) for its "
+                             f"first {args.ref_batches} batches of 2 000 000 pairs ({pairs} pairs, {dt:.1f} s), "
+                             "single-threaded like the reference; entries/s = 2*pairs/s"}
+        else:
+            v, pairs, dt = cpu_cov_sample(wl, args.cpu_rows)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"all i<j pairs with i in a {args.cpu_rows}-row block ({pairs} pairs, {dt:.1f} s), "
+                             f"numpy/scipy oracle port (the reference's build is single-threaded); entries/s = 2*pairs/s"}
+        subs = cpu_sub_baselines(args, ref)
+        for key, obj in (("kriging", kriging), ("kriging_1deg", kriging_1deg), ("stochastic", stochastic)):
+            if obj is not None and key in subs:
+                obj["cpu_baseline"] = subs[key]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, wl, world),
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": 3 * args.steps, "roofline": roofline,
-        "cpu_baseline": cpu, "kriging": kriging,
+        "cpu_baseline": cpu, "fp64_peaks": fp64_peaks, "kriging": kriging, "kriging_1deg": kriging_1deg,
+        "stochastic": stochastic,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_months(args, rank, world, device, barrier, max_over_ranks, local):
+def measure_fp64_peaks(L, device, local):
+    """DFMA-pipe and DMMA (mma.sync m8n8k4 f64) rates of THIS GPU in THIS run (`gmg_microbench_fp64`), with the
+    clocks sampled while they run: the denominators of the FP64 roofline fractions (MEASURED_PEAKS.json has none)."""
+    import ctypes
+
+    import torch
+
+    from glomargridding_b200._lib import check
+
+    scratch = torch.zeros(16, dtype=torch.float64, device=device)
+    out = {}
+    with ClockSampler(local) as clocks:
+        for name, what in (("dfma", 0), ("dmma", 1)):
+            best, sus = ctypes.c_double(), ctypes.c_double()
+            check(L.gmg_microbench_fp64(what, 1 << 14, 60, scratch.data_ptr(), ctypes.byref(best), ctypes.byref(sus),
+                                        torch.cuda.current_stream().cuda_stream), "gmg_microbench_fp64")
+            out[f"{name}_tflops"] = best.value
+            out[f"{name}_tflops_sustained"] = sus.value
+    out["clocks"] = clocks.summary()
+    out["how"] = ("gmg_microbench_fp64: register-only kernels, 8 CTAs x 256 threads per SM, 8 independent chains per "
+                  "thread; best single launch (burst) and 60 launches back to back (sustained); DFMA = 2 flop per "
+                  "lane-instruction, DMMA m8n8k4 = 512 flop per warp-instruction")
+    return out
+
+
+def run_months(args, rank, world, device, barrier, max_over_ranks, local, dmma_peak=DMMA_PEAK_TFLOPS):
     """kriged months/s: `--months` synthetic 5-degree months, ordinary kriging, months round-robin over ranks."""
     import torch
 
@@ -468,14 +757,179 @@ def run_months(args, rank, world, device, barrier, max_over_ranks, local):
                                    "construct + solve + uncertainty + constraint mask per month"},
             "clocks": clocks.summary(), "gpu_launches": launches * args.month_steps,
             "roofline": {"bound": "tensor", "kernel": "gemm_tile (DMMA m8n8k4 f64) inside trsm_step / potrf_update",
-                         "achieved": tflops_local, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": tflops_local / DMMA_PEAK_TFLOPS, "traffic": None,
-                         "peak_source": "measured mma.sync f64 peak, profiles/r01_microbench_fp64.json "
-                                        "(MEASURED_PEAKS.json has no FP64 figure)",
+                         "achieved": tflops_local, "peak": dmma_peak, "unit": "TFLOP/s",
+                         "frac": tflops_local / dmma_peak, "traffic": None,
+                         "peak_source": "mma.sync m8n8k4 f64 rate measured in this run (fp64_peaks.dmma_tflops; "
+                                        "MEASURED_PEAKS.json has no FP64 figure)",
                          "note": "flops actually executed, n^3/3 + n^2 (M+2) per month, over the whole "
                                  "gather+factor+solve+apply step of this rank.  SURVEY 8d counts 2 n^2 M for two "
                                  "triangular solves; field / variance / mask only need the forward one "
                                  "(d = ||L^-1 c||^2), so half of that work is not done at all"},
+            "e2e": e2e}
+
+
+def run_kriging_1deg(args, rank, world, device, barrier, max_over_ranks, local, dmma_peak):
+    """configs[3]: the 1-degree covariance is built in row blocks (one per rank, never gathered) and
+    `--nobs-1deg` observations are kriged against it: `distributed.krige_sharded` = assemble S (one exchange),
+    distributed Cholesky, column-sharded forward solve, apply, gather of the M-vectors.  One "solve" = one complete
+    ordinary kriging (field + uncertainty + constraint mask on all 64 800 cells)."""
+    import torch
+
+    from glomargridding_b200 import synthetic as synth
+    from glomargridding_b200.distributed import krige_sharded
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons, N, idx, obs = kriging_1deg_inputs(args.nobs_1deg)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    r0, nrows = row_block(N, rank, world)
+    n = idx.size
+
+    def build():
+        return EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office",
+                                        precision=np.float64, rows=(r0, nrows))
+
+    b = build()
+    del b
+    barrier()
+    t0 = time.perf_counter()
+    b = build()
+    barrier()
+    build_s = max_over_ranks(time.perf_counter() - t0)
+    cov_rows = b.cov_ns_device
+    E = synth.hadcrut_style_error_cov(idx, lons.size)            # host, n x n, identical on every rank
+    E_dev = torch.from_numpy(E).to(device)
+
+    def solve(err):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return krige_sharded(cov_rows, r0, idx, obs, err, "ordinary")
+
+    res = solve(E_dev)                                            # warm-up: communicators, workspaces, pinned buffers
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.krige_1deg_steps):
+            res = solve(E_dev)
+        e1.record()
+        barrier()
+    sec = max_over_ranks(e0.elapsed_time(e1)) * 1e-3 / args.krige_1deg_steps
+    flops = n ** 3 / 3.0 + float(n) ** 2 * (N + 2)
+    tflops_per_gpu = flops / sec / world / 1e12
+    e2e = None
+    if not args.no_e2e:
+        solve(E)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res_h = solve(E)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
+        mine = int(((idx >= r0) & (idx < r0 + nrows)).sum())
+        e2e = {"value": 1.0 / dt, "unit": "solves/s", "seconds": dt, "h2d_bytes_per_step": 8 * (mine * n + 2 * n),
+               "d2h_bytes_per_step": 5 * N * 8, "steps": args.e2e_steps,
+               "note": "krige_sharded(row block on device, host idx / obs / n x n error covariance) -> numpy field, "
+                       "uncertainty, constraint mask on every rank; each rank uploads only the rows of the error "
+                       "covariance that belong to its own observations (bytes are per rank)"}
+        assert np.array_equal(res_h["field"], res["field"])
+    golden = None
+    try:                                                         # parity evidence in the driver's own run
+        g = np.load(os.path.join(ROOT, "tests", "golden", "krige_1deg_n20000.npz"))
+        if int(g["n_obs"]) == n:
+            rel = lambda a, w: float(np.max(np.abs(a - w)) / np.max(np.abs(w)))  # noqa: E731
+            c = g["cells"]
+            golden = {"field": rel(res["field"][c], g["field"]),
+                      "variance": rel(res["uncertainty"][c] ** 2, g["uncertainty"] ** 2),
+                      "constraint_mask": rel(res["constraint_mask"][c], g["constraint_mask"]),
+                      "what": "max-norm relative difference to the unmodified reference's OrdinaryKriging on the "
+                              "reduced grid (tests/golden/make_golden_1deg_krige.py), 20 064 cells"}
+    except Exception as exc:  # pragma: no cover
+        golden = {"error": repr(exc)}
+    del cov_rows, b, E_dev
+    torch.cuda.empty_cache()
+    nblk = -(-n // 128)
+    return {"metric": "1deg ordinary kriging solves/s (n=%d)" % n, "value": 1.0 / sec, "unit": "solves/s",
+            "seconds": sec, "higher_is_better": True, "steps": args.krige_1deg_steps,
+            "covariance_build_seconds": build_s,
+            "config": {"workload": f"1deg grid (M={N}) ordinary kriging of {n} observations (default_rng(4)), "
+                                   "HadCRUT-style n x n error covariance, Met_Office ellipse covariance nu=1.5 built in "
+                                   f"row blocks x{world} and never gathered; field + uncertainty + constraint mask"},
+            "clocks": clocks.summary(), "gpu_launches": (1 + 3 * nblk + 2 * nblk + 2) * args.krige_1deg_steps,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tile (DMMA m8n8k4 f64) inside potrf_update / trsm_step_fwd",
+                         "achieved": tflops_per_gpu, "peak": dmma_peak, "unit": "TFLOP/s",
+                         "frac": tflops_per_gpu / dmma_peak, "traffic": None,
+                         "peak_source": "fp64_peaks.dmma_tflops of this run",
+                         "note": "n^3/3 + n^2 (M+2) flop of the whole job / seconds / n_gpus, against one GPU's DMMA "
+                                 "rate: the fraction covers EVERYTHING between host inputs on the device and numpy "
+                                 "results (assembly, exchanges, factorisation, solve, apply, gather)"},
+            "e2e": e2e, "golden_parity": golden}
+
+
+def run_stochastic(args, rank, world, device, barrier, max_over_ranks, local, dmma_peak):
+    """configs[4]: `--members` perturbed ordinary-kriging fields on the 5-degree grid (n = 1 341 observations,
+    HadCRUT-style error covariance), members sharded over the ranks (`batched.stochastic_ensemble`)."""
+    import torch
+
+    from glomargridding_b200 import synthetic as synth
+    from glomargridding_b200.batched import shard, stochastic_ensemble
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office",
+                                   precision=np.float64).cov_ns_device
+    M = cov.shape[0]
+    idx, obs = synth.fixed_observations(201403, M, 1341)
+    E = synth.hadcrut_style_error_cov(idx, lons.size)
+    mine = len(shard(args.members, rank, world))
+    n = idx.size
+
+    def step(dev_out):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return stochastic_ensemble(cov, idx, obs, E, mine, seed=20140371 + rank, return_device=dev_out)
+
+    for _ in range(2):
+        step(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.stochastic_steps):
+            r = step(True)
+        e1.record()
+        barrier()
+    sec = max_over_ranks(e0.elapsed_time(e1)) * 1e-3 / args.stochastic_steps
+    assert r["result"].shape == (mine, M)
+    flops = (M ** 3 / 3.0 + 2 * n ** 3 / 3.0 + float(n) ** 2 * (M + 2) + 2.0 * mine * M * M + 2.0 * mine * n * n
+             + 2.0 * n * n * mine + 2.0 * mine * n * M)
+    e2e = None
+    if not args.no_e2e:
+        step(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            rh = step(False)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
+        e2e = {"value": args.members / dt, "unit": "members/s", "seconds": dt,
+               "h2d_bytes_per_step": 8 * (n * n + 2 * n), "d2h_bytes_per_step": 8 * (2 * mine * M + 2 * M),
+               "steps": args.e2e_steps,
+               "note": "stochastic_ensemble(cov on device, host idx / obs / error_cov) -> numpy result, epsilon, "
+                       "gridded field, uncertainty; per-rank share of the members"}
+        assert np.isfinite(rh["result"]).all()
+    return {"metric": "stochastic kriging members/s", "value": args.members / sec, "unit": "members/s",
+            "seconds": sec, "higher_is_better": True, "steps": args.stochastic_steps, "members": args.members,
+            "config": {"workload": f"5deg grid (M={M}) stochastic kriging: {args.members} ensemble members, n={n} "
+                                   "observations, HadCRUT-style error covariance; per call three Cholesky factorisations "
+                                   "(C, E, C[idx,idx]+E), Philox normals, draws and epsilon as GEMMs; members sharded "
+                                   f"x{world} (every rank repeats the factorisations)"},
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "kernel": "gemm_tile (DMMA m8n8k4 f64)", "achieved": flops / sec / 1e12,
+                         "peak": dmma_peak, "unit": "TFLOP/s", "frac": flops / sec / 1e12 / dmma_peak, "traffic": None,
+                         "peak_source": "fp64_peaks.dmma_tflops of this run",
+                         "note": "flop of one rank's call / its seconds; the error-covariance upload (14 MB) is "
+                                 "inside the timed region (the class API takes host arrays), results stay on the device"},
             "e2e": e2e}
 
 

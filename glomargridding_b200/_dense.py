@@ -70,13 +70,15 @@ def _d2h_info(t: torch.Tensor) -> np.ndarray:
 _STAGE = None
 
 
-def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=None) -> torch.Tensor:
+def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=None, post=None) -> torch.Tensor:
     """Flattened concatenation of host floating-point arrays on the device, as float64.  `groups` is a list of
     lists of arrays (one list per kriging problem: the row blocks of its error covariance); every group is ONE task
     of a small thread pool that packs it into one of two pinned staging buffers (numpy copies release the GIL; a
     single thread packs at ~6 GB/s, far below PCIe) while the previous buffer is in flight, so packing overlaps the
     H2D copy - also inside one call, which is why the staging buffers are much smaller (128 MB) than a chunk of months
-    (~500 MB).  The per-month error covariances are the bulk of the kriging path's host-to-device traffic."""
+    (~500 MB).  The per-month error covariances are the bulk of the kriging path's host-to-device traffic.
+    `post` (optional, one entry per group): a callable (or None) run by the packing task right after it has packed
+    its group - the exact symmetry check of `KrigeBatch` rides here, on cache-warm data."""
     from concurrent.futures import ThreadPoolExecutor
 
     if out is None:
@@ -92,11 +94,11 @@ def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=No
     used = [False, False]
     # chunks of whole groups that fit one staging buffer
     chunks, cur, fill = [], [], 0
-    for g, size in zip(groups, sizes):
+    for gi, (g, size) in enumerate(zip(groups, sizes)):
         if fill + size > cap and cur:
             chunks.append((cur, fill))
             cur, fill = [], 0
-        cur.append((fill, g))
+        cur.append((fill, g, post[gi] if post is not None else None))
         fill += size
     if cur:
         chunks.append((cur, fill))
@@ -108,10 +110,12 @@ def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=No
         buf = stage[which]
 
         def pack(item, buf=buf):
-            off, g = item
+            off, g, after = item
             for a in g:                                  # one (strided) copy per block, any float dtype
                 np.copyto(buf[off:off + a.size].reshape(a.shape), a, casting="unsafe")
                 off += a.size
+            if after is not None:
+                after()
 
         list(_POOL.map(pack, chunk))
         out[pos:pos + n].copy_(_STAGE[which][:n], non_blocking=True)
@@ -139,16 +143,33 @@ _SYM_PAIRS: dict[int, tuple[np.ndarray, np.ndarray]] = {}
 
 
 def _looks_symmetric(E: np.ndarray, samples: int = 96) -> bool:
-    """E[i, j] == E[j, i] on a fixed pseudo-random sample of index pairs (O(samples), not O(n^2): a full scan of
-    480 monthly matrices would cost more host time than the upload it saves; every sample is two cache misses,
-    1024 of them cost 0.17 ms per matrix - 10 ms per chunk of 60 months - and hold the GIL).  Any asymmetry that is not confined
-    to a handful of entries is caught; the caller then uploads the whole matrix like the reference adds it."""
+    """Cheap PRE-FILTER of the symmetry test: E[i, j] == E[j, i] on a fixed pseudo-random sample of index pairs.
+    A matrix that fails it is uploaded whole straight away; one that passes is packed as its lower block trapezoid
+    and verified EXACTLY by `_block_row_symmetric` inside the packing tasks (every mirrored pair of entries)."""
     n = E.shape[0]
     if n not in _SYM_PAIRS:
         rng = np.random.default_rng(n)
         _SYM_PAIRS[n] = (rng.integers(0, n, samples), rng.integers(0, n, samples))
     i, j = _SYM_PAIRS[n]
     return bool(np.array_equal(E[i, j], E[j, i], equal_nan=True))
+
+
+def _block_row_symmetric(E: np.ndarray, r0: int, r1: int) -> bool:
+    """Rows r0:r1 of E against columns r0:r1, up to and including the diagonal block - exact, entry by entry, NaN
+    equal to NaN (both become 0 on the device).  Called by the packing task that has just read E[r0:r1, :r1], in
+    sub-blocks of 128 columns so that the transposed operand stays cache resident."""
+    for c0 in range(0, r1, NB):
+        c1 = min(r1, c0 + NB)
+        a, b = E[r0:r1, c0:c1], E[c0:c1, r0:r1].T
+        if not (a == b).all() and not np.array_equal(a, b, equal_nan=True):
+            return False
+    return True
+
+
+def is_symmetric(E: np.ndarray) -> bool:
+    """Exact symmetry test of a host matrix (blocked; the single-problem and pre-upload form of the check above)."""
+    n = E.shape[0]
+    return all(_block_row_symmetric(E, r0, min(n, r0 + NB)) for r0 in range(0, n, NB))
 
 
 def packed_error_cov_doubles(n: int) -> int:
@@ -232,6 +253,9 @@ def apply_reduce(cov: torch.Tensor, Cx: torch.Tensor, T: torch.Tensor, y: torch.
     (column M = S^-1 1 if `ordinary`); y (n,).  Returns the (5, M) result rows (OUT_* indices)."""
     M, n = cov.shape[0], T.shape[0]
     assert Cx.stride(1) == 1 and T.stride(1) == 1 and y.is_contiguous()
+    for name, t in (("cov", cov), ("Cx", Cx), ("T", T), ("y", y)):          # the kernels read double*
+        if t.dtype != torch.float64:
+            raise TypeError(f"apply_reduce: {name} must be float64, got {t.dtype}")
     slabs = (n + SLAB - 1) // SLAB
     partial = torch.empty(4 * slabs * M, dtype=torch.float64, device=cov.device)
     out = torch.empty((5, M), dtype=torch.float64, device=cov.device)
@@ -298,7 +322,10 @@ class KrigeBatch:
       T(b)    (n, ldt) tensor: S^-1 [C_cross | 1 | y]: simple-kriging weights transposed, column M = S^-1 1
     """
 
-    def __init__(self, cov: torch.Tensor, problems, ordinary: bool, alloc=None):
+    def __init__(self, cov: torch.Tensor, problems, ordinary: bool, alloc=None, assume_symmetric: bool = False):
+        """`assume_symmetric`: False (default) - every error covariance is tested for symmetry EXACTLY (entry by entry,
+        inside the packing tasks; an asymmetric one is solved by LU on the matrix as given, like the reference);
+        True - the caller vouches for symmetry: no test, the upper triangles are never read."""
         assert cov.is_cuda and cov.dtype == torch.float64 and cov.dim() == 2 and cov.stride(1) == 1
         import time
 
@@ -333,6 +360,16 @@ class KrigeBatch:
         self.out = alloc(B * 5 * M).view(B, 5, M)
         marks.append(("pools", time.perf_counter()))
         offs_n = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+        # observation cells index C like numpy indexes an array (`self.covariance[self.idx, :]`, kriging.py:337, :571):
+        # negative values count from the end, anything outside [-M, M) is an IndexError - checked here, on the host,
+        # because the gather kernel dereferences C + idx * ldc unchecked
+        idx_all = np.concatenate([np.asarray(p[0]).astype(np.int64, copy=False).reshape(-1) for p in problems])
+        lo, hi = int(idx_all.min()), int(idx_all.max())
+        if lo < -M or hi >= M:
+            bad = lo if lo < -M else hi
+            raise IndexError(f"index {bad} is out of bounds for axis 0 with size {M}")
+        if lo < 0:
+            idx_all = np.where(idx_all < 0, idx_all + M, idx_all)
         has_E = [p[2] is not None for p in problems]
         Es = []
         for p, n, h in zip(problems, ns, has_E):
@@ -345,30 +382,43 @@ class KrigeBatch:
         # blocks - row block b of 128 rows with its first 128 (b + 1) columns, a strided VIEW of the host array.
         # That is everything the Cholesky path reads and halves the H2D bytes of the kriging path
         # (GmgKrigeDesc.lde < 0; the LU fallback reads the mirrored entries).
-        groups, sizes_E, ldes, self._asym = [], [], [], []
+        groups, posts, sizes_E, ldes, self._asym = [], [], [], [], []
+        late_asym: set[int] = set()                              # found asymmetric by the exact test while packing
         task_cap = (4 << 20) if B >= 8 else (1 << 17)          # doubles per packing task: a lone problem still uses the pool
         for b, (E, n) in enumerate(zip(Es, ns)):
             size, lde = 0, n
             if E is not None:
-                sym = _looks_symmetric(E)
+                sym = True if assume_symmetric else _looks_symmetric(E)
                 if not sym:
                     self._asym.append(b)                 # no Cholesky for this system: LU like the reference
+                exact = sym and not assume_symmetric
+                rows = [(r0, min(n, r0 + NB)) for r0 in range(0, n, NB)]
                 if sym and n > NB and PACK_SYMMETRIC_ERROR_COV:
                     lde = -NB
-                    blocks = [E[r0:min(n, r0 + NB), :min(n, r0 + NB)] for r0 in range(0, n, NB)]
+                    blocks = [E[r0:r1, :r1] for r0, r1 in rows]
                 else:
-                    blocks = [E[r0:r0 + NB] for r0 in range(0, n, NB)]       # whole matrix, in row slabs
+                    blocks = [E[r0:r1] for r0, r1 in rows]                   # whole matrix, in row slabs
                 # packing tasks of at most ~32 MB (1 MB when there are few problems): one per 5-degree month of a batch,
                 # many for one large system (whose 1.6 - 3.2 GB would otherwise be ONE task and need staging buffers of
-                # that size)
-                task, fill = [], 0
-                for blk in blocks:
+                # that size).  The task that packs rows r0:r1 then tests them against columns r0:r1 - the EXACT symmetry
+                # test, on the pool threads and on data the task has just pulled through the cache.
+                def checker(spans, E=E, b=b):
+                    def run():
+                        if b not in late_asym and not all(_block_row_symmetric(E, r0, r1) for r0, r1 in spans):
+                            late_asym.add(b)
+                    return run
+
+                task, spans, fill = [], [], 0
+                for blk, span in zip(blocks, rows):
                     if task and fill + blk.size > task_cap:
                         groups.append(task)
-                        task, fill = [], 0
+                        posts.append(checker(spans) if exact else None)
+                        task, spans, fill = [], [], 0
                     task.append(blk)
+                    spans.append(span)
                     fill += blk.size
                 groups.append(task)
+                posts.append(checker(spans) if exact else None)
                 size = sum(blk.size for blk in blocks)
             sizes_E.append(size)
             ldes.append(lde)
@@ -404,12 +454,26 @@ class KrigeBatch:
             sd[b] = (S_ptr, lds[b], self._Linv.data_ptr() + f8 * int(oL[b]), T_ptr, self.ldt,
                      self._P.data_ptr() + f8 * int(oP[b]), ws[b][2], self.info.data_ptr() + 4 * b, n, self.nrhs)
         marks.append(("descriptors", time.perf_counter()))
-        idx_all = np.concatenate([np.asarray(p[0], dtype=np.int64) for p in problems])
-        y_all = np.concatenate([np.asarray(p[1], dtype=np.float64) for p in problems])
+        y_all = np.concatenate([np.asarray(p[1], dtype=np.float64).reshape(-1) for p in problems])
         groups += [[idx_all.view(np.float64)], [y_all], [kd.view(np.uint8).view(np.float64)],
                    [sd.view(np.uint8).view(np.float64)], [np.zeros((B + 1) // 2)]]
-        _h2d_concat(groups, blob.numel(), device, out=blob)
+        posts += [None] * 5
+        _h2d_concat(groups, blob.numel(), device, out=blob, post=posts)
         marks.append(("pack + H2D of all inputs", time.perf_counter()))
+        self._E_whole = []
+        if late_asym:
+            # The exact test found mirrored entries that differ in matrices the sample had passed: these systems are
+            # solved by LU on the matrix as given, like the reference (kriging.py:342-343, :576-585) - their whole
+            # matrix goes up now and their descriptors are patched.  Rare by construction (a covariance is symmetric).
+            for b in sorted(late_asym):
+                self._asym.append(b)
+                whole = _h2d(np.ascontiguousarray(Es[b], dtype=np.float64), device)
+                self._E_whole.append(whole)
+                kd[b]["E"], kd[b]["lde"] = whole.data_ptr(), ns[b]
+            self._asym.sort()
+            self._kd.copy_(_desc_tensor(kd, device).view(torch.float64))
+            torch.cuda.current_stream().synchronize()
+            marks.append(("re-upload of asymmetric error covariances", time.perf_counter()))
         if os.environ.get("GLOMAR_B200_TIMING") and B > 1:
             print(f"[KrigeBatch] {B} problems: " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.1f} ms"
                                                               for a, b in zip(marks, marks[1:])), flush=True)
@@ -615,6 +679,9 @@ def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.T
     (`factor_inplace_distributed`; `group=False` forces the local, replicated factorisation).
     Returns the (5, Mc) result rows.  Raises LinAlgError if S is not positive definite (no LU fallback here)."""
     n = S.shape[0]
+    for name, t in (("S", S), ("T", T), ("diag_base", diag_base), ("y", y)):  # the kernels read double*
+        if t.dtype != torch.float64:
+            raise TypeError(f"solve_prepared: {name} must be float64, got {t.dtype}")
     assert S.stride(1) == 1 and T.stride(1) == 1 and S.stride(0) % 2 == 0 and T.stride(0) % 2 == 0
     assert T.shape[1] >= Mc + 2
     import torch.distributed as dist

@@ -63,8 +63,13 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
                      (((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(d.T) |
                         reinterpret_cast<uintptr_t>(d.S) | reinterpret_cast<uintptr_t>(d.Cx)) & 15) == 0);
     // S columns of this thread: C[idx[a], idx[m]] is a gather, one index per column for all rows
+    // Observation cells are validated by the host (`KrigeBatch`: IndexError outside [-M, M), negatives wrapped like
+    // numpy); a caller of the C entry point that skips that gets CLAMPED cells here - wrong values for those
+    // observations, never an out-of-bounds read (a faulting read takes the CUDA context with it).
+    const int64_t top = M - 1;
     const bool s0 = m0 < d.n, s1 = m0 + 1 < d.n;
-    const int64_t j0 = s0 ? d.idx[m0] : 0, j1 = s1 ? d.idx[m0 + 1] : 0;
+    const int64_t j0 = s0 ? min(max(d.idx[m0], (int64_t)0), top) : 0;
+    const int64_t j1 = s1 ? min(max(d.idx[m0 + 1], (int64_t)0), top) : 0;
     // Rows past the end of a ragged last block are clamped to the last row: they redo its (identical) stores, and
     // the loop bodies stay branch-free so that all loads of the kGatherRows rows are in flight together.
     const double* crow[kGatherRows];
@@ -72,7 +77,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
 #pragma unroll
     for (int r = 0; r < kGatherRows; ++r) {
         arow[r] = min(a0 + r, d.n - 1);
-        crow[r] = C + d.idx[arow[r]] * ldc;
+        crow[r] = C + min(max(d.idx[arow[r]], (int64_t)0), top) * ldc;
     }
     // ---- T = [C[idx, :] | 1 | y] (and the C_cross copy of the full-solve paths) ----------------------------------
     if (m0 + 1 < M && vec) {

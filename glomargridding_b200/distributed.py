@@ -97,6 +97,10 @@ def krige_sharded(cov_rows: torch.Tensor, r0: int, idx, obs, error_cov=None, met
     import os
     import time
 
+    if cov_rows.dtype != torch.float64:
+        # the device kernels read double*; the builder's default precision is float32 (the reference's default)
+        raise ValueError(f"krige_sharded needs a float64 covariance row block, got {cov_rows.dtype}: build it with "
+                         "EllipseCovarianceBuilder(..., precision=np.float64)")
     device = cov_rows.device
     timing = bool(os.environ.get("GLOMAR_B200_TIMING")) and cov_rows.is_cuda
     marks = []

@@ -170,8 +170,10 @@ class Kriging(ABC):
 
     # -- shared device plumbing ---------------------------------------------------------------------------
     def _cov_device(self) -> torch.Tensor:
-        if getattr(self, "_cov_dev", None) is None:
+        # keyed on the identity of `self.covariance`: assigning a new matrix to the attribute drops the device copy
+        if getattr(self, "_cov_dev", None) is None or getattr(self, "_cov_src", None) is not self.covariance:
             self._cov_dev = _as_device_cov(self.covariance)
+            self._cov_src = self.covariance
         return self._cov_dev
 
     def _problem(self):
@@ -182,7 +184,35 @@ class Kriging(ABC):
         """gather -> Cholesky -> solves -> apply, once; results cached until the weights are replaced."""
         batch = dn.KrigeBatch(self._cov_device(), [self._problem()], ordinary=ordinary).run()
         self._out_host = batch.out[0].cpu().numpy()
+        self._obs_at_factor = np.array(self.obs, dtype=np.float64, copy=True)
         return batch
+
+    def _field_from_batch(self) -> np.ndarray:
+        """Kriged field of the kept factorisation for the CURRENT `self.obs`.
+
+        The weights do not depend on the observations, and the reference evaluates `kriging_weights @ self.obs` when
+        `solve` is called (`kriging.py:417`, `:677-679`), so `k.obs = other_member; k.solve()` (ensemble members on the
+        same cells) must see the new values.  The row cached by `_factorise` belongs to the observations of that
+        moment; for different ones the field is recomputed from the factorisation - one extra right-hand side,
+        z = S^-1 y, and one GEMM row:  C_cross^T z  [- alpha 1^T z  for ordinary kriging]."""
+        obs = np.asarray(self.obs, dtype=np.float64)
+        if obs.shape == self._obs_at_factor.shape and np.array_equal(obs, self._obs_at_factor, equal_nan=True):
+            return self._out_host[dn.OUT_FIELD]
+        b = self._batch
+        if obs.shape != (b.ns[0],):
+            raise ValueError(f"obs of shape {obs.shape} does not match the {b.ns[0]} observations of the weights")
+        cov = self._cov_device()
+        M = cov.shape[0]
+        y = dev.to_device(obs, torch.float64)
+        ordinary = b.ordinary and self.method != "simple"
+        if 0 in b.lu_fallback:
+            o = dn.apply_reduce(cov, b.Cx(0), b.T(0), y, ordinary=ordinary)
+            return o[dn.OUT_FIELD].cpu().numpy()
+        z = dn.padded(b.solve_vectors(0, y[:, None]))              # (n, 2): S^-1 y in column 0
+        field = dn.gemm(z[:, :1], b.Cx(0), transa=True)[0, :M]
+        if ordinary:
+            field = field - b.out[0, dn.OUT_ALPHA] * z[:, 0].sum()
+        return field.cpu().numpy()
 
     def _apply_user_weights(self, W: np.ndarray, n: int):
         """(W[:, :n] @ obs, rowdot(W[:, :n], C_cross^T)) on the device for externally supplied weights
@@ -255,7 +285,7 @@ class SimpleKriging(Kriging):
         if not self._has_weights():
             self.get_kriging_weights()
         if self._batch is not None:
-            field = self._out_host[dn.OUT_FIELD]
+            field = self._field_from_batch()
         else:
             field, _, _ = self._apply_user_weights(self._user_weights, len(self.idx))
         return field.astype(self._out_dtype(), copy=False) + mean
@@ -316,7 +346,7 @@ class OrdinaryKriging(Kriging):
         if not self._has_weights():
             self.get_kriging_weights()
         if self._batch is not None:
-            field = self._out_host[dn.OUT_FIELD]
+            field = self._field_from_batch()
         else:
             field, _, _ = self._apply_user_weights(self._user_weights, len(self.idx))
         return field.astype(self._out_dtype(), copy=False)

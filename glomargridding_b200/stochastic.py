@@ -165,7 +165,7 @@ class StochasticKriging(Kriging):
         self.epsilon = self.simulated_grid - simulated_state
         # first stage: ordinary kriging of the observations (:390-392)
         if self._batch is not None:
-            field = self._out_host[dn.OUT_FIELD]
+            field = self._field_from_batch()
         else:
             field, _, _ = self._apply_user_weights(self._user_weights, len(self.idx))
         self.gridded_field = field.astype(self._out_dtype(), copy=False)

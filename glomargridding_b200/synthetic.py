@@ -59,9 +59,14 @@ def hadcrut_style_error_cov(idx: np.ndarray, nlon: int, seed: int = 7, n_groups:
     s = rng.uniform(0.05, 0.2, size=n_groups)
     u = rng.uniform(0.2, 0.4, size=len(idx))
     g = ((idx % nlon) * n_groups) // nlon
-    E = (g[:, None] == g[None, :]) * (s[g] ** 2)[:, None]
-    E = E + np.diag(u ** 2)
-    return np.ascontiguousarray(E, dtype=np.float64)
+    n = len(idx)
+    s2 = s[g] ** 2
+    E = np.empty((n, n), dtype=np.float64)
+    for r0 in range(0, n, 2048):                  # row slabs: no n x n temporaries (3.2 GB each at n = 20 000)
+        r1 = min(n, r0 + 2048)
+        np.multiply(g[r0:r1, None] == g[None, :], s2[r0:r1, None], out=E[r0:r1])
+    E[np.arange(n), np.arange(n)] += u ** 2
+    return E
 
 
 def full_grid_error_cov(idx: np.ndarray, n_cells: int, nlon: int, seed: int = 7):

@@ -323,6 +323,19 @@ int gmg_pair_displacement_f64(const double* lat0, const double* lon0, const doub
                               int64_t n, int modified, double radius_km, double* dy, double* dx,
                               gmg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Measurement utility (no reference counterpart; SURVEY.md section 7: "FP64 peak is unmeasured - a DFMA-saturation
+ * and a DMMA microbenchmark must be run first; roofline fractions are against those").  Runs a register-only
+ * DFMA (what = GMG_MICROBENCH_DFMA) or mma.sync m8n8k4 f64 (GMG_MICROBENCH_DMMA) kernel that fills every SM, `reps`
+ * launches back to back plus three isolated ones, SYNCHRONISES the stream, and reports TFLOP/s: `tflops_best` from the
+ * fastest single launch (burst clocks), `tflops_sustained` (may be NULL) over the back-to-back window.
+ * `d_scratch`: at least 8 bytes of device memory.  bench.py calls this next to the timed kernels.
+ * ------------------------------------------------------------------------------------------- */
+#define GMG_MICROBENCH_DFMA 0
+#define GMG_MICROBENCH_DMMA 1
+int gmg_microbench_fp64(int what, int iters, int reps, double* d_scratch, double* tflops_best,
+                        double* tflops_sustained, gmg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

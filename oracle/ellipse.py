@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE ONLY (see `oracle/__init__.py`).  numpy/scipy restatement of
 `glomar_gridding/ellipse/covariance.py` in the reference; every function cites the lines it
 follows.  The arithmetic order of the pair formula is kept identical to the reference so that the
-restatement is bit-for-bit equal to it in float64 (checked in tests/test_oracle_vs_reference.py).
+restatement is bit-for-bit equal to it in float64 (checked in tests/test_oracle_vs_golden.py against fixtures made by the reference, and there against the live reference when /root/reference is present).
 
 The structure is NOT the reference's: instead of materialising all `itertools.combinations`
 index pairs (reference `:255`, 34 GB of indices at 1 degree) the matrix is evaluated by row strips

@@ -18,7 +18,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("GLOMAR_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """`/root/reference` in the build container; on the GPU box the copy that `__graft_entry__.build()` staged
+    under `oracle/_ref/` (git-ignored, shipped with the snapshot).  Same files either way."""
+    env = os.environ.get("GLOMAR_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    for root in ("/root/reference", staged):
+        if os.path.isdir(os.path.join(root, "glomar_gridding")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 _STUBS = [
     "netCDF4", "polars", "polars._typing", "xarray", "geopandas", "shapely",

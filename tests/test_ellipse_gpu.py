@@ -287,3 +287,83 @@ def test_reference_own_golden_atlantic_window(Builder):
     assert hasattr(b, "cor_ns") and np.isclose(1, np.max(np.diag(b.cor_ns)))
     b.uncompress_cov()
     assert b.cov_ns.shape[0] == b.cov_ns.shape[1] == g["Lx"].shape[0] ** 2
+
+
+# ---- 1 degree, full rows against the oracle (parity at the headline size) -----------------
+def _rows_1deg():
+    """Rows of the 64 800-point matrix that the tile kernel treats differently: both sides of every row-block
+    boundary of a 2 / 4 / 8-rank build (bench.row_block: 128-row macro tiles), macro-tile and tile edges, both poles,
+    the equator, the ragged last tile, and one row for EACH of the 360 longitudes (so that every longitude meets its
+    180-degree partner column - the 12 pairs whose difference is one ulp away from pi included - in both
+    orientations, since full rows hold the entries left and right of the diagonal)."""
+    N, T = 64800, 128
+    tiles = (N + T - 1) // T
+    rows = {0, 1, 63, 64, 127, 128, 359, 360, N - 1, N - 2, N - 64, N - 65, N - 360, N - 361, 32399, 32400, 32401}
+    for world in (2, 4, 8):
+        for r in range(1, world):
+            b = (tiles * r // world) * T
+            rows.update({b - 1, b, b + 1})
+    for lon in range(360):
+        rows.add(((lon * 7) % 180) * 360 + lon)
+    return np.array(sorted(rows), dtype=np.int64)
+
+
+def _oracle_rows(o, rows):
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=8) as ex:       # numpy / scipy ufuncs release the GIL
+        return np.concatenate(list(ex.map(lambda r: o.rows(int(r), int(r) + 1), rows)), axis=0)
+
+
+def test_1deg_full_rows_vs_oracle_f64(Builder):
+    """Tile kernel, general nu (the headline configuration): ~400 full rows = 2.6e7 entries at 1e-10."""
+    import torch
+    from oracle import EllipseOracle
+
+    lats, lons = synth.global_grid(1.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    rows = _rows_1deg()
+    assert rows.size >= 256
+    C = Builder(Lx, Ly, th, sd, lats, lons, v=2.2, precision=np.float64).cov_ns_device
+    got = C[torch.from_numpy(rows).cuda()].cpu().numpy()
+    got_cols = C[:, torch.from_numpy(rows[:32]).cuda()].T.cpu().numpy()      # the mirrored entries of 32 of them
+    del C
+    torch.cuda.empty_cache()
+    want = _oracle_rows(EllipseOracle(Lx, Ly, th, sd, lats, lons, 2.2), rows)
+    assert got.size >= 1.6e7
+    assert max_rel(got, want) <= TOL
+    assert np.array_equal(got_cols, got[:32])               # C[j, i] is bit-equal to C[i, j]
+
+
+def test_1deg_full_rows_vs_oracle_f32_default_precision(Builder):
+    """The builder's DEFAULT precision (float32, like the reference) at 1 degree, the reference's own criterion
+    `np.allclose(rtol=1e-5)` (test/test_ellipse.py:212): float32 inputs, float32 wrap decisions."""
+    import torch
+    from oracle import EllipseOracle
+
+    lats, lons = synth.global_grid(1.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    rows = _rows_1deg()[::4]
+    C = Builder(Lx, Ly, th, sd, lats, lons, v=1.5).cov_ns_device
+    assert C.dtype == torch.float32
+    got = C[torch.from_numpy(rows).cuda()].cpu().numpy()
+    del C
+    torch.cuda.empty_cache()
+    want = _oracle_rows(EllipseOracle(Lx, Ly, th, sd, lats, lons, 1.5, precision=np.float32), rows)
+    assert want.dtype == np.float32 and np.allclose(got, want, rtol=1e-5)
+
+
+def test_1deg_max_dist_rows_vs_oracle(Builder):
+    import torch
+    from oracle import EllipseOracle
+
+    lats, lons = synth.global_grid(1.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    rows = _rows_1deg()[::8]
+    for row0 in (0, 32384):                                 # two row blocks that hold some of the rows
+        sel = rows[(rows >= row0) & (rows < row0 + 8192)]
+        b = Builder(Lx, Ly, th, sd, lats, lons, v=0.5, max_dist=3000.0, precision=np.float64, rows=(row0, 8192))
+        got = b.cov_ns_device[torch.from_numpy(sel - row0).cuda()].cpu().numpy()
+        want = _oracle_rows(EllipseOracle(Lx, Ly, th, sd, lats, lons, 0.5, max_dist=3000.0), sel)
+        assert np.array_equal(got == 0, want == 0)
+        assert max_rel(got, want) <= TOL

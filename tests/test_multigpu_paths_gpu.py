@@ -1,0 +1,277 @@
+"""The multi-GPU code paths on ONE GPU: every kernel and host routine that the row-block / block-cyclic sharding goes
+through, with the ranks emulated sequentially in one process (the collectives of those paths only move data that a
+single process already holds), so the driver's one-GPU `-m gpu` run covers them.
+
+* `krige_sharded` at world = 1 against the oracle (5 degrees) - the routine that BASELINE configs[3] runs on 8 GPUs.
+* `gmg_potrf_step_f64` (diagonal / panel / update phases with tile-row ownership `tr_mod`, `tr_rem`): the ranks of a
+  1-D block-cyclic factorisation applied one after the other to one matrix must reproduce `gmg_potrf_batched_f64`
+  bit for bit.
+* `gmg_ellipse_cov_p2p_f64`: every rank's launch of the pair-once build, writing into "peer" row blocks that here
+  live on the same device, must reproduce the single-rank matrix bit for bit.
+* the distributed-factorisation driver (`_dense.factor_inplace_distributed`) on a one-rank group.
+"""
+
+import ctypes
+import warnings
+
+import numpy as np
+import pytest
+from conftest import max_norm_rel
+
+from glomargridding_b200 import synthetic as synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _cov5(torch, method="Met_Office", v=1.5):
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    b = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=v, delta_x_method=method, precision=np.float64)
+    return b, lons.size
+
+
+@pytest.mark.parametrize("method", ["ordinary", "simple"])
+def test_krige_sharded_world1_vs_oracle(cuda, method):
+    from glomargridding_b200.distributed import krige_sharded
+    from oracle import ordinary_kriging, simple_kriging
+
+    b, nlon = _cov5(cuda)
+    C = b.cov_ns_device
+    idx, obs = synth.fixed_observations(5, C.shape[0], 900)
+    E = synth.hadcrut_style_error_cov(idx, nlon)
+    got = krige_sharded(C, 0, idx, obs, E, method, mean=0.25)
+    cov = b.cov_ns
+    want = ordinary_kriging(cov, idx, obs, E) if method == "ordinary" else simple_kriging(cov, idx, obs, E, mean=0.25)
+    assert max_norm_rel(got["field"], want["field"]) <= TOL
+    assert max_norm_rel(got["uncertainty"] ** 2, want["uncertainty"] ** 2) <= TOL
+    assert max_norm_rel(got["constraint_mask"], want["constraint_mask"]) <= TOL
+    # no error covariance at all (the reference's error_cov=None)
+    got0 = krige_sharded(C, 0, idx, obs, None, method)
+    want0 = ordinary_kriging(cov, idx, obs, None) if method == "ordinary" else simple_kriging(cov, idx, obs, None)
+    assert max_norm_rel(got0["field"], want0["field"]) <= 1e-6       # S = C[idx, idx] alone is poorly conditioned
+
+
+def test_krige_sharded_rejects_float32_rows_and_unsorted_idx(cuda):
+    from glomargridding_b200.distributed import krige_sharded
+
+    b, nlon = _cov5(cuda)
+    idx, obs = synth.fixed_observations(5, 2592, 100)
+    with pytest.raises(ValueError, match="float64"):
+        krige_sharded(b.cov_ns_device.float(), 0, idx, obs, None)
+    with pytest.raises(ValueError, match="sorted"):
+        krige_sharded(b.cov_ns_device, 0, idx[::-1].copy(), obs, None)
+
+
+def _spd(torch, n, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g)
+    return A @ A.T / n + torch.eye(n, dtype=torch.float64, device="cuda")
+
+
+@pytest.mark.parametrize("n", [1000, 1152])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_potrf_step_emulated_ranks_bit_equal(cuda, n, world):
+    """Rank r of `world` owns the tile rows t with t % world == r.  Per block step: the owner's diagonal phase, then
+    every rank's panel phase, then every rank's update phase - the order the distributed driver enforces with its
+    exchanges - here on one matrix, one rank after the other."""
+    torch = cuda
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200 import _device as dev
+    from glomargridding_b200._lib import check, lib
+
+    S0 = dn.padded(_spd(torch, n, n + world))
+    ref = S0.clone()
+    ws_ref = dn.factor_inplace(ref, n)
+
+    S = S0.clone()
+    lin, pdb, ldp = dn.solve_ws(n)
+    Linv = torch.zeros(lin, dtype=torch.float64, device="cuda")
+    P = torch.empty(pdb, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d = np.zeros(1, dtype=dn.SOLVE_DESC)
+    d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"], d["n"] = (
+        S.data_ptr(), S.stride(0), Linv.data_ptr(), P.data_ptr(), ldp, info.data_ptr(), n)
+    dt = dn._desc_tensor(d, S.device)
+    L, s = lib(), dev.stream_ptr()
+    nblk = (n + dn.NB - 1) // dn.NB
+    for k in range(nblk):
+        check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 0, 1, 0, s), "diag")
+        for phase in (1, 2):
+            for r in range(world):
+                check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, phase, world, r, s), "step")
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0
+    tri = torch.tril(torch.ones((n, n), dtype=torch.bool, device="cuda"))
+    assert torch.equal(S[:n, :n][tri], ref[:n, :n][tri])
+    assert torch.equal(Linv, ws_ref["Linv"])
+    # and it is a Cholesky factor
+    Lf = torch.tril(S[:n, :n])
+    assert float((Lf @ Lf.T - S0[:n, :n]).abs().max() / S0[:n, :n].abs().max()) <= 1e-13
+
+
+def test_potrf_step_argument_checks(cuda):
+    from glomargridding_b200._lib import lib
+
+    L = lib()
+    assert L.gmg_potrf_step_f64(None, 1, 256, 0, 0, 1, 0, None) == -1
+    assert L.gmg_potrf_step_f64(ctypes.c_void_p(8), 1, 256, 2, 0, 1, 0, None) == -4      # block step past the end
+    assert L.gmg_potrf_step_f64(ctypes.c_void_p(8), 1, 256, 0, 3, 1, 0, None) == -5
+    assert L.gmg_potrf_step_f64(ctypes.c_void_p(8), 1, 256, 0, 1, 2, 2, None) == -6
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("v", [1.5, 2.2])
+def test_ellipse_cov_p2p_emulated_ranks_bit_equal(cuda, world, v):
+    """Every unordered pair of row blocks is computed by exactly one rank, which also stores the transposed tile
+    into the other block; after all `world` launches the blocks hold the same matrix as the one-rank build."""
+    torch = cuda
+    from glomargridding_b200 import _device as dev
+    from glomargridding_b200._lib import check, lib
+    from glomargridding_b200.ellipse.p2p import tile_aligned_blocks
+
+    b, _ = _cov5(torch, "Modified_Met_Office", v)
+    N = b.cov_ns_device.shape[0]
+    blocks = tile_aligned_blocks(N, world)
+    parts = [torch.full((int(blocks[g + 1] - blocks[g]), N), float("nan"), dtype=torch.float64, device="cuda")
+             for g in range(world)]
+    ptrs = (ctypes.c_void_p * world)(*[p.data_ptr() for p in parts])
+    row0 = (ctypes.c_int64 * (world + 1))(*[int(x) for x in blocks])
+    for r in range(world):
+        check(lib().gmg_ellipse_cov_p2p_f64(b._ws.data_ptr(), N, float(v), -1.0, 0, world, r, row0, ptrs, N, 0,
+                                            dev.stream_ptr()), "p2p")
+    torch.cuda.synchronize()
+    got = torch.cat(parts, dim=0)
+    assert not torch.isnan(got).any()                       # every entry was written by somebody
+    assert torch.equal(got, b.cov_ns_device)
+
+
+def test_factor_inplace_distributed_single_rank_group(cuda, tmp_path):
+    """The distributed driver itself (its exchanges degenerate on a one-rank group): same factor as the local one."""
+    torch = cuda
+    import torch.distributed as dist
+
+    from glomargridding_b200 import _dense as dn
+
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    dist.init_process_group("nccl", init_method=f"file://{tmp_path}/rdzv", rank=0, world_size=1,
+                            device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        n = 900
+        S0 = dn.padded(_spd(torch, n, 17))
+        a, bb = S0.clone(), S0.clone()
+        ws_a = dn.factor_inplace(a, n)
+        ws_b = dn.factor_inplace_distributed(bb, n)
+        tri = torch.tril(torch.ones((n, n), dtype=torch.bool, device="cuda"))
+        assert torch.equal(a[:n, :n][tri], bb[:n, :n][tri]) and torch.equal(ws_a["Linv"], ws_b["Linv"])
+        with pytest.raises(np.linalg.LinAlgError):
+            bad = S0.clone()
+            bad[5, 5] = -1.0
+            dn.factor_inplace_distributed(bad, n)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_obs_replaced_after_factorisation(cuda):
+    """`k.obs = other; k.solve()` re-evaluates the field with the kept weights (reference kriging.py:417, :677-679:
+    `kriging_weights @ self.obs` at call time) - for the Cholesky path, the LU fallback and the stochastic class."""
+    from glomargridding_b200.kriging import OrdinaryKriging, SimpleKriging
+    from glomargridding_b200.stochastic import StochasticKriging
+
+    b, nlon = _cov5(cuda)
+    C = b.cov_ns_device
+    idx, obs = synth.fixed_observations(9, C.shape[0], 700)
+    obs2 = np.random.default_rng(3).standard_normal(obs.size)
+    E = synth.hadcrut_style_error_cov(idx, nlon)
+    for cls in (SimpleKriging, OrdinaryKriging):
+        k = cls(C, idx, obs.copy(), E.copy())
+        z1 = k.solve()
+        fresh = cls(C, idx, obs2.copy(), E.copy()).solve()
+        k.obs = obs2.copy()
+        assert max_norm_rel(k.solve(), fresh) <= 1e-11
+        k.obs = obs.copy()
+        assert np.array_equal(k.solve(), z1)
+    # LU fallback: an indefinite covariance (default displacement method)
+    bi, _ = _cov5(cuda, "Modified_Met_Office")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        k = OrdinaryKriging(bi.cov_ns_device, idx, obs.copy(), E.copy())
+        k.solve()
+        if k._batch.lu_fallback:
+            fresh = OrdinaryKriging(bi.cov_ns_device, idx, obs2.copy(), E.copy()).solve()
+            k.obs = obs2.copy()
+            assert max_norm_rel(k.solve(), fresh) <= 1e-9
+    sk = StochasticKriging(C, idx, obs.copy(), E.copy())
+    state = np.zeros(C.shape[0])
+    np.random.seed(1)
+    sk.solve(simulated_state=state)
+    g1 = sk.gridded_field.copy()
+    sk.obs = obs2.copy()
+    np.random.seed(1)
+    sk.solve(simulated_state=state)
+    assert max_norm_rel(sk.gridded_field, OrdinaryKriging(C, idx, obs2.copy(), E.copy()).solve()) <= 1e-11
+    assert not np.allclose(g1, sk.gridded_field)
+
+
+def test_observation_cells_validated_like_numpy(cuda):
+    from glomargridding_b200.kriging import SimpleKriging
+
+    b, nlon = _cov5(cuda)
+    C = b.cov_ns_device
+    M = C.shape[0]
+    idx, obs = synth.fixed_observations(2, M, 50)
+    for bad in (M, M + 7, -M - 1):
+        i2 = idx.copy()
+        i2[3] = bad
+        with pytest.raises(IndexError, match="out of bounds"):
+            SimpleKriging(C, i2, obs, None).solve()
+    neg = idx.copy()
+    neg[-1] = idx[-1] - M                               # numpy wraps negative cells
+    assert np.array_equal(SimpleKriging(C, neg, obs, None).solve(), SimpleKriging(C, idx, obs, None).solve())
+
+
+def test_asymmetric_error_cov_in_few_entries_is_detected(cuda):
+    """An error covariance that is asymmetric in a handful of entries passes the sampled pre-filter; the exact test
+    inside the packing tasks must still route it to the LU solve of the matrix AS GIVEN (reference kriging.py:342-343,
+    :576-585), and `assume_symmetric=True` must read the lower triangle only."""
+    from glomargridding_b200 import _dense as dn
+    from oracle import ordinary_kriging
+
+    b, nlon = _cov5(cuda)
+    C = b.cov_ns_device
+    idx, obs = synth.fixed_observations(11, C.shape[0], 640)
+    E = synth.hadcrut_style_error_cov(idx, nlon)
+    Ea = E.copy()
+    Ea[17, 400] += 0.05                                 # one entry of the upper triangle
+    Ea[3, 630] -= 0.02
+    assert dn._looks_symmetric(Ea) and not dn.is_symmetric(Ea) and dn.is_symmetric(E)
+    prob = [(idx, obs, Ea)]
+    with pytest.warns(UserWarning, match="not symmetric"):
+        kb = dn.KrigeBatch(C, prob, ordinary=True).run()
+    assert kb.lu_fallback == [0]
+    want = ordinary_kriging(b.cov_ns, idx, obs, Ea)
+    assert max_norm_rel(kb.out[0, dn.OUT_FIELD].cpu().numpy(), want["field"]) <= TOL
+    # several problems, one of them asymmetric: only that one takes the LU route
+    probs = [(idx, obs, E), (idx, obs, Ea), (idx, obs * 2, E)]
+    with pytest.warns(UserWarning, match="not symmetric"):
+        kb3 = dn.KrigeBatch(C, probs, ordinary=True).run()
+    assert kb3.lu_fallback == [1]
+    assert max_norm_rel(kb3.out[1, dn.OUT_FIELD].cpu().numpy(), want["field"]) <= TOL
+    want_sym = ordinary_kriging(b.cov_ns, idx, obs, E)
+    assert max_norm_rel(kb3.out[0, dn.OUT_FIELD].cpu().numpy(), want_sym["field"]) <= TOL
+    # the caller vouches: upper triangle ignored -> the answer of the symmetric matrix
+    kbs = dn.KrigeBatch(C, prob, ordinary=True, assume_symmetric=True).run()
+    assert kbs.lu_fallback == []
+    assert max_norm_rel(kbs.out[0, dn.OUT_FIELD].cpu().numpy(), want_sym["field"]) <= TOL

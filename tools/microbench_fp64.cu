@@ -2,8 +2,11 @@
 // store-only HBM bandwidth.  MEASURED_PEAKS.json only has the HBM copy and bf16 GEMM
 // figures, so the FP64 kernels' fractions are taken against what this prints.
 //
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench_fp64 microbench_fp64.cu
-//   ./microbench_fp64            -> one JSON object on stdout
+//   mkdir -p build && nvcc -cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -o build/microbench_fp64 microbench_fp64.cu
+//   build/microbench_fp64        -> one JSON object on stdout
+// (-cudart shared: a statically linked runtime drags every runtime symbol name into the binary; build/ is git-ignored.
+//  The DFMA / DMMA figures are also available in the run through gmg_microbench_fp64 of the library, which is what
+//  bench.py uses.)
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
