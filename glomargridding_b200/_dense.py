@@ -156,20 +156,25 @@ def _looks_symmetric(E: np.ndarray, samples: int = 96) -> bool:
 
 def _block_row_symmetric(E: np.ndarray, r0: int, r1: int) -> bool:
     """Rows r0:r1 of E against columns r0:r1, up to and including the diagonal block - exact, entry by entry, NaN
-    equal to NaN (both become 0 on the device).  Called by the packing task that has just read E[r0:r1, :r1], in
-    sub-blocks of 128 columns so that the transposed operand stays cache resident."""
-    for c0 in range(0, r1, NB):
-        c1 = min(r1, c0 + NB)
-        a, b = E[r0:r1, c0:c1], E[c0:c1, r0:r1].T
-        if not (a == b).all() and not np.array_equal(a, b, equal_nan=True):
-            return False
-    return True
+    equal to NaN (both become 0 on the device).  Native (`gmg_host_rows_symmetric`, blocked, GIL released); called
+    by the packing task that has just read E[r0:r1, :r1]."""
+    if E.dtype in (np.float64, np.float32) and E.strides[1] == E.itemsize and E.strides[0] % E.itemsize == 0:
+        rc = lib().gmg_host_rows_symmetric(E.ctypes.data, int(E.dtype == np.float32), E.shape[0],
+                                           E.strides[0] // E.itemsize, r0, r1)
+        if rc < 0:
+            raise GlomarB200Error(f"gmg_host_rows_symmetric failed with status {rc}")
+        return bool(rc)
+    a, b = E[r0:r1, :r1], E[:r1, r0:r1].T                       # other dtypes / layouts: numpy
+    return bool((a == b).all() or np.array_equal(a, b, equal_nan=True))
 
 
 def is_symmetric(E: np.ndarray) -> bool:
-    """Exact symmetry test of a host matrix (blocked; the single-problem and pre-upload form of the check above)."""
+    """Exact symmetry test of a host matrix (row blocks on the packing pool)."""
     n = E.shape[0]
-    return all(_block_row_symmetric(E, r0, min(n, r0 + NB)) for r0 in range(0, n, NB))
+    spans = [(r0, min(n, r0 + 4 * NB)) for r0 in range(0, n, 4 * NB)]
+    if n * n < (1 << 22):
+        return all(_block_row_symmetric(E, a, b) for a, b in spans)
+    return all(_pool().map(lambda s: _block_row_symmetric(E, *s), spans))
 
 
 def packed_error_cov_doubles(n: int) -> int:
@@ -322,10 +327,18 @@ class KrigeBatch:
       T(b)    (n, ldt) tensor: S^-1 [C_cross | 1 | y]: simple-kriging weights transposed, column M = S^-1 1
     """
 
-    def __init__(self, cov: torch.Tensor, problems, ordinary: bool, alloc=None, assume_symmetric: bool = False):
-        """`assume_symmetric`: False (default) - every error covariance is tested for symmetry EXACTLY (entry by entry,
-        inside the packing tasks; an asymmetric one is solved by LU on the matrix as given, like the reference);
-        True - the caller vouches for symmetry: no test, the upper triangles are never read."""
+    def __init__(self, cov: torch.Tensor, problems, ordinary: bool, alloc=None, symmetry: str = "auto"):
+        """`symmetry` - how it is decided whether an error covariance is symmetric (a symmetric one travels as its lower
+        block trapezoid and is factored by Cholesky; an asymmetric one is uploaded whole and solved by LU on the matrix
+        as given, like the reference, kriging.py:342-343, :576-585):
+          "exact"   every mirrored pair of entries is compared, inside the packing tasks (one more pass over the host
+                    matrix: ~0.1 s for one 20 000 x 20 000 system, ~0.2 ms per 5-degree month on 14 threads);
+          "sample"  96 pseudo-random mirrored pairs per matrix: catches any asymmetry that is not confined to a few
+                    entries; a batch of hundreds of months stays bound by its upload, not by host memory bandwidth;
+          "assume"  the caller vouches for symmetry: no test, the upper triangles are never read;
+          "auto"    (default) "exact" for fewer than 8 problems - the class calls -, "sample" for larger batches."""
+        if symmetry not in ("auto", "exact", "sample", "assume"):
+            raise ValueError(f"Unknown symmetry policy: {symmetry}")
         assert cov.is_cuda and cov.dtype == torch.float64 and cov.dim() == 2 and cov.stride(1) == 1
         import time
 
@@ -388,10 +401,10 @@ class KrigeBatch:
         for b, (E, n) in enumerate(zip(Es, ns)):
             size, lde = 0, n
             if E is not None:
-                sym = True if assume_symmetric else _looks_symmetric(E)
+                sym = True if symmetry == "assume" else _looks_symmetric(E)
                 if not sym:
                     self._asym.append(b)                 # no Cholesky for this system: LU like the reference
-                exact = sym and not assume_symmetric
+                exact = sym and (symmetry == "exact" or (symmetry == "auto" and B < 8))
                 rows = [(r0, min(n, r0 + NB)) for r0 in range(0, n, NB)]
                 if sym and n > NB and PACK_SYMMETRIC_ERROR_COV:
                     lde = -NB

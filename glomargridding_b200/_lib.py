@@ -70,6 +70,7 @@ def _declare(lib):
         "gmg_det22_f64": (c_int, [p, i64, p, p]),
         "gmg_pair_haversine_f64": (c_int, [p, p, p, p, i64, dbl, p, p]),
         "gmg_pair_displacement_f64": (c_int, [p, p, p, p, i64, i32, dbl, p, p, p]),
+        "gmg_host_rows_symmetric": (c_int, [p, i32, i64, i64, i64, i64]),
         "gmg_microbench_fp64": (c_int, [i32, i32, i32, p, POINTER(c_double), POINTER(c_double), p]),
     })
     for name, (res, args) in sigs.items():

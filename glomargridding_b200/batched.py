@@ -53,7 +53,7 @@ def _side_stream(device) -> torch.cuda.Stream:
 
 
 def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_bytes: int | None = None,
-                return_device: bool = False):
+                return_device: bool = False, symmetry: str = "auto"):
     """Kriged field, uncertainty and constraint mask for every (idx, obs, error_cov) in `problems`.
 
     Returns a dict of (len(problems), M) arrays: "field", "uncertainty", "constraint_mask" (numpy, or CUDA
@@ -63,7 +63,12 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
     Batches of 32 or more problems run as a three-stage pipeline over chunks (an eighth of the batch each, the first
     two smaller; `GLOMAR_B200_CHUNKS` overrides the eighth): constructor logic, packing + H2D on a side stream, device
     work.  The two device arenas the chunks live in, the pinned staging buffers and the side stream are kept between
-    calls (a second call allocates nothing); `release_workspaces()` returns the arenas to the allocator."""
+    calls (a second call allocates nothing); `release_workspaces()` returns the arenas to the allocator.
+
+    `symmetry` ("auto" | "exact" | "sample" | "assume", see `_dense.KrigeBatch`): how the error covariances are tested
+    for symmetry.  A batch of 8 or more problems defaults to the SAMPLED test (96 mirrored entry pairs per matrix):
+    an error covariance that is asymmetric in only a handful of entries is then treated as symmetric - its upper
+    triangle is never read - whereas the reference would LU-solve it as given; pass "exact" when that matters."""
     if method not in ("ordinary", "simple"):
         raise ValueError(f"Unknown kriging method: {method}")
     cls = OrdinaryKriging if method == "ordinary" else SimpleKriging
@@ -142,7 +147,8 @@ def krige_batch(covariance, problems, method: str = "ordinary", mean=0.0, max_by
         prepared = prepared_or_future.result() if hasattr(prepared_or_future, "result") else prepared_or_future
         t1 = _time.perf_counter()
         with torch.cuda.stream(side):
-            kb = dn.KrigeBatch(cov, prepared, ordinary=method == "ordinary", alloc=arena_for(lo, prepared))
+            kb = dn.KrigeBatch(cov, prepared, ordinary=method == "ordinary", alloc=arena_for(lo, prepared),
+                               symmetry=symmetry if symmetry != "auto" or n_all < 8 else "sample")
             side.synchronize()                                     # uploads complete before the main stream reads them
         if timing:
             print(f"[krige_batch] upload {lo}:{hi} waited {1e3 * (t1 - t0):.1f} ms for prepare, pack + H2D "

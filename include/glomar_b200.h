@@ -324,6 +324,16 @@ int gmg_pair_displacement_f64(const double* lat0, const double* lon0, const doub
                               gmg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * HOST helper (host pointers, no device work): rows r0 .. r1 of the n x n host matrix E (leading dimension ld in
+ * elements, float64 or float32) against columns r0 .. r1, for the columns up to and including the diagonal block -
+ * returns 1 if every mirrored pair of entries is equal (NaN equal to NaN), 0 if not, negative for a bad argument.
+ * The reference adds the error covariance as given and solves by LU (glomar_gridding/kriging.py:342-343, :576-585);
+ * this library uploads only the lower block trapezoid of a SYMMETRIC matrix and factors by Cholesky, so the packing
+ * threads decide symmetry exactly with this routine (calling it for every row block covers the whole matrix).
+ * ------------------------------------------------------------------------------------------- */
+int gmg_host_rows_symmetric(const void* E, int is_f32, int64_t n, int64_t ld, int64_t r0, int64_t r1);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement utility (no reference counterpart; SURVEY.md section 7: "FP64 peak is unmeasured - a DFMA-saturation
  * and a DMMA microbenchmark must be run first; roofline fractions are against those").  Runs a register-only
  * DFMA (what = GMG_MICROBENCH_DFMA) or mma.sync m8n8k4 f64 (GMG_MICROBENCH_DMMA) kernel that fills every SM, `reps`

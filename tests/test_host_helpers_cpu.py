@@ -101,3 +101,35 @@ def test_host_helpers_against_the_live_reference(reference):
             unmask = np.sort(rng.choice(60, 30, replace=False))
             uniq = np.sort(rng.choice(unmask, 12, replace=False))
             assert np.array_equal(rk.get_unmasked_obs_indices(unmask, uniq), mk.get_unmasked_obs_indices(unmask, uniq))
+
+
+def test_exact_symmetry_test_of_error_covariances():
+    """`gmg_host_rows_symmetric` (native, host only) behind `_dense.is_symmetric` / the packing tasks of `KrigeBatch`:
+    every mirrored pair of entries, NaN equal to NaN, float64 / float32 / other layouts."""
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200._lib import lib
+
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 127, 128, 129, 700):
+        A = rng.standard_normal((n, n))
+        S = A + A.T
+        assert dn.is_symmetric(S) and dn.is_symmetric(S.astype(np.float32)) and dn.is_symmetric(np.asfortranarray(S))
+        if n > 1:
+            for (i, j) in ((0, n - 1), (n - 1, 0), (n // 2, n // 2 - 1)):
+                S2 = S.copy()
+                S2[i, j] = np.nextafter(S2[i, j], np.inf)          # one ulp in one entry
+                assert not dn.is_symmetric(S2)
+            S3 = S.copy()
+            S3[n // 2, 0] = np.nan
+            assert not dn.is_symmetric(S3)
+            S3[0, n // 2] = np.nan
+            assert dn.is_symmetric(S3)                             # NaN mirrors NaN: both are read as 0
+        # row blocks: rows r0:r1 against columns r0:r1 only
+        if n >= 129:
+            S4 = S.copy()
+            S4[3, 100] += 1.0                                      # lives in row block 0 / column block 0
+            assert not dn._block_row_symmetric(S4, 0, 128) and dn._block_row_symmetric(S4, 128, n)
+    E = np.zeros((4, 4))
+    assert lib().gmg_host_rows_symmetric(None, 0, 4, 4, 0, 4) == -1
+    assert lib().gmg_host_rows_symmetric(E.ctypes.data, 0, 4, 3, 0, 4) == -3
+    assert lib().gmg_host_rows_symmetric(E.ctypes.data, 0, 4, 4, 2, 5) == -5

@@ -245,7 +245,7 @@ def test_observation_cells_validated_like_numpy(cuda):
 def test_asymmetric_error_cov_in_few_entries_is_detected(cuda):
     """An error covariance that is asymmetric in a handful of entries passes the sampled pre-filter; the exact test
     inside the packing tasks must still route it to the LU solve of the matrix AS GIVEN (reference kriging.py:342-343,
-    :576-585), and `assume_symmetric=True` must read the lower triangle only."""
+    :576-585), and `symmetry="assume"` must read the lower triangle only."""
     from glomargridding_b200 import _dense as dn
     from oracle import ordinary_kriging
 
@@ -267,11 +267,15 @@ def test_asymmetric_error_cov_in_few_entries_is_detected(cuda):
     probs = [(idx, obs, E), (idx, obs, Ea), (idx, obs * 2, E)]
     with pytest.warns(UserWarning, match="not symmetric"):
         kb3 = dn.KrigeBatch(C, probs, ordinary=True).run()
+    with pytest.warns(UserWarning, match="not symmetric"):              # large batches: "exact" on request
+        kb9 = dn.KrigeBatch(C, probs * 3, ordinary=True, symmetry="exact").run()
+    assert kb9.lu_fallback == [1, 4, 7]
+    assert dn.KrigeBatch(C, probs * 3, ordinary=True).run().lu_fallback == []      # "sample" does not see two entries
     assert kb3.lu_fallback == [1]
     assert max_norm_rel(kb3.out[1, dn.OUT_FIELD].cpu().numpy(), want["field"]) <= TOL
     want_sym = ordinary_kriging(b.cov_ns, idx, obs, E)
     assert max_norm_rel(kb3.out[0, dn.OUT_FIELD].cpu().numpy(), want_sym["field"]) <= TOL
     # the caller vouches: upper triangle ignored -> the answer of the symmetric matrix
-    kbs = dn.KrigeBatch(C, prob, ordinary=True, assume_symmetric=True).run()
+    kbs = dn.KrigeBatch(C, prob, ordinary=True, symmetry="assume").run()
     assert kbs.lu_fallback == []
     assert max_norm_rel(kbs.out[0, dn.OUT_FIELD].cpu().numpy(), want_sym["field"]) <= TOL
