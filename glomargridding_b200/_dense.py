@@ -198,7 +198,9 @@ def factor_inplace(S: torch.Tensor, n: int, what: str = "matrix") -> dict:
     d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"], d["n"] = (
         S.data_ptr(), S.stride(0), ws["Linv"].data_ptr(), ws["P"].data_ptr(), ldp, ws["info"].data_ptr(), n)
     dt = _desc_tensor(d, S.device)
-    check(lib().gmg_potrf_batched_f64(dt.data_ptr(), 1, n, dev.stream_ptr()), "gmg_potrf_batched_f64")
+    # look-ahead factorisation (gmg_potrf_solve_f64 with no right-hand sides): same tiles, same arithmetic as
+    # gmg_potrf_batched_f64, the diagonal-block / panel chain overlapped with the bulk of the trailing update
+    check(lib().gmg_potrf_solve_f64(None, dt.data_ptr(), 1, n, 0, None, 0, dev.stream_ptr()), "gmg_potrf_solve_f64")
     code = int(ws["info"].item())
     if code != 0:
         raise np.linalg.LinAlgError(
@@ -526,7 +528,14 @@ class KrigeBatch:
         C, M, ldc = self.cov.data_ptr(), self.M, self.cov.stride(0)
         self.full[:] = False
         check(L.gmg_krige_gather_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, s), "gather")
-        check(L.gmg_potrf_batched_f64(self._sd.data_ptr(), self.B, self.n_max, s), "gmg_potrf_batched_f64")
+        # Cholesky and the forward triangular solve as ONE overlapped pipeline (gmg_potrf_solve_f64: the solve step of
+        # block row k starts as soon as diagonal block k exists, the serial diagonal-block kernel of the factorisation
+        # hides behind the GEMMs of the solve), then the apply pass - all enqueued before the factorisation status is
+        # read, so the common case (every system positive definite) has no host synchronisation inside it.  A system
+        # whose Cholesky failed produced garbage that the LU pass below overwrites.
+        check(L.gmg_potrf_solve_f64(None, self._sd.data_ptr(), self.B, self.n_max, self.nrhs, None, 0, s),
+              "gmg_potrf_solve_f64")
+        check(L.gmg_krige_apply_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, 1, s), "apply")
         info = _d2h_info(self.info)                  # synchronises: the factorisation outcome decides the path
         asym = np.asarray(self._asym, dtype=np.int64)
         if asym.size:
@@ -536,9 +545,6 @@ class KrigeBatch:
         bad = np.union1d(not_spd, asym)
         self.lu_fallback = bad.tolist()
         if bad.size == 0:
-            check(L.gmg_potrs_batched_f64(self._sd.data_ptr(), self.B, self.n_max, self.nrhs, 1, s),
-                  "gmg_potrs_batched_f64")
-            check(L.gmg_krige_apply_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, 1, s), "apply")
             return self
         if not allow_lu_fallback and not_spd.size:
             self.raise_if_not_spd(info)
@@ -558,14 +564,7 @@ class KrigeBatch:
         check(L.gmg_krige_gather_batched_f64(C, M, ldc, kd_bad.data_ptr(), int(bad.size), n_bad, s), "gather")
         check(L.gmg_gesv_batched_f64(sd_bad.data_ptr(), int(bad.size), self.nrhs, s), "gmg_gesv_batched_f64")
         check(L.gmg_krige_apply_batched_f64(C, M, ldc, kd_bad.data_ptr(), int(bad.size), n_bad, 0, s), "apply")
-        self.full[bad] = True
-        if good.size:
-            kd_good = _desc_tensor(self._kd_np[good], self.cov.device)
-            sd_good = _desc_tensor(self._sd_np[good], self.cov.device)
-            n_good = max(self.ns[int(b)] for b in good)
-            check(L.gmg_potrs_batched_f64(sd_good.data_ptr(), int(good.size), n_good, self.nrhs, 1, s),
-                  "gmg_potrs_batched_f64")
-            check(L.gmg_krige_apply_batched_f64(C, M, ldc, kd_good.data_ptr(), int(good.size), n_good, 1, s), "apply")
+        self.full[bad] = True                        # (the good systems were completed by the overlapped pass above)
         if np.any(_d2h_info(self.info)):             # also synchronises before the temporaries die
             raise np.linalg.LinAlgError("Singular matrix")
         return self
@@ -621,19 +620,55 @@ class KrigeBatch:
         return W
 
 
+_DIST_CTX: dict = {}
+
+
+def dist_context(group=None):
+    """The library's communicator handle (`gmg_dist_init`) for the ranks of `group` (default: the world group), created
+    on first use - one rank draws the NCCL unique id (`gmg_dist_unique_id`), `torch.distributed` carries its 128 bytes
+    to the others (plumbing), every rank joins - and kept for the life of the process.  None for a single rank."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    key = id(group) if group is not None else 0
+    if key not in _DIST_CTX:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        on_gpu = dist.get_backend(group) == "nccl"
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = ctypes.create_string_buffer(128)
+            check(lib().gmg_dist_unique_id(raw), "gmg_dist_unique_id")
+            uid = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        if on_gpu:
+            uid = uid.cuda()
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(uid, src=src, group=group)
+        handle = ctypes.c_void_p()
+        torch.cuda.synchronize()
+        check(lib().gmg_dist_init(uid.cpu().numpy().tobytes(), world, rank, ctypes.byref(handle)), "gmg_dist_init")
+        _DIST_CTX[key] = handle
+    return _DIST_CTX[key]
+
+
+def _dist_workspace(n: int, world: int, device) -> torch.Tensor | None:
+    need = ctypes.c_int64()
+    check(lib().gmg_dist_ws_doubles(n, world, ctypes.byref(need)), "gmg_dist_ws_doubles")
+    return torch.empty(max(need.value, 2), dtype=torch.float64, device=device) if need.value else None
+
+
 def factor_inplace_distributed(S: torch.Tensor, n: int, group=None, what: str = "matrix") -> dict:
     """The blocked Cholesky of `factor_inplace` spread over the ranks of `group` (one process per GPU).
 
     S is REPLICATED (every rank holds the same n x n matrix) and ends up holding the complete factor on every rank,
-    which is what the column-sharded triangular solve needs.  Ownership is 1-D block-cyclic by tile row
-    (row block r belongs to rank r % world):  per block step the owner factors + inverts the 128 x 128 diagonal
-    block and broadcasts it (256 KB); every rank forms ITS rows of the panel L21 = S21 L11^-T; one NCCL all_reduce
-    of the zero-padded panel (<= (n - 128 k) x 128 doubles) gives everyone the whole panel - each element has
-    exactly one non-zero contributor, so the sum is exact; every rank then updates its own tile rows of the
-    trailing matrix.  Same kernels, same per-tile arithmetic as the single-GPU path: the factor is bit-identical."""
+    which is what the column-sharded triangular solve needs.  Ownership is 1-D block-cyclic by tile row (row block r
+    belongs to rank r % world).  The whole block loop runs inside the library (`gmg_potrf_solve_f64` on a
+    `gmg_dist_init` handle): per block step the owner factors + inverts the 128 x 128 diagonal block and broadcasts it
+    (256 KB), every rank forms and packs ITS tile rows of the panel, one all-gather of the packed tiles gives everyone
+    the whole panel, every rank updates its own tile rows - the next panel column first (look-ahead), the rest on a
+    second stream.  Same kernels, same per-tile arithmetic as the single-GPU path: the factor is bit-identical."""
     import torch.distributed as dist
 
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
     assert S.is_cuda and S.dtype == torch.float64 and S.stride(1) == 1 and S.stride(0) % 2 == 0
     lin, pdb, ldp = solve_ws(n)
     ws = {"Linv": torch.empty(lin, dtype=torch.float64, device=S.device),
@@ -643,42 +678,27 @@ def factor_inplace_distributed(S: torch.Tensor, n: int, group=None, what: str = 
     d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"], d["n"] = (
         S.data_ptr(), S.stride(0), ws["Linv"].data_ptr(), ws["P"].data_ptr(), ldp, ws["info"].data_ptr(), n)
     dt = _desc_tensor(d, S.device)
-    L, s = lib(), dev.stream_ptr()
-    nblk = (n + NB - 1) // NB
-    rows = torch.arange(n, device=S.device)
-    mine = ((rows // NB) % world == rank).to(torch.float64).unsqueeze(1)      # 1.0 on the tile rows this rank owns
-    blockbuf = torch.empty((2, NB, NB), dtype=torch.float64, device=S.device)
-    Linv = ws["Linv"].view(nblk, NB, NB)
-    for k in range(nblk):
-        k0 = k * NB
-        nb = min(NB, n - k0)
-        owner = k % world
-        if rank == owner:
-            check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 0, 1, 0, s), "gmg_potrf_step_f64")
-            blockbuf.zero_()
-            blockbuf[0, :nb, :nb] = S[k0:k0 + nb, k0:k0 + nb]
-            blockbuf[1] = Linv[k]
-        dist.broadcast(blockbuf, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-        if rank != owner:
-            S[k0:k0 + nb, k0:k0 + nb] = blockbuf[0, :nb, :nb]
-            Linv[k] = blockbuf[1]
-        m = n - k0 - NB
-        if m <= 0:
-            break
-        check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 1, world, rank, s), "gmg_potrf_step_f64")
-        panel = S[k0 + NB:n, k0:k0 + NB]
-        buf = panel * mine[k0 + NB:n]                     # own rows, zeros elsewhere (contiguous copy)
-        dist.all_reduce(buf, group=group)
-        panel.copy_(buf)
-        check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 2, world, rank, s), "gmg_potrf_step_f64")
-    info = ws["info"].clone()
-    dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
+    ctx = dist_context(group)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    xbuf = _dist_workspace(n, world, S.device)
+    check(lib().gmg_potrf_solve_f64(ctx, dt.data_ptr(), 1, n, 0, xbuf.data_ptr() if xbuf is not None else None,
+                                    xbuf.numel() if xbuf is not None else 0, dev.stream_ptr()), "gmg_potrf_solve_f64")
+    _raise_unless_spd(ws["info"], n, group, what)
+    return ws
+
+
+def _raise_unless_spd(info_t: torch.Tensor, n: int, group, what: str) -> None:
+    """Factorisation status of a (possibly distributed) factorisation: only the owner of a block sees its pivots."""
+    import torch.distributed as dist
+
+    info = info_t.clone()
+    if dist.is_initialized() and group is not False and dist.get_world_size(group) > 1:
+        dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
     code = int(info.item())
     if code != 0:
         raise np.linalg.LinAlgError(
             f"{what} is not positive definite (Cholesky pivot {code} of {n} is not positive); "
             "apply glomar_gridding.covariance_tools.eigenvalue_clip or use delta_x_method='Met_Office'")
-    return ws
 
 
 def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.Tensor, ldc: int, y: torch.Tensor,
@@ -705,14 +725,11 @@ def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.T
     if timing:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-    if group is not False and dist.is_initialized() and dist.get_world_size(group) > 1:
-        ws = factor_inplace_distributed(S, n, group, "observation covariance C[idx, idx] + E")
-    else:
-        ws = factor_inplace(S, n, "observation covariance C[idx, idx] + E")
-    if timing:
-        torch.cuda.synchronize()
-        if not dist.is_initialized() or dist.get_rank() == 0:
-            print(f"[solve_prepared] Cholesky n = {n}: {1e3 * (time.perf_counter() - t0):.1f} ms", flush=True)
+    distributed = group is not False and dist.is_initialized() and dist.get_world_size(group) > 1
+    lin, pdb, ldp = solve_ws(n)
+    ws = {"Linv": torch.empty(lin, dtype=torch.float64, device=S.device),
+          "P": torch.empty(pdb, dtype=torch.float64, device=S.device),
+          "info": torch.zeros(1, dtype=torch.int32, device=S.device), "ldp": ldp}
     slabs = (n + SLAB - 1) // SLAB
     partial = torch.empty(4 * slabs * Mc, dtype=torch.float64, device=S.device)
     out = torch.empty((5, Mc), dtype=torch.float64, device=S.device)
@@ -724,7 +741,18 @@ def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.T
              int(ordinary))
     sdt, kdt = _desc_tensor(sd, S.device), _desc_tensor(kd, S.device)
     L, s = lib(), dev.stream_ptr()
-    check(L.gmg_potrs_batched_f64(sdt.data_ptr(), 1, n, Mc + 2, 1, s), "gmg_potrs_batched_f64")
+    ctx = dist_context(group) if distributed else None
+    xbuf = _dist_workspace(n, dist.get_world_size(group), S.device) if distributed else None
+    # factorisation (distributed over the ranks, or local) and the forward solve of this rank's columns as one
+    # overlapped pipeline, then the apply pass; the status is read afterwards
+    check(L.gmg_potrf_solve_f64(ctx, sdt.data_ptr(), 1, n, Mc + 2, xbuf.data_ptr() if xbuf is not None else None,
+                                xbuf.numel() if xbuf is not None else 0, s), "gmg_potrf_solve_f64")
     check(L.gmg_krige_apply_batched_f64(diag_base.data_ptr(), Mc, ldc, kdt.data_ptr(), 1, n, 1, s), "apply")
+    _raise_unless_spd(ws["info"], n, group if distributed else False, "observation covariance C[idx, idx] + E")
+    if timing:
+        torch.cuda.synchronize()
+        if not dist.is_initialized() or dist.get_rank() == 0:
+            print(f"[solve_prepared] factor + forward solve + apply, n = {n}: {1e3 * (time.perf_counter() - t0):.1f} ms",
+                  flush=True)
     torch.cuda.current_stream().synchronize()
     return out

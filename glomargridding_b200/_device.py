@@ -16,14 +16,16 @@ def require_cuda() -> torch.device:
 
 def host_threads(cap: int) -> int:
     """Worker threads for host-side packing / bookkeeping: the cores of the box divided by the ranks that share
-    it (`LOCAL_WORLD_SIZE`, set by torchrun - one process per GPU), one left free, at most `cap`."""
+    it (`LOCAL_WORLD_SIZE`, set by torchrun - one process per GPU), one left free when a rank has more than two, at
+    most `cap`.  (The thread that waits for the pool is idle, so two cores per rank give two packing threads.)"""
     import os
 
     try:
         ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
     except ValueError:
         ranks = 1
-    return max(1, min(cap, (os.cpu_count() or 2) // ranks - 1))
+    share = (os.cpu_count() or 2) // ranks
+    return max(1, min(cap, share - 1 if share > 2 else share))
 
 
 def stream_ptr() -> int:

@@ -19,6 +19,7 @@ const char* gmg_strerror(int code) {
         case GMG_ERR_WORKSPACE: return "workspace too small or misaligned";
         case GMG_ERR_UNSUPPORTED: return "unsupported argument combination";
         case GMG_ERR_SINGULAR: return "matrix is singular (zero LU pivot)";
+        case GMG_ERR_COMM: return "NCCL is not loaded in this process or a collective call failed";
         default: return "unknown error";
     }
 }

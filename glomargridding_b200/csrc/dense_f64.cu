@@ -13,6 +13,9 @@
 // One descriptor per system (device memory, uploaded by the caller); every kernel takes the descriptor
 // array and the block step, so a batch of 480 months with different observation counts runs as ONE launch
 // per step (blockIdx.z = system), not as 480 streams of small launches.
+#include <dlfcn.h>
+#include <mutex>
+#include <vector>
 #include "gmg_common.cuh"
 #include "dense_f64.cuh"
 #include "../../include/glomar_b200.h"
@@ -213,8 +216,11 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
 // grid = (ceil((n_max - k0 - NB) / BM), 1, batch)
 // (tr_mod, tr_rem): only tile rows with (global tile row) % tr_mod == tr_rem are processed - the 1-D block-cyclic
 // ownership of the multi-GPU factorisation (tr_mod = 1: every row).
+// `pack` (optional, batch 1): the tiles this rank computes are ALSO written, tile after tile (128 x 128 doubles each,
+// leading dimension 128), into the send buffer of the panel exchange - the j-th tile row this rank owns below the
+// diagonal goes to pack + j * 128 * 128 (see `panel_unpack_kernel` for the receiving side).
 __global__ void __launch_bounds__(GEMM_THREADS) potrf_panel_kernel(const GmgSolveDesc* __restrict__ descs, int kblk,
-                                                                   int tr_mod, int tr_rem) {
+                                                                   int tr_mod, int tr_rem, double* pack) {
     if ((kblk + 1 + (int)blockIdx.x) % tr_mod != tr_rem) return;
     const GmgSolveDesc d = descs[blockIdx.z];
     const int k0 = kblk * NB;
@@ -231,19 +237,72 @@ __global__ void __launch_bounds__(GEMM_THREADS) potrf_panel_kernel(const GmgSolv
     g.D = const_cast<double*>(g.A); g.ldd = d.lds;
     g.m = m; g.n = NB; g.k = NB;
     g.alpha = 1.0; g.beta = 0.0;
+    if (pack) {
+        const int x0 = ((tr_rem - (kblk + 1)) % tr_mod + tr_mod) % tr_mod;     // first tile row below the diagonal it owns
+        const int j = ((int)blockIdx.x - x0) / tr_mod;
+        g.D2 = pack + (int64_t)j * NB * NB - (int64_t)m0 * NB;                  // gemm_tile indexes rows from the panel top
+        g.ldd2 = NB;
+    }
     gemm_tile<false, true>(g, m0, 0, sm);
+}
+
+// Receiving side of the panel exchange (all_gather of the packed tiles): recv = [rank q][j-th owned tile][128 x 128];
+// every tile row below the diagonal that ANOTHER rank owns is copied into the panel column of this rank's S.
+// grid = (tile rows below the diagonal, 1, 1), 256 threads.
+__global__ void __launch_bounds__(256) panel_unpack_kernel(const GmgSolveDesc* __restrict__ descs, int kblk,
+                                                           const double* __restrict__ recv, int world, int rank,
+                                                           int64_t cap) {
+    const GmgSolveDesc d = descs[0];
+    const int x = blockIdx.x;
+    const int t = kblk + 1 + x;
+    const int q = t % world;
+    if (q == rank) return;
+    const int x0 = ((q - (kblk + 1)) % world + world) % world;
+    const int j = (x - x0) / world;
+    const double* src = recv + ((int64_t)q * cap + j) * NB * NB;
+    const int rows = min(NB, d.n - t * NB);
+    double* dst = d.S + (int64_t)t * NB * d.lds + (int64_t)kblk * NB;
+    for (int e = threadIdx.x; e < rows * (NB / 2); e += 256) {
+        const int i = e / (NB / 2), c2 = e % (NB / 2);
+        *reinterpret_cast<double2*>(dst + (int64_t)i * d.lds + 2 * c2) = *reinterpret_cast<const double2*>(src + i * NB + 2 * c2);
+    }
+}
+
+// Diagonal exchange: buf = [L_kk as a full 128 x 128 block (zeros above the diagonal / outside a partial block) |
+// Linv_k].  unpack = 0: the owner fills buf from its S and Linv; unpack = 1: the others write buf into theirs.
+// grid = (64, 1, 1), 256 threads.
+__global__ void __launch_bounds__(256) diag_xchg_kernel(const GmgSolveDesc* __restrict__ descs, int kblk,
+                                                        double* __restrict__ buf, int unpack) {
+    const GmgSolveDesc d = descs[0];
+    const int k0 = kblk * NB;
+    const int nb = min(NB, d.n - k0);
+    double* X = d.Linv + (int64_t)kblk * NB * NB;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < NB * NB; e += gridDim.x * 256) {
+        const int i = e / NB, j = e % NB;
+        const bool inside = i < nb && j <= i;
+        if (!unpack) {
+            buf[e] = inside ? d.S[(int64_t)(k0 + i) * d.lds + k0 + j] : 0.0;
+            buf[NB * NB + e] = X[e];
+        } else {
+            if (inside) d.S[(int64_t)(k0 + i) * d.lds + k0 + j] = buf[e];
+            X[e] = buf[NB * NB + e];
+        }
+    }
 }
 
 // ---- trailing update: S22 -= L21 L21^T, lower tiles only ---------------------------------------------------
 // grid = (tiles, tiles, batch) with tiles = ceil((n_max - k0 - NB) / BM); tiles above the diagonal exit.
+// x_off: first column tile of this launch (the look-ahead split of the overlapped driver: column tile 0 - the next
+// panel - is updated on the critical-path stream, column tiles 1.. on another one).
 __global__ void __launch_bounds__(GEMM_THREADS) potrf_update_kernel(const GmgSolveDesc* __restrict__ descs, int kblk,
-                                                                    int tr_mod, int tr_rem) {
-    if (blockIdx.x > blockIdx.y) return;         // x = column tile, y = row tile: keep the lower triangle
+                                                                    int tr_mod, int tr_rem, int x_off) {
+    const int cx = (int)blockIdx.x + x_off;
+    if (cx > (int)blockIdx.y) return;            // cx = column tile, y = row tile: keep the lower triangle
     if ((kblk + 1 + (int)blockIdx.y) % tr_mod != tr_rem) return;
     const GmgSolveDesc d = descs[blockIdx.z];
     const int k0 = kblk * NB;
     const int m = d.n - k0 - NB;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * BM, n0 = cx * BN;
     if (m <= 0 || m0 >= m || n0 >= m) return;
     extern __shared__ __align__(16) double sm[];
     TileArgs g;
@@ -454,9 +513,9 @@ int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, g
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
         if (rem <= 0) break;
         const unsigned tiles = (unsigned)gmg_ceil_div(rem, BM);
-        potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, 1, 0);
+        potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, 1, 0, nullptr);
         GMG_LAUNCH_CHECK();
-        potrf_update_kernel<<<dim3(tiles, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, 1, 0);
+        potrf_update_kernel<<<dim3(tiles, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, 1, 0, 0);
         GMG_LAUNCH_CHECK();
     }
     return GMG_OK;
@@ -468,7 +527,7 @@ int gmg_potrf_step_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int 
     if (batch <= 0 || batch > 65535) return -2;
     if (n_max <= 0 || n_max > 0x7fffffff) return -3;
     if (kblk < 0 || (int64_t)kblk * NB >= n_max) return -4;
-    if (phase < GMG_POTRF_DIAG || phase > GMG_POTRF_UPDATE) return -5;
+    if (phase < GMG_POTRF_DIAG || phase > GMG_POTRF_UPDATE_REST) return -5;
     if (tr_mod < 1 || tr_rem < 0 || tr_rem >= tr_mod) return -6;
     int rc = ensure_attrs();
     if (rc) return rc;
@@ -480,9 +539,13 @@ int gmg_potrf_step_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int 
     } else if (tiles == 0) {
         return GMG_OK;
     } else if (phase == GMG_POTRF_PANEL) {
-        potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem);
-    } else {
-        potrf_update_kernel<<<dim3(tiles, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem);
+        potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem, nullptr);
+    } else if (phase == GMG_POTRF_UPDATE) {
+        potrf_update_kernel<<<dim3(tiles, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem, 0);
+    } else if (phase == GMG_POTRF_UPDATE_NEXT) {         // column tile 0 only: what the next panel needs
+        potrf_update_kernel<<<dim3(1, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem, 0);
+    } else if (tiles > 1) {                              // GMG_POTRF_UPDATE_REST: column tiles 1..
+        potrf_update_kernel<<<dim3(tiles - 1, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem, 1);
     }
     GMG_LAUNCH_CHECK();
     return GMG_OK;
@@ -527,6 +590,281 @@ int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, i
         GMG_LAUNCH_CHECK();
     }
     return GMG_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Overlapped factor + forward solve, one GPU or the ranks of one box (gmg_dist_* / gmg_potrf_solve_f64)
+// =====================================================================================================================
+// The right-looking factorisation has a latency-bound critical path (diagonal block -> panel -> update of the NEXT panel
+// column) next to bulk work that nothing waits for immediately (the rest of the trailing update), and the forward
+// triangular solve of block row k only needs row k of L and the inverted diagonal block k - both final as soon as
+// step k's diagonal block is done.  So the driver below runs three streams:
+//   F (high priority)  diagonal block, [exchange], panel, [exchange], update of column tile k+1 (look-ahead)
+//   R                  update of column tiles k+2.. of step k               (waits for panel k; F's step k+1 look-ahead
+//                                                                            waits for it: per-tile update order kept)
+//   U (low priority)   forward-solve step k = prep + one GEMM               (waits for diagonal block k)
+// Every tile receives the same updates in the same order as in gmg_potrf_batched_f64 + gmg_potrs_batched_f64, so the
+// factor and the solved right-hand sides are bit-identical to the sequential path - on any number of ranks.
+// Multi-GPU (one process per GPU, 1-D block-cyclic tile rows): the owner of block k broadcasts [L_kk | Linv_k]
+// (256 KB), every rank forms its tile rows of the panel and packs them, ONE all_gather of the packed tiles gives
+// everyone the whole panel.  The collectives are NCCL calls issued from this C loop on stream F (no Python, no
+// per-step host synchronisation); NCCL is resolved at run time from the libnccl.so.2 the process already has loaded
+// (PyTorch's), so the library has no link-time dependency on it.
+namespace {
+
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+    int (*GetUniqueId)(NcclUid*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    bool ok = false;
+};
+constexpr int kNcclFloat64 = 8;      // ncclDouble / ncclFloat64 of nccl.h
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy PyTorch brought in, if any
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+        api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(h, "ncclBroadcast"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.AllGather;
+    });
+    return api;
+}
+
+struct DistCtx {
+    int world = 1, rank = 0, device = 0;
+    void* comm = nullptr;
+    cudaStream_t sF = nullptr, sR = nullptr, sU = nullptr;
+    std::vector<cudaEvent_t> events;
+    std::mutex mu;                       // one factorisation at a time per context
+};
+
+int ctx_streams(DistCtx* c) {
+    GMG_CUDA_CHECK(cudaGetDevice(&c->device));
+    int lo = 0, hi = 0;                  // lo = lowest priority (largest number), hi = highest
+    GMG_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const int mid = (lo + hi) / 2;
+    GMG_CUDA_CHECK(cudaStreamCreateWithPriority(&c->sF, cudaStreamNonBlocking, hi));
+    GMG_CUDA_CHECK(cudaStreamCreateWithPriority(&c->sR, cudaStreamNonBlocking, mid));
+    GMG_CUDA_CHECK(cudaStreamCreateWithPriority(&c->sU, cudaStreamNonBlocking, lo));
+    return GMG_OK;
+}
+
+int ctx_event(DistCtx* c, size_t i, cudaEvent_t* out) {
+    while (c->events.size() <= i) {
+        cudaEvent_t e;
+        GMG_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->events.push_back(e);
+    }
+    *out = c->events[i];
+    return GMG_OK;
+}
+
+// process-wide context of the plain single-GPU calls, one per device
+DistCtx* local_ctx() {
+    static std::mutex mu;
+    static DistCtx* ctxs[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ctxs[dev]) {
+        DistCtx* c = new DistCtx();
+        if (ctx_streams(c) != GMG_OK) { delete c; return nullptr; }
+        ctxs[dev] = c;
+    }
+    return ctxs[dev];
+}
+
+inline int64_t panel_cap(int64_t n, int world) {           // packed tiles per rank in the largest (first) panel
+    const int64_t nblk = gmg_ceil_div(n, NB);
+    return nblk > 1 ? gmg_ceil_div(nblk - 1, world) : 1;
+}
+
+#define GMG_NCCL_CHECK(expr)                                 \
+    do {                                                     \
+        if ((expr) != 0) return GMG_ERR_COMM;                \
+    } while (0)
+
+int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max, double* xbuf,
+                 cudaStream_t caller) {
+    const int world = c->world, rank = c->rank;
+    const int nblk = (int)gmg_ceil_div(n_max, NB);
+    NcclApi& nc = nccl_api();
+    double* dbuf = xbuf;                                   // [2][NB][NB]
+    const int64_t cap0 = panel_cap(n_max, world);
+    double* sendbuf = xbuf ? xbuf + 2 * NB * NB : nullptr; // [cap0][NB][NB]
+    double* recvbuf = xbuf ? sendbuf + cap0 * NB * NB : nullptr;   // [world][cap][NB][NB], cap = this step's
+    int sms = 0;
+    GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const bool narrow = nrhs_max > 0 && gmg_ceil_div(nrhs_max, BN) * (int64_t)batch * 4 < (int64_t)sms * 3;
+    const unsigned rhs_tiles = nrhs_max > 0 ? (unsigned)gmg_ceil_div(nrhs_max, narrow ? 64 : BN) : 0;
+
+    size_t ne = 0;
+    cudaEvent_t ev_fork, ev;
+    int rc;
+    if ((rc = ctx_event(c, ne++, &ev_fork))) return rc;
+    GMG_CUDA_CHECK(cudaEventRecord(ev_fork, caller));
+    GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sF, ev_fork, 0));
+    GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sR, ev_fork, 0));
+    GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sU, ev_fork, 0));
+    cudaEvent_t ev_rest_prev = nullptr;
+    for (int k = 0; k < nblk; ++k) {
+        const int owner = k % world;
+        // ---- F: diagonal block (its column was brought up to date by the look-ahead update of step k - 1) ----------
+        if (rank == owner) {
+            potrf_diag_kernel<<<dim3(1, 1, batch), DIAG_THREADS, DIAG_SMEM, c->sF>>>(descs, k);
+            GMG_LAUNCH_CHECK();
+        }
+        if (world > 1) {
+            if (rank == owner) {
+                diag_xchg_kernel<<<64, 256, 0, c->sF>>>(descs, k, dbuf, 0);
+                GMG_LAUNCH_CHECK();
+            }
+            GMG_NCCL_CHECK(nc.Broadcast(dbuf, dbuf, (size_t)2 * NB * NB, kNcclFloat64, owner, c->comm, c->sF));
+            if (rank != owner) {
+                diag_xchg_kernel<<<64, 256, 0, c->sF>>>(descs, k, dbuf, 1);
+                GMG_LAUNCH_CHECK();
+            }
+        }
+        // ---- U: forward-solve step k ---------------------------------------------------------------------------------
+        if (nrhs_max > 0) {
+            if ((rc = ctx_event(c, ne++, &ev))) return rc;
+            GMG_CUDA_CHECK(cudaEventRecord(ev, c->sF));
+            GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sU, ev, 0));
+            trsm_prep_fwd_kernel<<<dim3((unsigned)k + 1, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sU>>>(descs, k);
+            GMG_LAUNCH_CHECK();
+            if (narrow)
+                trsm_step_fwd_kernel<64><<<dim3(rhs_tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sU>>>(descs, k);
+            else
+                trsm_step_fwd_kernel<128><<<dim3(rhs_tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sU>>>(descs, k);
+            GMG_LAUNCH_CHECK();
+        }
+        const int64_t rem = n_max - (int64_t)(k + 1) * NB;
+        if (rem <= 0) break;
+        const unsigned tiles = (unsigned)gmg_ceil_div(rem, BM);
+        // ---- F: panel (own tile rows), exchange ------------------------------------------------------------------------
+        potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sF>>>(
+            descs, k, world, rank, world > 1 ? sendbuf : nullptr);
+        GMG_LAUNCH_CHECK();
+        if (world > 1) {
+            const int64_t cap = gmg_ceil_div((int64_t)tiles, world);
+            GMG_NCCL_CHECK(nc.AllGather(sendbuf, recvbuf, (size_t)cap * NB * NB, kNcclFloat64, c->comm, c->sF));
+            panel_unpack_kernel<<<tiles, 256, 0, c->sF>>>(descs, k, recvbuf, world, rank, cap);
+            GMG_LAUNCH_CHECK();
+        }
+        // ---- R: trailing update of column tiles k + 2 .. ------------------------------------------------------------
+        cudaEvent_t ev_rest = nullptr;
+        if (tiles > 1) {
+            if ((rc = ctx_event(c, ne++, &ev))) return rc;
+            GMG_CUDA_CHECK(cudaEventRecord(ev, c->sF));                        // the whole panel is in S
+            GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sR, ev, 0));
+            potrf_update_kernel<<<dim3(tiles - 1, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sR>>>(
+                descs, k, world, rank, 1);
+            GMG_LAUNCH_CHECK();
+            if ((rc = ctx_event(c, ne++, &ev_rest))) return rc;
+            GMG_CUDA_CHECK(cudaEventRecord(ev_rest, c->sR));
+        }
+        // ---- F: look-ahead - column tile k + 1, after every earlier update of it (rest of step k - 1) ------------------
+        if (ev_rest_prev) GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sF, ev_rest_prev, 0));
+        potrf_update_kernel<<<dim3(1, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sF>>>(descs, k, world, rank, 0);
+        GMG_LAUNCH_CHECK();
+        ev_rest_prev = ev_rest;
+    }
+    // join: the caller's stream continues when all three are done
+    for (cudaStream_t s : {c->sF, c->sR, c->sU}) {
+        if ((rc = ctx_event(c, ne++, &ev))) return rc;
+        GMG_CUDA_CHECK(cudaEventRecord(ev, s));
+        GMG_CUDA_CHECK(cudaStreamWaitEvent(caller, ev, 0));
+    }
+    return GMG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gmg_dist_unique_id(void* id128) {
+    if (!id128) return -1;
+    NcclApi& nc = nccl_api();
+    if (!nc.ok) return GMG_ERR_COMM;
+    NcclUid uid;
+    if (nc.GetUniqueId(&uid) != 0) return GMG_ERR_COMM;
+    memcpy(id128, &uid, sizeof(uid));
+    return GMG_OK;
+}
+
+int gmg_dist_init(const void* id128, int world, int rank, void** ctx) {
+    if (world < 1 || world > 64) return -2;
+    if (rank < 0 || rank >= world) return -3;
+    if (!ctx) return -4;
+    if (world > 1 && !id128) return -1;
+    DistCtx* c = new DistCtx();
+    c->world = world;
+    c->rank = rank;
+    int rc = ctx_streams(c);
+    if (rc) { delete c; return rc; }
+    if (world > 1) {
+        NcclApi& nc = nccl_api();
+        NcclUid uid;
+        memcpy(&uid, id128, sizeof(uid));
+        if (!nc.ok || nc.CommInitRank(&c->comm, world, uid, rank) != 0) { delete c; return GMG_ERR_COMM; }
+    }
+    *ctx = c;
+    return GMG_OK;
+}
+
+int gmg_dist_destroy(void* ctx) {
+    if (!ctx) return -1;
+    DistCtx* c = static_cast<DistCtx*>(ctx);
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    for (cudaStream_t s : {c->sF, c->sR, c->sU})
+        if (s) cudaStreamDestroy(s);
+    delete c;
+    return GMG_OK;
+}
+
+int gmg_dist_ws_doubles(int64_t n, int world, int64_t* doubles) {
+    if (n <= 0) return -1;
+    if (world < 1) return -2;
+    if (!doubles) return -3;
+    *doubles = world > 1 ? (int64_t)NB * NB * (2 + panel_cap(n, world) * (1 + world)) : 0;
+    return GMG_OK;
+}
+
+int gmg_potrf_solve_f64(void* ctx, const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max,
+                        double* xbuf, int64_t xbuf_doubles, gmg_stream_t stream) {
+    if (!descs) return -2;
+    if (batch <= 0 || batch > 65535) return -3;
+    if (n_max <= 0 || n_max > 0x7fffffff) return -4;
+    if (nrhs_max < 0 || nrhs_max > 0x7fffffff) return -5;
+    DistCtx* c = ctx ? static_cast<DistCtx*>(ctx) : local_ctx();
+    if (!c) return GMG_ERR_CUDA;
+    if (c->world > 1) {
+        if (batch != 1) return GMG_ERR_UNSUPPORTED;
+        int64_t need = 0;
+        gmg_dist_ws_doubles(n_max, c->world, &need);
+        if (!xbuf || xbuf_doubles < need || (reinterpret_cast<uintptr_t>(xbuf) & 15)) return GMG_ERR_WORKSPACE;
+    }
+    int rc = ensure_attrs();
+    if (rc) return rc;
+    int dev = 0;
+    GMG_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev != c->device) return GMG_ERR_UNSUPPORTED;     // a context belongs to the device it was created on
+    std::lock_guard<std::mutex> lock(c->mu);
+    return factor_solve(c, descs, batch, n_max, nrhs_max, xbuf, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -38,6 +38,8 @@ struct TileArgs {
     int m, n, k;
     int64_t lda, ldb, ldc, ldd;
     double alpha, beta;
+    double* D2 = nullptr;   // optional second copy of the result tile (D2[row * ldd2 + col], same row / col indices as D):
+    int64_t ldd2 = 0;       // the panel kernel of the distributed factorisation packs its tiles for the exchange with it
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
@@ -173,6 +175,11 @@ __device__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
                     if (g.beta != 0.0) v1 = fma(g.beta, g.C[(int64_t)row * g.ldc + col + 1], v1);
                     d[1] = v1;
                 }
+            }
+            if (g.D2) {
+                double* d2 = g.D2 + (int64_t)row * g.ldd2 + col;
+                d2[0] = v0;
+                if (col + 1 < g.n) d2[1] = v1;
             }
         }
     }

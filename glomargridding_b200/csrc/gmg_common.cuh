@@ -13,6 +13,7 @@ enum GmgStatus : int {
     GMG_ERR_WORKSPACE = 3,     // workspace too small / misaligned
     GMG_ERR_UNSUPPORTED = 4,   // argument combination not supported
     GMG_ERR_SINGULAR = 5,      // LU met an exactly zero pivot
+    GMG_ERR_COMM = 6,          // NCCL is not available in the process or a collective call failed
 };
 
 extern thread_local int g_gmg_last_cuda_error;

@@ -35,46 +35,76 @@ def assemble_obs_system(cov_rows: torch.Tensor, r0: int, idx: torch.Tensor, erro
     rows each rank contributes are contiguous in S).  `error_cov` (n x n, host numpy or tensor, identical on every
     rank, or None): each rank adds - and, for a host array, uploads - only the rows of E that belong to the
     observations it owns, so the host-to-device traffic of E is split across the ranks instead of repeated on each.
-    Works on any device / backend (gloo test on CPU)."""
+    Works on any device / backend (gloo test on CPU).
+
+    The upload of this rank's rows of E runs on a side stream while the rank cuts its rows of C[idx, idx] out of its
+    row block; the only exchange is ONE all-gather, straight into the buffer that becomes S (rows padded to the
+    largest per-rank count, compacted in place when the counts differ)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n = idx.numel()
     nrows = cov_rows.shape[0]
     mine = (idx >= r0) & (idx < r0 + nrows)
-    piece = cov_rows[(idx[mine] - r0).unsqueeze(1), idx.unsqueeze(0)]        # (n_mine, n), one fused gather
-    if error_cov is not None:
-        own = torch.nonzero(mine).flatten()
-        lo, hi = (int(own[0]), int(own[-1]) + 1) if own.numel() else (0, 0)
-        contiguous = own.numel() == hi - lo                                  # always, for sorted idx and row blocks
+    own = torch.nonzero(mine).flatten()
+    lo, hi = (int(own[0]), int(own[-1]) + 1) if own.numel() else (0, 0)
+    contiguous = own.numel() == hi - lo                                      # always, for sorted idx and row blocks
+    ldn = n + (n & 1)                                                        # even leading dimension (16-byte rows)
+    counts = [hi - lo]
+    if world > 1:
+        ct = torch.zeros(world, dtype=torch.int64, device=cov_rows.device)
+        ct[dist.get_rank(group)] = hi - lo
+        dist.all_reduce(ct, group=group)
+        counts = ct.cpu().tolist()
+    cap = max(counts)
+    rank = dist.get_rank(group) if world > 1 else 0
+    buf = torch.zeros((world * cap, ldn), dtype=cov_rows.dtype, device=cov_rows.device)
+    piece = buf[rank * cap: rank * cap + (hi - lo), :n]
+    if own.numel():
+        piece.copy_(cov_rows[(idx[own] - r0).unsqueeze(1), idx.unsqueeze(0)])   # (n_mine, n), one fused gather (async)
+    # ---- error-covariance rows of this rank: the upload (side stream; the host waits for it) overlaps the gather above --
+    e_rows, side = None, None
+    if error_cov is not None and own.numel():
         if isinstance(error_cov, torch.Tensor):
             e_rows = (error_cov[lo:hi] if contiguous else error_cov[own.to(error_cov.device)]).to(piece.device)
-        elif piece.is_cuda and own.numel():
+        elif piece.is_cuda:
             # host array: the rows of this rank's observations are one contiguous slice - a VIEW, packed into pinned
             # staging buffers by a thread pool while the previous buffer is in flight (`_dense._h2d_concat`); a
             # boolean-mask copy + pageable upload of the same 400 MB cost 0.13 s per rank at n = 20 000 on 8 GPUs
             E = np.asarray(error_cov)
             block = E[lo:hi] if contiguous else E[own.cpu().numpy()]
             slabs = [[block[r:r + 128]] for r in range(0, block.shape[0], 128)]      # one packing task per 128 rows
-            e_rows = dn._h2d_concat(slabs, int(block.size), piece.device).view(block.shape)
+            side = _upload_stream(piece.device)
+            with torch.cuda.stream(side):
+                e_rows = dn._h2d_concat(slabs, int(block.size), piece.device).view(block.shape)
         else:
             E = np.asarray(error_cov, dtype=np.float64)
             e_rows = torch.from_numpy(np.ascontiguousarray(E[lo:hi] if contiguous else E[own.cpu().numpy()])).to(piece.device)
+    if e_rows is not None:
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         piece += e_rows.to(piece.dtype)
-    if world == 1:
-        S = piece
-    else:
-        counts = torch.zeros(world, dtype=torch.int64, device=cov_rows.device)
-        counts[dist.get_rank(group)] = piece.shape[0]
-        dist.all_reduce(counts, group=group)
-        counts = counts.cpu().tolist()
-        cap = max(counts)
-        buf = torch.zeros((cap, n), dtype=cov_rows.dtype, device=cov_rows.device)
-        buf[: piece.shape[0]] = piece
-        parts = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(parts, buf, group=group)
-        S = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
-    if S.shape[0] != n:
+    if world > 1:
+        dist.all_gather_into_tensor(buf, buf[rank * cap:(rank + 1) * cap].clone(), group=group)
+    if sum(counts) != n:
         raise ValueError("the row blocks of the ranks do not cover every observation index")
-    return S
+    if all(c == cap for c in counts):
+        return buf[:n, :n]
+    # compact the padded blocks in place, front to back (block r moves up by the padding of the blocks before it)
+    pos = counts[0]
+    for r in range(1, world):
+        if counts[r]:
+            buf[pos:pos + counts[r]] = buf[r * cap:r * cap + counts[r]].clone() if r * cap < pos + counts[r] else buf[r * cap:r * cap + counts[r]]
+        pos += counts[r]
+    return buf[:n, :n]                                                       # view: row stride ldn (even)
+
+
+_UPLOAD_STREAMS: dict = {}
+
+
+def _upload_stream(device) -> torch.cuda.Stream:
+    key = (device.type, device.index)
+    if key not in _UPLOAD_STREAMS:
+        _UPLOAD_STREAMS[key] = torch.cuda.Stream(device)
+    return _UPLOAD_STREAMS[key]
 
 
 def local_rhs(cov_rows: torch.Tensor, idx: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
@@ -116,7 +146,7 @@ def krige_sharded(cov_rows: torch.Tensor, r0: int, idx, obs, error_cov=None, met
         raise ValueError("idx must be sorted ascending and unique for the sharded path")
     idx_t = torch.from_numpy(idx_np).to(device)
     y = torch.from_numpy(np.asarray(obs, dtype=np.float64)).to(device)
-    S = dn.padded(assemble_obs_system(cov_rows, r0, idx_t, error_cov, group))
+    S = assemble_obs_system(cov_rows, r0, idx_t, error_cov, group)       # rows of an even-stride buffer
     mark("assemble S (gather + E upload + all_gather)")
     T = local_rhs(cov_rows, idx_t, y)
     mark("local right-hand sides")

@@ -16,7 +16,7 @@
  *    default stream) and does not synchronise, except where documented.
  *  - Return value: 0 ok; negative = 1-based index of a bad argument; positive = failure class
  *    (1 CUDA error, 2 matrix not positive definite, 3 workspace too small, 4 unsupported,
- *    5 singular).  `gmg_strerror` / `gmg_last_cuda_error` give detail.  No exceptions, no exit().
+ *    5 singular, 6 NCCL unavailable / collective failed).  `gmg_strerror` / `gmg_last_cuda_error` give detail.  No exceptions, no exit().
  *  - Matrices are row-major (C order, numpy default) with an explicit leading dimension in
  *    elements.
  */
@@ -160,6 +160,8 @@ int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, g
 #define GMG_POTRF_DIAG 0
 #define GMG_POTRF_PANEL 1
 #define GMG_POTRF_UPDATE 2
+#define GMG_POTRF_UPDATE_NEXT 3 /* only the first column tile of the trailing matrix (what the next panel needs) */
+#define GMG_POTRF_UPDATE_REST 4 /* the other column tiles: NEXT + REST == UPDATE, the look-ahead split             */
 int gmg_potrf_step_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int kblk, int phase,
                        int tr_mod, int tr_rem, gmg_stream_t stream);
 
@@ -171,6 +173,29 @@ int gmg_potrf_step_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int 
 #define GMG_SOLVE_BOTH 3
 int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max,
                           int which, gmg_stream_t stream);
+
+/* Factorisation AND forward solve as one overlapped pipeline: S = L L^T and R <- L^-1 R (nrhs_max = 0: factor only)
+ * with exactly the arithmetic of gmg_potrf_batched_f64 followed by gmg_potrs_batched_f64(GMG_SOLVE_FORWARD) - results
+ * are bit-identical - but on three internal streams: the latency-bound critical path of the factorisation (diagonal
+ * block, panel, update of the next panel column), the bulk of the trailing update, and the forward-solve step of
+ * every block row as soon as its diagonal block exists.  The call only enqueues: the work starts after everything
+ * already in `stream`, and `stream` continues after all of it.
+ *
+ * Multi-GPU (the SURVEY 8b "gmg_dist_*" handles; replaces the LU inside np.linalg.solve, kriging.py:585, for a system
+ * that one GPU factors too slowly): one process per GPU, every rank holds a replica of S and ITS OWN columns of the
+ * right-hand sides.  Tile rows (128 rows) are owned block-cyclically, rank = tile row % world; per block step the owner
+ * broadcasts the factored + inverted diagonal block, every rank forms and packs its tile rows of the panel and one
+ * all-gather hands everyone the whole panel; all ranks end up with the complete factor.  The collectives are NCCL
+ * calls issued by this library on its own communicator: gmg_dist_unique_id (one rank) -> the caller distributes the
+ * 128 bytes -> gmg_dist_init on every rank (collective).  NCCL is taken from the libnccl.so.2 already loaded in the
+ * process; GMG_ERR_COMM (6) if there is none.  ctx = NULL: single GPU, no communication.
+ *   xbuf: device workspace of gmg_dist_ws_doubles(n_max, world) doubles (0 for one GPU), 16-byte aligned. */
+int gmg_dist_unique_id(void* id128);
+int gmg_dist_init(const void* id128, int world, int rank, void** ctx);
+int gmg_dist_destroy(void* ctx);
+int gmg_dist_ws_doubles(int64_t n, int world, int64_t* doubles);
+int gmg_potrf_solve_f64(void* ctx, const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max,
+                        double* xbuf, int64_t xbuf_doubles, gmg_stream_t stream);
 
 /* Indefinite-safe fallback: R <- S^-1 R by LU with partial pivoting (what the reference's
  * np.linalg.solve does, kriging.py:343, :585, :768).  S is the FULL n x n matrix (both triangles) and is

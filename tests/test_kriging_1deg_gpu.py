@@ -102,7 +102,7 @@ def test_emulated_8_rank_factorisation_at_size(case):
     world = 8
     for k in range((n + dn.NB - 1) // dn.NB):
         check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 0, 1, 0, s), "diag")
-        for phase in (1, 2):
+        for phase in (1, 4, 3):                             # panel, rest of the update, next panel column (look-ahead)
             for r in range(world):
                 check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, phase, world, r, s), "step")
     torch.cuda.synchronize()

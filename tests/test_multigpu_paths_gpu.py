@@ -106,9 +106,11 @@ def test_potrf_step_emulated_ranks_bit_equal(cuda, n, world):
     dt = dn._desc_tensor(d, S.device)
     L, s = lib(), dev.stream_ptr()
     nblk = (n + dn.NB - 1) // dn.NB
+    # the look-ahead split of the overlapped driver: phase 3 (next panel column) + phase 4 (the rest) == phase 2
+    split = world == 4
     for k in range(nblk):
         check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 0, 1, 0, s), "diag")
-        for phase in (1, 2):
+        for phase in ((1, 4, 3) if split else (1, 2)):
             for r in range(world):
                 check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, phase, world, r, s), "step")
     torch.cuda.synchronize()
@@ -121,13 +123,91 @@ def test_potrf_step_emulated_ranks_bit_equal(cuda, n, world):
     assert float((Lf @ Lf.T - S0[:n, :n]).abs().max() / S0[:n, :n].abs().max()) <= 1e-13
 
 
+@pytest.mark.parametrize("sizes,nrhs", [([900], 300), ([128], 2), ([1000, 257, 640], 70), ([1341] * 5, 2594)])
+def test_overlapped_factor_solve_bit_equal_to_sequential(cuda, sizes, nrhs):
+    """`gmg_potrf_solve_f64` (three streams: critical path / bulk update / forward-solve steps) against
+    `gmg_potrf_batched_f64` + `gmg_potrs_batched_f64(FORWARD)`: same factor, same solved right-hand sides, bit for bit -
+    for one system, a ragged batch and a batch of month-sized systems."""
+    torch = cuda
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200 import _device as dev
+    from glomargridding_b200._lib import check, lib
+
+    L, s = lib(), dev.stream_ptr()
+    B, n_max = len(sizes), max(sizes)
+
+    def system(seed):
+        mats, rhs = [], []
+        for b, n in enumerate(sizes):
+            mats.append(dn.padded(_spd(torch, n, seed + b)))
+            g = torch.Generator(device="cuda").manual_seed(100 + b)
+            rhs.append(dn.padded(torch.randn((n, nrhs), dtype=torch.float64, device="cuda", generator=g)))
+        ws = [dn.solve_ws(n) for n in sizes]
+        Linv = [torch.zeros(w[0], dtype=torch.float64, device="cuda") for w in ws]
+        P = [torch.empty(w[1], dtype=torch.float64, device="cuda") for w in ws]
+        info = torch.zeros(B, dtype=torch.int32, device="cuda")
+        d = np.zeros(B, dtype=dn.SOLVE_DESC)
+        for b, n in enumerate(sizes):
+            d[b] = (mats[b].data_ptr(), mats[b].stride(0), Linv[b].data_ptr(), rhs[b].data_ptr(), rhs[b].stride(0),
+                    P[b].data_ptr(), ws[b][2], info.data_ptr() + 4 * b, n, nrhs)
+        return mats, rhs, Linv, P, info, dn._desc_tensor(d, "cuda")
+
+    m0, r0_, li0, _p0, info0, d0 = system(7)
+    check(L.gmg_potrf_batched_f64(d0.data_ptr(), B, n_max, s), "potrf")
+    check(L.gmg_potrs_batched_f64(d0.data_ptr(), B, n_max, nrhs, 1, s), "potrs")
+    m1, r1_, li1, _p1, info1, d1 = system(7)
+    for _ in range(2):                                   # twice: the event pool / streams of the context are reused
+        for a, b_ in zip(m1 + r1_, system(7)[0] + system(7)[1]):
+            a.copy_(b_)
+        check(L.gmg_potrf_solve_f64(None, d1.data_ptr(), B, n_max, nrhs, None, 0, s), "potrf_solve")
+    torch.cuda.synchronize()
+    assert int(info0.abs().sum()) == 0 and int(info1.abs().sum()) == 0
+    for b, n in enumerate(sizes):
+        tri = torch.tril(torch.ones((n, n), dtype=torch.bool, device="cuda"))
+        assert torch.equal(m1[b][:n, :n][tri], m0[b][:n, :n][tri])
+        assert torch.equal(li1[b], li0[b])
+        assert torch.equal(r1_[b][:, :nrhs], r0_[b][:, :nrhs])
+    # factor only
+    m2, _r2, li2, _p2, info2, d2 = system(7)
+    check(L.gmg_potrf_solve_f64(None, d2.data_ptr(), B, n_max, 0, None, 0, s), "potrf_solve")
+    torch.cuda.synchronize()
+    for b, n in enumerate(sizes):
+        tri = torch.tril(torch.ones((n, n), dtype=torch.bool, device="cuda"))
+        assert torch.equal(m2[b][:n, :n][tri], m0[b][:n, :n][tri])
+    # a non-positive pivot is reported through info like gmg_potrf_batched_f64 reports it
+    m3, _r3, _l3, _p3, info3, d3 = system(7)
+    m3[0][5, 5] = -1.0
+    check(L.gmg_potrf_solve_f64(None, d3.data_ptr(), B, n_max, nrhs, None, 0, s), "potrf_solve")
+    torch.cuda.synchronize()
+    assert int(info3[0]) == 6 and int(info3[1:].abs().sum()) == 0
+
+
+def test_dist_api_argument_checks(cuda):
+    from glomargridding_b200._lib import lib
+
+    L = lib()
+    need = ctypes.c_int64()
+    assert L.gmg_dist_ws_doubles(20000, 8, ctypes.byref(need)) == 0
+    assert need.value == 128 * 128 * (2 + 20 * 9)        # [L_kk | Linv_k] + (1 + world) x ceil(156 / 8) packed tiles
+    assert L.gmg_dist_ws_doubles(20000, 1, ctypes.byref(need)) == 0 and need.value == 0
+    assert L.gmg_dist_ws_doubles(0, 2, ctypes.byref(need)) == -1
+    h = ctypes.c_void_p()
+    assert L.gmg_dist_init(None, 2, 0, ctypes.byref(h)) == -1          # a multi-rank context needs the unique id
+    assert L.gmg_dist_init(None, 1, 1, ctypes.byref(h)) == -3
+    assert L.gmg_dist_init(None, 1, 0, ctypes.byref(h)) == 0 and h.value  # one rank: streams only, no communicator
+    assert L.gmg_potrf_solve_f64(h, None, 1, 128, 0, None, 0, None) == -2
+    assert L.gmg_dist_destroy(h) == 0
+    uid = ctypes.create_string_buffer(128)
+    assert L.gmg_dist_unique_id(uid) == 0 and any(uid.raw)              # NCCL is reachable in this process
+
+
 def test_potrf_step_argument_checks(cuda):
     from glomargridding_b200._lib import lib
 
     L = lib()
     assert L.gmg_potrf_step_f64(None, 1, 256, 0, 0, 1, 0, None) == -1
     assert L.gmg_potrf_step_f64(ctypes.c_void_p(8), 1, 256, 2, 0, 1, 0, None) == -4      # block step past the end
-    assert L.gmg_potrf_step_f64(ctypes.c_void_p(8), 1, 256, 0, 3, 1, 0, None) == -5
+    assert L.gmg_potrf_step_f64(ctypes.c_void_p(8), 1, 256, 0, 5, 1, 0, None) == -5
     assert L.gmg_potrf_step_f64(ctypes.c_void_p(8), 1, 256, 0, 1, 2, 2, None) == -6
 
 
