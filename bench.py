@@ -39,10 +39,10 @@ TILE = 128                  # row blocks start on a macro-tile (2 x 2 tiles of 6
 DMMA_PEAK_TFLOPS = 37.1     # mma.sync m8n8k4 f64, measured on this pool's B200 (profiles/r01_microbench_fp64.json)
 DFMA_PEAK_TFLOPS = 34.2     # plain DFMA, same file
 # FP64-pipe instructions per evaluated pair of the general-nu tile kernel (SASS of the shipped row loop, two pairs
-# per iteration: 48 DFMA + 32 DMUL + 16 DADD + 2 DSETP; frozen, re-counted when the kernel changes - see
+# per iteration: 44 DFMA + 32 DMUL + 16 DADD + 2 DSETP with the degree-6 table; frozen, re-counted when the kernel changes - see
 # profiles/r02_k1_instruction_mix.md).  Every one of them holds an FP64 issue slot, so the pipe-bound figure counts
 # each as one FMA slot (2 flop) against the measured DFMA rate.
-K1_FP64_INSTR_PER_PAIR = {"table": 49.0, "closed": 43.0}
+K1_FP64_INSTR_PER_PAIR = {"table": 47.0, "closed": 43.0}
 
 
 def parse_args():

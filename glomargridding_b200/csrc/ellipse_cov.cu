@@ -20,7 +20,7 @@
 //
 // The Matern factor x^nu K_nu(x) / (Gamma(nu) 2^(nu-1)) is evaluated as g(x) e^-x with
 //   nu = 0.5 / 1.5 / 2.5 : g = 1, 1 + x, 1 + x + x^2/3              (closed forms)
-//   otherwise            : g from a piecewise degree-7 polynomial table in the mantissa of x
+//   otherwise            : g from a piecewise degree-6 polynomial table in the mantissa of x
 //                          (16 linear sub-intervals per octave, 2^-12 <= x < 2^9), built on the
 //                          device from the Temme/CF2 Bessel-K in bessel_k.cuh for the build's nu;
 //                          lanes outside the table range fall back to the direct evaluation.
@@ -51,10 +51,16 @@ constexpr int kTabEmax = 9;                         // exclusive: the table ends
 constexpr int kTabSubLog2 = 4;
 constexpr int kTabSub = 1 << kTabSubLog2;                   // linear sub-intervals of the mantissa per octave
 constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 336
-constexpr int kTabDeg = 7;
+#ifndef K1_TABDEG
+#define K1_TABDEG 6         // A/B on B200 (gpurun_out/r02_k1_ab.log): degree 7 10.8-11.1 ms, degree 6 10.55 ms at nu = 2.2
+#endif
+#ifndef K1_TSHIFT
+#define K1_TSHIFT 1
+#endif
+constexpr int kTabDeg = K1_TABDEG;                          // 7: 5e-14 relative; 6: 2e-13 (one LDS + one DFMA less per pair)
 constexpr int kTabCoef = kTabDeg + 1;
-constexpr int kTabDoubles = kTabNint * kTabCoef;            // 2688 (21.5 KB), layout [coef][interval]
-static_assert(kTabCoef == 8, "table_horner is written for degree 7");
+constexpr int kTabDoubles = (kTabNint * kTabCoef + 1) / 2 * 2;   // 2688 (21.5 KB) at degree 7, layout [coef][interval]
+static_assert(kTabDeg >= 4 && kTabDeg <= 7, "matern_table_kernel samples kTabCoef <= 8 Chebyshev nodes");
 
 enum { MODE_NU05 = 0, MODE_NU15 = 1, MODE_NU25 = 2, MODE_TABLE = 3, MODE_DIRECT = 4 };
 
@@ -150,14 +156,14 @@ struct MaternCtx {
     const double* table;   // shared-memory (tile kernel) or global (pairs kernel) pointer, [coef][interval]
 };
 
-// degree-7 Horner; the table is coefficient-major, [coef][interval]: neighbouring lanes of a warp fall into the
+// Horner (degree kTabDeg); the table is coefficient-major, [coef][interval]: neighbouring lanes of a warp fall into the
 // same or adjacent intervals (x varies smoothly along a row of the tile), so each of the eight 8-byte loads touches
 // one or two 128-byte lines - one shared-memory wavefront - where a 64-byte-record layout read with LDS.128 needed
 // ~6 per load (ncu r01: 39 shared wavefronts per warp-pair, the LSU pipe 69 % busy, against 14 for the closed forms).
 __device__ __forceinline__ double table_horner(const double* c, double t) {
-    double p = fma(c[7 * kTabNint], t, c[6 * kTabNint]);
+    double p = fma(c[kTabDeg * kTabNint], t, c[(kTabDeg - 1) * kTabNint]);
 #pragma unroll
-    for (int k = 5; k >= 0; --k) p = fma(p, t, c[k * kTabNint]);
+    for (int k = kTabDeg - 2; k >= 0; --k) p = fma(p, t, c[k * kTabNint]);
     return p;
 }
 
@@ -245,13 +251,13 @@ __device__ const double kExp2Neg[kExpTab] = {
 // whereas a 64-bit immediate costs two extra MOV issue slots per use once registers are short (ncu r01c: the
 // loop was issue-bound, 53 non-FP64 instructions per pair for 45 FP64 ones).
 struct HotConsts {
-    double magic, inv_ln2_128, ln2_128, c4, c3, half, one, c38, pi, third, tab_scale;
+    double magic, inv_ln2_128, ln2_128, c4, c3, half, one, c38, pi, third, tab_scale, two, three;
 };
 __constant__ HotConsts kHot = {6755399441055744.0,        // 1.5 * 2^52
                                184.6649652337873,        // 128 / ln 2
                                0.0054152123481245725,      // ln 2 / 128, correctly rounded
                                4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5, 1.0, 0.375,
-                               3.141592653589793, 1.0 / 3.0, (double)(2 * kTabSub)};
+                               3.141592653589793, 1.0 / 3.0, (double)(2 * kTabSub), 2.0, 3.0};
 
 // 1/sqrt(a), a > 0 normal: MUFU.RSQ64H seed and one cubically convergent step
 //   e = 1 - a r^2,  r <- r + r e (1/2 + 3/8 e)      (error ~ 5/16 e^3)       5 FP64 instructions
@@ -276,9 +282,14 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ s
     const int k = __double2loint(t);
     const double kf = t - kHot.magic;
     const double s = fma(kf, kHot.ln2_128, -x);
+#ifdef K1_EXPDEG3                                                // degree-3 Taylor: truncation s^4/24 <= 2.2e-12
+    double p = fma(kHot.c3, s, kHot.half);
+    p = fma(p, s, kHot.one);
+#else
     double p = fma(kHot.c4, s, kHot.c3);                          // 1/4!, 1/3!
     p = fma(p, s, kHot.half);
     p = fma(p, s, kHot.one);
+#endif
     const double ts = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(sexp) +
                                                        (k & (kExpTab - 1)) * (STRIDE * (int)sizeof(double)));
     p = fma(ts * s, p, ts);                                       // T (1 + s p)
@@ -308,11 +319,20 @@ __device__ __forceinline__ double matern_scaled_fast(const MaternCtx& m, double 
     const unsigned u = (unsigned)((hi >> 16) - kTabSub * (1023 + kTabEmin));
     slow = u >= (unsigned)kTabNint;
     const unsigned idx = min(u, (unsigned)(kTabNint - 1));
+#if K1_TSHIFT
+    // t = 2 frac(16 mant) - 1: the 48 mantissa bits below the four sub-interval bits, shifted up by four, ARE the
+    // fraction - d = 1.f in [1, 2) is put together with one funnel shift, one LOP3 and one shift (no zero low word to
+    // materialise, no second constant double), and t = 2 d - 3
+    const unsigned hs = __funnelshift_l((unsigned)lo, (unsigned)hi, 4);
+    const double d = __hiloint2double((int)((hs & 0x000FFFFFu) | 0x3FF00000u), (int)((unsigned)lo << 4));
+    const double t = fma(d, kHot.two, -kHot.three);
+#else
     const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     // t = (mant - centre) * 32 = mant * 32 - (33 + 2 sub): the subtrahend is the integer-valued double
     // 1.(2 sub + 1) x 2^5, whose high word is 0x40400000 | sub << 16 | 1 << 15 - one LOP3 on hi
     const double c32 = __hiloint2double((hi & 0x000F0000) | 0x40408000, 0);
     const double t = fma(mant, kHot.tab_scale, -c32);
+#endif
     return table_horner(m.table + idx, t);
 }
 

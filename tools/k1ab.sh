@@ -1,0 +1,8 @@
+for rep in 1 2; do
+for v in default k1_a k1_b k1_c k1_d; do
+  if [ $v = default ]; then unset GLOMAR_B200_LIB; else export GLOMAR_B200_LIB=$PWD/variants/$v/libglomar_b200.so; fi
+  python tools/time_ellipse.py --nus 2.2 --reps 7
+done; done > gpurun_out/r02_k1_ab.log 2>&1
+unset GLOMAR_B200_LIB
+GLOMAR_B200_LIB=$PWD/variants/k1_a/libglomar_b200.so python tools/ellipse_accuracy.py >> gpurun_out/r02_k1_ab.log 2>&1
+cat gpurun_out/r02_k1_ab.log
