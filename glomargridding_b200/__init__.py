@@ -12,7 +12,7 @@ import sys
 
 __version__ = "0.1.0"
 
-_SUBMODULES = ["ellipse", "ellipse.covariance", "kriging", "stochastic", "utils", "constants", "types",
+_SUBMODULES = ["ellipse", "ellipse.covariance", "ellipse.model", "ellipse.estimate", "grid", "kriging", "stochastic", "utils", "constants", "types",
                "distances", "variogram", "covariance_tools", "batched", "distributed"]
 
 

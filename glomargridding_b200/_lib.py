@@ -70,6 +70,12 @@ def _declare(lib):
         "gmg_det22_f64": (c_int, [p, i64, p, p]),
         "gmg_pair_haversine_f64": (c_int, [p, p, p, p, i64, dbl, p, p]),
         "gmg_pair_displacement_f64": (c_int, [p, p, p, p, i64, i32, dbl, p, p, p]),
+        "gmg_nearest_index_f64": (c_int, [p, i64, p, i64, p, i64, i32, p]),
+        "gmg_ellipse_fit_f64": (c_int, [p, i64, i64, p, p, p, i32, i32, i32, dbl, p, p, p, dbl, dbl, i32, i32, p, p, p, p,
+                                        p, p, p]),
+        "gmg_ellipse_nll_f64": (c_int, [p, i64, i64, p, p, p, i32, i32, i32, dbl, p, p, p, p]),
+        "gmg_ellipse_train_f64": (c_int, [p, p, i64, p, i64, p, i64, i32, i32, i32, i32, dbl, dbl, i32, p, p, p, p, p,
+                                          p]),
         "gmg_dist_unique_id": (c_int, [p]),
         "gmg_dist_init": (c_int, [p, i32, i32, POINTER(c_void_p)]),
         "gmg_dist_destroy": (c_int, [p]),

@@ -134,3 +134,43 @@ int gmg_pair_displacement_f64(const double* lat0, const double* lon0, const doub
 }
 
 }  // extern "C"
+
+// ---- observation -> grid index (map_to_grid / find_nearest) ---------------------------------------------------------
+// replaces `utils.find_nearest` (glomar_gridding/utils.py:178-214: `int(np.argmin(np.abs(array - value)))` per value,
+// FIRST minimum on ties, NaN differences win like numpy's argmin) as used by `grid.map_to_grid`
+// (glomar_gridding/grid.py:28-124) once per coordinate, and the row-major `np.ravel_multi_index` that follows.
+namespace {
+
+__global__ void __launch_bounds__(256) nearest_index_kernel(const double* __restrict__ grid, int64_t g,
+                                                            const double* __restrict__ values, int64_t n,
+                                                            int64_t* __restrict__ idx, int64_t stride, int accumulate) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double v = values[k];
+    int64_t best = 0;
+    double bd = fabs(grid[0] - v);
+    if (bd == bd) {                                   // a NaN difference is numpy's argmin at its first occurrence
+        for (int64_t i = 1; i < g; ++i) {
+            const double d = fabs(grid[i] - v);
+            if (d != d) { best = i; break; }
+            if (d < bd) { bd = d; best = i; }
+        }
+    }
+    idx[k] = (accumulate ? idx[k] : 0) + best * stride;
+}
+
+}  // namespace
+
+extern "C" int gmg_nearest_index_f64(const double* grid, int64_t g, const double* values, int64_t n, int64_t* idx,
+                                     int64_t stride, int accumulate, gmg_stream_t stream) {
+    if (!grid) return -1;
+    if (g <= 0) return -2;
+    if (!values) return -3;
+    if (n < 0) return -4;
+    if (!idx) return -5;
+    if (n == 0) return GMG_OK;
+    nearest_index_kernel<<<(unsigned)gmg_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(grid, g, values, n, idx,
+                                                                                            stride, accumulate);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}

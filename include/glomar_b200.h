@@ -349,6 +349,49 @@ int gmg_pair_displacement_f64(const double* lat0, const double* lon0, const doub
                               gmg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Observation -> grid index ("map_to_grid index production"): idx[k] (+)= stride * argmin_i |grid[i] -
+ * values[k]| - the nearest grid coordinate of every value, FIRST minimum on ties (utils.find_nearest,
+ * glomar_gridding/utils.py:178-214, as grid.map_to_grid calls it per coordinate, grid.py:28-124).  Calling it for
+ * latitude with stride = n_lon, accumulate = 0 and for longitude with stride = 1, accumulate = 1 yields the row-major
+ * flat index of np.ravel_multi_index - the `grid_idx` the kriging classes take as `idx`.
+ * ------------------------------------------------------------------------------------------- */
+int gmg_nearest_index_f64(const double* grid, int64_t g, const double* values, int64_t n, int64_t* idx,
+                          int64_t stride, int accumulate, gmg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ellipse-parameter fit: the maximum-likelihood estimate of (Lx, Ly, theta[, sigma]) per grid cell that
+ * produces the inputs of the covariance builder.  Replaces EllipseModel.negative_log_likelihood / .fit
+ * (glomar_gridding/ellipse/model.py:266-384, :402-500: scipy Nelder-Mead with bounds on the Gaussian likelihood of the
+ * Fisher-transformed correlations), cov_ij_anisotropic / cov_ij_isotropic (:582-686) and the per-cell Python loop of
+ * EllipseBuilder.compute_params with its training-set selection (ellipse/estimate.py:441-513, :515-715).
+ *
+ * Problems are given in CSR form: problem b owns training pairs offs[b] .. offs[b + 1] of x0 (east-west displacement,
+ * or the distance for the 1-parameter isotropic form), x1 (north-south displacement; NULL for isotropic) and y
+ * (observed correlations); `total` = offs[n_problems].  n_params = 1 (R), 2 (Lx, Ly) or 3 (Lx, Ly, theta); unless
+ * unit_sigma the likelihood's sigma is fitted as one more parameter.  h_guess / h_lo / h_hi: HOST arrays of
+ * n_params [+ 1] initial values and bounds shared by all problems.  xatol / fatol / maxiter / maxfun as scipy's
+ * options (maxiter, maxfun <= 0: N * 200).  scratch: 2 * total doubles.  Outputs per problem: x (n_params [+ 1]),
+ * fun, nit, nfev, status (0 converged, 1 function-evaluation budget, 2 iteration budget - scipy's codes).
+ * gmg_ellipse_nll_f64 evaluates the negative log-likelihood of given parameters (params: n_problems x N, device).
+ * gmg_ellipse_train_f64 builds the training pairs of `cells` from the unmasked cells' coordinates (degrees) and their
+ * correlation matrix: call with fill = 0 to get counts[n_cells], scan them into offs, call with fill = 1.
+ * disp_method: -1 none (degrees), 0 Met_Office, 1 Modified_Met_Office.
+ * ------------------------------------------------------------------------------------------- */
+int gmg_ellipse_fit_f64(const int64_t* offs, int64_t n_problems, int64_t total, const double* x0, const double* x1,
+                        const double* y, int n_params, int unit_sigma, int arctanh, double nu, const double* h_guess,
+                        const double* h_lo, const double* h_hi, double xatol, double fatol, int maxiter, int maxfun,
+                        double* scratch, double* x_out, double* fun_out, int* nit_out, int* nfev_out, int* status_out,
+                        gmg_stream_t stream);
+int gmg_ellipse_nll_f64(const int64_t* offs, int64_t n_problems, int64_t total, const double* x0, const double* x1,
+                        const double* y, int n_params, int unit_sigma, int arctanh, double nu, const double* params,
+                        double* scratch, double* fun_out, gmg_stream_t stream);
+int gmg_ellipse_train_f64(const double* lat_deg, const double* lon_deg, int64_t N, const double* cor, int64_t ldc,
+                          const int64_t* cells, int64_t n_cells, int anisotropic, int physical_distance,
+                          int disp_method, int physical_distance_selection, double min_distance, double max_distance,
+                          int fill, int64_t* counts, const int64_t* offs, double* x0, double* x1, double* y,
+                          gmg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * HOST helper (host pointers, no device work): rows r0 .. r1 of the n x n host matrix E (leading dimension ld in
  * elements, float64 or float32) against columns r0 .. r1, for the columns up to and including the diagonal block -
  * returns 1 if every mirrored pair of entries is equal (NaN equal to NaN), 0 if not, negative for a bad argument.

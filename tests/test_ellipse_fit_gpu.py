@@ -1,0 +1,199 @@
+"""Parity of the device ellipse-parameter fit with the UNMODIFIED reference:
+
+* `EllipseModel` (model.py:156-500): Matern correlation of a displacement, negative log-likelihood and the Nelder-Mead
+  fit for the six functional forms against `tests/golden/ellipse_fit.npz` - parameters at the oracle test's own
+  tolerance (rtol 1e-6), and the SAME number of iterations and function evaluations: the device simplex walks the
+  path scipy walks.
+* `EllipseBuilder` (estimate.py:41-760): covariance / correlation over time, `_get_train_data` in every selection mode
+  and the fit of EVERY unmasked cell of a 10-degree training cube against `tests/golden/ellipse_builder.npz`
+  (`fit_ellipse_model` looped by the reference; here one batched launch through `compute_params`).
+"""
+
+import warnings
+
+import numpy as np
+import pytest
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import glomargridding_b200.ellipse as e
+    import glomargridding_b200.ellipse.model as m
+
+    e.cov_ij_anisotropic, e.cov_ij_isotropic = m.cov_ij_anisotropic, m.cov_ij_isotropic
+    return e
+
+
+def _cases(E):
+    g = load_golden("ellipse_fit.npz")
+    for c in range(int(g["n_cases"])):
+        aniso, rot, pd, unit = (bool(x) for x in g[f"c{c}_meta"])
+        yield c, g, E.EllipseModel(aniso, rot, pd, float(g[f"c{c}_v"]), unit_sigma=unit)
+
+
+def test_correlation_and_likelihood_vs_reference_golden(E):
+    for c, g, m in _cases(E):
+        X, y, true = g[f"c{c}_X"], g[f"c{c}_y"], list(g[f"c{c}_true"])
+        kw = dict(zip(("Lx", "Ly", "theta"), true)) if m.anisotropic else {"R": true[0]}
+        assert np.allclose(m.cov_ij(X, **kw), g[f"c{c}_cov"], rtol=1e-12, atol=0)
+        p_true = true + ([] if m.unit_sigma else [0.05])
+        p_guess = list(m.default_guesses)[: m.n_params] + ([] if m.unit_sigma else [0.1])
+        got = [m.negative_log_likelihood(X, y.copy(), p_true), m.negative_log_likelihood(X, y.copy(), p_guess)]
+        assert np.allclose(got, g[f"c{c}_nll"], rtol=1e-11, atol=0), (c, got, g[f"c{c}_nll"])
+        f = m.negative_log_likelihood_function(X, y.copy())
+        assert f(p_true) == got[0]
+        # plain Gaussian likelihood (arctanh_transform=False, model.py:320-322) against scipy
+        from scipy import stats
+
+        want = -np.sum(stats.norm.logpdf(y, loc=g[f"c{c}_cov"], scale=1 if m.unit_sigma else 0.05))
+        assert np.isclose(m.negative_log_likelihood(X, y.copy(), p_true, arctanh_transform=False), want, rtol=1e-11)
+
+
+def test_nelder_mead_fit_follows_scipys_path(E):
+    for c, g, m in _cases(E):
+        res, se, bounds = m.fit(g[f"c{c}_X"], g[f"c{c}_y"].copy())
+        want_fun, want_nit, want_nfev, want_ok = g[f"c{c}_fit"]
+        assert se is None and np.array_equal(np.array(bounds), g[f"c{c}_bounds"])
+        assert np.allclose(res.x, g[f"c{c}_fit_x"], rtol=1e-6, atol=1e-9), (c, res.x, g[f"c{c}_fit_x"])
+        assert np.isclose(res.fun, want_fun, rtol=1e-9)
+        assert (res.nit, res.nfev, res.success) == (int(want_nit), int(want_nfev), bool(want_ok)), (c, res)
+        assert np.allclose(res.x, g[f"c{c}_fit_x"], rtol=1e-9, atol=1e-12)      # same path => same vertex, to rounding
+
+
+def test_fit_options_and_errors(E):
+    g = load_golden("ellipse_fit.npz")
+    m = E.EllipseModel(True, True, True, 1.5, unit_sigma=True)
+    X, y = g["c1_X"], g["c1_y"]
+    from scipy.optimize import minimize
+
+    # a budget of function evaluations that runs out mid-iteration: scipy's _MaxFuncCallError path
+    for maxfev in (7, 30, 61):
+        res = m.fit_many([(X, y)], maxfev=maxfev)[0][0]
+        ref = minimize(lambda p: _nll_scipy(p, X, y, 1.5), m.default_guesses[:3], bounds=m.default_bounds[:3],
+                       method="Nelder-Mead", options={"maxfev": maxfev})
+        assert (res.nfev, res.nit, res.status) == (ref.nfev, ref.nit, ref.status)
+        assert np.allclose(res.x, ref.x, rtol=1e-9)
+    res = m.fit_many([(X, y)], maxiter=12)[0][0]
+    ref = minimize(lambda p: _nll_scipy(p, X, y, 1.5), m.default_guesses[:3], bounds=m.default_bounds[:3],
+                   method="Nelder-Mead", options={"maxiter": 12})
+    assert (res.nfev, res.nit, res.status, res.success) == (ref.nfev, ref.nit, 2, False)
+    # guesses outside the bounds are clipped, an upper bound inside the initial simplex reflects it (scipy's rule)
+    res = m.fit_many([(X, y)], guesses=[5000.0, 40.0, 0.0], bounds=[(500.0, 1500.0), (50.0, 1600.0), (-1.0, 1.0)])[0][0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = minimize(lambda p: _nll_scipy(p, X, y, 1.5), [5000.0, 40.0, 0.0],
+                       bounds=[(500.0, 1500.0), (50.0, 1600.0), (-1.0, 1.0)], method="Nelder-Mead")
+    assert (res.nfev, res.nit) == (ref.nfev, ref.nit) and np.allclose(res.x, ref.x, rtol=1e-9)
+    with pytest.raises(ValueError, match="must be > 0"):
+        E.EllipseModel(True, True, True, 0.0)
+    with pytest.raises(ValueError, match="isotropic rotated"):
+        E.EllipseModel(False, True, True, 1.5)
+    with pytest.raises(NotImplementedError):
+        m.fit(X, y, estimate_SE="bootstrap_parallel")
+    with pytest.raises(NotImplementedError):
+        m.fit(X, y, opt_method="BFGS")
+    with pytest.raises(ValueError, match="lower bounds"):
+        m.fit_many([(X, y)], bounds=[(2.0, 1.0), (0.0, 1.0), (0.0, 1.0)])
+    with pytest.raises(ValueError, match="shape"):
+        m.fit(X[:, 0], y)
+
+
+def _nll_scipy(p, X, y, v):
+    """The reference's likelihood with numpy / scipy (unit sigma, rotated ellipse) - only to drive scipy's optimiser."""
+    from scipy import stats
+    from scipy.special import gamma, kv
+
+    Lx, Ly, th = p
+    c, s = np.cos(th), np.sin(th)
+    R = np.array([[c, -s], [s, c]])
+    sig = R @ np.diag([Lx ** 2.0, Ly ** 2.0]) @ R.T
+    det = sig[0, 0] * sig[1, 1] - sig[0, 1] * sig[1, 0]
+    inv = np.array([[sig[1, 1], -sig[0, 1]], [-sig[1, 0], sig[0, 0]]]) / det
+    dx, dy = X[:, 0], X[:, 1]
+    tau = np.sqrt(dx * (dx * inv[0, 0] + dy * inv[0, 1]) + dy * (dx * inv[1, 0] + dy * inv[1, 1]))
+    inner = 2.0 * tau * np.sqrt(v)
+    yll = inner ** v * kv(v, inner) / (gamma(v) * 2.0 ** (v - 1))
+    yc = np.where(np.abs(y) > 0.999999, np.sign(y) * 0.999999, y) if np.max(np.abs(y)) >= 0.999999 else y
+    if np.max(np.abs(yll)) >= 1:
+        yll = np.where(np.abs(yll) > 0.999999, np.sign(yll) * 0.999999, yll)
+    return -np.sum(stats.norm.logpdf(np.arctanh(yc), loc=np.arctanh(yll), scale=1))
+
+
+class _Coord:
+    def __init__(self, values):
+        self.values = np.asarray(values)
+
+
+@pytest.fixture(scope="module")
+def builder(E):
+    g = load_golden("ellipse_builder.npz")
+    data = np.ma.masked_array(g["data"], g["mask"])
+    coords = {"time": _Coord(np.arange(data.shape[0])), "latitude": _Coord(g["lats"]), "longitude": _Coord(g["lons"])}
+    return g, E.EllipseBuilder(data, coords)
+
+
+def test_builder_covariance_and_correlation(builder):
+    g, b = builder
+    n = int(g["n_cells"])
+    assert int(b.small_covar_size) == n and b.cov.shape == (n, n)
+    assert np.allclose(b.cov[np.triu_indices(n)], g["cov_triu"], rtol=1e-11, atol=1e-13)
+    assert np.array_equal(b.cov, b.cov.T)
+    assert np.allclose(b.cor[g["train_cells"]], g["cor_rows"], rtol=1e-11, atol=1e-13)
+    assert np.array_equal(np.diag(b.cor), np.ones(n))
+
+
+def test_builder_training_data_every_selection_mode(builder):
+    g, b = builder
+    modes = [(True, True, "Modified_Met_Office", True, 0.3, 3000.0), (True, True, "Met_Office", True, 0.3, 3000.0),
+             (True, True, "Modified_Met_Office", False, 0.3, 35.0), (False, True, "Modified_Met_Office", True, 0.3, 3000.0),
+             (False, True, "Met_Office", False, 0.3, 35.0), (False, False, None, True, 0.3, 35.0),
+             (True, False, None, True, 0.3, 35.0), (True, False, "Met_Office", True, 0.3, 3000.0)]
+    for mi, (an, pd, meth, sel, dmin, dmax) in enumerate(modes):
+        for c in g["train_cells"]:
+            X, y = b._get_train_data(int(c), dmin, dmax, an, meth, physical_distance=pd, physical_distance_selection=sel)
+            wX, wy = g[f"train_m{mi}_c{c}_X"], g[f"train_m{mi}_c{c}_y"]
+            assert X.shape == wX.shape and y.shape == wy.shape, (mi, c, X.shape, wX.shape)
+            assert np.allclose(X, wX, rtol=1e-12, atol=1e-12) and np.allclose(y, wy, rtol=1e-11, atol=1e-13)
+    with pytest.raises(ValueError, match="physical_distance"):
+        b._get_train_data(0, 0.3, 35.0, True, None, physical_distance=True)
+
+
+@pytest.mark.parametrize("tag", ["ard_pd", "iso_deg"])
+def test_builder_fits_every_cell_like_the_reference(E, builder, tag):
+    g, b = builder
+    if tag == "ard_pd":
+        m = E.EllipseModel(anisotropic=True, rotated=True, physical_distance=True, v=1.5, unit_sigma=False)
+        kw = dict(max_distance=3000.0, min_distance=0.3, delta_x_method="Modified_Met_Office", tol=1e-4)
+    else:
+        m = E.EllipseModel(anisotropic=False, rotated=False, physical_distance=False, v=0.5, unit_sigma=True)
+        kw = dict(max_distance=35.0, min_distance=0.3, delta_x_method=None, tol=1e-4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        params = b.compute_params(default_value=-999.0, matern_ellipse=m, **kw)
+    want, aux = g[f"fit_{tag}"], g[f"fit_{tag}_aux"]              # rows: ModelParams of every unmasked cell
+    names = list(m.supercategory_params.keys())
+    got = np.column_stack([np.asarray(params[n])[b.yi_masked, b.xi_masked] for n in names])
+    assert got.shape == want.shape
+    nit_same = got[:, -1] == want[:, -1]
+    nfev_same = np.array([r.nfev for r in b.fit_results]) == aux[:, 0]
+    # the simplex follows scipy's path: same iteration and evaluation counts, same QC code, parameters to rounding
+    assert nit_same.all() and nfev_same.all(), (np.flatnonzero(~nit_same)[:10], np.flatnonzero(~nfev_same)[:10])
+    assert np.array_equal(got[:, -2], want[:, -2])
+    assert np.allclose(got[:, :-2], want[:, :-2], rtol=1e-6, atol=1e-9)
+    assert np.allclose([r.fun for r in b.fit_results], aux[:, 2], rtol=1e-9)
+    # masked cells keep the default value
+    assert (np.asarray(params[names[0]])[b.mask] == -999.0).all()
+    # one cell through the per-cell method
+    k = int(g["train_cells"][2])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        one = b.fit_ellipse_model(k, m, estimate_SE=None, **kw)
+    assert np.allclose(one["ModelParams"], want[k], rtol=1e-6, atol=1e-9) and one["Success"] == want[k, -2]
+    assert one["Correlation"].shape == b.xy_shape
