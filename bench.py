@@ -63,6 +63,10 @@ def parse_args():
     ap.add_argument("--no-kriging", action="store_true")
     ap.add_argument("--no-kriging-1deg", action="store_true")
     ap.add_argument("--no-stochastic", action="store_true")
+    ap.add_argument("--no-ellipse-fit", action="store_true")
+    ap.add_argument("--fit-res", type=float, default=5.0, help="grid of the training cube of the ellipse-fit workload")
+    ap.add_argument("--fit-steps", type=int, default=5)
+    ap.add_argument("--cpu-fit-cells", type=int, default=48, help="cells the CPU arm of the ellipse fit fits")
     ap.add_argument("--nobs-1deg", type=int, default=20000)
     ap.add_argument("--krige-1deg-steps", type=int, default=3)
     ap.add_argument("--members", type=int, default=200)
@@ -107,7 +111,8 @@ def config_dict(args, wl, world):
                         f"(general nu via Bessel-K), Modified_Met_Office, FP64 [BASELINE configs[2]]; secondary: "
                         f"5deg grid ordinary kriging of {args.months} synthetic months [configs[1]]; 1deg ordinary "
                         f"kriging of {args.nobs_1deg} observations against the sharded covariance [configs[3]]; "
-                        f"5deg stochastic kriging, {args.members} members [configs[4]]",
+                        f"5deg stochastic kriging, {args.members} members [configs[4]]; {args.fit_res:g}deg ellipse-"
+                        f"parameter fit of every cell [SURVEY 8f N4]",
             "N": wl["N"], "nu": args.nu, "sharding": f"row blocks x{world}; months round-robin x{world}",
             "l2": "output (8*N^2/world bytes per GPU) is far larger than the 126 MB L2; no flush needed"}
 
@@ -344,6 +349,75 @@ def use_all_host_threads():
         pass
 
 
+_FIT_KW = dict(max_distance=3000.0, min_distance=0.3, delta_x_method="Modified_Met_Office", tol=1e-4)
+_FIT_MODEL = dict(anisotropic=True, rotated=True, physical_distance=True, v=1.5, unit_sigma=False)
+
+
+class _Coord:
+    def __init__(self, values):
+        self.values = np.asarray(values)
+
+
+def fit_cube(res):
+    from glomargridding_b200 import synthetic as synth
+
+    data, lats, lons = synth.training_cube(res, 48, 11)
+    coords = {"time": _Coord(np.arange(data.shape[0])), "latitude": _Coord(lats), "longitude": _Coord(lons)}
+    return data, coords
+
+
+def cpu_ellipse_fit_sample(res, n_cells, ref=None):
+    """The reference's per-cell fit (`EllipseBuilder.fit_ellipse_model`, estimate.py:187-400: training-pair selection +
+    scipy Nelder-Mead on the Fisher-transformed likelihood) for `n_cells` cells spread over the unmasked cells of the
+    training cube - the unmodified classes when `ref` is given, else the oracle's likelihood + scipy's optimiser on
+    the same training pairs.  cells/s."""
+    import importlib
+
+    data, coords = fit_cube(res)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if ref is not None:
+            model = importlib.import_module("glomar_gridding.ellipse.model")
+            sys.modules["glomar_gridding.ellipse"].EllipseModel = model.EllipseModel
+            estimate = importlib.import_module("glomar_gridding.ellipse.estimate")
+            import contextlib
+            import io
+
+            with contextlib.redirect_stdout(io.StringIO()):
+                b = estimate.EllipseBuilder(data, coords)
+            m = model.EllipseModel(**_FIT_MODEL)
+            cells = np.linspace(0, int(b.small_covar_size) - 1, n_cells).astype(int)
+            t0 = time.perf_counter()
+            for k in cells:
+                b.fit_ellipse_model(int(k), m, estimate_SE=None, **_FIT_KW)
+            dt = time.perf_counter() - t0
+            return n_cells / dt, dt, int(b.small_covar_size)
+        from oracle.ellipse_fit import EllipseModelOracle
+
+        flat = np.ma.getdata(data).reshape(data.shape[0], -1)
+        keep = ~np.any(np.ma.getmaskarray(data), axis=0).ravel()
+        flat = flat[:, keep] - flat[:, keep].mean(0, keepdims=True)
+        cov = flat.T @ flat / (data.shape[0] - 1)
+        sd = np.sqrt(np.diag(cov))
+        cor = cov / np.outer(sd, sd)
+        lon_g, lat_g = np.meshgrid(coords["longitude"].values, coords["latitude"].values)
+        lat, lon = lat_g.ravel()[keep], lon_g.ravel()[keep]
+        m = EllipseModelOracle(True, True, True, 1.5, unit_sigma=False)
+        cells = np.linspace(0, lat.size - 1, n_cells).astype(int)
+        t0 = time.perf_counter()
+        for k in cells:
+            dy, dx = lat - lat[k], lon - lon[k]
+            dx = np.where(dx > 180, dx - 360, np.where(dx < -180, dx + 360, dx))
+            la, lk = np.radians(lat), np.radians(lat[k])
+            hav = 2 * np.arcsin(np.sqrt(np.sin(0.5 * (lk - la)) ** 2 + np.cos(lk) * np.cos(la)
+                                        * np.sin(0.5 * np.radians(lon[k] - lon)) ** 2)) * 6371.0
+            ok = (hav <= 3000.0) & (hav >= 0.3) & (hav != 0)
+            X = 6371.0 * np.column_stack([np.radians(dx) * 0.5 * (np.cos(la) + np.cos(lk)), np.radians(dy)])[ok]
+            m.fit(X, cor[k, ok].copy(), tol=1e-4)
+        dt = time.perf_counter() - t0
+        return n_cells / dt, dt, int(lat.size)
+
+
 def cpu_sub_baselines(args, ref):
     """cpu_baseline objects of the three secondary workloads (rank 0, N = 1 / the reference arm)."""
     kind = "reference" if ref is not None else "port"
@@ -363,6 +437,13 @@ def cpu_sub_baselines(args, ref):
                       f"({r['t_solve_sample']:.2f} s, scaled x{64800 / r['n_cols']:.1f}); what np.linalg.solve does "
                       "at kriging.py:584-586; the reference's get_uncertainty needs two 64800^2 temporaries (67 GB) "
                       f"and cannot run; matrix assembly by the oracle untimed ({r['t_setup']:.0f} s)"}
+    if not args.no_ellipse_fit:
+        cps, dt, n_all = cpu_ellipse_fit_sample(args.fit_res, args.cpu_fit_cells, ref)
+        out["ellipse_fit"] = {"value": cps, "unit": "cells/s", "cores": 1, "kind": kind,
+                              "sample": f"{args.cpu_fit_cells} of the {n_all} unmasked cells of the {args.fit_res:g}deg "
+                                        f"training cube ({dt:.1f} s): EllipseBuilder.fit_ellipse_model (training-pair "
+                                        "selection + scipy Nelder-Mead, anisotropic_rotated_pd, v = 1.5, sigma "
+                                        "fitted), a serial Python loop like the reference's compute_params"}
     if not args.no_stochastic:
         mps, dt = cpu_stochastic_sample(args.members, ref)
         out["stochastic"] = {"value": mps, "unit": "members/s", "cores": host_threads(), "kind": kind,
@@ -412,7 +493,7 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     names = {"kriging": "kriged months/s", "kriging_1deg": "1deg ordinary kriging solves/s (n=20000)",
-             "stochastic": "stochastic kriging members/s"}
+             "stochastic": "stochastic kriging members/s", "ellipse_fit": "ellipse fits (grid cells)/s"}
     for key, cb in cpu_sub_baselines(args, ref).items():
         line[key] = {"metric": names[key], "value": cb["value"], "unit": cb["unit"], "cpu_baseline": cb,
                      "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0,
@@ -599,6 +680,9 @@ def run_b200(args):
     stochastic = None
     if not args.no_stochastic:
         stochastic = run_stochastic(args, rank, world, device, barrier, max_over_ranks, local, dmma_peak)
+    ellipse_fit = None
+    if not args.no_ellipse_fit:
+        ellipse_fit = run_ellipse_fit(args, rank, world, device, barrier, max_over_ranks, local)
 
     if rank != 0:
         if world > 1:
@@ -652,7 +736,8 @@ def run_b200(args):
                    "sample": f"all i<j pairs with i in a {args.cpu_rows}-row block ({pairs} pairs, {dt:.1f} s), "
                              f"numpy/scipy oracle port (the reference's build is single-threaded); entries/s = 2*pairs/s"}
         subs = cpu_sub_baselines(args, ref)
-        for key, obj in (("kriging", kriging), ("kriging_1deg", kriging_1deg), ("stochastic", stochastic)):
+        for key, obj in (("kriging", kriging), ("kriging_1deg", kriging_1deg), ("stochastic", stochastic),
+                         ("ellipse_fit", ellipse_fit)):
             if obj is not None and key in subs:
                 obj["cpu_baseline"] = subs[key]
     line = {
@@ -661,7 +746,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, wl, world),
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": 3 * args.steps, "roofline": roofline,
         "cpu_baseline": cpu, "fp64_peaks": fp64_peaks, "kriging": kriging, "kriging_1deg": kriging_1deg,
-        "stochastic": stochastic,
+        "stochastic": stochastic, "ellipse_fit": ellipse_fit,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -931,6 +1016,69 @@ def run_stochastic(args, rank, world, device, barrier, max_over_ranks, local, dm
                          "note": "flop of one rank's call / its seconds; the error-covariance upload (14 MB) is "
                                  "inside the timed region (the class API takes host arrays), results stay on the device"},
             "e2e": e2e}
+
+
+def run_ellipse_fit(args, rank, world, device, barrier, max_over_ranks, local):
+    """the ellipse parameters of every unmasked cell of a training cube (`EllipseBuilder.compute_params`:
+    covariance over time, training-pair selection, batched Nelder-Mead) - cells sharded over the ranks."""
+    import torch
+
+    from glomargridding_b200.ellipse import EllipseBuilder, EllipseModel
+    from glomargridding_b200.ellipse.model import _run_fit
+
+    data, coords = fit_cube(args.fit_res)
+    b = EllipseBuilder(data, coords)
+    m = EllipseModel(**_FIT_MODEL)
+    n_all = int(b.small_covar_size)
+    cells = np.arange(rank, n_all, world, dtype=np.int64)
+    g, bnd = m._guesses_bounds(None, None)
+
+    def step(e2e):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if e2e:                                  # host cube in -> parameter fields out (one rank's share of cells)
+                bb = EllipseBuilder(data, coords)
+                offs, x0, x1, y, total, _ = bb._train_device(cells, True, True, _FIT_KW["delta_x_method"], True,
+                                                             _FIT_KW["min_distance"], _FIT_KW["max_distance"])
+                return _run_fit(m, offs, x0, x1, y, total, cells.size, g, bnd, _FIT_KW["tol"])
+            offs, x0, x1, y, total, _ = b._train_device(cells, True, True, _FIT_KW["delta_x_method"], True,
+                                                        _FIT_KW["min_distance"], _FIT_KW["max_distance"])
+            return _run_fit(m, offs, x0, x1, y, total, cells.size, g, bnd, _FIT_KW["tol"])
+
+    for _ in range(2):
+        res = step(False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.fit_steps):
+            res = step(False)
+        e1.record()
+        barrier()
+    sec = max_over_ranks(e0.elapsed_time(e1)) * 1e-3 / args.fit_steps
+    nfev = int(sum(r.nfev for r in res))
+    e2e = None
+    if not args.no_e2e:
+        step(True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step(True)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
+        e2e = {"value": n_all / dt, "unit": "cells/s", "seconds": dt,
+               "h2d_bytes_per_step": int(8 * data.shape[0] * n_all), "d2h_bytes_per_step": int(cells.size * 5 * 8 + 8 * n_all * n_all * 2),
+               "steps": args.e2e_steps,
+               "note": "EllipseBuilder(host training cube) - covariance and correlation over time (one GEMM), mirrored "
+                       "to the host like the reference's attributes - then training pairs + fit of this rank's cells"}
+    return {"metric": "ellipse fits (grid cells)/s", "value": n_all / sec, "unit": "cells/s", "seconds": sec,
+            "higher_is_better": True, "steps": args.fit_steps, "cells": n_all,
+            "config": {"workload": f"{args.fit_res:g}deg training cube (48 time steps, {n_all} unmasked cells): "
+                                   "anisotropic_rotated_pd ellipse (Lx, Ly, theta, sigma), v = 1.5, neighbours within "
+                                   f"3000 km, Nelder-Mead tol 1e-4; cells sharded x{world}"},
+            "clocks": clocks.summary(), "gpu_launches": 3 * args.fit_steps,
+            "likelihood_evaluations_per_step": nfev,
+            "roofline": None, "e2e": e2e}
 
 
 if __name__ == "__main__":

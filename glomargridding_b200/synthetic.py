@@ -76,3 +76,27 @@ def full_grid_error_cov(idx: np.ndarray, n_cells: int, nlon: int, seed: int = 7)
     E[np.arange(n_cells), np.arange(n_cells)] = 0.0
     E[np.ix_(idx, idx)] = hadcrut_style_error_cov(idx, nlon, seed)
     return E
+
+
+def training_cube(res_deg: float = 10.0, nt: int = 48, seed: int = 11):
+    """Synthetic training data for the ellipse fit (`EllipseBuilder`): `nt` time steps on a regular global grid drawn
+    from a smooth non-stationary exponential covariance (length scale 1 500 km at the poles, 2 400 km at the equator),
+    with the land mask of `ellipse_fields` (all times) and three cells masked at a single time each (the time-varying
+    mask the reference discards, estimate.py:126-132).  Returns (numpy MaskedArray (nt, nlat, nlon), lats, lons)."""
+    lats = np.arange(-90.0 + res_deg / 2, 90.0, res_deg)
+    lons = np.arange(-180.0 + res_deg / 2, 180.0, res_deg)
+    lon_g, lat_g = np.meshgrid(np.deg2rad(lons), np.deg2rad(lats))
+    xyz = np.stack([np.cos(lat_g) * np.cos(lon_g), np.cos(lat_g) * np.sin(lon_g), np.sin(lat_g)], -1).reshape(-1, 3)
+    chord = np.linalg.norm(xyz[:, None, :] - xyz[None, :, :], axis=-1) * 6371.0
+    scale = (1500.0 + 900.0 * np.cos(lat_g).ravel())
+    L = np.sqrt(scale[:, None] * scale[None, :])
+    C = np.exp(-chord / L) + 1e-6 * np.eye(chord.shape[0])
+    w, V = np.linalg.eigh(C)
+    A = V * np.sqrt(np.clip(w, 1e-9, None))
+    rng = np.random.default_rng(seed)
+    data = (rng.standard_normal((nt, A.shape[0])) @ A.T).reshape(nt, lats.size, lons.size)
+    land = (np.sin(3 * lon_g + 0.7) * np.cos(2 * lat_g - 0.3) + 0.35 * np.sin(lat_g)) > 0.42
+    mask = np.broadcast_to(land, data.shape).copy()
+    for t, i, j in ((5, 3, 4), (17, 9, 20), (30, 12, 1)):
+        mask[t % nt, i % lats.size, j % lons.size] = True
+    return np.ma.masked_array(data, mask), lats, lons

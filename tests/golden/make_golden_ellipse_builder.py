@@ -39,22 +39,9 @@ class _Coord:
 
 
 def cube(seed=11, nt=48):
-    lats = np.arange(-85.0, 90.0, 10.0)
-    lons = np.arange(-175.0, 180.0, 10.0)
-    lon_g, lat_g = np.meshgrid(np.deg2rad(lons), np.deg2rad(lats))
-    xyz = np.stack([np.cos(lat_g) * np.cos(lon_g), np.cos(lat_g) * np.sin(lon_g), np.sin(lat_g)], -1).reshape(-1, 3)
-    chord = np.linalg.norm(xyz[:, None, :] - xyz[None, :, :], axis=-1) * 6371.0
-    scale = (1500.0 + 900.0 * np.cos(lat_g).ravel())                              # km, longer in the tropics
-    L = np.sqrt(scale[:, None] * scale[None, :])
-    C = np.exp(-chord / L) + 1e-6 * np.eye(chord.shape[0])
-    w, V = np.linalg.eigh(C)
-    A = V * np.sqrt(np.clip(w, 1e-9, None))
-    rng = np.random.default_rng(seed)
-    data = (rng.standard_normal((nt, A.shape[0])) @ A.T).reshape(nt, lats.size, lons.size)
-    land = (np.sin(3 * lon_g + 0.7) * np.cos(2 * lat_g - 0.3) + 0.35 * np.sin(lat_g)) > 0.42
-    mask = np.broadcast_to(land, data.shape).copy()
-    mask[5, 3, 4] = mask[17, 9, 20] = mask[30, 12, 1] = True                      # masked at one time only
-    return np.ma.masked_array(data, mask), lats, lons
+    from glomargridding_b200 import synthetic as synth
+
+    return synth.training_cube(10.0, nt, seed)          # numpy only, seeded: the cube is also stored in the fixture
 
 
 def main():
