@@ -89,6 +89,7 @@ def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=No
     if _STAGE is None or _STAGE[0].numel() < cap:       # pinned allocations are slow (~0.3 s): keep them
         _STAGE = [torch.empty(cap, dtype=torch.float64, pin_memory=True) for _ in range(2)]
     _pool()
+    L = lib()
     stage = [t.numpy() for t in _STAGE]
     done = [torch.cuda.Event(), torch.cuda.Event()]
     used = [False, False]
@@ -112,7 +113,13 @@ def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=No
         def pack(item, buf=buf):
             off, g, after = item
             for a in g:                                  # one (strided) copy per block, any float dtype
-                np.copyto(buf[off:off + a.size].reshape(a.shape), a, casting="unsafe")
+                if (a.ndim == 2 and a.dtype in (np.float64, np.float32) and a.strides[1] == a.itemsize
+                        and a.strides[0] % a.itemsize == 0 and a.strides[0] >= a.shape[1] * a.itemsize):
+                    # native packer: streaming stores into the pinned buffer, float32 widened on the way
+                    L.gmg_host_pack_f64(a.ctypes.data, int(a.dtype == np.float32), a.shape[0], a.shape[1],
+                                        a.strides[0] // a.itemsize, buf.ctypes.data + 8 * off)
+                else:
+                    np.copyto(buf[off:off + a.size].reshape(a.shape), a, casting="unsafe")
                 off += a.size
             if after is not None:
                 after()

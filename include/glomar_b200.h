@@ -400,6 +400,9 @@ int gmg_ellipse_train_f64(const double* lat_deg, const double* lon_deg, int64_t 
  * threads decide symmetry exactly with this routine (calling it for every row block covers the whole matrix).
  * ------------------------------------------------------------------------------------------- */
 int gmg_host_rows_symmetric(const void* E, int is_f32, int64_t n, int64_t ld, int64_t r0, int64_t r1);
+/* HOST helper: rows x cols block of a host matrix (row stride ld_src elements, float64 or float32) -> contiguous
+ * float64 at dst (a pinned staging buffer of the upload pipeline) with streaming stores; float32 is widened. */
+int gmg_host_pack_f64(const void* src, int is_f32, int64_t rows, int64_t cols, int64_t ld_src, double* dst);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement utility (no reference counterpart; SURVEY.md section 7: "FP64 peak is unmeasured - a DFMA-saturation
