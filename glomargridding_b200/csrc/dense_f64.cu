@@ -14,6 +14,7 @@
 // array and the block step, so a batch of 480 months with different observation counts runs as ONE launch
 // per step (blockIdx.z = system), not as 480 streams of small launches.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include "gmg_common.cuh"
@@ -294,15 +295,19 @@ __global__ void __launch_bounds__(256) diag_xchg_kernel(const GmgSolveDesc* __re
 // grid = (tiles, tiles, batch) with tiles = ceil((n_max - k0 - NB) / BM); tiles above the diagonal exit.
 // x_off: first column tile of this launch (the look-ahead split of the overlapped driver: column tile 0 - the next
 // panel - is updated on the critical-path stream, column tiles 1.. on another one).
-__global__ void __launch_bounds__(GEMM_THREADS) potrf_update_kernel(const GmgSolveDesc* __restrict__ descs, int kblk,
-                                                                    int tr_mod, int tr_rem, int x_off) {
+// Tiles are 128 x 64 on the two-CTAs-per-SM configuration (K is only 128 here: with one 512-thread CTA per SM a third of
+// a CTA's life was prologue and epilogue with the tensor pipe idle; batched months factored at 10.7 TFLOP/s).
+// x_off and gridDim.x count 64-column tiles.
+constexpr int UBN = 64;
+__global__ void __launch_bounds__(CfgSmall::THREADS, 2) potrf_update_kernel(const GmgSolveDesc* __restrict__ descs,
+                                                                            int kblk, int tr_mod, int tr_rem, int x_off) {
     const int cx = (int)blockIdx.x + x_off;
-    if (cx > (int)blockIdx.y) return;            // cx = column tile, y = row tile: keep the lower triangle
+    const int m0 = blockIdx.y * BM, n0 = cx * UBN;
+    if (n0 >= m0 + BM) return;                   // cx = column tile, y = row tile: keep the lower triangle
     if ((kblk + 1 + (int)blockIdx.y) % tr_mod != tr_rem) return;
     const GmgSolveDesc d = descs[blockIdx.z];
     const int k0 = kblk * NB;
     const int m = d.n - k0 - NB;
-    const int m0 = blockIdx.y * BM, n0 = cx * BN;
     if (m <= 0 || m0 >= m || n0 >= m) return;
     extern __shared__ __align__(16) double sm[];
     TileArgs g;
@@ -315,7 +320,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) potrf_update_kernel(const GmgSol
     g.D = const_cast<double*>(g.C); g.ldd = d.lds;
     g.m = m; g.n = m; g.k = NB;
     g.alpha = -1.0; g.beta = 1.0;
-    gemm_tile<false, true>(g, m0, n0, sm);
+    gemm_tile_cfg<CfgSmall, false, true, UBN>(g, m0, n0, sm);
 }
 
 // ---- triangular solves with the inverted diagonal blocks ---------------------------------------------------
@@ -328,18 +333,21 @@ __global__ void __launch_bounds__(GEMM_THREADS) potrf_update_kernel(const GmgSol
 //   X_k = Linv_kk^T Y_k - Linv_kk^T L[k+1:, k]^T X_{k+1:}  =  Q_k^T [ Y_k ; X_{k+1:} ]
 // with Q_k = [ Linv_kk ; -L[k+1:, k] Linv_kk ]  ((n - k NB) x NB, stored row-major: op(A) = Q_k^T).
 
-// grid = (ceil(k0 / BN) , 1, batch): strip[:, 0:k0] = -Linv_kk L[k, 0:k0]; the Linv_kk part is copied.
-__global__ void __launch_bounds__(GEMM_THREADS) trsm_prep_fwd_kernel(const GmgSolveDesc* __restrict__ descs, int kblk) {
+// grid = (ceil(k0 / BNT) + 1, 1, batch): strip[:, 0:k0] = -Linv_kk L[k, 0:k0]; the LAST CTA copies the Linv_kk part.
+// Cfg / BNT: CfgBig / 128, or CfgSmall / 64 (two CTAs per SM) for short strips.
+template <typename Cfg, int BNT>
+__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS == 256 ? 2 : 1)) trsm_prep_fwd_kernel(
+    const GmgSolveDesc* __restrict__ descs, int kblk) {
     const GmgSolveDesc d = descs[blockIdx.z];
     const int k0 = kblk * NB;
     if (k0 >= d.n) return;
     const int64_t ldp = d.ldp;                   // leading dimension of the coefficient strip (>= n, even)
     const double* X = d.Linv + (int64_t)kblk * NB * NB;
     const int nb = min(NB, d.n - k0);
-    if ((int)blockIdx.x * BN >= k0) {
-        // last CTA: copy Linv_kk into columns k0..k0+NB of the strip
-        if ((int)blockIdx.x * BN == k0 || k0 == 0) {
-            for (int e = threadIdx.x; e < NB * NB; e += GEMM_THREADS) {
+    const int gemm_ctas = (k0 + BNT - 1) / BNT;
+    if ((int)blockIdx.x >= gemm_ctas) {
+        if ((int)blockIdx.x == gemm_ctas) {      // copy Linv_kk into columns k0..k0+NB of the strip
+            for (int e = threadIdx.x; e < NB * NB; e += Cfg::THREADS) {
                 const int i = e / NB, j = e % NB;
                 if (k0 + j < ldp) d.P[(int64_t)i * ldp + k0 + j] = X[e];
             }
@@ -355,12 +363,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) trsm_prep_fwd_kernel(const GmgSo
     g.D = d.P; g.ldd = ldp;
     g.m = NB; g.n = k0; g.k = nb;
     g.alpha = -1.0; g.beta = 0.0;
-    gemm_tile<false, false>(g, 0, blockIdx.x * BN, sm);
+    gemm_tile_cfg<Cfg, false, false, BNT>(g, 0, blockIdx.x * BNT, sm);
 }
 
 // grid = (ceil(nrhs_max / BNT), 1, batch)
-template <int BNT>
-__global__ void __launch_bounds__(GEMM_THREADS) trsm_step_fwd_kernel(const GmgSolveDesc* __restrict__ descs, int kblk) {
+template <typename Cfg, int BNT>
+__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS == 256 ? 2 : 1)) trsm_step_fwd_kernel(
+    const GmgSolveDesc* __restrict__ descs, int kblk) {
     const GmgSolveDesc d = descs[blockIdx.z];
     const int k0 = kblk * NB;
     const int n0 = blockIdx.x * BNT;
@@ -374,7 +383,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) trsm_step_fwd_kernel(const GmgSo
     g.D = d.R + (int64_t)k0 * d.ldr; g.ldd = d.ldr;
     g.m = nb; g.n = d.nrhs; g.k = k0 + nb;
     g.alpha = 1.0; g.beta = 0.0;
-    gemm_tile<false, false, BNT>(g, 0, n0, sm);
+    gemm_tile_cfg<Cfg, false, false, BNT>(g, 0, n0, sm);
 }
 
 // grid = (ceil((n_max - k0) / BM), 1, batch): Q_k rows: [Linv_kk ; -L[k+1:, k] Linv_kk] into P (ld NB)
@@ -442,10 +451,12 @@ int ensure_attrs() {
     int rc;
     if ((rc = set_smem(potrf_diag_kernel, DIAG_SMEM))) return rc;
     if ((rc = set_smem(potrf_panel_kernel, GEMM_SMEM_BYTES))) return rc;
-    if ((rc = set_smem(potrf_update_kernel, GEMM_SMEM_BYTES))) return rc;
-    if ((rc = set_smem(trsm_prep_fwd_kernel, GEMM_SMEM_BYTES))) return rc;
-    if ((rc = set_smem(trsm_step_fwd_kernel<128>, GEMM_SMEM_BYTES))) return rc;
-    if ((rc = set_smem(trsm_step_fwd_kernel<64>, GEMM_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(potrf_update_kernel, GEMM_SMALL_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(trsm_prep_fwd_kernel<CfgBig, 128>, GEMM_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(trsm_prep_fwd_kernel<CfgSmall, 64>, GEMM_SMALL_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(trsm_step_fwd_kernel<CfgBig, 128>, GEMM_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(trsm_step_fwd_kernel<CfgBig, 64>, GEMM_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(trsm_step_fwd_kernel<CfgSmall, 64>, GEMM_SMALL_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_prep_bwd_kernel, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_bwd_kernel<128>, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_bwd_kernel<64>, GEMM_SMEM_BYTES))) return rc;
@@ -455,6 +466,58 @@ int ensure_attrs() {
     if ((rc = set_smem(gemm_kernel<true, true>, GEMM_SMEM_BYTES))) return rc;
     done = true;
     done_dev = dev;
+    return GMG_OK;
+}
+
+
+// ---- launch helpers shared by the sequential entry points and the overlapped driver ---------------------------------
+enum { UPD_ALL = 0, UPD_NEXT = 1, UPD_REST = 2 };
+
+// trailing update of block step k: all column tiles, only the next panel column (128 columns), or the rest
+int launch_update(const GmgSolveDesc* descs, int k, int tr_mod, int tr_rem, unsigned tiles, int batch, int which,
+                  cudaStream_t s) {
+    constexpr unsigned per = BM / UBN;           // 64-column tiles per 128-column panel
+    unsigned gx = tiles * per, x_off = 0;
+    if (which == UPD_NEXT) gx = per;
+    if (which == UPD_REST) { gx = (tiles - 1) * per; x_off = per; }
+    if (gx == 0) return GMG_OK;
+    potrf_update_kernel<<<dim3(gx, tiles, batch), CfgSmall::THREADS, GEMM_SMALL_SMEM_BYTES, s>>>(descs, k, tr_mod, tr_rem,
+                                                                                                 (int)x_off);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+// K up to which a forward-solve step runs on the two-CTAs-per-SM tile (bit-identical either way; GMG_SMALL_K overrides)
+int small_k_limit() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GMG_SMALL_K");
+        v = e ? atoi(e) : 2048;   // A/B on B200, 480 months: K limit 0 / 512 / 1024 / 2048 -> forward solve 71.8 / 69.9 / 66.6 / 64.3 ms
+    }
+    return v;
+}
+
+// forward-solve step of block row k: coefficient strip, then one GEMM
+int launch_fwd_step(const GmgSolveDesc* descs, int k, int batch, int64_t nrhs_max, bool narrow, cudaStream_t s) {
+    const int k0 = k * NB;
+    if (k0 + NB <= small_k_limit()) {
+        trsm_prep_fwd_kernel<CfgSmall, 64><<<dim3((unsigned)gmg_ceil_div(k0, 64) + 1, 1, batch), CfgSmall::THREADS,
+                                             GEMM_SMALL_SMEM_BYTES, s>>>(descs, k);
+        GMG_LAUNCH_CHECK();
+        trsm_step_fwd_kernel<CfgSmall, 64><<<dim3((unsigned)gmg_ceil_div(nrhs_max, 64), 1, batch), CfgSmall::THREADS,
+                                             GEMM_SMALL_SMEM_BYTES, s>>>(descs, k);
+        GMG_LAUNCH_CHECK();
+        return GMG_OK;
+    }
+    trsm_prep_fwd_kernel<CfgBig, 128><<<dim3((unsigned)k + 1, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
+    GMG_LAUNCH_CHECK();
+    if (narrow)
+        trsm_step_fwd_kernel<CfgBig, 64><<<dim3((unsigned)gmg_ceil_div(nrhs_max, 64), 1, batch), GEMM_THREADS,
+                                           GEMM_SMEM_BYTES, s>>>(descs, k);
+    else
+        trsm_step_fwd_kernel<CfgBig, 128><<<dim3((unsigned)gmg_ceil_div(nrhs_max, BN), 1, batch), GEMM_THREADS,
+                                            GEMM_SMEM_BYTES, s>>>(descs, k);
+    GMG_LAUNCH_CHECK();
     return GMG_OK;
 }
 
@@ -515,8 +578,7 @@ int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, g
         const unsigned tiles = (unsigned)gmg_ceil_div(rem, BM);
         potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, 1, 0, nullptr);
         GMG_LAUNCH_CHECK();
-        potrf_update_kernel<<<dim3(tiles, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, 1, 0, 0);
-        GMG_LAUNCH_CHECK();
+        if ((rc = launch_update(descs, k, 1, 0, tiles, batch, UPD_ALL, s))) return rc;
     }
     return GMG_OK;
 }
@@ -541,11 +603,11 @@ int gmg_potrf_step_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int 
     } else if (phase == GMG_POTRF_PANEL) {
         potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem, nullptr);
     } else if (phase == GMG_POTRF_UPDATE) {
-        potrf_update_kernel<<<dim3(tiles, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem, 0);
-    } else if (phase == GMG_POTRF_UPDATE_NEXT) {         // column tile 0 only: what the next panel needs
-        potrf_update_kernel<<<dim3(1, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem, 0);
-    } else if (tiles > 1) {                              // GMG_POTRF_UPDATE_REST: column tiles 1..
-        potrf_update_kernel<<<dim3(tiles - 1, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, kblk, tr_mod, tr_rem, 1);
+        return launch_update(descs, kblk, tr_mod, tr_rem, tiles, batch, UPD_ALL, s);
+    } else if (phase == GMG_POTRF_UPDATE_NEXT) {         // the next panel column only
+        return launch_update(descs, kblk, tr_mod, tr_rem, tiles, batch, UPD_NEXT, s);
+    } else {                                             // GMG_POTRF_UPDATE_REST: everything right of it
+        return launch_update(descs, kblk, tr_mod, tr_rem, tiles, batch, UPD_REST, s);
     }
     GMG_LAUNCH_CHECK();
     return GMG_OK;
@@ -569,15 +631,8 @@ int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, i
     GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const bool narrow = gmg_ceil_div(nrhs_max, BN) * (int64_t)batch * 4 < (int64_t)sms * 3;
     const unsigned rhs_tiles = (unsigned)gmg_ceil_div(nrhs_max, narrow ? 64 : BN);
-    for (int k = 0; k < nblk && (which & GMG_SOLVE_FORWARD); ++k) {             // L Y = B
-        trsm_prep_fwd_kernel<<<dim3((unsigned)k + 1, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
-        GMG_LAUNCH_CHECK();
-        if (narrow)
-            trsm_step_fwd_kernel<64><<<dim3(rhs_tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
-        else
-            trsm_step_fwd_kernel<128><<<dim3(rhs_tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
-        GMG_LAUNCH_CHECK();
-    }
+    for (int k = 0; k < nblk && (which & GMG_SOLVE_FORWARD); ++k)               // L Y = B
+        if ((rc = launch_fwd_step(descs, k, batch, nrhs_max, narrow, s))) return rc;
     for (int k = nblk - 1; k >= 0 && (which & GMG_SOLVE_BACKWARD); --k) {       // L^T X = Y
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
         const unsigned tiles = 1 + (rem > 0 ? (unsigned)gmg_ceil_div(rem, BM) : 0);
@@ -743,13 +798,7 @@ int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max
             if ((rc = ctx_event(c, ne++, &ev))) return rc;
             GMG_CUDA_CHECK(cudaEventRecord(ev, c->sF));
             GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sU, ev, 0));
-            trsm_prep_fwd_kernel<<<dim3((unsigned)k + 1, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sU>>>(descs, k);
-            GMG_LAUNCH_CHECK();
-            if (narrow)
-                trsm_step_fwd_kernel<64><<<dim3(rhs_tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sU>>>(descs, k);
-            else
-                trsm_step_fwd_kernel<128><<<dim3(rhs_tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sU>>>(descs, k);
-            GMG_LAUNCH_CHECK();
+            if ((rc = launch_fwd_step(descs, k, batch, nrhs_max, narrow, c->sU))) return rc;
         }
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
         if (rem <= 0) break;
@@ -770,16 +819,13 @@ int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max
             if ((rc = ctx_event(c, ne++, &ev))) return rc;
             GMG_CUDA_CHECK(cudaEventRecord(ev, c->sF));                        // the whole panel is in S
             GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sR, ev, 0));
-            potrf_update_kernel<<<dim3(tiles - 1, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sR>>>(
-                descs, k, world, rank, 1);
-            GMG_LAUNCH_CHECK();
+            if ((rc = launch_update(descs, k, world, rank, tiles, batch, UPD_REST, c->sR))) return rc;
             if ((rc = ctx_event(c, ne++, &ev_rest))) return rc;
             GMG_CUDA_CHECK(cudaEventRecord(ev_rest, c->sR));
         }
         // ---- F: look-ahead - column tile k + 1, after every earlier update of it (rest of step k - 1) ------------------
         if (ev_rest_prev) GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sF, ev_rest_prev, 0));
-        potrf_update_kernel<<<dim3(1, tiles, batch), GEMM_THREADS, GEMM_SMEM_BYTES, c->sF>>>(descs, k, world, rank, 0);
-        GMG_LAUNCH_CHECK();
+        if ((rc = launch_update(descs, k, world, rank, tiles, batch, UPD_NEXT, c->sF))) return rc;
         ev_rest_prev = ev_rest;
     }
     // join: the caller's stream continues when all three are done

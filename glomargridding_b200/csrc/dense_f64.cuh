@@ -55,51 +55,81 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// Fetch one [rows][BK] k-slab of a matrix stored rows x k (row-major) into a [row][k] tile (ld = LDK).
-__device__ __forceinline__ void load_rowk(double* s, const double* G, int64_t ld, int row0, int rows_total, int k0,
-                                          int k_total, int tid) {
+// Tile configurations.  BIG: 512 threads = 16 warps as 4 (m) x 4 (n), k-slab 32, 3 stages, 221 KB of shared memory -
+// one CTA per SM, the shape for long-K GEMMs (31.5 TFLOP/s at 4096^3).  SMALL: 256 threads = 8 warps as 4 x 2 on a
+// 128 x 64 tile, k-slab 16, 3 stages, 92 KB - TWO CTAs per SM, so that one CTA's prologue (first slabs in flight, no
+// math yet) and epilogue (tile read-modify-write) overlap the other's main loop: the shape for the short-K GEMMs of
+// batched small systems (K = 128 trailing updates, the first triangular-solve steps), where a lone CTA per SM spends a
+// third of its life outside the main loop.  Every output element is accumulated over k in the same order in both, so
+// results are bit-identical.
+struct CfgBig {
+    static constexpr int THREADS = GEMM_THREADS, WARPS_N = 4, KB = BK, NST = STAGES;
+};
+struct CfgSmall {
+    static constexpr int THREADS = 256, WARPS_N = 2, KB = 16, NST = 3;
+};
+template <typename Cfg, int BNT>
+struct TileGeom {
+    static constexpr int LDK_ = Cfg::KB + 4;                 // [row][k] tile: KB + 4 doubles per row (8 mod 32 words)
+    static constexpr int LDN_A = BM + 4;                     // [k][col] tile of A^T
+    static constexpr int LDN_B = BNT + 4;                    // [k][col] tile of B
+    static constexpr int A_DOUBLES = (BM * LDK_ > Cfg::KB * LDN_A) ? BM * LDK_ : Cfg::KB * LDN_A;
+    static constexpr int B_DOUBLES = (Cfg::KB * LDN_B > BNT * LDK_) ? Cfg::KB * LDN_B : BNT * LDK_;
+    static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
+    static constexpr size_t SMEM_BYTES = (size_t)Cfg::NST * STAGE_DOUBLES * sizeof(double);
+};
+constexpr size_t GEMM_SMALL_SMEM_BYTES = TileGeom<CfgSmall, 64>::SMEM_BYTES;      // 92 160
+
+// Fetch one [rows][KB] k-slab of a matrix stored rows x k (row-major) into a [row][k] tile (ld = KB + 4); NR = rows.
+template <typename Cfg, int NR>
+__device__ __forceinline__ void load_rowk_c(double* s, const double* G, int64_t ld, int row0, int rows_total, int k0,
+                                            int k_total, int tid) {
+    constexpr int KB = Cfg::KB, LD = KB + 4;
 #pragma unroll
-    for (int c = tid; c < BM * (BK / 2); c += GEMM_THREADS) {
-        const int r = c / (BK / 2), c2 = c % (BK / 2);
+    for (int c = tid; c < NR * (KB / 2); c += Cfg::THREADS) {
+        const int r = c / (KB / 2), c2 = c % (KB / 2);
         const int gr = row0 + r, gk = k0 + 2 * c2;
         int bytes = (gr < rows_total) ? (k_total - gk) * 8 : 0;
         bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
         const double* src = bytes ? G + (int64_t)gr * ld + gk : G;
-        cp_async16_zfill(s + r * LDK + 2 * c2, src, bytes);
+        cp_async16_zfill(s + r * LD + 2 * c2, src, bytes);
     }
 }
 
-// Fetch one [BK][cols] k-slab of a matrix stored k x cols (row-major) into a [k][col] tile (ld = LDN); NC = columns.
-template <int NC = BN>
-__device__ __forceinline__ void load_kcol(double* s, const double* G, int64_t ld, int col0, int cols_total, int k0,
-                                          int k_total, int tid) {
+// Fetch one [KB][cols] k-slab of a matrix stored k x cols (row-major) into a [k][col] tile (ld = NC + 4); NC = columns.
+template <typename Cfg, int NC>
+__device__ __forceinline__ void load_kcol_c(double* s, const double* G, int64_t ld, int col0, int cols_total, int k0,
+                                            int k_total, int tid) {
+    constexpr int KB = Cfg::KB, LD = NC + 4;
 #pragma unroll
-    for (int c = tid; c < BK * (NC / 2); c += GEMM_THREADS) {
+    for (int c = tid; c < KB * (NC / 2); c += Cfg::THREADS) {
         const int r = c / (NC / 2), c2 = c % (NC / 2);
         const int gk = k0 + r, gc = col0 + 2 * c2;
         int bytes = (gk < k_total) ? (cols_total - gc) * 8 : 0;
         bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
         const double* src = bytes ? G + (int64_t)gk * ld + gc : G;
-        cp_async16_zfill(s + r * LDN + 2 * c2, src, bytes);
+        cp_async16_zfill(s + r * LD + 2 * c2, src, bytes);
     }
 }
 
-// D[m0.., n0..] = alpha op(A) op(B) + beta C for one BM x BNT tile.  `smem` = GEMM_SMEM_BYTES, 16 B aligned.
-// BNT = 128 (default) or 64: the narrow tile halves the work per CTA (warp tile 32 x 16) and is used by the
-// triangular-solve steps when the right-hand sides give fewer 128-column strips than the GPU has SMs (a column-sharded
-// solve on 8 GPUs has 64 of them for 148 SMs).  Every output element is accumulated over k in the same order either
-// way, so the two tile shapes give bit-identical results.
-// Every thread of the 512-thread CTA must call this (it contains __syncthreads).
+// D[m0.., n0..] = alpha op(A) op(B) + beta C for one BM x BNT tile.  `smem` = TileGeom<Cfg, BNT>::SMEM_BYTES, 16 B
+// aligned.  BNT = 128 or 64 for CfgBig (the narrow tile halves the work per CTA and is used by the triangular-solve
+// steps when the right-hand sides give fewer 128-column strips than the GPU has SMs), 64 for CfgSmall.
+// Every thread of the Cfg::THREADS-thread CTA must call this (it contains __syncthreads).
 // In-place note: a CTA reads all of its A / B slabs before the epilogue writes D, so D may alias rows of A
 // or B that only THIS tile reads (used by the panel solve and the triangular solves).
-template <bool TA, bool TB, int BNT = BN>
-__device__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
+template <typename Cfg, bool TA, bool TB, int BNT>
+__device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem) {
     static_assert(BNT == 128 || BNT == 64, "tile widths: 128 or 64 columns");
-    constexpr int NJ = BNT / 32;          // 8-column DMMA tiles per warp along n
-    constexpr int WN = BNT / 4;           // columns per warp
+    using G_ = TileGeom<Cfg, BNT>;
+    constexpr int KB = Cfg::KB, NST = Cfg::NST;
+    constexpr int WN = BNT / Cfg::WARPS_N;    // columns per warp
+    constexpr int NJ = WN / 8;                // 8-column DMMA tiles per warp along n
+    constexpr int LDK_ = G_::LDK_, LDA = G_::LDN_A, LDB = G_::LDN_B;
+    static_assert(Cfg::THREADS / 32 / Cfg::WARPS_N * 32 == BM, "warps along m must cover the 128 tile rows");
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
     const int grp = lane >> 2, t4 = lane & 3;
 
     double acc[4][NJ][2];
@@ -108,38 +138,38 @@ __device__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    const int nk = (g.k + BK - 1) / BK;
+    const int nk = (g.k + KB - 1) / KB;
     auto load_stage = [&](int kt) {
-        double* sA = smem + (size_t)(kt % STAGES) * 2 * TILE_DOUBLES;
-        double* sB = sA + TILE_DOUBLES;
-        if (TA) load_kcol(sA, g.A, g.lda, m0, g.m, kt * BK, g.k, tid);
-        else    load_rowk(sA, g.A, g.lda, m0, g.m, kt * BK, g.k, tid);
-        if (TB) load_rowk(sB, g.B, g.ldb, n0, g.n, kt * BK, g.k, tid);
-        else    load_kcol<BNT>(sB, g.B, g.ldb, n0, g.n, kt * BK, g.k, tid);
+        double* sA = smem + (size_t)(kt % NST) * G_::STAGE_DOUBLES;
+        double* sB = sA + G_::A_DOUBLES;
+        if (TA) load_kcol_c<Cfg, BM>(sA, g.A, g.lda, m0, g.m, kt * KB, g.k, tid);
+        else    load_rowk_c<Cfg, BM>(sA, g.A, g.lda, m0, g.m, kt * KB, g.k, tid);
+        if (TB) load_rowk_c<Cfg, BNT>(sB, g.B, g.ldb, n0, g.n, kt * KB, g.k, tid);
+        else    load_kcol_c<Cfg, BNT>(sB, g.B, g.ldb, n0, g.n, kt * KB, g.k, tid);
     };
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
+    for (int s = 0; s < NST - 1; ++s) {
         if (s < nk) load_stage(s);
         cp_commit();
     }
     for (int kt = 0; kt < nk; ++kt) {
-        cp_wait<STAGES - 2>();
+        cp_wait<NST - 2>();
         __syncthreads();                     // slab kt has landed; slab kt-1's buffer is free for the prefetch
-        if (kt + STAGES - 1 < nk) load_stage(kt + STAGES - 1);
+        if (kt + NST - 1 < nk) load_stage(kt + NST - 1);
         cp_commit();
-        const double* sA = smem + (size_t)(kt % STAGES) * 2 * TILE_DOUBLES;
-        const double* sB = sA + TILE_DOUBLES;
+        const double* sA = smem + (size_t)(kt % NST) * G_::STAGE_DOUBLES;
+        const double* sB = sA + G_::A_DOUBLES;
 #pragma unroll
-        for (int k4 = 0; k4 < BK / 4; ++k4) {
+        for (int k4 = 0; k4 < KB / 4; ++k4) {
             double a[4], b[NJ];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                a[i] = TA ? sA[(k4 * 4 + t4) * LDN + wm * 32 + i * 8 + grp]
-                          : sA[(wm * 32 + i * 8 + grp) * LDK + k4 * 4 + t4];
+                a[i] = TA ? sA[(k4 * 4 + t4) * LDA + wm * 32 + i * 8 + grp]
+                          : sA[(wm * 32 + i * 8 + grp) * LDK_ + k4 * 4 + t4];
 #pragma unroll
             for (int j = 0; j < NJ; ++j)
-                b[j] = TB ? sB[(wn * WN + j * 8 + grp) * LDK + k4 * 4 + t4]
-                          : sB[(k4 * 4 + t4) * LDN + wn * WN + j * 8 + grp];
+                b[j] = TB ? sB[(wn * WN + j * 8 + grp) * LDK_ + k4 * 4 + t4]
+                          : sB[(k4 * 4 + t4) * LDB + wn * WN + j * 8 + grp];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -183,6 +213,12 @@ __device__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
             }
         }
     }
+}
+
+// the 512-thread tile (what every kernel used so far)
+template <bool TA, bool TB, int BNT = BN>
+__device__ __forceinline__ void gemm_tile(const TileArgs& g, int m0, int n0, double* smem) {
+    gemm_tile_cfg<CfgBig, TA, TB, BNT>(g, m0, n0, smem);
 }
 
 }  // namespace gmg

@@ -57,3 +57,14 @@ for rep in range(a.reps):
     print(f"rep {rep}: gather {t[0]:.2f} ms | potrf {t[1]:.2f} ms ({f_potrf / t[1] / 1e9:.2f} TFLOP/s) | "
           f"fwd-trsm {t[2]:.2f} ms ({f_potrs / t[2] / 1e9:.2f} TFLOP/s) | apply {t[3]:.2f} ms | total {tot:.2f} ms "
           f"-> {len(problems) / tot * 1e3:.1f} problems/s, info max {int(kb.info.max())}", flush=True)
+# the overlapped driver (gmg_potrf_solve_f64): factorisation + forward solve on three streams
+for rep in range(a.reps):
+    kb.info.zero_()
+    check(L.gmg_krige_gather_batched_f64(C, M, ldc, kb._kd.data_ptr(), kb.B, kb.n_max, s), "gather")
+    e1 = ev()
+    check(L.gmg_potrf_solve_f64(None, kb._sd.data_ptr(), kb.B, kb.n_max, nrhs, None, 0, s), "potrf_solve")
+    e2 = ev()
+    torch.cuda.synchronize()
+    t = e1.elapsed_time(e2)
+    print(f"overlapped rep {rep}: factor + fwd solve {t:.2f} ms ({(f_potrf + f_potrs) / t / 1e9:.2f} TFLOP/s), "
+          f"GMG_SMALL_K={os.environ.get('GMG_SMALL_K', 'default')}", flush=True)
