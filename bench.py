@@ -771,13 +771,13 @@ def measure_fp64_peaks(L, device, local):
     with ClockSampler(local) as clocks:
         for name, what in (("dfma", 0), ("dmma", 1)):
             best, sus = ctypes.c_double(), ctypes.c_double()
-            check(L.gmg_microbench_fp64(what, 1 << 14, 60, scratch.data_ptr(), ctypes.byref(best), ctypes.byref(sus),
+            check(L.gmg_microbench_fp64(what, 1 << 12, 40, scratch.data_ptr(), ctypes.byref(best), ctypes.byref(sus),
                                         torch.cuda.current_stream().cuda_stream), "gmg_microbench_fp64")
             out[f"{name}_tflops"] = best.value
             out[f"{name}_tflops_sustained"] = sus.value
     out["clocks"] = clocks.summary()
     out["how"] = ("gmg_microbench_fp64: register-only kernels, 8 CTAs x 256 threads per SM, 8 independent chains per "
-                  "thread; best single launch (burst) and 60 launches back to back (sustained); DFMA = 2 flop per "
+                  "thread; best single launch (burst) and 40 launches back to back (sustained); DFMA = 2 flop per "
                   "lane-instruction, DMMA m8n8k4 = 512 flop per warp-instruction")
     return out
 

@@ -44,16 +44,26 @@ static_assert(sizeof(GmgSolveDesc) == 72, "GmgSolveDesc layout is part of the C 
 constexpr int SB = 16;                          // sub-block
 constexpr int NSB = NB / SB;                    // 8
 constexpr int DIAG_G_LD = NB - SB + 1;          // staging of one block row of L X (16 x 112), odd ld
-constexpr size_t DIAG_SMEM = (size_t)(NB * DIAG_LD + NSB * SB * SB + SB * DIAG_G_LD + SB) * sizeof(double);
+// The kernel only ever touches the LOWER triangle of the block (factor and inverse are lower triangular), so the
+// triangle is stored FOLDED: row i < 64 shares a row of 129 doubles with row 127 - i - the long row from the left,
+// the short one reversed from the right (i + 1 and 128 - i entries: 129 together).  66 KB instead of 132: the CTA needs
+// 97 KB in all, so two of them - or one and a 92 KB GEMM CTA of the solve stream - fit on an SM (round 1 / early
+// round 2: 163 KB, one CTA per SM, 480 months = 3.2 waves of 134 us per block step with the rest of the SM idle).
+constexpr int DIAG_ROWS = NB / 2;
+constexpr size_t DIAG_SMEM = (size_t)(DIAG_ROWS * DIAG_LD + NSB * SB * SB + SB * DIAG_G_LD + SB) * sizeof(double);
+__device__ __forceinline__ int diag_at(int i, int j) {           // element (i, j), j <= i, of the folded lower triangle
+    return i < DIAG_ROWS ? i * DIAG_LD + (NB - j) : (NB - 1 - i) * DIAG_LD + j;
+}
+#define AT(i, j) A[diag_at((i), (j))]
 
-__global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolveDesc* __restrict__ descs, int kblk) {
+__global__ void __launch_bounds__(DIAG_THREADS, 2) potrf_diag_kernel(const GmgSolveDesc* __restrict__ descs, int kblk) {
     const GmgSolveDesc d = descs[blockIdx.z];
     const int k0g = kblk * NB;
     if (k0g >= d.n) return;
     const int nb = min(NB, d.n - k0g);
     extern __shared__ __align__(16) double sm[];
-    double* A = sm;                              // [NB][DIAG_LD]
-    double* Dinv = A + NB * DIAG_LD;             // [NSB][SB][SB] inverted diagonal sub-blocks
+    double* A = sm;                              // [DIAG_ROWS][DIAG_LD], folded lower triangle (see diag_at)
+    double* Dinv = A + DIAG_ROWS * DIAG_LD;      // [NSB][SB][SB] inverted diagonal sub-blocks
     double* G = Dinv + NSB * SB * SB;            // [SB][DIAG_G_LD]
     double* rd = G + SB * DIAG_G_LD;             // [SB] reciprocal diagonal of the current sub-block
     __shared__ int s_info;
@@ -63,7 +73,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
         const int i = e / NB, j = e % NB;
         double v = (i == j) ? 1.0 : 0.0;         // identity padding of a partial last block
         if (i < nb && j < nb && j <= i) v = d.S[(int64_t)(k0g + i) * d.lds + k0g + j];
-        A[i * DIAG_LD + j] = v;
+        if (j <= i) AT(i, j) = v;                // only the lower triangle is stored
     }
     __syncthreads();
 
@@ -76,7 +86,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
             double r[SB];
             double my_rinv = 0.0;
 #pragma unroll
-            for (int c = 0; c < SB; ++c) r[c] = (c <= l) ? A[(k0 + l) * DIAG_LD + k0 + c] : 0.0;
+            for (int c = 0; c < SB; ++c) r[c] = (c <= l) ? AT(k0 + l, k0 + c) : 0.0;
 #pragma unroll
             for (int j = 0; j < SB; ++j) {
                 const double piv = __shfl_sync(0xffffffffu, r[j], j);
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
             if (lane < SB) {
 #pragma unroll
                 for (int c = 0; c < SB; ++c)
-                    if (c <= l) A[(k0 + l) * DIAG_LD + k0 + c] = r[c];
+                    if (c <= l) AT(k0 + l, k0 + c) = r[c];
                 rd[l] = my_rinv;                                     // reciprocal diagonal 1 / L_ll
             }
         }
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
                 for (int i = 0; i < SB; ++i) {
                     double acc = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-                    for (int k = 0; k < i; ++k) acc = fma(-A[(k0 + i) * DIAG_LD + k0 + k], x[k], acc);
+                    for (int k = 0; k < i; ++k) acc = fma(-AT(k0 + i, k0 + k), x[k], acc);
                     x[i] = (i < lane) ? 0.0 : acc * rd[i];
                     Dinv[(kb * SB + i) * SB + lane] = x[i];
                 }
@@ -125,13 +135,13 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
                 double x[SB];
 #pragma unroll
                 for (int j = 0; j < SB; ++j) {
-                    double acc = A[i * DIAG_LD + k0 + j];
+                    double acc = AT(i, k0 + j);
 #pragma unroll
-                    for (int k = 0; k < j; ++k) acc = fma(-x[k], A[(k0 + j) * DIAG_LD + k0 + k], acc);
+                    for (int k = 0; k < j; ++k) acc = fma(-x[k], AT(k0 + j, k0 + k), acc);
                     x[j] = acc * rd[j];
                 }
 #pragma unroll
-                for (int j = 0; j < SB; ++j) A[i * DIAG_LD + k0 + j] = x[j];
+                for (int j = 0; j < SB; ++j) AT(i, k0 + j) = x[j];
             }
         }
         __syncthreads();
@@ -154,8 +164,8 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
                 double ai[4], ac[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    ai[a] = A[(i0 + a) * DIAG_LD + k0 + j];
-                    ac[a] = A[(c0 + a) * DIAG_LD + k0 + j];
+                    ai[a] = AT(i0 + a, k0 + j);
+                    ac[a] = AT(c0 + a, k0 + j);
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                    if (c0 + b <= i0 + a) A[(i0 + a) * DIAG_LD + c0 + b] -= acc[a][b];
+                    if (c0 + b <= i0 + a) AT(i0 + a, c0 + b) -= acc[a][b];
         }
         __syncthreads();
     }
@@ -174,14 +184,14 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
     // write L_kk
     for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
         const int i = e / NB, j = e % NB;
-        if (i < nb && j <= i) d.S[(int64_t)(k0g + i) * d.lds + k0g + j] = A[i * DIAG_LD + j];
+        if (i < nb && j <= i) d.S[(int64_t)(k0g + i) * d.lds + k0g + j] = AT(i, j);
     }
     __syncthreads();
     // ---- X = L^-1, in place over the lower triangle: diagonal sub-blocks first, then block rows top to bottom:
     //      X_ij = -Dinv_i (L_i,j..i-1 X_j..i-1,j)
     for (int e = tid; e < NSB * SB * SB; e += DIAG_THREADS) {
         const int kb = e / (SB * SB), i = (e / SB) % SB, j = e % SB;
-        if (j <= i) A[(kb * SB + i) * DIAG_LD + kb * SB + j] = Dinv[e];
+        if (j <= i) AT(kb * SB + i, kb * SB + j) = Dinv[e];
     }
     __syncthreads();
     for (int bi = 1; bi < NSB; ++bi) {
@@ -191,10 +201,10 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
             double s0 = 0.0, s1 = 0.0;
             int k = c;
             for (; k + 1 < i0; k += 2) {
-                s0 = fma(A[(i0 + r) * DIAG_LD + k], A[k * DIAG_LD + c], s0);
-                s1 = fma(A[(i0 + r) * DIAG_LD + k + 1], A[(k + 1) * DIAG_LD + c], s1);
+                s0 = fma(AT(i0 + r, k), AT(k, c), s0);
+                s1 = fma(AT(i0 + r, k + 1), AT(k + 1, c), s1);
             }
-            if (k < i0) s0 = fma(A[(i0 + r) * DIAG_LD + k], A[k * DIAG_LD + c], s0);
+            if (k < i0) s0 = fma(AT(i0 + r, k), AT(k, c), s0);
             G[r * DIAG_G_LD + c] = s0 + s1;
         }
         __syncthreads();
@@ -202,14 +212,14 @@ __global__ void __launch_bounds__(DIAG_THREADS) potrf_diag_kernel(const GmgSolve
             const int r = e % SB, c = e / SB;
             double s = 0.0;
             for (int q = 0; q <= r; ++q) s = fma(Dinv[(bi * SB + r) * SB + q], G[q * DIAG_G_LD + c], s);
-            A[(i0 + r) * DIAG_LD + c] = -s;
+            AT(i0 + r, c) = -s;
         }
         __syncthreads();
     }
     double* X = d.Linv + (int64_t)kblk * NB * NB;
     for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
         const int i = e / NB, j = e % NB;
-        X[e] = (j <= i) ? A[i * DIAG_LD + j] : 0.0;
+        X[e] = (j <= i) ? AT(i, j) : 0.0;
     }
 }
 
@@ -319,6 +329,37 @@ __global__ void __launch_bounds__(CfgSmall::THREADS, 2) potrf_update_kernel(cons
     g.ldc = d.lds;
     g.D = const_cast<double*>(g.C); g.ldd = d.lds;
     g.m = m; g.n = m; g.k = NB;
+    g.alpha = -1.0; g.beta = 1.0;
+    gemm_tile_cfg<CfgSmall, false, true, UBN>(g, m0, n0, sm);
+}
+
+
+// ---- left-looking column update: S[k:, k] -= L[k:, 0:k] L[k, 0:k]^T  (batched small systems) -----------------------
+// The right-looking trailing update touches every tile of the trailing matrix once per block step with K = 128: for
+// hundreds of month-sized systems (4.6 GB of S in total, far beyond L2) that is a DRAM-bound read-modify-write - ncu
+// r02: tensor pipe 56 % active, 5.9 long-scoreboard stalls per issue, 10.7-11.6 TFLOP/s for the whole factorisation.
+// Left-looking, block column k receives ALL its updates in one GEMM with K = 128 k right before it is factored: every
+// tile of S is read and written once per factorisation instead of once per step.  Same flops, different summation
+// order (one long accumulation instead of k rounded subtractions), so the two variants agree to rounding, not bit
+// for bit; which one runs depends only on n_max (see `use_left_looking`), never on the batch size.
+// grid = (2, tile rows of rows k.., batch)
+__global__ void __launch_bounds__(CfgSmall::THREADS, 2) potrf_colupdate_kernel(const GmgSolveDesc* __restrict__ descs,
+                                                                               int kblk) {
+    const GmgSolveDesc d = descs[blockIdx.z];
+    const int k0 = kblk * NB;
+    const int m = d.n - k0;                       // rows of block column k, diagonal block included
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * UBN;
+    if (k0 == 0 || m <= 0 || m0 >= m || n0 >= min(NB, m)) return;
+    extern __shared__ __align__(16) double sm[];
+    TileArgs g;
+    g.A = d.S + (int64_t)k0 * d.lds;              // L[k:, 0:k0]: m x k0
+    g.lda = d.lds;
+    g.B = g.A;                                    // op(B) = L[k, 0:k0]^T: stored n x k, the first 128 rows of A
+    g.ldb = d.lds;
+    g.C = d.S + (int64_t)k0 * d.lds + k0;
+    g.ldc = d.lds;
+    g.D = const_cast<double*>(g.C); g.ldd = d.lds;
+    g.m = m; g.n = min(NB, m); g.k = k0;
     g.alpha = -1.0; g.beta = 1.0;
     gemm_tile_cfg<CfgSmall, false, true, UBN>(g, m0, n0, sm);
 }
@@ -452,6 +493,7 @@ int ensure_attrs() {
     if ((rc = set_smem(potrf_diag_kernel, DIAG_SMEM))) return rc;
     if ((rc = set_smem(potrf_panel_kernel, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(potrf_update_kernel, GEMM_SMALL_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(potrf_colupdate_kernel, GEMM_SMALL_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_prep_fwd_kernel<CfgBig, 128>, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_prep_fwd_kernel<CfgSmall, 64>, GEMM_SMALL_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_fwd_kernel<CfgBig, 128>, GEMM_SMEM_BYTES))) return rc;
@@ -483,6 +525,26 @@ int launch_update(const GmgSolveDesc* descs, int k, int tr_mod, int tr_rem, unsi
     if (gx == 0) return GMG_OK;
     potrf_update_kernel<<<dim3(gx, tiles, batch), CfgSmall::THREADS, GEMM_SMALL_SMEM_BYTES, s>>>(descs, k, tr_mod, tr_rem,
                                                                                                  (int)x_off);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+// Systems of up to this order are factored left-looking on one GPU (GMG_LEFT_MAX overrides; 0 = never).  The choice
+// depends on n_max alone, so that a month solved on its own and the same month inside a batch take the same route.
+bool use_left_looking(int64_t n_max, int world) {
+    static int64_t v = -1;
+    if (v < 0) {
+        const char* e = getenv("GMG_LEFT_MAX");
+        v = e ? atoll(e) : 4096;
+    }
+    return world == 1 && n_max <= v;
+}
+
+int launch_colupdate(const GmgSolveDesc* descs, int k, int64_t n_max, int batch, cudaStream_t s) {
+    const int64_t m = n_max - (int64_t)k * NB;
+    if (k == 0 || m <= 0) return GMG_OK;
+    potrf_colupdate_kernel<<<dim3(BM / UBN, (unsigned)gmg_ceil_div(m, BM), batch), CfgSmall::THREADS,
+                             GEMM_SMALL_SMEM_BYTES, s>>>(descs, k);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
 }
@@ -570,7 +632,9 @@ int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, g
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int nblk = (int)gmg_ceil_div(n_max, NB);
+    const bool left = use_left_looking(n_max, 1);
     for (int k = 0; k < nblk; ++k) {
+        if (left && (rc = launch_colupdate(descs, k, n_max, batch, s))) return rc;
         potrf_diag_kernel<<<dim3(1, 1, batch), DIAG_THREADS, DIAG_SMEM, s>>>(descs, k);
         GMG_LAUNCH_CHECK();
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
@@ -578,7 +642,7 @@ int gmg_potrf_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, g
         const unsigned tiles = (unsigned)gmg_ceil_div(rem, BM);
         potrf_panel_kernel<<<dim3(tiles, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, 1, 0, nullptr);
         GMG_LAUNCH_CHECK();
-        if ((rc = launch_update(descs, k, 1, 0, tiles, batch, UPD_ALL, s))) return rc;
+        if (!left && (rc = launch_update(descs, k, 1, 0, tiles, batch, UPD_ALL, s))) return rc;
     }
     return GMG_OK;
 }
@@ -775,8 +839,10 @@ int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max
     GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sR, ev_fork, 0));
     GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sU, ev_fork, 0));
     cudaEvent_t ev_rest_prev = nullptr;
+    const bool left = use_left_looking(n_max, world);
     for (int k = 0; k < nblk; ++k) {
         const int owner = k % world;
+        if (left && (rc = launch_colupdate(descs, k, n_max, batch, c->sF))) return rc;
         // ---- F: diagonal block (its column was brought up to date by the look-ahead update of step k - 1) ----------
         if (rank == owner) {
             potrf_diag_kernel<<<dim3(1, 1, batch), DIAG_THREADS, DIAG_SMEM, c->sF>>>(descs, k);
@@ -813,6 +879,7 @@ int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max
             panel_unpack_kernel<<<tiles, 256, 0, c->sF>>>(descs, k, recvbuf, world, rank, cap);
             GMG_LAUNCH_CHECK();
         }
+        if (left) continue;                     // left-looking: block column k + 1 is brought up to date at the top of its step
         // ---- R: trailing update of column tiles k + 2 .. ------------------------------------------------------------
         cudaEvent_t ev_rest = nullptr;
         if (tiles > 1) {

@@ -244,10 +244,14 @@ class Kriging(ABC):
 
 def _finish_uncertainty(u2: np.ndarray, dtype) -> np.ndarray:
     """`adjust_small_negative` -> sqrt -> NaN -> 0 (reference `kriging.py:436-438`, `:702-704`)."""
-    u2 = adjust_small_negative(u2.astype(dtype, copy=False))
+    u2 = u2.astype(dtype, copy=False)
+    if (u2 < 0).any():                         # the helper only acts on (and warns about) negative values
+        u2 = adjust_small_negative(u2)
     with np.errstate(invalid="ignore"):
         uncert = np.sqrt(u2)
-    uncert[np.isnan(uncert)] = 0.0
+    nan = np.isnan(uncert)
+    if nan.any():
+        uncert[nan] = 0.0
     return uncert
 
 

@@ -92,32 +92,39 @@ def test_potrf_step_emulated_ranks_bit_equal(cuda, n, world):
     from glomargridding_b200._lib import check, lib
 
     S0 = dn.padded(_spd(torch, n, n + world))
-    ref = S0.clone()
-    ws_ref = dn.factor_inplace(ref, n)
-
-    S = S0.clone()
-    lin, pdb, ldp = dn.solve_ws(n)
-    Linv = torch.zeros(lin, dtype=torch.float64, device="cuda")
-    P = torch.empty(pdb, dtype=torch.float64, device="cuda")
-    info = torch.zeros(1, dtype=torch.int32, device="cuda")
-    d = np.zeros(1, dtype=dn.SOLVE_DESC)
-    d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"], d["n"] = (
-        S.data_ptr(), S.stride(0), Linv.data_ptr(), P.data_ptr(), ldp, info.data_ptr(), n)
-    dt = dn._desc_tensor(d, S.device)
     L, s = lib(), dev.stream_ptr()
     nblk = (n + dn.NB - 1) // dn.NB
+
+    def run(ranks, phases):
+        S = S0.clone()
+        lin, pdb, ldp = dn.solve_ws(n)
+        Linv = torch.zeros(lin, dtype=torch.float64, device="cuda")
+        P = torch.empty(pdb, dtype=torch.float64, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        d = np.zeros(1, dtype=dn.SOLVE_DESC)
+        d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"], d["n"] = (
+            S.data_ptr(), S.stride(0), Linv.data_ptr(), P.data_ptr(), ldp, info.data_ptr(), n)
+        dt = dn._desc_tensor(d, S.device)
+        for k in range(nblk):
+            check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 0, 1, 0, s), "diag")
+            for phase in phases:
+                for r in range(ranks):
+                    check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, phase, ranks, r, s), "step")
+        torch.cuda.synchronize()
+        assert int(info.item()) == 0
+        return S, Linv
+
+    # the one-rank right-looking factorisation (systems this small are factored LEFT-looking by gmg_potrf_solve_f64 /
+    # gmg_potrf_batched_f64 on one GPU - same factor to rounding; the multi-GPU driver is right-looking at any size)
+    ref, Linv_ref = run(1, (1, 2))
     # the look-ahead split of the overlapped driver: phase 3 (next panel column) + phase 4 (the rest) == phase 2
-    split = world == 4
-    for k in range(nblk):
-        check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, 0, 1, 0, s), "diag")
-        for phase in ((1, 4, 3) if split else (1, 2)):
-            for r in range(world):
-                check(L.gmg_potrf_step_f64(dt.data_ptr(), 1, n, k, phase, world, r, s), "step")
-    torch.cuda.synchronize()
-    assert int(info.item()) == 0
+    S, Linv = run(world, (1, 4, 3) if world == 4 else (1, 2))
     tri = torch.tril(torch.ones((n, n), dtype=torch.bool, device="cuda"))
     assert torch.equal(S[:n, :n][tri], ref[:n, :n][tri])
-    assert torch.equal(Linv, ws_ref["Linv"])
+    assert torch.equal(Linv, Linv_ref)
+    left = S0.clone()
+    dn.factor_inplace(left, n)                                  # left-looking on one GPU: equal to rounding
+    assert float((left[:n, :n][tri] - ref[:n, :n][tri]).abs().max() / ref[:n, :n].abs().max()) <= 1e-13
     # and it is a Cholesky factor
     Lf = torch.tril(S[:n, :n])
     assert float((Lf @ Lf.T - S0[:n, :n]).abs().max() / S0[:n, :n].abs().max()) <= 1e-13
