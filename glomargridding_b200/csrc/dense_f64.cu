@@ -549,6 +549,18 @@ int launch_colupdate(const GmgSolveDesc* descs, int k, int64_t n_max, int batch,
     return GMG_OK;
 }
 
+// Column-strip width of the long-K solve steps (512-thread tile): 128, or 64 when that takes fewer "column-waves" - the
+// CTAs of a step all run the same K, so a step costs ceil(strips / SMs) x width; the narrow tile re-reads the
+// coefficient strip twice as often (~6 % slower per column).  One 1-degree rank of 8: 8 102 columns = 64 strips of 128
+// (1 wave x 128) or 127 of 64 (1 wave x 64); the whole grid on one GPU: 507 x 128 (4 waves = 512) or 1 013 x 64
+// (7 waves = 448).  Bit-identical either way.
+bool use_narrow_strips(int64_t nrhs_max, int batch, int sms) {
+    if (nrhs_max <= 0) return false;
+    const double wide = (double)gmg_ceil_div(gmg_ceil_div(nrhs_max, BN) * (int64_t)batch, sms) * 128.0;
+    const double narrow = (double)gmg_ceil_div(gmg_ceil_div(nrhs_max, 64) * (int64_t)batch, sms) * 64.0 * 1.06;
+    return narrow < wide;
+}
+
 // K up to which a forward-solve step runs on the two-CTAs-per-SM tile (bit-identical either way; GMG_SMALL_K overrides)
 int small_k_limit() {
     static int v = -1;
@@ -693,7 +705,7 @@ int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, i
     int dev = 0, sms = 0;
     GMG_CUDA_CHECK(cudaGetDevice(&dev));
     GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const bool narrow = gmg_ceil_div(nrhs_max, BN) * (int64_t)batch * 4 < (int64_t)sms * 3;
+    const bool narrow = use_narrow_strips(nrhs_max, batch, sms);
     const unsigned rhs_tiles = (unsigned)gmg_ceil_div(nrhs_max, narrow ? 64 : BN);
     for (int k = 0; k < nblk && (which & GMG_SOLVE_FORWARD); ++k)               // L Y = B
         if ((rc = launch_fwd_step(descs, k, batch, nrhs_max, narrow, s))) return rc;
@@ -827,7 +839,7 @@ int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max
     double* recvbuf = xbuf ? sendbuf + cap0 * NB * NB : nullptr;   // [world][cap][NB][NB], cap = this step's
     int sms = 0;
     GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    const bool narrow = nrhs_max > 0 && gmg_ceil_div(nrhs_max, BN) * (int64_t)batch * 4 < (int64_t)sms * 3;
+    const bool narrow = use_narrow_strips(nrhs_max, batch, sms);
     const unsigned rhs_tiles = nrhs_max > 0 ? (unsigned)gmg_ceil_div(nrhs_max, narrow ? 64 : BN) : 0;
 
     size_t ne = 0;
