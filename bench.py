@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--no-kriging-1deg", action="store_true")
     ap.add_argument("--no-stochastic", action="store_true")
     ap.add_argument("--no-ellipse-fit", action="store_true")
+    ap.add_argument("--no-fp64-peaks", action="store_true", help="skip the in-run DFMA / DMMA microbenchmark (ncu passes)")
     ap.add_argument("--fit-res", type=float, default=5.0, help="grid of the training cube of the ellipse-fit workload")
     ap.add_argument("--fit-steps", type=int, default=5)
     ap.add_argument("--cpu-fit-cells", type=int, default=48, help="cells the CPU arm of the ellipse fit fits")
@@ -647,7 +648,7 @@ def run_b200(args):
             kernel_ms.append(k0.elapsed_time(k1))
     ms_per_step = max_over_ranks(total_ms) / args.steps
     value = float(N) * float(N) / (ms_per_step * 1e-3)
-    fp64_peaks = measure_fp64_peaks(L, device, local) if rank == 0 else None
+    fp64_peaks = measure_fp64_peaks(L, device, local) if rank == 0 and not args.no_fp64_peaks else None
 
     # ---- end to end through the public API: host inputs -> numpy cov_ns (pinned) ------------------
     e2e = None

@@ -62,7 +62,7 @@ def launches():
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(PR, f"{TAG}_launches.md"), "w") as f:
         f.write(f"# {TAG}: launch list of `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --months 120 "
-                "--month-steps 1 --no-kriging-1deg --no-stochastic --no-ellipse-fit`\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 900` (per-launch times are "
+                "--month-steps 1 --no-kriging-1deg --no-stochastic --no-ellipse-fit --no-fp64-peaks`\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 900` (per-launch times are "
                 "cold-cache and serialised: read the SHARES).  Includes warm-up launches.\n\n"
                 "| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
