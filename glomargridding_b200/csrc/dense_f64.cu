@@ -499,6 +499,7 @@ int ensure_attrs() {
     if ((rc = set_smem(trsm_step_fwd_kernel<CfgBig, 128>, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_fwd_kernel<CfgBig, 64>, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_fwd_kernel<CfgSmall, 64>, GEMM_SMALL_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(trsm_step_fwd_kernel<CfgTall, 56>, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_prep_bwd_kernel, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_bwd_kernel<128>, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_bwd_kernel<64>, GEMM_SMEM_BYTES))) return rc;
@@ -554,12 +555,24 @@ int launch_colupdate(const GmgSolveDesc* descs, int k, int64_t n_max, int batch,
 // coefficient strip twice as often (~6 % slower per column).  One 1-degree rank of 8: 8 102 columns = 64 strips of 128
 // (1 wave x 128) or 127 of 64 (1 wave x 64); the whole grid on one GPU: 507 x 128 (4 waves = 512) or 1 013 x 64
 // (7 waves = 448).  Bit-identical either way.
-bool use_narrow_strips(int64_t nrhs_max, int batch, int sms) {
-    if (nrhs_max <= 0) return false;
-    const double wide = (double)gmg_ceil_div(gmg_ceil_div(nrhs_max, BN) * (int64_t)batch, sms) * 128.0;
-    const double narrow = (double)gmg_ceil_div(gmg_ceil_div(nrhs_max, 64) * (int64_t)batch, sms) * 64.0 * 1.06;
-    return narrow < wide;
+// A third width, 56 columns on the 16 x 1 warp layout (CfgTall), is taken when it saves a further ~10 %: one rank of 8
+// then runs 145 strips on 148 SMs instead of 127.  GMG_STRIP forces a width (experiments).
+int strip_width(int64_t nrhs_max, int batch, int sms) {
+    if (nrhs_max <= 0) return BN;
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("GMG_STRIP");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 128 || forced == 64 || forced == 56) return forced;
+    auto cost = [&](int w, double penalty) {
+        return (double)gmg_ceil_div(gmg_ceil_div(nrhs_max, w) * (int64_t)batch, sms) * w * penalty;
+    };
+    const double c128 = cost(128, 1.0), c64 = cost(64, 1.06), c56 = cost(56, 1.14);
+    if (c56 < c64 && c56 < c128) return 56;
+    return c64 < c128 ? 64 : 128;
 }
+bool use_narrow_strips(int64_t nrhs_max, int batch, int sms) { return strip_width(nrhs_max, batch, sms) != BN; }
 
 // K up to which a forward-solve step runs on the two-CTAs-per-SM tile (bit-identical either way; GMG_SMALL_K overrides)
 int small_k_limit() {
@@ -572,7 +585,7 @@ int small_k_limit() {
 }
 
 // forward-solve step of block row k: coefficient strip, then one GEMM
-int launch_fwd_step(const GmgSolveDesc* descs, int k, int batch, int64_t nrhs_max, bool narrow, cudaStream_t s) {
+int launch_fwd_step(const GmgSolveDesc* descs, int k, int batch, int64_t nrhs_max, int width, cudaStream_t s) {
     const int k0 = k * NB;
     if (k0 + NB <= small_k_limit()) {
         trsm_prep_fwd_kernel<CfgSmall, 64><<<dim3((unsigned)gmg_ceil_div(k0, 64) + 1, 1, batch), CfgSmall::THREADS,
@@ -585,7 +598,10 @@ int launch_fwd_step(const GmgSolveDesc* descs, int k, int batch, int64_t nrhs_ma
     }
     trsm_prep_fwd_kernel<CfgBig, 128><<<dim3((unsigned)k + 1, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
     GMG_LAUNCH_CHECK();
-    if (narrow)
+    if (width == 56)
+        trsm_step_fwd_kernel<CfgTall, 56><<<dim3((unsigned)gmg_ceil_div(nrhs_max, 56), 1, batch), GEMM_THREADS,
+                                            GEMM_SMEM_BYTES, s>>>(descs, k);
+    else if (width == 64)
         trsm_step_fwd_kernel<CfgBig, 64><<<dim3((unsigned)gmg_ceil_div(nrhs_max, 64), 1, batch), GEMM_THREADS,
                                            GEMM_SMEM_BYTES, s>>>(descs, k);
     else
@@ -705,10 +721,11 @@ int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, i
     int dev = 0, sms = 0;
     GMG_CUDA_CHECK(cudaGetDevice(&dev));
     GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const bool narrow = use_narrow_strips(nrhs_max, batch, sms);
+    const int width = strip_width(nrhs_max, batch, sms);
+    const bool narrow = width != BN;              // the backward steps know 128 and 64
     const unsigned rhs_tiles = (unsigned)gmg_ceil_div(nrhs_max, narrow ? 64 : BN);
     for (int k = 0; k < nblk && (which & GMG_SOLVE_FORWARD); ++k)               // L Y = B
-        if ((rc = launch_fwd_step(descs, k, batch, nrhs_max, narrow, s))) return rc;
+        if ((rc = launch_fwd_step(descs, k, batch, nrhs_max, width, s))) return rc;
     for (int k = nblk - 1; k >= 0 && (which & GMG_SOLVE_BACKWARD); --k) {       // L^T X = Y
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
         const unsigned tiles = 1 + (rem > 0 ? (unsigned)gmg_ceil_div(rem, BM) : 0);
@@ -839,8 +856,7 @@ int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max
     double* recvbuf = xbuf ? sendbuf + cap0 * NB * NB : nullptr;   // [world][cap][NB][NB], cap = this step's
     int sms = 0;
     GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    const bool narrow = use_narrow_strips(nrhs_max, batch, sms);
-    const unsigned rhs_tiles = nrhs_max > 0 ? (unsigned)gmg_ceil_div(nrhs_max, narrow ? 64 : BN) : 0;
+    const int width = strip_width(nrhs_max, batch, sms);
 
     size_t ne = 0;
     cudaEvent_t ev_fork, ev;
@@ -876,7 +892,7 @@ int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max
             if ((rc = ctx_event(c, ne++, &ev))) return rc;
             GMG_CUDA_CHECK(cudaEventRecord(ev, c->sF));
             GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sU, ev, 0));
-            if ((rc = launch_fwd_step(descs, k, batch, nrhs_max, narrow, c->sU))) return rc;
+            if ((rc = launch_fwd_step(descs, k, batch, nrhs_max, width, c->sU))) return rc;
         }
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
         if (rem <= 0) break;

@@ -68,6 +68,13 @@ struct CfgBig {
 struct CfgSmall {
     static constexpr int THREADS = 256, WARPS_N = 2, KB = 16, NST = 3;
 };
+// TALL: the 512 threads as 16 (m) x 1 (n) warps, each warp one 8-row DMMA tile deep and the whole strip wide - the only
+// layout that admits strip widths that are not multiples of 32 (56 = 7 x 8).  A column-sharded solve whose strips do
+// not fill the SMs picks its width from {128, 64, 56}: one 1-degree rank of 8 has 8 102 columns = 127 strips of 64 on
+// 148 SMs, or 145 strips of 56.  Costs more shared-memory traffic per DMMA (8 fragment loads per 7) than the 4 x 4 layout.
+struct CfgTall {
+    static constexpr int THREADS = GEMM_THREADS, WARPS_N = 1, KB = BK, NST = STAGES;
+};
 template <typename Cfg, int BNT>
 struct TileGeom {
     static constexpr int LDK_ = Cfg::KB + 4;                 // [row][k] tile: KB + 4 doubles per row (8 mod 32 words)
@@ -120,21 +127,23 @@ __device__ __forceinline__ void load_kcol_c(double* s, const double* G, int64_t 
 // or B that only THIS tile reads (used by the panel solve and the triangular solves).
 template <typename Cfg, bool TA, bool TB, int BNT>
 __device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem) {
-    static_assert(BNT == 128 || BNT == 64, "tile widths: 128 or 64 columns");
     using G_ = TileGeom<Cfg, BNT>;
     constexpr int KB = Cfg::KB, NST = Cfg::NST;
     constexpr int WN = BNT / Cfg::WARPS_N;    // columns per warp
     constexpr int NJ = WN / 8;                // 8-column DMMA tiles per warp along n
+    constexpr int WARPS_M = Cfg::THREADS / 32 / Cfg::WARPS_N;
+    constexpr int MI = BM / (WARPS_M * 8);    // 8-row DMMA tiles per warp along m (4 for the 4 x 4 and 4 x 2 layouts, 1 for 16 x 1)
     constexpr int LDK_ = G_::LDK_, LDA = G_::LDN_A, LDB = G_::LDN_B;
-    static_assert(Cfg::THREADS / 32 / Cfg::WARPS_N * 32 == BM, "warps along m must cover the 128 tile rows");
+    static_assert(WN * Cfg::WARPS_N == BNT && NJ * 8 == WN && BNT % 2 == 0, "strip width: a multiple of 8 columns per warp");
+    static_assert(MI * WARPS_M * 8 == BM, "warps along m must cover the 128 tile rows");
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
     const int grp = lane >> 2, t4 = lane & 3;
 
-    double acc[4][NJ][2];
+    double acc[MI][NJ][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -161,17 +170,17 @@ __device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem) {
         const double* sB = sA + G_::A_DOUBLES;
 #pragma unroll
         for (int k4 = 0; k4 < KB / 4; ++k4) {
-            double a[4], b[NJ];
+            double a[MI], b[NJ];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                a[i] = TA ? sA[(k4 * 4 + t4) * LDA + wm * 32 + i * 8 + grp]
-                          : sA[(wm * 32 + i * 8 + grp) * LDK_ + k4 * 4 + t4];
+            for (int i = 0; i < MI; ++i)
+                a[i] = TA ? sA[(k4 * 4 + t4) * LDA + wm * (MI * 8) + i * 8 + grp]
+                          : sA[(wm * (MI * 8) + i * 8 + grp) * LDK_ + k4 * 4 + t4];
 #pragma unroll
             for (int j = 0; j < NJ; ++j)
                 b[j] = TB ? sB[(wn * WN + j * 8 + grp) * LDK_ + k4 * 4 + t4]
                           : sB[(k4 * 4 + t4) * LDB + wn * WN + j * 8 + grp];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
@@ -182,8 +191,8 @@ __device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem) {
     const bool vec_ok = ((g.ldd & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.D) & 15) == 0) &&
                         ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = m0 + wm * 32 + i * 8 + grp;
+    for (int i = 0; i < MI; ++i) {
+        const int row = m0 + wm * (MI * 8) + i * 8 + grp;
         if (row >= g.m) continue;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {

@@ -189,6 +189,41 @@ def test_overlapped_factor_solve_bit_equal_to_sequential(cuda, sizes, nrhs):
     assert int(info3[0]) == 6 and int(info3[1:].abs().sum()) == 0
 
 
+def test_solve_strip_widths_bit_identical(cuda):
+    """The forward solve picks its column-strip width from {128, 64, 56} by how the strips fill the SMs (8 104 columns -
+    one 1-degree rank of 8 - take 56 on the 16 x 1 warp layout, 64 802 take 64, a month's 2 594 take the two-CTA 64):
+    every column must come out the same whichever strip it rode in."""
+    torch = cuda
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200 import _device as dev
+    from glomargridding_b200._lib import check, lib
+
+    L, s = lib(), dev.stream_ptr()
+    n = 2500                                                  # K beyond the two-CTA limit in the later block steps
+    S = dn.padded(_spd(torch, n, 3))
+    ws = dn.factor_inplace(S, n)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    cols = {w: c for w, c in (("rank of 8", 8104), ("whole grid", 64802), ("month", 2594))}
+    base = torch.randn((n, 8104), dtype=torch.float64, device="cuda", generator=g)
+    out = {}
+    for name, nrhs in cols.items():
+        R = torch.zeros((n, nrhs + (nrhs & 1)), dtype=torch.float64, device="cuda")
+        k = min(nrhs, 8104)
+        R[:, :k] = base[:, :k]
+        d = np.zeros(1, dtype=dn.SOLVE_DESC)
+        d[0] = (S.data_ptr(), S.stride(0), ws["Linv"].data_ptr(), R.data_ptr(), R.stride(0), ws["P"].data_ptr(),
+                ws["ldp"], ws["info"].data_ptr(), n, nrhs)
+        dt = dn._desc_tensor(d, "cuda")
+        check(L.gmg_potrs_batched_f64(dt.data_ptr(), 1, n, nrhs, 1, s), "potrs")
+        torch.cuda.synchronize()
+        out[name] = R[:, :k].clone()
+    assert torch.equal(out["rank of 8"], out["whole grid"])
+    assert torch.equal(out["rank of 8"][:, :2594], out["month"])
+    Lf = torch.tril(S[:n, :n])
+    want = torch.linalg.solve_triangular(Lf, base, upper=False)
+    assert float((out["rank of 8"] - want).abs().max() / want.abs().max()) <= 1e-11
+
+
 def test_dist_api_argument_checks(cuda):
     from glomargridding_b200._lib import lib
 
