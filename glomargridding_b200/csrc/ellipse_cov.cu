@@ -20,8 +20,8 @@
 //
 // The Matern factor x^nu K_nu(x) / (Gamma(nu) 2^(nu-1)) is evaluated as g(x) e^-x with
 //   nu = 0.5 / 1.5 / 2.5 : g = 1, 1 + x, 1 + x + x^2/3              (closed forms)
-//   otherwise            : g from a piecewise degree-6 polynomial table in the mantissa of x
-//                          (16 linear sub-intervals per octave, 2^-12 <= x < 2^9), built on the
+//   otherwise            : g from a piecewise degree-5 polynomial table in the mantissa of x
+//                          (32 linear sub-intervals per octave, 2^-6 <= x < 2^9), built on the
 //                          device from the Temme/CF2 Bessel-K in bessel_k.cuh for the build's nu;
 //                          lanes outside the table range fall back to the direct evaluation.
 #include <cstring>
@@ -46,13 +46,22 @@ constexpr int kPadTail = kMaxMT * kTile;            // padding records after the
 constexpr int kThreads = 256;
 
 // Matern table geometry
-constexpr int kTabEmin = -12;
+// Table geometry (A/B on B200, nu = 2.2, gpurun_out/r02_k1_ab*.log): 16 sub-intervals per octave from 2^-12 with
+// degree 7: 10.8-11.1 ms; degree 6: 10.54-10.74; 32 sub-intervals from 2^-6 with degree 5 (shipped): 10.45 ms and
+// 3e-14 relative error.  Arguments below 2^-6 = 0.016 (a few pairs next to the poles) take the cold path.
+#ifndef K1_TABEMIN
+#define K1_TABEMIN -6
+#endif
+#ifndef K1_TABSUBLOG2
+#define K1_TABSUBLOG2 5
+#endif
+constexpr int kTabEmin = K1_TABEMIN;
 constexpr int kTabEmax = 9;                         // exclusive: the table ends at x = 512 < 700
-constexpr int kTabSubLog2 = 4;
+constexpr int kTabSubLog2 = K1_TABSUBLOG2;
 constexpr int kTabSub = 1 << kTabSubLog2;                   // linear sub-intervals of the mantissa per octave
 constexpr int kTabNint = (kTabEmax - kTabEmin) * kTabSub;   // 336
 #ifndef K1_TABDEG
-#define K1_TABDEG 6         // A/B on B200 (gpurun_out/r02_k1_ab.log): degree 7 10.8-11.1 ms, degree 6 10.55 ms at nu = 2.2
+#define K1_TABDEG 5
 #endif
 #ifndef K1_TSHIFT
 #define K1_TSHIFT 1
@@ -315,18 +324,19 @@ __device__ __forceinline__ double matern_scaled_fast(const MaternCtx& m, double 
     // its pipe per warp), so the index arithmetic is kept to 6 of them.  With a positive x the interval index
     // (exponent - emin) * 16 + top 4 mantissa bits is simply (hi >> 16) - 16 * (1023 + emin); one unsigned
     // compare rejects everything outside [2^emin, 2^emax) - which includes x >= 700 (emax = 9), x <= 0 and NaN.
-    static_assert(kTabSubLog2 == 4 && kTabEmax <= 9, "index arithmetic below assumes 16 sub-intervals, table end <= 512");
-    const unsigned u = (unsigned)((hi >> 16) - kTabSub * (1023 + kTabEmin));
+    static_assert(kTabEmax <= 9, "the range check below relies on the table ending at or below 512 < 700");
+    const unsigned u = (unsigned)((hi >> (20 - kTabSubLog2)) - kTabSub * (1023 + kTabEmin));
     slow = u >= (unsigned)kTabNint;
     const unsigned idx = min(u, (unsigned)(kTabNint - 1));
 #if K1_TSHIFT
-    // t = 2 frac(16 mant) - 1: the 48 mantissa bits below the four sub-interval bits, shifted up by four, ARE the
+    // t = 2 frac(kTabSub mant) - 1: the mantissa bits below the sub-interval bits, shifted up past them, ARE the
     // fraction - d = 1.f in [1, 2) is put together with one funnel shift, one LOP3 and one shift (no zero low word to
     // materialise, no second constant double), and t = 2 d - 3
-    const unsigned hs = __funnelshift_l((unsigned)lo, (unsigned)hi, 4);
-    const double d = __hiloint2double((int)((hs & 0x000FFFFFu) | 0x3FF00000u), (int)((unsigned)lo << 4));
+    const unsigned hs = __funnelshift_l((unsigned)lo, (unsigned)hi, kTabSubLog2);
+    const double d = __hiloint2double((int)((hs & 0x000FFFFFu) | 0x3FF00000u), (int)((unsigned)lo << kTabSubLog2));
     const double t = fma(d, kHot.two, -kHot.three);
 #else
+    static_assert(kTabSubLog2 == 4, "the constant below is written for 16 sub-intervals");
     const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     // t = (mant - centre) * 32 = mant * 32 - (33 + 2 sub): the subtrahend is the integer-valued double
     // 1.(2 sub + 1) x 2^5, whose high word is 0x40400000 | sub << 16 | 1 << 15 - one LOP3 on hi
