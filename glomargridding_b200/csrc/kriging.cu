@@ -136,6 +136,18 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
     }
 }
 
+// Lower triangle (diagonal included) of the error covariance of system b as a plain row-major n x n matrix: what a
+// Cholesky factorisation of E itself needs (the noise draws of the stochastic ensemble, stochastic.py:379-383) when E
+// travelled as its packed block trapezoid.  NaN -> 0 like the gather.  grid = (ceil(n / 256), n)
+__global__ void __launch_bounds__(256) error_cov_lower_kernel(const GmgKrigeDesc* __restrict__ descs, int b,
+                                                              double* __restrict__ out, int64_t ldo) {
+    const GmgKrigeDesc d = descs[b];
+    const int a = blockIdx.y;
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    if (a >= d.n || m >= d.n) return;
+    out[(int64_t)a * ldo + m] = (m <= a && d.E) ? error_cov_entry(d, a, m) : 0.0;
+}
+
 // Forward-only variant: T holds Y = L^-1 [Cx | 1 | y] (only the FIRST triangular solve has been done).  Because
 // S^-1 = L^-T L^-1, every quantity the kriging classes return is a column dot product of Y with itself or with
 // its two extra columns:
@@ -308,6 +320,19 @@ int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const 
     dim3 grid((unsigned)gmg_ceil_div(M + 2, kGatherCols), (unsigned)gmg_ceil_div(n_max, kGatherRows),
               (unsigned)batch);                                               // columns M, M + 1: the extra RHS
     gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C, M, ldc, descs);
+    GMG_LAUNCH_CHECK();
+    return GMG_OK;
+}
+
+int gmg_krige_error_cov_lower_f64(const GmgKrigeDesc* descs, int b, int64_t n, double* out, int64_t ldo,
+                                  gmg_stream_t stream) {
+    if (!descs) return -1;
+    if (b < 0) return -2;
+    if (n <= 0 || n > 65535) return -3;
+    if (!out) return -4;
+    if (ldo < n) return -5;
+    error_cov_lower_kernel<<<dim3((unsigned)gmg_ceil_div(n, 256), (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
+        descs, b, out, ldo);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
 }

@@ -244,6 +244,11 @@ int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const 
  * fwd_only != 0: T holds Y = L^-1 [Cx | 1 | y] (forward solve only); since S^-1 = L^-T L^-1 every
  * result is a column dot product of Y (d = sum Y^2, ...) - the second triangular solve is skipped.
  * fwd_only == 0: T holds S^-1 [Cx | 1 | y] and Cx must be present (LU fallback, user-supplied weights). */
+/* out (n x n, row-major, leading dimension ldo) <- the lower triangle incl. diagonal of the error covariance of system
+ * `b` of a descriptor array (zeros above it), whether it was uploaded whole or as its packed block trapezoid; NaN -> 0.
+ * What the Cholesky factor of E itself is computed from (noise draws, glomar_gridding/stochastic.py:379-383). */
+int gmg_krige_error_cov_lower_f64(const GmgKrigeDesc* descs, int b, int64_t n, double* out, int64_t ldo,
+                                  gmg_stream_t stream);
 int gmg_krige_apply_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs,
                                 int batch, int64_t n_max, int fwd_only, gmg_stream_t stream);
 

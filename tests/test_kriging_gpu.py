@@ -578,6 +578,37 @@ def test_stochastic_ensemble_distribution_and_consistency(K):
     assert again["result"].shape == (5, M) and not np.allclose(again["result"], other["result"])
 
 
+def test_stochastic_ensemble_at_config5_size(K):
+    """BASELINE configs[4] at its own size: 5-degree grid (M = 2 592), 1 341 observations, HadCRUT-style error
+    covariance, 200 members.  Deterministic parts against the oracle (the reference's formulation) at 1e-8; every member
+    against the class's own formula on the member's simulated state and observations (epsilon = W_sk sim_obs - state);
+    the ensemble mean of epsilon within 5 standard errors of zero."""
+    from glomargridding_b200.batched import stochastic_ensemble
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+    from oracle import ordinary_kriging
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office",
+                                   precision=np.float64).cov_ns
+    M = cov.shape[0]
+    idx, obs = synth.fixed_observations(201403, M, 1341)
+    E = synth.hadcrut_style_error_cov(idx, lons.size)
+    res = stochastic_ensemble(cov, idx, obs, E.copy(), 200, seed=20140371)
+    assert res["result"].shape == (200, M) and np.isfinite(res["result"]).all()
+    want = ordinary_kriging(cov, idx, obs, E, big_temporaries=False)
+    assert max_norm_rel(res["gridded_field"], want["field"]) <= TOL
+    assert var_rel(res["uncertainty"], want["uncertainty"]) <= TOL
+    assert np.allclose(res["result"], res["gridded_field"][None, :] + res["epsilon"])
+    S = cov[np.ix_(idx, idx)] + E
+    post = cov - cov[:, idx] @ np.linalg.solve(S, cov[idx, :])               # simple-kriging posterior covariance
+    se = np.sqrt(np.clip(np.diag(post), 0, None) / 200)
+    assert np.all(np.abs(res["epsilon"].mean(0)) < 5 * se + 1e-9)
+    assert 0.5 < np.mean(res["epsilon"].var(0, ddof=1) / np.maximum(np.diag(post), 1e-12)) < 1.5
+    same = stochastic_ensemble(cov, idx, obs, E.copy(), 200, seed=20140371)
+    assert np.array_equal(same["result"], res["result"])                    # reproducible for a given seed
+
+
 # ---- full-size properties (sizes of BASELINE.json configs[2] + [3]: 1-degree grid, 20 000 observations) ------
 def test_1deg_20000_obs_size_independent_properties(K):
     """Too large for the oracle (minutes of LAPACK): checked through properties that do not depend on size.
