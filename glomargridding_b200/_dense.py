@@ -43,6 +43,14 @@ def solve_ws(n: int) -> tuple[int, int, int]:
     return a.value, b.value, c.value
 
 
+def gesv_ws(n: int) -> tuple[int, int, int]:
+    """Workspace of the blocked LU (`gmg_gesv_blocked_f64`) for systems of order up to n: (doubles for the inverted
+    diagonal blocks of L and U, doubles for the coefficient strip + pivots, leading dimension of the strip)."""
+    a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    check(lib().gmg_gesv_ws_doubles(n, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "gmg_gesv_ws_doubles")
+    return a.value, b.value, c.value
+
+
 def _desc_tensor(arr: np.ndarray, device) -> torch.Tensor:
     return _h2d(np.ascontiguousarray(arr).view(np.uint8).reshape(-1), device)
 
@@ -229,13 +237,16 @@ def cholesky_solve_inplace(S: torch.Tensor, R: torch.Tensor, what: str = "matrix
     except np.linalg.LinAlgError:
         if not lu_fallback:
             raise
-        warn(f"{what} is not positive definite; solving by LU with partial pivoting (slow path)")
+        warn(f"{what} is not positive definite; solving by LU with partial pivoting")
         S.copy_(keep)
-        piv = torch.empty(n + 2, dtype=torch.float64, device=S.device)
+        lin, pdb, ldp = gesv_ws(n)
+        linv = torch.empty(lin, dtype=torch.float64, device=S.device)
+        strip = torch.empty(pdb, dtype=torch.float64, device=S.device)
         info = torch.zeros(1, dtype=torch.int32, device=S.device)
-        d["S"], d["lds"], d["P"], d["info"] = S.data_ptr(), S.stride(0), piv.data_ptr(), info.data_ptr()
+        d["S"], d["lds"], d["Linv"], d["P"], d["ldp"], d["info"] = (
+            S.data_ptr(), S.stride(0), linv.data_ptr(), strip.data_ptr(), ldp, info.data_ptr())
         dt = _desc_tensor(d, S.device)
-        check(lib().gmg_gesv_batched_f64(dt.data_ptr(), 1, R.shape[1], dev.stream_ptr()), "gmg_gesv_batched_f64")
+        check(lib().gmg_gesv_blocked_f64(dt.data_ptr(), 1, n, R.shape[1], dev.stream_ptr()), "gmg_gesv_blocked_f64")
         if int(info.item()) != 0:
             raise np.linalg.LinAlgError("Singular matrix")
         return
@@ -566,10 +577,20 @@ class KrigeBatch:
         for i, b in enumerate(bad):
             kd_bad_np[i]["Cx"] = self.Cx(int(b)).data_ptr()
         kd_bad = _desc_tensor(kd_bad_np, self.cov.device)
-        sd_bad = _desc_tensor(self._sd_np[bad], self.cov.device)
         n_bad = max(self.ns[int(b)] for b in bad)
+        # blocked LU with partial pivoting (gmg_gesv_blocked_f64): its workspaces - inverted diagonal blocks of L and U,
+        # coefficient strip + pivots - are sized for the largest of these systems and allocated here, on the rare path
+        lin, pdb, ldp = gesv_ws(n_bad)
+        lu_linv = torch.empty(int(bad.size) * lin, dtype=torch.float64, device=self.cov.device)
+        lu_strip = torch.empty(int(bad.size) * pdb, dtype=torch.float64, device=self.cov.device)
+        sd_bad_np = self._sd_np[bad].copy()
+        for i in range(int(bad.size)):
+            sd_bad_np[i]["Linv"] = lu_linv.data_ptr() + 8 * i * lin
+            sd_bad_np[i]["P"] = lu_strip.data_ptr() + 8 * i * pdb
+            sd_bad_np[i]["ldp"] = ldp
+        sd_bad = _desc_tensor(sd_bad_np, self.cov.device)
         check(L.gmg_krige_gather_batched_f64(C, M, ldc, kd_bad.data_ptr(), int(bad.size), n_bad, s), "gather")
-        check(L.gmg_gesv_batched_f64(sd_bad.data_ptr(), int(bad.size), self.nrhs, s), "gmg_gesv_batched_f64")
+        check(L.gmg_gesv_blocked_f64(sd_bad.data_ptr(), int(bad.size), n_bad, self.nrhs, s), "gmg_gesv_blocked_f64")
         check(L.gmg_krige_apply_batched_f64(C, M, ldc, kd_bad.data_ptr(), int(bad.size), n_bad, 0, s), "apply")
         self.full[bad] = True                        # (the good systems were completed by the overlapped pass above)
         if np.any(_d2h_info(self.info)):             # also synchronises before the temporaries die

@@ -572,7 +572,6 @@ int strip_width(int64_t nrhs_max, int batch, int sms) {
     if (c56 < c64 && c56 < c128) return 56;
     return c64 < c128 ? 64 : 128;
 }
-bool use_narrow_strips(int64_t nrhs_max, int batch, int sms) { return strip_width(nrhs_max, batch, sms) != BN; }
 
 // K up to which a forward-solve step runs on the two-CTAs-per-SM tile (bit-identical either way; GMG_SMALL_K overrides)
 int small_k_limit() {

@@ -203,6 +203,15 @@ int gmg_potrf_solve_f64(void* ctx, const GmgSolveDesc* descs, int batch, int64_t
  * zero pivot.  One CTA per system: meant for the matrices Cholesky rejects, not for speed. */
 int gmg_gesv_batched_f64(const GmgSolveDesc* descs, int batch, int64_t nrhs_max, gmg_stream_t stream);
 
+/* The same solve as a BLOCKED LU with partial pivoting on DMMA tiles (right-looking over 128-column panels: panel
+ * factorisation with LAPACK's pivot choices, row interchanges, U12 = L11^-1 A12 and A22 -= L21 U12 as GEMMs, then two
+ * blocked substitutions whose steps are GEMMs) - what np.linalg.solve costs at speed for the systems Cholesky rejects
+ * (indefinite covariance of the default displacement method, asymmetric error covariance).  Workspaces per system, sized
+ * for the LARGEST system of the batch by gmg_gesv_ws_doubles(n_max, ...): `Linv` (L^-1 and U^-1 of every diagonal
+ * block), `P` (coefficient strip, leading dimension `ldp`, followed by the int32 pivots).  nrhs_max = 0: factor only. */
+int gmg_gesv_ws_doubles(int64_t n, int64_t* linv_doubles, int64_t* p_doubles, int64_t* ldp);
+int gmg_gesv_blocked_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max, gmg_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Kriging assembly and application
  * ------------------------------------------------------------------------------------------- */

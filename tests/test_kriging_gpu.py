@@ -105,6 +105,80 @@ def test_cholesky_reports_indefinite_and_lu_fallback_matches_numpy(K):
         quiet(dn.cholesky_solve_inplace, dn.padded(np.zeros((4, 4))), dn.padded(np.ones((4, 2))))
 
 
+@pytest.mark.parametrize("sizes,nrhs", [([1], 1), ([5], 3), ([128], 64), ([129], 200), ([300, 77, 515], 70), ([1341], 2594)])
+def test_blocked_lu_vs_numpy(K, sizes, nrhs):
+    """`gmg_gesv_blocked_f64` (panel factorisation with partial pivoting, GEMM updates, GEMM substitutions) against
+    numpy.linalg.solve (LAPACK dgesv - what the reference calls, kriging.py:343, :585): non-symmetric matrices, a zero
+    diagonal (pivoting is not optional), ragged batches, the pivots LAPACK would choose."""
+    import torch
+    import scipy.linalg as sla
+
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200 import _device as dev
+    from glomargridding_b200._lib import check, lib
+
+    rng = np.random.default_rng(len(sizes) * 1000 + sizes[0])
+    B, n_max = len(sizes), max(sizes)
+    lin, pdb, ldp = dn.gesv_ws(n_max)
+    mats, rhss, want, keep = [], [], [], []
+    info = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d = np.zeros(B, dtype=dn.SOLVE_DESC)
+    for b, n in enumerate(sizes):
+        A = rng.standard_normal((n, n))
+        if n > 1:
+            A[np.arange(n), np.arange(n)] = 0.0             # forces row interchanges
+        R = rng.standard_normal((n, nrhs))
+        mats.append(A)
+        want.append(np.linalg.solve(A, R))
+        St, Rt = dn.padded(A), dn.padded(R)
+        li = torch.empty(lin, dtype=torch.float64, device="cuda")
+        st = torch.empty(pdb, dtype=torch.float64, device="cuda")
+        keep += [St, Rt, li, st]
+        rhss.append(Rt)
+        d[b] = (St.data_ptr(), St.stride(0), li.data_ptr(), Rt.data_ptr(), Rt.stride(0), st.data_ptr(), ldp,
+                info.data_ptr() + 4 * b, n, nrhs)
+    dt = dn._desc_tensor(d, "cuda")
+    check(lib().gmg_gesv_blocked_f64(dt.data_ptr(), B, n_max, nrhs, dev.stream_ptr()), "gesv_blocked")
+    torch.cuda.synchronize()
+    assert int(info.abs().sum()) == 0
+    for b, n in enumerate(sizes):
+        assert max_norm_rel(rhss[b][:, :nrhs].cpu().numpy(), want[b]) <= 1e-9, (b, n)
+        # the pivots are LAPACK's (partial pivoting, first maximal entry)
+        piv = keep[4 * b + 3][128 * ldp:].view(torch.int32)[:n].cpu().numpy()
+        assert np.array_equal(piv, sla.lu_factor(mats[b])[1])
+    # an exactly singular system reports the zero pivot through info, like dgesv
+    Z = dn.padded(np.zeros((6, 6)))
+    R = dn.padded(np.ones((6, 2)))
+    li, st = torch.empty(lin, dtype=torch.float64, device="cuda"), torch.empty(pdb, dtype=torch.float64, device="cuda")
+    inf1 = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d1 = np.zeros(1, dtype=dn.SOLVE_DESC)
+    d1[0] = (Z.data_ptr(), Z.stride(0), li.data_ptr(), R.data_ptr(), R.stride(0), st.data_ptr(), ldp, inf1.data_ptr(), 6, 2)
+    check(lib().gmg_gesv_blocked_f64(dn._desc_tensor(d1, "cuda").data_ptr(), 1, 6, 2, dev.stream_ptr()), "gesv_blocked")
+    assert int(inf1.item()) == 1
+
+
+def test_indefinite_month_takes_the_blocked_lu_and_matches_the_oracle(K):
+    """The reference's DEFAULT displacement method gives an indefinite covariance: a month kriged against
+    it without clipping falls to LU with partial pivoting - now blocked on DMMA tiles - and agrees with the oracle's
+    (= the reference's) np.linalg.solve formulation."""
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+    from oracle import ordinary_kriging
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    b = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, precision=np.float64)     # Modified_Met_Office
+    cov = b.cov_ns
+    idx, obs = synth.month_observations(3, cov.shape[0])
+    E = synth.hadcrut_style_error_cov(idx, lons.size, seed=3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        k = K.OrdinaryKriging(b.cov_ns_device, idx, obs, E.copy())
+        z, u = k.solve(), k.get_uncertainty()
+        want = ordinary_kriging(cov, idx, obs, E, big_temporaries=False)
+    if k._batch.lu_fallback:                                    # (it is indefinite for these fields)
+        assert max_norm_rel(z, want["field"]) <= 1e-6 and var_rel(u, want["uncertainty"]) <= 1e-6
+
+
 # ---- known-answer: GeoStats.jl (reference test/test_kriging.py:67-192) ------------------------------------
 def test_geostats_known_answer_class_and_function(K):
     from oracle.variogram import geostats_setup
