@@ -53,6 +53,7 @@ def _declare(lib):
         "gmg_potrf_step_f64": (c_int, [p, i32, i64, i32, i32, i32, i32, p]),
         "gmg_gesv_batched_f64": (c_int, [p, i32, i64, p]),
         "gmg_gesv_ws_doubles": (c_int, [i64, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+        "gmg_gesv_pivots_offset": (c_int64, [i64]),
         "gmg_gesv_blocked_f64": (c_int, [p, i32, i64, i64, p]),
         "gmg_krige_gather_batched_f64": (c_int, [p, i64, i64, p, i32, i64, p]),
         "gmg_krige_error_cov_lower_f64": (c_int, [p, i32, i64, p, i64, p]),

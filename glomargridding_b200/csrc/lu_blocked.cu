@@ -16,6 +16,9 @@
 // diagonal blocks - the forward one REUSES the Cholesky path's kernels (a unit-lower L stored in place of L), the
 // backward one mirrors them for the upper factor.  Pivot choices are those of the unblocked algorithm (the panel is
 // fully updated before each search), i.e. LAPACK's.
+#include <algorithm>
+#include <cstdlib>
+
 #include "gmg_common.cuh"
 #include "dense_f64.cuh"
 #include "../../include/glomar_b200.h"
@@ -25,85 +28,278 @@ namespace {
 using namespace gmg;
 
 constexpr int NB = 128;
-constexpr int PANEL_THREADS = 1024;
 constexpr int UBN = 64;
 
+
+// ---- panel factorisation with partial pivoting: columns k0 .. k0 + nb, rows k0 .. n ------------------------------------
+// The one part of LU with a column-by-column dependency.  grid = (G, 1, systems): the rows below the diagonal are split
+// over G co-resident CTAs per system (cooperative launch), which meet at a per-system barrier once per column.  The
+// panel is worked in sub-panels of SW = 16 columns:
+//   * a CTA holds its rows of the sub-panel in shared memory, column-major (one thread per row, conflict free);
+//   * per column: local pivot candidate -> every CTA publishes (|value|, row, the candidate ROW's 16 entries) and the
+//     owner of row k publishes row k -> ONE barrier -> everyone picks the winner (largest magnitude, lowest row: the
+//     unblocked algorithm's / LAPACK's choice), the owners of rows k and p exchange them from the published copies,
+//     and every CTA scales and rank-1 updates its own rows.  Publications are double buffered by column parity, which
+//     is what lets one barrier per column suffice;
+//   * per sub-panel: rows are written back, CTA 0 applies the sixteen interchanges to the panel's other columns as ONE
+//     gather (the net permutation of the <= 32 touched rows, all loads before all stores), a barrier, then every CTA
+//     forms U12 = L11^-1 A12 for the remaining columns of the panel redundantly in shared memory and updates its own
+//     rows with it (CTA 0 writes U12 back after the next barrier, when nobody reads the original any more).
+// Global memory written by another CTA is always read with ld.cg (L1 is not coherent).
+constexpr int SW = 16;
+constexpr int COOP_THREADS = 512;
+constexpr int COOP_WARPS = COOP_THREADS / 32;
+constexpr int COOP_MAX_G = 296;
+constexpr int SLOT = 2 + SW;                                  // |value|, row, the candidate row
+constexpr int COOP_DOUBLES = 16 + 2 * COOP_MAX_G * SLOT + 2 * SW;   // barrier counter, slots x 2, row k x 2
+constexpr int COOP_MAX_ROWS = 1536;                           // rows of one CTA (shared memory)
+constexpr int NOROW = 0x7fffffff;
+
+__device__ __forceinline__ double* coop_of(const GmgSolveDesc& d) { return d.P + (int64_t)NB * d.ldp; }
 __device__ __forceinline__ int* piv_of(const GmgSolveDesc& d) {
-    // pivots live behind the coefficient strip in the P workspace (see gmg_gesv_ws_doubles)
-    return reinterpret_cast<int*>(d.P + (int64_t)NB * d.ldp);
+    // pivots live behind the coefficient strip and the panel's exchange area in the P workspace (gmg_gesv_ws_doubles)
+    return reinterpret_cast<int*>(d.P + (int64_t)NB * d.ldp + COOP_DOUBLES);
+}
+__host__ __device__ constexpr int coop_stride(int rows_cap) { return rows_cap | 1; }
+static size_t coop_smem(int rows_cap) { return sizeof(double) * ((size_t)SW * coop_stride(rows_cap) + (size_t)SW * NB + SW * SW + SW) + 512; }
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// all CTAs of one system; `target` = arrivals expected so far in this launch (the counter is zeroed between launches)
+__device__ __forceinline__ void system_barrier(unsigned* cnt, unsigned target, int G) {
+    __syncthreads();
+    if (G > 1 && threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(cnt, 1u);
+        while (ld_acquire_u32(cnt) < target) {}
+        __threadfence();
+    }
+    __syncthreads();
 }
 
-// ---- panel factorisation with partial pivoting: columns k0 .. k0 + nb, rows k0 .. n.  grid = (1, 1, batch) -----------
-__global__ void __launch_bounds__(PANEL_THREADS) lu_panel_kernel(const GmgSolveDesc* __restrict__ descs, int kblk) {
+__global__ void __launch_bounds__(COOP_THREADS, 2)
+lu_panel_kernel(const GmgSolveDesc* __restrict__ descs, int kblk, int G, int rows_cap, int rows_target) {
     const GmgSolveDesc d = descs[blockIdx.z];
     const int n = d.n, k0 = kblk * NB;
     if (k0 >= n) return;
-    const int nb = min(NB, n - k0);
+    const int nb = min(NB, n - k0), m = n - k0;
+    // CTAs this system really uses: one per rows_target rows, and enough for its rows to fit the shared memory
+    const int Gs = min(G, max(max(1, (m + rows_target - 1) / rows_target), (m + rows_cap - 1) / rows_cap));
+    const int g = blockIdx.x;
+    if (g >= Gs) return;
+    const int RL = (m + Gs - 1) / Gs;
+    const int r0 = k0 + g * RL, r1 = min(n, r0 + RL);
+    const int nloc = max(0, r1 - r0);
+    const int RLP = coop_stride(rows_cap);
     double* A = d.S;
     const int64_t ld = d.lds;
     int* piv = piv_of(d);
-    __shared__ double s_val[PANEL_THREADS / 32];
-    __shared__ int s_idx[PANEL_THREADS / 32];
+    double* ws = coop_of(d);
+    unsigned* cnt = reinterpret_cast<unsigned*>(ws);
+    double* slots = ws + 16;
+    double* rowk = slots + 2 * COOP_MAX_G * SLOT;
+
+    extern __shared__ __align__(16) double sm[];
+    double* s_P = sm;                              // [SW][RLP]  my rows of the sub-panel, column-major
+    double* s_U = s_P + (size_t)SW * RLP;          // [SW][NB]   U12 of the sub-panel
+    double* s_L11 = s_U + SW * NB;                 // [SW][SW]
+    double* s_prow = s_L11 + SW * SW;              // [SW]       the pivot row
+    __shared__ double s_wval[COOP_WARPS];
+    __shared__ int s_widx[COOP_WARPS];
+    __shared__ int s_piv[SW], s_src[2 * SW], s_dst[2 * SW];
     __shared__ int s_p;
-    __shared__ double s_pivinv;
-    __shared__ double s_row[NB];                  // the pivot row of the panel
+    __shared__ double s_pinv;
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int j = 0; j < nb; ++j) {
-        const int k = k0 + j;
-        // pivot: first row of maximal |A[i][k]|, i >= k (idamax tie rule: lowest index)
-        double best = -1.0;
-        int bi = k;
-        for (int i = k + tid; i < n; i += PANEL_THREADS) {
-            const double v = fabs(A[(int64_t)i * ld + k]);
-            if (v > best) { best = v; bi = i; }
+    unsigned bar = 0;
+    int pend_row = -1, pend_col = 0, pend_rest = 0;                 // U12 waiting to be written back (CTA 0)
+
+    for (int j0 = 0; j0 < nb; j0 += SW) {
+        const int w = min(SW, nb - j0), kk0 = k0 + j0;
+        for (int e = tid; e < nloc * SW; e += COOP_THREADS) {
+            const int i = e / SW, c = e % SW;
+            s_P[c * RLP + i] = c < w ? __ldcg(A + (int64_t)(r0 + i) * ld + kk0 + c) : 0.0;
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
         __syncthreads();
-        if (warp == 0) {
-            best = lane < PANEL_THREADS / 32 ? s_val[lane] : -1.0;
-            bi = lane < PANEL_THREADS / 32 ? s_idx[lane] : 0x7fffffff;
+        for (int j = 0; j < w; ++j) {
+            const int k = kk0 + j, par = j & 1;
+            // candidate among my rows: first row of maximal magnitude
+            double best = -1.0;
+            int bi = NOROW;
+            for (int i = max(k, r0) - r0 + tid; i < nloc; i += COOP_THREADS) {
+                const double v = fabs(s_P[j * RLP + i]);
+                if (v > best) { best = v; bi = r0 + i; }
+            }
             for (int o = 16; o > 0; o >>= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, best, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
             }
-            if (lane == 0) {
-                s_p = bi;
-                piv[k] = bi;
-                const double pv = A[(int64_t)bi * ld + k];
-                if (pv == 0.0 || pv != pv) atomicCAS(d.info, 0, k + 1);
-                s_pivinv = 1.0 / pv;
+            if (lane == 0) { s_wval[warp] = best; s_widx[warp] = bi; }
+            __syncthreads();
+            if (warp == 0) {
+                best = lane < COOP_WARPS ? s_wval[lane] : -1.0;
+                bi = lane < COOP_WARPS ? s_widx[lane] : NOROW;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                double* slot = slots + (size_t)(par * COOP_MAX_G + g) * SLOT;
+                if (lane == 0) { slot[0] = best; slot[1] = (double)bi; }
+                if (lane < SW && bi != NOROW) slot[2 + lane] = s_P[lane * RLP + (bi - r0)];
+                if (k >= r0 && k < r1 && lane < SW) rowk[par * SW + lane] = s_P[lane * RLP + (k - r0)];
+            }
+            system_barrier(cnt, (unsigned)Gs * (++bar), Gs);
+            if (pend_row >= 0) {                                        // (CTA 0) the previous sub-panel's U12
+                for (int e = tid; e < SW * pend_rest; e += COOP_THREADS) {
+                    const int t = e / pend_rest, c = e % pend_rest;
+                    A[(int64_t)(pend_row + t) * ld + pend_col + c] = s_U[t * NB + c];
+                }
+                pend_row = -1;
+            }
+            if (warp == 0) {
+                double bv = -1.0;
+                int bp = NOROW, bg = 0;
+                for (int q = lane; q < Gs; q += 32) {
+                    const double* sl = slots + (size_t)(par * COOP_MAX_G + q) * SLOT;
+                    const double v = __ldcg(sl);
+                    const int ix = (int)__ldcg(sl + 1);
+                    if (v > bv || (v == bv && ix < bp)) { bv = v; bp = ix; bg = q; }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bp, o);
+                    const int og = __shfl_xor_sync(0xffffffffu, bg, o);
+                    if (ov > bv || (ov == bv && oi < bp)) { bv = ov; bp = oi; bg = og; }
+                }
+                // (a column of NaNs has no candidate: keep row k, and report it)
+                const double* src = bp == NOROW ? rowk + par * SW : slots + (size_t)(par * COOP_MAX_G + bg) * SLOT + 2;
+                if (bp == NOROW) bp = k;
+                double pr = 0.0;
+                if (lane < SW) { pr = __ldcg(src + lane); s_prow[lane] = pr; }
+                const double pv = __shfl_sync(0xffffffffu, pr, j);
+                if (lane == 0) {
+                    s_p = bp;
+                    s_piv[j] = bp;
+                    s_pinv = 1.0 / pv;
+                    if (g == 0) {
+                        piv[k] = bp;
+                        if (pv == 0.0 || pv != pv) atomicCAS(d.info, 0, k + 1);
+                    }
+                }
+            }
+            __syncthreads();
+            const int p = s_p;
+            if (p != k) {                                                // rows k and p trade places (published copies)
+                if (p >= r0 && p < r1 && tid < SW) s_P[tid * RLP + (p - r0)] = __ldcg(rowk + par * SW + tid);
+                if (k >= r0 && k < r1 && tid >= 32 && tid < 32 + SW) s_P[(tid - 32) * RLP + (k - r0)] = s_prow[tid - 32];
+            }
+            __syncthreads();
+            const double pinv = s_pinv;
+            for (int i = max(k + 1, r0) - r0 + tid; i < nloc; i += COOP_THREADS) {
+                const double l = s_P[j * RLP + i] * pinv;
+                s_P[j * RLP + i] = l;
+                for (int c = j + 1; c < w; ++c) s_P[c * RLP + i] = fma(-l, s_prow[c], s_P[c * RLP + i]);
             }
         }
         __syncthreads();
-        const int p = s_p;
-        // swap rows k and p inside the panel, and stage the (new) pivot row
-        if (tid < nb) {
-            const double a = A[(int64_t)k * ld + k0 + tid], b = A[(int64_t)p * ld + k0 + tid];
-            if (p != k) {
-                A[(int64_t)k * ld + k0 + tid] = b;
-                A[(int64_t)p * ld + k0 + tid] = a;
+        // my rows of the finished sub-panel go back (rows above kk0 are earlier sub-panels' U rows: not mine to touch)
+        for (int e = tid; e < nloc * SW; e += COOP_THREADS) {
+            const int i = e / SW, c = e % SW;
+            if (r0 + i >= kk0 && c < w) A[(int64_t)(r0 + i) * ld + kk0 + c] = s_P[c * RLP + i];
+        }
+        if (g == 0) {
+            // the w interchanges on the panel's other columns: where does the final content of each touched row come from
+            if (tid < 2 * w) {
+                const int q = tid < w ? kk0 + tid : s_piv[tid - w];
+                int cur = q;
+                for (int t = w - 1; t >= 0; --t) {
+                    const int kt = kk0 + t, pt = s_piv[t];
+                    if (cur == kt) cur = pt;
+                    else if (cur == pt) cur = kt;
+                }
+                s_dst[tid] = q;
+                s_src[tid] = cur;
             }
-            s_row[tid] = (p != k) ? b : a;
+            __syncthreads();
+            const int nother = nb - w, total = 2 * w * nother;
+            constexpr int PER = (2 * SW * NB + COOP_THREADS - 1) / COOP_THREADS;
+            double v[PER];
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int e = tid + u * COOP_THREADS;
+                if (e < total) {
+                    const int qi = e / nother, cc = e % nother;
+                    v[u] = __ldcg(A + (int64_t)s_src[qi] * ld + k0 + (cc < j0 ? cc : cc + w));
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int e = tid + u * COOP_THREADS;
+                if (e < total) {
+                    const int qi = e / nother, cc = e % nother;
+                    if (s_src[qi] != s_dst[qi]) A[(int64_t)s_dst[qi] * ld + k0 + (cc < j0 ? cc : cc + w)] = v[u];
+                }
+            }
+        }
+        const int rest = nb - j0 - w;
+        if (rest <= 0) break;
+        system_barrier(cnt, (unsigned)Gs * (++bar), Gs);
+        // U12 = L11^-1 A12 (here w == SW), by everyone
+        for (int e = tid; e < SW * SW; e += COOP_THREADS) s_L11[e] = __ldcg(A + (int64_t)(kk0 + e / SW) * ld + kk0 + e % SW);
+        for (int e = tid; e < SW * rest; e += COOP_THREADS) {
+            const int t = e / rest, c = e % rest;
+            s_U[t * NB + c] = __ldcg(A + (int64_t)(kk0 + t) * ld + kk0 + SW + c);
         }
         __syncthreads();
-        const double pinv = s_pivinv;
-        // multipliers and rank-1 update of the panel columns right of j: one warp per row, lanes over columns
-        const int c0 = j + 1;
-        for (int i = k + 1 + warp; i < n; i += PANEL_THREADS / 32) {
-            double* row = A + (int64_t)i * ld + k0;
-            const double l = row[j] * pinv;
-            for (int c = c0 + lane; c < nb; c += 32) row[c] = fma(-l, s_row[c], row[c]);
-            __syncwarp();
-            if (lane == 0) row[j] = l;
+        if (tid < rest) {
+            double x[SW];
+#pragma unroll
+            for (int t = 0; t < SW; ++t) {
+                double acc = s_U[t * NB + tid];
+#pragma unroll
+                for (int q = 0; q < t; ++q) acc = fma(-s_L11[t * SW + q], x[q], acc);
+                x[t] = acc;
+            }
+#pragma unroll
+            for (int t = 0; t < SW; ++t) s_U[t * NB + tid] = x[t];
+        }
+        __syncthreads();
+        if (g == 0) { pend_row = kk0; pend_col = kk0 + SW; pend_rest = rest; }
+        // my rows below the sub-panel: A[i][c] -= sum_t L[i][t] U12[t][c]; a warp per row, lanes over the columns
+        for (int i = max(kk0 + SW, r0) - r0 + warp; i < nloc; i += COOP_WARPS) {
+            const double lv = lane < SW ? s_P[lane * RLP + i] : 0.0;
+            double l[SW];
+#pragma unroll
+            for (int t = 0; t < SW; ++t) l[t] = __shfl_sync(0xffffffffu, lv, t);
+            double* row = A + (int64_t)(r0 + i) * ld + kk0 + SW;
+            double a[NB / 32];
+#pragma unroll
+            for (int u = 0; u < NB / 32; ++u) a[u] = lane + 32 * u < rest ? __ldcg(row + lane + 32 * u) : 0.0;
+#pragma unroll
+            for (int u = 0; u < NB / 32; ++u) {
+                const int c = lane + 32 * u;
+                if (c < rest) {
+                    double acc = a[u];
+#pragma unroll
+                    for (int t = 0; t < SW; ++t) acc = fma(-l[t], s_U[t * NB + c], acc);
+                    row[c] = acc;
+                }
+            }
         }
         __syncthreads();
     }
+}
+
+// zero the panel barrier's counter (before the first panel; lu_laswp_kernel re-zeroes it after every panel)
+__global__ void lu_init_kernel(const GmgSolveDesc* __restrict__ descs, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) *reinterpret_cast<unsigned*>(coop_of(descs[b])) = 0u;
 }
 
 // ---- the panel's row interchanges on the columns outside the panel.  grid = (ceil(n_max / 256), 1, batch) -------------
@@ -113,6 +309,7 @@ __global__ void __launch_bounds__(256) lu_laswp_kernel(const GmgSolveDesc* __res
     if (k0 >= n) return;
     const int nb = min(NB, n - k0);
     const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c == 0) *reinterpret_cast<unsigned*>(coop_of(d)) = 0u;           // the panel barrier's counter, for the next panel
     if (c >= n || (c >= k0 && c < k0 + nb)) return;
     const int* piv = piv_of(d);
     double* col = d.S + c;
@@ -317,6 +514,52 @@ int set_smem(K kern, size_t bytes) {
     return GMG_OK;
 }
 
+// The panel of the largest remaining order m over `batch` systems: as many co-resident CTAs per system as the device
+// holds (two per SM while their rows fit in half the shared memory), at least enough for the rows to fit at all, and
+// no more than one per `rows_target` rows; systems that do not fit together go in successive launches.
+int panel_rows_target() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GMG_LU_ROWS");
+        v = e ? atoi(e) : 128;
+        if (v < 32) v = 32;
+    }
+    return v;
+}
+
+int launch_panel(const GmgSolveDesc* descs, int batch, int kblk, int m, int sms, cudaStream_t s) {
+    const int target = panel_rows_target();
+    const int g_need = (int)gmg_ceil_div(m, COOP_MAX_ROWS), g_want = (int)gmg_ceil_div(m, target);
+    int G = 1, rows_cap = m, chunk = batch;
+    size_t smem = 0;
+    for (int occ_try = 2; occ_try >= 1; --occ_try) {
+        const int cap = std::min(occ_try * sms, COOP_MAX_G);
+        if (g_need > cap) return -3;
+        chunk = std::min(batch, std::max(1, cap / std::max(g_need, 1)));
+        G = std::max(g_need, std::min(cap / chunk, g_want));
+        rows_cap = (int)gmg_ceil_div(m, G);
+        smem = coop_smem(rows_cap);
+        int occ = 0;
+        GMG_CUDA_CHECK(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lu_panel_kernel, COOP_THREADS, smem));
+        if (occ >= occ_try) break;
+        if (occ_try == 1) return GMG_ERR_CUDA;
+    }
+    int rows_target = target;
+    for (int b0 = 0; b0 < batch; b0 += chunk) {
+        const GmgSolveDesc* dd = descs + b0;
+        const int nb = std::min(chunk, batch - b0);
+        if (G == 1) {
+            lu_panel_kernel<<<dim3(1, 1, nb), COOP_THREADS, smem, s>>>(dd, kblk, G, rows_cap, rows_target);
+            GMG_LAUNCH_CHECK();
+        } else {
+            void* args[] = {(void*)&dd, (void*)&kblk, (void*)&G, (void*)&rows_cap, (void*)&rows_target};
+            GMG_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lu_panel_kernel, dim3(G, 1, nb), dim3(COOP_THREADS), args, smem, s));
+        }
+    }
+    return GMG_OK;
+}
+
 int lu_attrs() {
     static int done_dev = -1;
     int dev = 0;
@@ -345,10 +588,12 @@ int gmg_gesv_ws_doubles(int64_t n, int64_t* linv_doubles, int64_t* p_doubles, in
     const int64_t nblk = gmg_ceil_div(n, NB);
     const int64_t ld = nblk * NB;
     if (linv_doubles) *linv_doubles = 2 * nblk * NB * NB;              // L^-1 and U^-1 of every diagonal block
-    if (p_doubles) *p_doubles = (int64_t)NB * ld + (n + 1) / 2 + 2;     // coefficient strip + n int32 pivots
+    if (p_doubles) *p_doubles = (int64_t)NB * ld + COOP_DOUBLES + (n + 1) / 2 + 2;   // strip + panel exchange + pivots
     if (ldp) *ldp = ld;
     return GMG_OK;
 }
+
+int64_t gmg_gesv_pivots_offset(int64_t ldp) { return (int64_t)NB * ldp + COOP_DOUBLES; }
 
 int gmg_gesv_blocked_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max, gmg_stream_t stream) {
     if (!descs) return -1;
@@ -359,9 +604,13 @@ int gmg_gesv_blocked_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, in
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int nblk = (int)gmg_ceil_div(n_max, NB);
+    int dev = 0, sms = 0;
+    GMG_CUDA_CHECK(cudaGetDevice(&dev));
+    GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    lu_init_kernel<<<(unsigned)gmg_ceil_div(batch, 256), 256, 0, s>>>(descs, batch);
+    GMG_LAUNCH_CHECK();
     for (int k = 0; k < nblk; ++k) {
-        lu_panel_kernel<<<dim3(1, 1, batch), PANEL_THREADS, 0, s>>>(descs, k);
-        GMG_LAUNCH_CHECK();
+        if ((rc = launch_panel(descs, batch, k, (int)(n_max - (int64_t)k * NB), sms, s))) return rc;
         lu_laswp_kernel<<<dim3((unsigned)gmg_ceil_div(n_max, 256), 1, batch), 256, 0, s>>>(descs, k);
         GMG_LAUNCH_CHECK();
         lu_blocks_kernel<<<dim3(1, 1, batch), 256, LU_BLOCKS_SMEM, s>>>(descs, k, nblk);
@@ -375,9 +624,6 @@ int gmg_gesv_blocked_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, in
         GMG_LAUNCH_CHECK();
     }
     if (nrhs_max == 0) return GMG_OK;
-    int dev = 0, sms = 0;
-    GMG_CUDA_CHECK(cudaGetDevice(&dev));
-    GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const bool narrow = gmg_ceil_div(gmg_ceil_div(nrhs_max, 64) * (int64_t)batch, sms) * 64.0 * 1.06 <
                         gmg_ceil_div(gmg_ceil_div(nrhs_max, BN) * (int64_t)batch, sms) * 128.0;
     const unsigned rhs_tiles = (unsigned)gmg_ceil_div(nrhs_max, narrow ? 64 : BN);

@@ -208,8 +208,11 @@ int gmg_gesv_batched_f64(const GmgSolveDesc* descs, int batch, int64_t nrhs_max,
  * blocked substitutions whose steps are GEMMs) - what np.linalg.solve costs at speed for the systems Cholesky rejects
  * (indefinite covariance of the default displacement method, asymmetric error covariance).  Workspaces per system, sized
  * for the LARGEST system of the batch by gmg_gesv_ws_doubles(n_max, ...): `Linv` (L^-1 and U^-1 of every diagonal
- * block), `P` (coefficient strip, leading dimension `ldp`, followed by the int32 pivots).  nrhs_max = 0: factor only. */
+ * block), `P` (coefficient strip, leading dimension `ldp`, then the panel's exchange area, then the int32 pivots - row
+ * interchanged with row k at step k, 0-based, at double offset gmg_gesv_pivots_offset(ldp) of P).  nrhs_max = 0: factor
+ * only.  The panel splits its rows over co-resident CTAs (cooperative launch) that meet once per column. */
 int gmg_gesv_ws_doubles(int64_t n, int64_t* linv_doubles, int64_t* p_doubles, int64_t* ldp);
+int64_t gmg_gesv_pivots_offset(int64_t ldp);
 int gmg_gesv_blocked_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max, gmg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

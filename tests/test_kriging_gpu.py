@@ -105,7 +105,8 @@ def test_cholesky_reports_indefinite_and_lu_fallback_matches_numpy(K):
         quiet(dn.cholesky_solve_inplace, dn.padded(np.zeros((4, 4))), dn.padded(np.ones((4, 2))))
 
 
-@pytest.mark.parametrize("sizes,nrhs", [([1], 1), ([5], 3), ([128], 64), ([129], 200), ([300, 77, 515], 70), ([1341], 2594)])
+@pytest.mark.parametrize("sizes,nrhs", [([1], 1), ([5], 3), ([128], 64), ([129], 200), ([300, 77, 515], 70), ([1341], 2594),
+                                        ([3000], 5), ([900, 700, 1100], 9), ([40] * 400, 2)])
 def test_blocked_lu_vs_numpy(K, sizes, nrhs):
     """`gmg_gesv_blocked_f64` (panel factorisation with partial pivoting, GEMM updates, GEMM substitutions) against
     numpy.linalg.solve (LAPACK dgesv - what the reference calls, kriging.py:343, :585): non-symmetric matrices, a zero
@@ -144,7 +145,7 @@ def test_blocked_lu_vs_numpy(K, sizes, nrhs):
     for b, n in enumerate(sizes):
         assert max_norm_rel(rhss[b][:, :nrhs].cpu().numpy(), want[b]) <= 1e-9, (b, n)
         # the pivots are LAPACK's (partial pivoting, first maximal entry)
-        piv = keep[4 * b + 3][128 * ldp:].view(torch.int32)[:n].cpu().numpy()
+        piv = keep[4 * b + 3][int(lib().gmg_gesv_pivots_offset(ldp)):].view(torch.int32)[:n].cpu().numpy()
         assert np.array_equal(piv, sla.lu_factor(mats[b])[1])
     # an exactly singular system reports the zero pivot through info, like dgesv
     Z = dn.padded(np.zeros((6, 6)))

@@ -27,6 +27,9 @@ def run(sizes, nrhs):
         ns = np.array(sizes, dtype=np.float64)
         fl = (2 * ns ** 3 / 3).sum() + (2 * ns ** 2 * nr).sum()
         print(f"{B} system(s), n_max={n_max}, nrhs={nr}: {what} {e0.elapsed_time(e1):.1f} ms = {fl / e0.elapsed_time(e1) / 1e9:.2f} TFLOP/s", flush=True)
-run([1341] * 60, 2594)
-run([8000], 2594)
-run([20000], 1024)
+if len(sys.argv) > 1:                                   # e.g.  time_lu.py 8000 1 2594
+    run([int(sys.argv[1])] * int(sys.argv[2]), int(sys.argv[3]))
+else:
+    run([1341] * 60, 2594)
+    run([8000], 2594)
+    run([20000], 1024)
