@@ -72,10 +72,9 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void system_barrier(unsigned* cnt, unsigned target, int G) {
     __syncthreads();
     if (G > 1 && threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(cnt, 1u);
+        // release: the CTA's writes before the barrier above are ordered before the arrival; acquire on the way out
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
         while (ld_acquire_u32(cnt) < target) {}
-        __threadfence();
     }
     __syncthreads();
 }
@@ -112,6 +111,7 @@ lu_panel_kernel(const GmgSolveDesc* __restrict__ descs, int kblk, int G, int row
     __shared__ int s_piv[SW], s_src[2 * SW], s_dst[2 * SW];
     __shared__ int s_p;
     __shared__ double s_pinv;
+    __shared__ double s_rowk[SW];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned bar = 0;
@@ -161,6 +161,7 @@ lu_panel_kernel(const GmgSolveDesc* __restrict__ descs, int kblk, int G, int row
                 }
                 pend_row = -1;
             }
+            if (warp == 1 && lane < SW) s_rowk[lane] = __ldcg(rowk + par * SW + lane);
             if (warp == 0) {
                 double bv = -1.0;
                 int bp = NOROW, bg = 0;
@@ -195,7 +196,7 @@ lu_panel_kernel(const GmgSolveDesc* __restrict__ descs, int kblk, int G, int row
             __syncthreads();
             const int p = s_p;
             if (p != k) {                                                // rows k and p trade places (published copies)
-                if (p >= r0 && p < r1 && tid < SW) s_P[tid * RLP + (p - r0)] = __ldcg(rowk + par * SW + tid);
+                if (p >= r0 && p < r1 && tid < SW) s_P[tid * RLP + (p - r0)] = s_rowk[tid];
                 if (k >= r0 && k < r1 && tid >= 32 && tid < 32 + SW) s_P[(tid - 32) * RLP + (k - r0)] = s_prow[tid - 32];
             }
             __syncthreads();
@@ -341,11 +342,13 @@ __global__ void __launch_bounds__(256) lu_laswp_rhs_kernel(const GmgSolveDesc* _
 }
 
 // ---- inverses of the factored diagonal block: Linv_k = L11^-1 (unit lower), Uinv_k = U11^-1 (upper), both identity
-// padded to 128 x 128.  One CTA of 256 threads per system; the factored block sits in shared memory, thread c < 128
-// computes column c of L11^-1 by forward substitution, thread 128 + c column c of U11^-1 by backward substitution -
-// each thread only ever reads back its OWN column, so the inverses are built directly in their global destination
-// (coalesced across threads, L1 resident).
-__global__ void __launch_bounds__(256) lu_blocks_kernel(const GmgSolveDesc* __restrict__ descs, int kblk, int nblk_max) {
+// padded to 128 x 128.  grid = (2, 1, batch): CTA 0 inverts L11, CTA 1 U11, each by BLOCKED substitution over 16-row
+// groups - the contribution of the rows already solved is a (16 x 16 I) x (16 I x 128) product spread over all 512
+// threads (four outputs each), the 16 x 16 diagonal group a short per-column substitution - so the dependent chain is
+// 8 x (<= 112 + 16 x 8) steps instead of 128 x 64.  The factored block sits in shared memory; the inverse is built in
+// its global destination and read back through L1 (same CTA, after a barrier).
+constexpr int IG = 16;                            // rows per group
+__global__ void __launch_bounds__(512) lu_blocks_kernel(const GmgSolveDesc* __restrict__ descs, int kblk, int nblk_max) {
     const GmgSolveDesc d = descs[blockIdx.z];
     const int n = d.n, k0 = kblk * NB;
     if (k0 >= n) return;
@@ -353,26 +356,55 @@ __global__ void __launch_bounds__(256) lu_blocks_kernel(const GmgSolveDesc* __re
     extern __shared__ __align__(16) double sm[];
     double* B = sm;                               // [NB][NB + 1] the factored block
     constexpr int LD = NB + 1;
-    for (int e = threadIdx.x; e < NB * NB; e += 256) {
+    double* T = B + NB * LD;                      // [IG][NB] right-hand side of the current group
+    for (int e = threadIdx.x; e < NB * NB; e += 512) {
         const int i = e / NB, j = e % NB;
         B[i * LD + j] = (i < nb && j < nb) ? d.S[(int64_t)(k0 + i) * d.lds + k0 + j] : (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
-    const int c = threadIdx.x & (NB - 1);
-    if (threadIdx.x < NB) {
-        double* x = d.Linv + (int64_t)kblk * NB * NB;                   // L^-1, column c
-        for (int i = 0; i < NB; ++i) {
-            double acc = (i == c) ? 1.0 : 0.0;
-            for (int k = c; k < i; ++k) acc = fma(-B[i * LD + k], x[k * NB + c], acc);
-            x[i * NB + c] = (i < c) ? 0.0 : acc;                        // unit diagonal: no division
+    const bool lower = blockIdx.x == 0;
+    double* X = d.Linv + (int64_t)((lower ? 0 : nblk_max) + kblk) * NB * NB;
+    const int c = threadIdx.x & (NB - 1), rq = (threadIdx.x >> 7) * 4;       // my column, my four rows of the group
+    for (int g = 0; g < NB / IG; ++g) {
+        const int i0 = lower ? g * IG : NB - IG - g * IG;
+        const int ka = lower ? 0 : i0 + IG, kb = lower ? i0 : NB;           // rows already solved
+        double acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = (i0 + rq + u == c) ? 1.0 : 0.0;
+        for (int k = ka; k < kb; ++k) {
+            const double xv = X[k * NB + c];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fma(-B[(i0 + rq + u) * LD + k], xv, acc[u]);
         }
-    } else {
-        double* x = d.Linv + (int64_t)(nblk_max + kblk) * NB * NB;      // U^-1, column c
-        for (int i = NB - 1; i >= 0; --i) {
-            double acc = (i == c) ? 1.0 : 0.0;
-            for (int k = i + 1; k <= c; ++k) acc = fma(-B[i * LD + k], x[k * NB + c], acc);
-            x[i * NB + c] = (i > c) ? 0.0 : acc / B[i * LD + i];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) T[(rq + u) * NB + c] = acc[u];
+        __syncthreads();
+        if (threadIdx.x < NB) {
+            double x[IG];
+            if (lower) {
+#pragma unroll
+                for (int r = 0; r < IG; ++r) {
+                    double a = T[r * NB + c];
+#pragma unroll
+                    for (int q = 0; q < r; ++q) a = fma(-B[(i0 + r) * LD + i0 + q], x[q], a);
+                    x[r] = a;                                                  // unit diagonal: no division
+                }
+            } else {
+#pragma unroll
+                for (int r = IG - 1; r >= 0; --r) {
+                    double a = T[r * NB + c];
+#pragma unroll
+                    for (int q = r + 1; q < IG; ++q) a = fma(-B[(i0 + r) * LD + i0 + q], x[q], a);
+                    x[r] = a / B[(i0 + r) * LD + i0 + r];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < IG; ++r) {
+                const int i = i0 + r;
+                X[i * NB + c] = (lower ? i < c : i > c) ? 0.0 : x[r];
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -506,7 +538,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) lu_step_bwd_kernel(const GmgSolv
     gemm_tile<false, false, BNT>(g, 0, n0, sm);
 }
 
-constexpr size_t LU_BLOCKS_SMEM = (size_t)NB * (NB + 1) * sizeof(double);
+constexpr size_t LU_BLOCKS_SMEM = ((size_t)NB * (NB + 1) + (size_t)IG * NB) * sizeof(double);
 
 template <typename K>
 int set_smem(K kern, size_t bytes) {
@@ -613,7 +645,7 @@ int gmg_gesv_blocked_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, in
         if ((rc = launch_panel(descs, batch, k, (int)(n_max - (int64_t)k * NB), sms, s))) return rc;
         lu_laswp_kernel<<<dim3((unsigned)gmg_ceil_div(n_max, 256), 1, batch), 256, 0, s>>>(descs, k);
         GMG_LAUNCH_CHECK();
-        lu_blocks_kernel<<<dim3(1, 1, batch), 256, LU_BLOCKS_SMEM, s>>>(descs, k, nblk);
+        lu_blocks_kernel<<<dim3(2, 1, batch), 512, LU_BLOCKS_SMEM, s>>>(descs, k, nblk);
         GMG_LAUNCH_CHECK();
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
         if (rem <= 0) break;
