@@ -69,6 +69,7 @@ def _declare(lib):
         "gmg_sym_eigvals_ws_bytes": (c_int, [i64, POINTER(c_size_t)]),
         "gmg_sym_eigvals_f64": (c_int, [p, i64, i64, p, p, c_size_t, p]),
         "gmg_variogram_f64": (c_int, [i32, p, i64, i64, i64, dbl, dbl, dbl, dbl, i32, i32, i32, dbl, p, i64, p]),
+        "gmg_stationary_cov_f64": (c_int, [i32, p, p, i64, dbl, dbl, dbl, dbl, dbl, i32, i32, i32, dbl, p, i64, p]),
         "gmg_tril_f64": (c_int, [p, i64, i64, p]),
         "gmg_sigma_rot_f64": (c_int, [p, p, p, i64, p, p]),
         "gmg_det22_f64": (c_int, [p, i64, p, p]),

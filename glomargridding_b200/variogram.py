@@ -149,6 +149,53 @@ class MaternVariogram(Variogram):
                          fill_diag=True)
 
 
+def _model_of(variogram: Variogram) -> tuple[str, float, str, bool]:
+    if isinstance(variogram, SphericalVariogram):
+        return "spherical", 0.5, "sklearn", False
+    if isinstance(variogram, GaussianVariogram):
+        return "gaussian", 0.5, "sklearn", False
+    if isinstance(variogram, ExponentialVariogram):
+        return "exponential", 0.5, "sklearn", False
+    if isinstance(variogram, MaternVariogram):
+        if variogram.method not in _METHOD:
+            raise ValueError("Unexpected 'method' value")
+        return "matern", variogram.nu, variogram.method, True
+    raise TypeError("variogram must be one of the Spherical/Gaussian/Exponential/Matern models")
+
+
+def stationary_covariance(lats_deg, lons_deg, variogram: Variogram, variance=None, radius: float = 6371.0,
+                          return_device: bool = False):
+    """The reference workflow's stationary route in ONE pass (notebook cells 6-7):
+
+        dist = haversine_distance_from_frame(frame)          # distances.py:191-218
+        cov = variogram_to_covariance(variogram.fit(dist), variance)    # variogram.py:96-476, :479-504
+
+    for cells at (`lats_deg`, `lons_deg`), decimal degrees, in the frame's row order.  The N x N result is written
+    once (`gmg_stationary_cov_f64`: distance, model and `variance - variogram` fused, upper triangle evaluated and
+    mirrored) and is bit-identical to the three separate calls of this package.  `variance=None` returns the
+    variogram matrix itself."""
+    model, nu, method, fill = _model_of(variogram)
+    if variogram.range is None:
+        raise ValueError(_RANGE_ERR)
+    for name, val in (("psill", variogram.psill), ("nugget", variogram.nugget), ("range", variogram.range), ("nu", nu)):
+        if np.ndim(val) != 0:
+            raise NotImplementedError(f"array-valued '{name}' is not supported by the device variogram models")
+    if variance is not None and np.ndim(variance) != 0:
+        raise NotImplementedError("array-valued 'variance' is not supported by the fused stationary covariance")
+    lat = dev.to_device(np.radians(np.asarray(lats_deg, dtype=np.float64)), torch.float64)
+    lon = dev.to_device(np.radians(np.asarray(lons_deg, dtype=np.float64)), torch.float64)
+    if lat.shape != lon.shape or lat.dim() != 1:
+        raise ValueError("lats and lons must be 1-d arrays of equal length")
+    N = lat.numel()
+    out = torch.empty((N, N), dtype=torch.float64, device=lat.device)
+    check(lib().gmg_stationary_cov_f64(_MODEL[model], lat.data_ptr(), lon.data_ptr(), N, float(radius),
+                                       float(variogram.psill), float(variogram.nugget), float(variogram.range),
+                                       float(nu), _METHOD[method], int(fill), int(variance is not None),
+                                       0.0 if variance is None else float(variance), out.data_ptr(), out.stride(0),
+                                       dev.stream_ptr()), "gmg_stationary_cov_f64")
+    return out if return_device else dev.to_host(out)
+
+
 def variogram_to_covariance(variogram, variance):
     """Covariance from a variogram matrix: variance - variogram (reference `variogram.py:479-504`)."""
     return variance - variogram

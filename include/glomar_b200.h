@@ -303,6 +303,15 @@ int gmg_variogram_f64(int model, const double* dist, int64_t rows, int64_t cols,
                       int fill_diag, int to_covariance, double variance, double* out, int64_t ldo,
                       gmg_stream_t stream);
 
+/* The stationary route FUSED: haversine distance matrix (distances.py:191-218: sklearn's asin form x radius) ->
+ * variogram model (.fit) -> variance - variogram (variogram.py:479-504) in one pass over the N x N output, which is
+ * written once and never read; lat/lon in radians, cells in the order of the frame's rows.  Bit-identical to
+ * gmg_haversine_f64 followed by gmg_variogram_f64 (same arithmetic; only the upper triangle is evaluated, the
+ * distance being symmetric bit for bit).  to_covariance = 0 returns the variogram itself. */
+int gmg_stationary_cov_f64(int model, const double* lat_rad, const double* lon_rad, int64_t N, double radius,
+                           double psill, double nugget, double range, double nu, int matern_method, int fill_diag,
+                           int to_covariance, double variance, double* out, int64_t ldo, gmg_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Small symmetric eigensolver (cyclic two-sided Jacobi, cooperative launch) for the device
  * `eigenvalue_clip`: the reference takes a full numpy.linalg.eigh of the covariance
