@@ -78,7 +78,13 @@ def _d2h_info(t: torch.Tensor) -> np.ndarray:
 _STAGE = None
 
 
-def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=None, post=None) -> torch.Tensor:
+def _group_doubles(g, raw_f32: bool) -> int:
+    """Doubles a group occupies in the blob: float32 arrays kept as float32 count 4 bytes per element."""
+    return (sum(int(a.size) * (4 if raw_f32 and a.dtype == np.float32 else 8) for a in g) + 7) // 8
+
+
+def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=None, post=None,
+                raw_f32: bool = False) -> torch.Tensor:
     """Flattened concatenation of host floating-point arrays on the device, as float64.  `groups` is a list of
     lists of arrays (one list per kriging problem: the row blocks of its error covariance); every group is ONE task
     of a small thread pool that packs it into one of two pinned staging buffers (numpy copies release the GIL; a
@@ -86,12 +92,14 @@ def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=No
     H2D copy - also inside one call, which is why the staging buffers are much smaller (128 MB) than a chunk of months
     (~500 MB).  The per-month error covariances are the bulk of the kriging path's host-to-device traffic.
     `post` (optional, one entry per group): a callable (or None) run by the packing task right after it has packed
-    its group - the exact symmetry check of `KrigeBatch` rides here, on cache-warm data."""
+    its group - the exact symmetry check of `KrigeBatch` rides here, on cache-warm data.
+    `raw_f32`: float32 arrays are NOT widened - they are packed as float32, back to back inside their group, and a
+    group is padded to a whole number of doubles (the device then reads them as float32, GMG_KRIGE_E_FLOAT32)."""
     from concurrent.futures import ThreadPoolExecutor
 
     if out is None:
         out = torch.empty(total, dtype=torch.float64, device=device)
-    sizes = [sum(int(a.size) for a in g) for g in groups]
+    sizes = [_group_doubles(g, raw_f32) for g in groups]
     cap = max(chunk_bytes // 8, max(sizes))
     global _STAGE, _POOL
     if _STAGE is None or _STAGE[0].numel() < cap:       # pinned allocations are slow (~0.3 s): keep them
@@ -120,15 +128,22 @@ def _h2d_concat(groups, total: int, device, chunk_bytes: int = 128 << 20, out=No
 
         def pack(item, buf=buf):
             off, g, after = item
+            at = 8 * off                                 # byte position in the staging buffer
             for a in g:                                  # one (strided) copy per block, any float dtype
-                if (a.ndim == 2 and a.dtype in (np.float64, np.float32) and a.strides[1] == a.itemsize
-                        and a.strides[0] % a.itemsize == 0 and a.strides[0] >= a.shape[1] * a.itemsize):
+                keep32 = raw_f32 and a.dtype == np.float32
+                native = (a.ndim == 2 and a.dtype in (np.float64, np.float32) and a.strides[1] == a.itemsize
+                          and a.strides[0] % a.itemsize == 0 and a.strides[0] >= a.shape[1] * a.itemsize)
+                if keep32 and native:
+                    L.gmg_host_pack_f32(a.ctypes.data, a.shape[0], a.shape[1], a.strides[0] // 4, buf.ctypes.data + at)
+                elif keep32:
+                    np.copyto(buf.view(np.float32)[at // 4:at // 4 + a.size].reshape(a.shape), a)
+                elif native:
                     # native packer: streaming stores into the pinned buffer, float32 widened on the way
                     L.gmg_host_pack_f64(a.ctypes.data, int(a.dtype == np.float32), a.shape[0], a.shape[1],
-                                        a.strides[0] // a.itemsize, buf.ctypes.data + 8 * off)
+                                        a.strides[0] // a.itemsize, buf.ctypes.data + at)
                 else:
-                    np.copyto(buf[off:off + a.size].reshape(a.shape), a, casting="unsafe")
-                off += a.size
+                    np.copyto(buf[at // 8:at // 8 + a.size].reshape(a.shape), a, casting="unsafe")
+                at += a.size * (4 if keep32 else 8)
             if after is not None:
                 after()
 
@@ -153,6 +168,7 @@ def _pool():
     return _POOL
 
 
+E_FLOAT32 = 2                       # GMG_KRIGE_E_FLOAT32 (include/glomar_b200.h): the descriptor's E holds float32 values
 PACK_SYMMETRIC_ERROR_COV = True     # tests switch the trapezoid packing off to compare it with whole uploads
 _SYM_PAIRS: dict[int, tuple[np.ndarray, np.ndarray]] = {}
 
@@ -415,6 +431,10 @@ class KrigeBatch:
         # blocks - row block b of 128 rows with its first 128 (b + 1) columns, a strided VIEW of the host array.
         # That is everything the Cholesky path reads and halves the H2D bytes of the kriging path
         # (GmgKrigeDesc.lde < 0; the LU fallback reads the mirrored entries).
+        # float32 error covariances (HadCRUT's are) stay float32 all the way to the gather kernel, which widens them -
+        # exactly what numpy's `C[idx][:, idx] + E` does with a float32 E - when every matrix of the batch is float32
+        f32 = any(has_E) and all(E is None or E.dtype == np.float32 for E in Es)
+        self.error_cov_dtype = np.float32 if f32 else np.float64
         groups, posts, sizes_E, ldes, self._asym = [], [], [], [], []
         late_asym: set[int] = set()                              # found asymmetric by the exact test while packing
         task_cap = (4 << 20) if B >= 8 else (1 << 17)          # doubles per packing task: a lone problem still uses the pool
@@ -441,6 +461,8 @@ class KrigeBatch:
                             late_asym.add(b)
                     return run
 
+                # (float32 mode: every block but a matrix's last has an even number of entries - 128 rows - so tasks start
+                # on 8-byte boundaries and only the end of a matrix is padded)
                 task, spans, fill = [], [], 0
                 for blk, span in zip(blocks, rows):
                     if task and fill + blk.size > task_cap:
@@ -453,6 +475,8 @@ class KrigeBatch:
                 groups.append(task)
                 posts.append(checker(spans) if exact else None)
                 size = sum(blk.size for blk in blocks)
+                if f32:
+                    size = (size + 1) // 2
             sizes_E.append(size)
             ldes.append(lde)
         offs_E = np.concatenate([[0], np.cumsum(sizes_E)]).astype(np.int64)
@@ -483,7 +507,7 @@ class KrigeBatch:
                      (blob.data_ptr() + f8 * int(offs_E[b])) if has_E[b] else 0, ldes[b],
                      self._y.data_ptr() + f8 * int(offs_n[b]), S_ptr, lds[b], 0, self.ldx, T_ptr, self.ldt,
                      self._partial.data_ptr() + f8 * int(oPa[b]), self.out.data_ptr() + f8 * 5 * M * b, n,
-                     int(self.ordinary))
+                     int(self.ordinary) | (E_FLOAT32 if f32 and has_E[b] else 0))
             sd[b] = (S_ptr, lds[b], self._Linv.data_ptr() + f8 * int(oL[b]), T_ptr, self.ldt,
                      self._P.data_ptr() + f8 * int(oP[b]), ws[b][2], self.info.data_ptr() + 4 * b, n, self.nrhs)
         marks.append(("descriptors", time.perf_counter()))
@@ -491,7 +515,7 @@ class KrigeBatch:
         groups += [[idx_all.view(np.float64)], [y_all], [kd.view(np.uint8).view(np.float64)],
                    [sd.view(np.uint8).view(np.float64)], [np.zeros((B + 1) // 2)]]
         posts += [None] * 5
-        _h2d_concat(groups, blob.numel(), device, out=blob, post=posts)
+        _h2d_concat(groups, blob.numel(), device, out=blob, post=posts, raw_f32=f32)
         marks.append(("pack + H2D of all inputs", time.perf_counter()))
         self._E_whole = []
         if late_asym:
@@ -502,7 +526,7 @@ class KrigeBatch:
                 self._asym.append(b)
                 whole = _h2d(np.ascontiguousarray(Es[b], dtype=np.float64), device)
                 self._E_whole.append(whole)
-                kd[b]["E"], kd[b]["lde"] = whole.data_ptr(), ns[b]
+                kd[b]["E"], kd[b]["lde"], kd[b]["ordinary"] = whole.data_ptr(), ns[b], int(self.ordinary)
             self._asym.sort()
             self._kd.copy_(_desc_tensor(kd, device).view(torch.float64))
             torch.cuda.current_stream().synchronize()

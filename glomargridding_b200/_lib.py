@@ -87,6 +87,7 @@ def _declare(lib):
         "gmg_dist_ws_doubles": (c_int, [i64, i32, POINTER(c_int64)]),
         "gmg_potrf_solve_f64": (c_int, [p, p, i32, i64, i64, p, i64, p]),
         "gmg_host_pack_f64": (c_int, [p, i32, i64, i64, i64, p]),
+        "gmg_host_pack_f32": (c_int, [p, i64, i64, i64, p]),
         "gmg_host_rows_symmetric": (c_int, [p, i32, i64, i64, i64, i64]),
         "gmg_microbench_fp64": (c_int, [i32, i32, i32, p, POINTER(c_double), POINTER(c_double), p]),
     })

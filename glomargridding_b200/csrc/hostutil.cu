@@ -78,3 +78,28 @@ extern "C" int gmg_host_pack_f64(const void* src, int is_f32, int64_t rows, int6
     _mm_sfence();
     return 0;
 }
+
+// float32 block that stays float32 (the descriptor's GMG_KRIGE_E_FLOAT32 flag): the same streaming copy, 4-byte elements
+extern "C" int gmg_host_pack_f32(const float* src, int64_t rows, int64_t cols, int64_t ld_src, float* dst) {
+    if (!src) return -1;
+    if (rows < 0 || cols < 0 || ld_src < cols) return -3;
+    if (!dst) return -5;
+    for (int64_t i = 0; i < rows; ++i) {
+        const float* s = src + i * ld_src;
+        float* d = dst + i * cols;
+        int64_t j = 0;
+        while (j < cols && (reinterpret_cast<uintptr_t>(d + j) & 15)) { d[j] = s[j]; ++j; }
+        for (; j + 16 <= cols; j += 16) {
+            const __m128 a = _mm_loadu_ps(s + j), b = _mm_loadu_ps(s + j + 4);
+            const __m128 c = _mm_loadu_ps(s + j + 8), e = _mm_loadu_ps(s + j + 12);
+            _mm_stream_ps(d + j, a);
+            _mm_stream_ps(d + j + 4, b);
+            _mm_stream_ps(d + j + 8, c);
+            _mm_stream_ps(d + j + 12, e);
+        }
+        for (; j + 4 <= cols; j += 4) _mm_stream_ps(d + j, _mm_loadu_ps(s + j));
+        for (; j < cols; ++j) d[j] = s[j];
+    }
+    _mm_sfence();
+    return 0;
+}

@@ -26,10 +26,15 @@ constexpr int kGatherCols = 512;      // columns per CTA: two per thread
 
 // Error-covariance entry (a, m) of system d, NaN read as 0.0 (kriging.py:120); `have` = false where a packed
 // symmetric E holds nothing the Cholesky path reads.
+__device__ __forceinline__ double error_cov_load(const GmgKrigeDesc& d, int64_t off) {
+    // float32 error covariances (HadCRUT's are) travel and stay as float32: widened here, exactly
+    return (d.ordinary & GMG_KRIGE_E_FLOAT32) ? (double)reinterpret_cast<const float*>(d.E)[off] : d.E[off];
+}
+
 __device__ __forceinline__ double error_cov_entry(const GmgKrigeDesc& d, int a, int m) {
     double e = 0.0;
     if (d.lde > 0) {
-        e = d.E[(int64_t)a * d.lde + m];
+        e = error_cov_load(d, (int64_t)a * d.lde + m);
     } else {
         // block-trapezoid packed lower triangle of a SYMMETRIC E (see GmgKrigeDesc): row i of row block
         // b = i / hb holds its first L_b = min(n, hb (b + 1)) entries.  The Cholesky path only reads the
@@ -43,7 +48,7 @@ __device__ __forceinline__ double error_cov_entry(const GmgKrigeDesc& d, int a, 
         if (have) {
             const int b = i / hb;
             const int Lb = min(d.n, hb * (b + 1));
-            e = d.E[(int64_t)hb * hb * ((int64_t)b * (b + 1) / 2) + (int64_t)(i - hb * b) * Lb + j];
+            e = error_cov_load(d, (int64_t)hb * hb * ((int64_t)b * (b + 1) / 2) + (int64_t)(i - hb * b) * Lb + j);
         }
     }
     return e != e ? 0.0 : e;
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(kColsPerBlock) reduce_kernel(int64_t M, const 
     __shared__ double sy[kSlab], so[kSlab];
     for (int e = threadIdx.x; e < a1 - a0; e += blockDim.x) {
         sy[e] = d.y[a0 + e];
-        so[e] = d.ordinary ? d.T[(int64_t)(a0 + e) * d.ldt + M] : 0.0;
+        so[e] = (d.ordinary & 1) ? d.T[(int64_t)(a0 + e) * d.ldt + M] : 0.0;
     }
     __syncthreads();
     if (m >= M) return;
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     // next to M and the order of summation is fixed)
     __shared__ double red[2][256];
     double so = 0.0, soy = 0.0;
-    if (d.ordinary) {
+    if (d.ordinary & 1) {
         for (int a = threadIdx.x; a < d.n; a += blockDim.x) {
             const double o = d.T[(int64_t)a * d.ldt + M];
             if (fwd_only) {                      // o = L^-1 1, T[:, M+1] = L^-1 y: 1^T S^-1 1 and 1^T S^-1 y
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     }
     const double cmm = C[m * ldc + m];
     double field = yT, rowdot = dd, alpha = 0.0, u2 = cmm - dd;
-    if (d.ordinary) {
+    if (d.ordinary & 1) {
         // Schur complement of the bordered system (:579-586): alpha = (1^T S^-1 c - 1) / (1^T S^-1 1).  On the
         // Cholesky path S is symmetric and 1^T S^-1 c = o^T c; the full-solve path (LU: indefinite or asymmetric S,
         // user-supplied weights) sums the solved column itself

@@ -620,7 +620,9 @@ int gmg_gesv_ws_doubles(int64_t n, int64_t* linv_doubles, int64_t* p_doubles, in
     const int64_t nblk = gmg_ceil_div(n, NB);
     const int64_t ld = nblk * NB;
     if (linv_doubles) *linv_doubles = 2 * nblk * NB * NB;              // L^-1 and U^-1 of every diagonal block
-    if (p_doubles) *p_doubles = (int64_t)NB * ld + COOP_DOUBLES + (n + 1) / 2 + 2;   // strip + panel exchange + pivots
+    // strip + panel exchange + pivots, rounded to 16 bytes: workspaces carved one after the other out of one allocation
+    // stay 16-byte aligned (the GEMM tiles read the strip with 16-byte cp.async)
+    if (p_doubles) *p_doubles = ((int64_t)NB * ld + COOP_DOUBLES + (n + 1) / 2 + 2 + 1) / 2 * 2;
     if (ldp) *ldp = ld;
     return GMG_OK;
 }

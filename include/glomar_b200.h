@@ -210,7 +210,9 @@ int gmg_gesv_batched_f64(const GmgSolveDesc* descs, int batch, int64_t nrhs_max,
  * for the LARGEST system of the batch by gmg_gesv_ws_doubles(n_max, ...): `Linv` (L^-1 and U^-1 of every diagonal
  * block), `P` (coefficient strip, leading dimension `ldp`, then the panel's exchange area, then the int32 pivots - row
  * interchanged with row k at step k, 0-based, at double offset gmg_gesv_pivots_offset(ldp) of P).  nrhs_max = 0: factor
- * only.  The panel splits its rows over co-resident CTAs (cooperative launch) that meet once per column. */
+ * only.  The panel splits its rows over co-resident CTAs (cooperative launch) that meet once per column.
+ * S, R, Linv and P must be 16-byte aligned and lds, ldr even (the sizes gmg_gesv_ws_doubles returns are even, so
+ * workspaces carved back to back out of one aligned allocation qualify). */
 int gmg_gesv_ws_doubles(int64_t n, int64_t* linv_doubles, int64_t* p_doubles, int64_t* ldp);
 int64_t gmg_gesv_pivots_offset(int64_t ldp);
 int gmg_gesv_blocked_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max, gmg_stream_t stream);
@@ -225,7 +227,8 @@ int gmg_gesv_blocked_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, in
  * (the "transposed weights", column M = o = S^-1 1). */
 typedef struct GmgKrigeDesc {
     const int64_t* idx;  /* n observation cells                                                    */
-    const double* E;     /* n x n error covariance or NULL                                         */
+    const double* E;     /* n x n error covariance or NULL (float32 values when `ordinary` has
+                          * GMG_KRIGE_E_FLOAT32 set: same layouts, 4-byte elements, widened on the device)  */
     int64_t lde;         /* > 0: row-major, leading dimension lde.  < 0: E is SYMMETRIC and packed as a block
                           * trapezoid with row blocks of hb = -lde rows: row i of block b = i / hb stores its first
                           * min(n, hb (b + 1)) entries, blocks one after the other (half the bytes to upload)    */
@@ -239,8 +242,10 @@ typedef struct GmgKrigeDesc {
     double* partial;     /* workspace: 4 * ceil(n/256) * M doubles                                 */
     double* out;         /* 5 x M: field, u2 (variance before clamping), mask, alpha, rowdot       */
     int32_t n;
-    int32_t ordinary;    /* 0 simple kriging, 1 ordinary kriging (Lagrange-extended system)        */
+    int32_t ordinary;    /* bit 0: 0 simple kriging, 1 ordinary kriging (Lagrange-extended system);
+                          * bit 1 (GMG_KRIGE_E_FLOAT32): E points at float32 values                  */
 } GmgKrigeDesc;
+#define GMG_KRIGE_E_FLOAT32 2
 
 /* S = C[idx, idx] + E, Cx = C[idx, :], T = [Cx | 1 | y]   (reference kriging.py:337-342, :571-583).
  * NaN entries of E are read as 0.0 (kriging.py:120).  With even leading dimensions and 16-byte aligned base
@@ -429,6 +434,9 @@ int gmg_host_rows_symmetric(const void* E, int is_f32, int64_t n, int64_t ld, in
 /* HOST helper: rows x cols block of a host matrix (row stride ld_src elements, float64 or float32) -> contiguous
  * float64 at dst (a pinned staging buffer of the upload pipeline) with streaming stores; float32 is widened. */
 int gmg_host_pack_f64(const void* src, int is_f32, int64_t rows, int64_t cols, int64_t ld_src, double* dst);
+/* The same for a float32 block that STAYS float32 (GMG_KRIGE_E_FLOAT32: half the staging writes and half the bytes over
+ * PCIe for HadCRUT-style float32 error covariances). */
+int gmg_host_pack_f32(const float* src, int64_t rows, int64_t cols, int64_t ld_src, float* dst);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement utility (no reference counterpart; SURVEY.md section 7: "FP64 peak is unmeasured - a DFMA-saturation

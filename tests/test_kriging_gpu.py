@@ -176,8 +176,23 @@ def test_indefinite_month_takes_the_blocked_lu_and_matches_the_oracle(K):
         k = K.OrdinaryKriging(b.cov_ns_device, idx, obs, E.copy())
         z, u = k.solve(), k.get_uncertainty()
         want = ordinary_kriging(cov, idx, obs, E, big_temporaries=False)
-    if k._batch.lu_fallback:                                    # (it is indefinite for these fields)
-        assert max_norm_rel(z, want["field"]) <= 1e-6 and var_rel(u, want["uncertainty"]) <= 1e-6
+    assert k._batch.lu_fallback                                 # (it is indefinite for these fields)
+    assert max_norm_rel(z, want["field"]) <= 1e-6 and var_rel(u, want["uncertainty"]) <= 1e-6
+    # several systems of different sizes in ONE LU batch (workspaces carved out of one allocation), each against the
+    # oracle: three indefinite months next to ones Cholesky accepts (no error covariance: nothing lifts the spectrum)
+    from glomargridding_b200.batched import krige_batch
+
+    probs = []
+    for m, n in enumerate((129, 301, 517, 77, 640)):
+        i2, o2 = synth.month_observations(10 + m, cov.shape[0], n_min=n, n_max=n + 1)
+        probs.append((i2, o2, None if m % 2 else synth.hadcrut_style_error_cov(i2, lons.size, seed=10 + m)))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = krige_batch(b.cov_ns_device, probs, "ordinary")
+        for m, (i2, o2, E2) in enumerate(probs):
+            want = ordinary_kriging(cov, i2, o2, E2, big_temporaries=False)
+            assert max_norm_rel(got["field"][m], want["field"]) <= 1e-6, m
+            assert max_norm_rel(got["constraint_mask"][m], want["constraint_mask"]) <= 1e-6, m
 
 
 # ---- known-answer: GeoStats.jl (reference test/test_kriging.py:67-192) ------------------------------------
@@ -554,6 +569,66 @@ def test_packed_symmetric_error_cov_upload_is_bit_identical_and_asymmetric_falls
     got = quiet(lambda: K.OrdinaryKriging(cov, idx.copy(), obs.copy(), E.copy()).solve())
     want = ok.ordinary_kriging(C, idx, obs, E, big_temporaries=False)["field"]
     assert max_norm_rel(got, want) < 1e-8
+
+
+def test_float32_error_covariances_stay_float32_and_give_the_same_bits(K, monkeypatch):
+    """HadCRUT's error covariances are float32 (tests/conftest.py).  A batch whose matrices are ALL float32 is uploaded
+    as float32 (`GMG_KRIGE_E_FLOAT32`: half the staging writes and PCIe bytes) and widened by the gather kernel - the
+    same exact widening numpy does in `C[idx][:, idx] + E` (kriging.py:342, :576), so the results carry the bits of the
+    float64 upload: packed trapezoid and whole upload, Cholesky path and LU fallback, odd sizes (a matrix with an odd
+    number of entries is padded to 8 bytes), no error covariance in between, a lone problem split over several packing
+    tasks, an asymmetric matrix found by the exact test (re-uploaded whole, as float64), the stochastic class."""
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    for method in ("Met_Office", "Modified_Met_Office"):          # SPD -> Cholesky; indefinite -> LU fallback
+        cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method=method,
+                                       precision=np.float64).cov_ns_device
+        p32 = []
+        for m, n in enumerate((129, 301, 517, 77)):               # 301 x 301 and 77 x 77: odd numbers of entries
+            idx, obs = synth.month_observations(m, cov.shape[0], n_min=n, n_max=n + 1)
+            p32.append((idx.astype(np.int64), obs.astype(np.float64),
+                        synth.hadcrut_style_error_cov(idx, lons.size, seed=m).astype(np.float32)))
+        p32.insert(2, (p32[0][0], p32[0][1], None))
+        p64 = [(i, o, None if E is None else E.astype(np.float64)) for i, o, E in p32]
+        for pack in (True, False):
+            with monkeypatch.context() as mp:
+                mp.setattr(dn, "PACK_SYMMETRIC_ERROR_COV", pack)
+                a = quiet(lambda: dn.KrigeBatch(cov, p32, ordinary=True).run())
+                b = quiet(lambda: dn.KrigeBatch(cov, p64, ordinary=True).run())
+            assert a.error_cov_dtype == np.float32 and b.error_cov_dtype == np.float64
+            assert a.h2d_bytes < 0.62 * b.h2d_bytes
+            assert bool(a.lu_fallback) == bool(b.lu_fallback) == (method == "Modified_Met_Office")
+            assert np.array_equal(a.out.cpu().numpy(), b.out.cpu().numpy())
+    # a lone month-sized problem: several packing tasks per matrix, exact symmetry test; and one entry off
+    idx, obs = synth.month_observations(5, cov.shape[0])
+    E32 = synth.hadcrut_style_error_cov(idx, lons.size, seed=5).astype(np.float32)
+    cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office",
+                                   precision=np.float64).cov_ns_device
+    for E in (E32, _one_entry_off(E32)):
+        k32 = quiet(K.OrdinaryKriging, cov, idx.copy(), obs.copy(), E.copy())
+        k64 = quiet(K.OrdinaryKriging, cov, idx.copy(), obs.copy(), E.astype(np.float64))
+        assert np.array_equal(quiet(k32.solve), quiet(k64.solve))
+        assert np.array_equal(quiet(k32.get_uncertainty), quiet(k64.get_uncertainty))
+    # a mixed batch keeps the float64 upload (float32 widened while packing)
+    mixed = [p32[0], p64[1]]
+    assert quiet(lambda: dn.KrigeBatch(cov, mixed, ordinary=True)).error_cov_dtype == np.float64
+    # the stochastic ensemble factors E itself from the same (float32) upload
+    from glomargridding_b200.batched import stochastic_ensemble
+
+    s32 = quiet(stochastic_ensemble, cov, idx, obs, E32, n_members=4, seed=3)
+    s64 = quiet(stochastic_ensemble, cov, idx, obs, E32.astype(np.float64), n_members=4, seed=3)
+    for key in s32:
+        if isinstance(s32[key], np.ndarray):
+            assert np.array_equal(s32[key], s64[key]), key
+
+
+def _one_entry_off(E):
+    E = E.copy()
+    E[700, 3] *= 1.5                     # asymmetric in one entry: passes the sampled pre-filter, fails the exact test
+    return E
 
 
 def test_pipelined_driver_many_small_months(K):
