@@ -841,7 +841,23 @@ def run_months(args, rank, world, device, barrier, max_over_ranks, local, dmma_p
             e2e_step()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
+        # the same months with the error covariances as float32 - what HadCRUT.5 ships (tests/conftest.py) and what the
+        # reference's notebook feeds: they travel as float32 and are widened by the gather kernel (same bits out)
+        probs64 = probs
+        probs = [(i, o, E.astype(np.float32)) for i, o, E in probs64]
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt32 = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
+        probs = probs64
         e2e = {"value": args.months / dt, "unit": "months/s",
+               "float32_error_cov": {"value": args.months / dt32, "unit": "months/s",
+                                     "note": "the same call with float32 error covariances (HadCRUT.5's dtype): "
+                                             "uploaded as float32, half the host-to-device bytes, identical results"},
                "h2d_bytes_per_step": int(sum(8 * (dn.packed_error_cov_doubles(len(p[0])) + 2 * len(p[0])) for p in probs)),
                "d2h_bytes_per_step": int(len(probs) * 5 * M * 8), "steps": args.e2e_steps,
                "note": "krige_batch(cov on device, host idx/obs/error_cov per month) -> numpy field, uncertainty, "

@@ -556,8 +556,12 @@ int launch_colupdate(const GmgSolveDesc* descs, int k, int64_t n_max, int batch,
 // (1 wave x 128) or 127 of 64 (1 wave x 64); the whole grid on one GPU: 507 x 128 (4 waves = 512) or 1 013 x 64
 // (7 waves = 448).  Bit-identical either way.
 // A third width, 56 columns on the 16 x 1 warp layout (CfgTall), is taken when it saves a further ~10 %: one rank of 8
-// then runs 145 strips on 148 SMs instead of 127.  GMG_STRIP forces a width (experiments).
-int strip_width(int64_t nrhs_max, int batch, int sms) {
+// then runs 145 strips on 148 SMs instead of 127 - but ONLY for a solve that has the GPU to itself (`alone`).  Inside
+// the overlapped factor + solve pipeline the 21 SMs the 64-wide strips leave idle are what the factorisation's
+// latency-bound critical path (diagonal block, panel, look-ahead update: high-priority stream, but CTAs are not
+// pre-empted) runs on: measured on 8 GPUs, 1 degree / 20 000 observations, 0.172 s with 64-wide strips and 0.214 s
+// with 56-wide ones (profiles/r02_strip_n8_ab.txt).  GMG_STRIP forces a width (experiments).
+int strip_width(int64_t nrhs_max, int batch, int sms, bool alone) {
     if (nrhs_max <= 0) return BN;
     static int forced = -1;
     if (forced < 0) {
@@ -569,7 +573,7 @@ int strip_width(int64_t nrhs_max, int batch, int sms) {
         return (double)gmg_ceil_div(gmg_ceil_div(nrhs_max, w) * (int64_t)batch, sms) * w * penalty;
     };
     const double c128 = cost(128, 1.0), c64 = cost(64, 1.06), c56 = cost(56, 1.14);
-    if (c56 < c64 && c56 < c128) return 56;
+    if (alone && c56 < c64 && c56 < c128) return 56;
     return c64 < c128 ? 64 : 128;
 }
 
@@ -720,7 +724,7 @@ int gmg_potrs_batched_f64(const GmgSolveDesc* descs, int batch, int64_t n_max, i
     int dev = 0, sms = 0;
     GMG_CUDA_CHECK(cudaGetDevice(&dev));
     GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int width = strip_width(nrhs_max, batch, sms);
+    const int width = strip_width(nrhs_max, batch, sms, true);
     const bool narrow = width != BN;              // the backward steps know 128 and 64
     const unsigned rhs_tiles = (unsigned)gmg_ceil_div(nrhs_max, narrow ? 64 : BN);
     for (int k = 0; k < nblk && (which & GMG_SOLVE_FORWARD); ++k)               // L Y = B
@@ -855,7 +859,7 @@ int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max
     double* recvbuf = xbuf ? sendbuf + cap0 * NB * NB : nullptr;   // [world][cap][NB][NB], cap = this step's
     int sms = 0;
     GMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    const int width = strip_width(nrhs_max, batch, sms);
+    const int width = strip_width(nrhs_max, batch, sms, false);
 
     size_t ne = 0;
     cudaEvent_t ev_fork, ev;
