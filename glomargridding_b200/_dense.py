@@ -168,6 +168,8 @@ def _pool():
     return _POOL
 
 
+GMG_ERR_UNSUPPORTED = 4             # gmg_common.cuh
+FUSED_RHS_GATHER = True             # tests switch it off to compare with the separate gather + solve calls
 E_FLOAT32 = 2                       # GMG_KRIGE_E_FLOAT32 (include/glomar_b200.h): the descriptor's E holds float32 values
 PACK_SYMMETRIC_ERROR_COV = True     # tests switch the trapezoid packing off to compare it with whole uploads
 _SYM_PAIRS: dict[int, tuple[np.ndarray, np.ndarray]] = {}
@@ -569,14 +571,23 @@ class KrigeBatch:
         L, s = lib(), dev.stream_ptr()
         C, M, ldc = self.cov.data_ptr(), self.M, self.cov.stride(0)
         self.full[:] = False
-        check(L.gmg_krige_gather_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, s), "gather")
-        # Cholesky and the forward triangular solve as ONE overlapped pipeline (gmg_potrf_solve_f64: the solve step of
-        # block row k starts as soon as diagonal block k exists, the serial diagonal-block kernel of the factorisation
-        # hides behind the GEMMs of the solve), then the apply pass - all enqueued before the factorisation status is
-        # read, so the common case (every system positive definite) has no host synchronisation inside it.  A system
-        # whose Cholesky failed produced garbage that the LU pass below overwrites.
-        check(L.gmg_potrf_solve_f64(None, self._sd.data_ptr(), self.B, self.n_max, self.nrhs, None, 0, s),
-              "gmg_potrf_solve_f64")
+        # Cholesky and the forward triangular solve as ONE overlapped pipeline (the solve step of block row k starts as
+        # soon as diagonal block k exists, the serial diagonal-block kernel of the factorisation hides behind the GEMMs
+        # of the solve), then the apply pass - all enqueued before the factorisation status is read, so the common case
+        # (every system positive definite) has no host synchronisation inside it.  A system whose Cholesky failed
+        # produced garbage that the LU pass below overwrites.
+        # gmg_krige_solve_f64 also folds the gather of the right-hand sides C[idx, :] into the solve steps (T is never
+        # written by a gather kernel: 23 MB less to write and to read back per 5-degree month); a covariance with an odd
+        # order or leading dimension takes the two separate calls - same bits either way.
+        rc = GMG_ERR_UNSUPPORTED
+        if FUSED_RHS_GATHER:
+            rc = L.gmg_krige_solve_f64(C, M, ldc, self._kd.data_ptr(), self._sd.data_ptr(), self.B, self.n_max, s)
+        if rc == GMG_ERR_UNSUPPORTED:
+            check(L.gmg_krige_gather_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, s), "gather")
+            check(L.gmg_potrf_solve_f64(None, self._sd.data_ptr(), self.B, self.n_max, self.nrhs, None, 0, s),
+                  "gmg_potrf_solve_f64")
+        else:
+            check(rc, "gmg_krige_solve_f64")
         check(L.gmg_krige_apply_batched_f64(C, M, ldc, self._kd.data_ptr(), self.B, self.n_max, 1, s), "apply")
         info = _d2h_info(self.info)                  # synchronises: the factorisation outcome decides the path
         asym = np.asarray(self._asym, dtype=np.int64)

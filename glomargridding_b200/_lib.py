@@ -57,6 +57,7 @@ def _declare(lib):
         "gmg_gesv_blocked_f64": (c_int, [p, i32, i64, i64, p]),
         "gmg_krige_gather_batched_f64": (c_int, [p, i64, i64, p, i32, i64, p]),
         "gmg_krige_error_cov_lower_f64": (c_int, [p, i32, i64, p, i64, p]),
+        "gmg_krige_solve_f64": (c_int, [p, i64, i64, p, p, i32, i64, p]),
         "gmg_krige_apply_batched_f64": (c_int, [p, i64, i64, p, i32, i64, i32, p]),
         "gmg_krige_weights_f64": (c_int, [p, i64, p, i64, p, i64, i64, p, i64, p]),
         "gmg_extended_inverse_f64": (c_int, [p, i64, i64, p, p, i64, p]),

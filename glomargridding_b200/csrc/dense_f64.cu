@@ -408,9 +408,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS == 256 ? 2 : 1)) t
 }
 
 // grid = (ceil(nrhs_max / BNT), 1, batch)
-template <typename Cfg, int BNT>
+// GATHER: the right-hand-side rows of block row k (the last nb k-rows of the GEMM) are read from the covariance matrix,
+// rows idx[k0 ..], for the columns < M - the kriging path's T = [C[idx, :] | 1 | y] is then never written by a gather
+// kernel, only its two extra columns are (gmg_krige_solve_f64).  Same values, same arithmetic: bit-identical.
+struct RhsGather {
+    const double* C;               // M x M covariance, leading dimension ldc (even, 16-byte aligned base)
+    int64_t M, ldc;
+    const GmgKrigeDesc* kd;        // same systems, same order as the solve descriptors
+};
+
+template <typename Cfg, int BNT, bool GATHER = false>
 __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS == 256 ? 2 : 1)) trsm_step_fwd_kernel(
-    const GmgSolveDesc* __restrict__ descs, int kblk) {
+    const GmgSolveDesc* __restrict__ descs, int kblk, RhsGather rg) {
     const GmgSolveDesc d = descs[blockIdx.z];
     const int k0 = kblk * NB;
     const int n0 = blockIdx.x * BNT;
@@ -424,7 +433,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS == 256 ? 2 : 1)) t
     g.D = d.R + (int64_t)k0 * d.ldr; g.ldd = d.ldr;
     g.m = nb; g.n = d.nrhs; g.k = k0 + nb;
     g.alpha = 1.0; g.beta = 0.0;
-    gemm_tile_cfg<Cfg, false, false, BNT>(g, 0, n0, sm);
+    if constexpr (GATHER) {
+        __shared__ int64_t rowoff[NB];
+        const int64_t* idx = rg.kd[blockIdx.z].idx;
+        for (int r = threadIdx.x; r < nb; r += Cfg::THREADS)
+            rowoff[r] = min(max(idx[k0 + r], (int64_t)0), rg.M - 1) * rg.ldc;   // clamped like the gather kernel
+        __syncthreads();
+        GatherArgs ga;
+        ga.G = rg.C; ga.rowoff = rowoff; ga.kg0 = k0; ga.ng = (int)rg.M;
+        gemm_tile_cfg<Cfg, false, false, BNT, true>(g, 0, n0, sm, &ga);
+    } else {
+        gemm_tile_cfg<Cfg, false, false, BNT>(g, 0, n0, sm);
+    }
 }
 
 // grid = (ceil((n_max - k0) / BM), 1, batch): Q_k rows: [Linv_kk ; -L[k+1:, k] Linv_kk] into P (ld NB)
@@ -500,6 +520,9 @@ int ensure_attrs() {
     if ((rc = set_smem(trsm_step_fwd_kernel<CfgBig, 64>, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_fwd_kernel<CfgSmall, 64>, GEMM_SMALL_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_fwd_kernel<CfgTall, 56>, GEMM_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(trsm_step_fwd_kernel<CfgBig, 128, true>, GEMM_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(trsm_step_fwd_kernel<CfgBig, 64, true>, GEMM_SMEM_BYTES))) return rc;
+    if ((rc = set_smem(trsm_step_fwd_kernel<CfgSmall, 64, true>, GEMM_SMALL_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_prep_bwd_kernel, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_bwd_kernel<128>, GEMM_SMEM_BYTES))) return rc;
     if ((rc = set_smem(trsm_step_bwd_kernel<64>, GEMM_SMEM_BYTES))) return rc;
@@ -587,29 +610,36 @@ int small_k_limit() {
     return v;
 }
 
-// forward-solve step of block row k: coefficient strip, then one GEMM
-int launch_fwd_step(const GmgSolveDesc* descs, int k, int batch, int64_t nrhs_max, int width, cudaStream_t s) {
+// forward-solve step of block row k: coefficient strip, then one GEMM (rg != nullptr: right-hand sides of the block row
+// gathered from the covariance matrix on the fly)
+int launch_fwd_step(const GmgSolveDesc* descs, int k, int batch, int64_t nrhs_max, int width, cudaStream_t s,
+                    const RhsGather* rg = nullptr) {
     const int k0 = k * NB;
+    const RhsGather none{nullptr, 0, 0, nullptr};
     if (k0 + NB <= small_k_limit()) {
         trsm_prep_fwd_kernel<CfgSmall, 64><<<dim3((unsigned)gmg_ceil_div(k0, 64) + 1, 1, batch), CfgSmall::THREADS,
                                              GEMM_SMALL_SMEM_BYTES, s>>>(descs, k);
         GMG_LAUNCH_CHECK();
-        trsm_step_fwd_kernel<CfgSmall, 64><<<dim3((unsigned)gmg_ceil_div(nrhs_max, 64), 1, batch), CfgSmall::THREADS,
-                                             GEMM_SMALL_SMEM_BYTES, s>>>(descs, k);
+        const dim3 grid((unsigned)gmg_ceil_div(nrhs_max, 64), 1, batch);
+        if (rg) trsm_step_fwd_kernel<CfgSmall, 64, true><<<grid, CfgSmall::THREADS, GEMM_SMALL_SMEM_BYTES, s>>>(descs, k, *rg);
+        else trsm_step_fwd_kernel<CfgSmall, 64><<<grid, CfgSmall::THREADS, GEMM_SMALL_SMEM_BYTES, s>>>(descs, k, none);
         GMG_LAUNCH_CHECK();
         return GMG_OK;
     }
     trsm_prep_fwd_kernel<CfgBig, 128><<<dim3((unsigned)k + 1, 1, batch), GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k);
     GMG_LAUNCH_CHECK();
-    if (width == 56)
+    if (width == 56 && !rg)
         trsm_step_fwd_kernel<CfgTall, 56><<<dim3((unsigned)gmg_ceil_div(nrhs_max, 56), 1, batch), GEMM_THREADS,
-                                            GEMM_SMEM_BYTES, s>>>(descs, k);
-    else if (width == 64)
-        trsm_step_fwd_kernel<CfgBig, 64><<<dim3((unsigned)gmg_ceil_div(nrhs_max, 64), 1, batch), GEMM_THREADS,
-                                           GEMM_SMEM_BYTES, s>>>(descs, k);
-    else
-        trsm_step_fwd_kernel<CfgBig, 128><<<dim3((unsigned)gmg_ceil_div(nrhs_max, BN), 1, batch), GEMM_THREADS,
-                                            GEMM_SMEM_BYTES, s>>>(descs, k);
+                                            GEMM_SMEM_BYTES, s>>>(descs, k, none);
+    else if (width == 64 || width == 56) {
+        const dim3 grid((unsigned)gmg_ceil_div(nrhs_max, 64), 1, batch);
+        if (rg) trsm_step_fwd_kernel<CfgBig, 64, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, *rg);
+        else trsm_step_fwd_kernel<CfgBig, 64><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, none);
+    } else {
+        const dim3 grid((unsigned)gmg_ceil_div(nrhs_max, BN), 1, batch);
+        if (rg) trsm_step_fwd_kernel<CfgBig, 128, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, *rg);
+        else trsm_step_fwd_kernel<CfgBig, 128><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(descs, k, none);
+    }
     GMG_LAUNCH_CHECK();
     return GMG_OK;
 }
@@ -849,7 +879,7 @@ inline int64_t panel_cap(int64_t n, int world) {           // packed tiles per r
     } while (0)
 
 int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max, double* xbuf,
-                 cudaStream_t caller) {
+                 cudaStream_t caller, const RhsGather* rg = nullptr) {
     const int world = c->world, rank = c->rank;
     const int nblk = (int)gmg_ceil_div(n_max, NB);
     NcclApi& nc = nccl_api();
@@ -895,7 +925,7 @@ int factor_solve(DistCtx* c, const GmgSolveDesc* descs, int batch, int64_t n_max
             if ((rc = ctx_event(c, ne++, &ev))) return rc;
             GMG_CUDA_CHECK(cudaEventRecord(ev, c->sF));
             GMG_CUDA_CHECK(cudaStreamWaitEvent(c->sU, ev, 0));
-            if ((rc = launch_fwd_step(descs, k, batch, nrhs_max, width, c->sU))) return rc;
+            if ((rc = launch_fwd_step(descs, k, batch, nrhs_max, width, c->sU, rg))) return rc;
         }
         const int64_t rem = n_max - (int64_t)(k + 1) * NB;
         if (rem <= 0) break;
@@ -986,6 +1016,19 @@ int gmg_dist_ws_doubles(int64_t n, int world, int64_t* doubles) {
     if (!doubles) return -3;
     *doubles = world > 1 ? (int64_t)NB * NB * (2 + panel_cap(n, world) * (1 + world)) : 0;
     return GMG_OK;
+}
+
+// The overlapped factor + forward-solve pipeline of gmg_potrf_solve_f64 on this GPU, with the right-hand-side rows of
+// every block row read from C[idx, :] on the fly (used by gmg_krige_solve_f64, kriging.cu).
+int gmg_internal_potrf_solve_gathered(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max,
+                                      const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* kd, cudaStream_t stream) {
+    DistCtx* c = local_ctx();
+    if (!c) return GMG_ERR_CUDA;
+    int rc = ensure_attrs();
+    if (rc) return rc;
+    const RhsGather rg{C, M, ldc, kd};
+    std::lock_guard<std::mutex> lock(c->mu);
+    return factor_solve(c, descs, batch, n_max, nrhs_max, nullptr, stream, &rg);
 }
 
 int gmg_potrf_solve_f64(void* ctx, const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max,

@@ -119,14 +119,41 @@ __device__ __forceinline__ void load_kcol_c(double* s, const double* G, int64_t 
     }
 }
 
+// Rows of op(B) (TB = false) that are GATHERED from another matrix instead of read from B: k-rows kg0 .. k - 1, columns
+// < ng, come from G[rowoff[kk - kg0] + col] (rowoff = row index x leading dimension, in SHARED memory).  The kriging
+// path uses it to read the right-hand sides C[idx, :] of block row k straight from the covariance matrix inside the
+// forward-solve step, instead of from a copy a gather kernel would have to write first (n x M doubles per system).
+struct GatherArgs {
+    const double* G;
+    const int64_t* rowoff;   // shared memory, NB entries
+    int kg0, ng;
+};
+
+template <typename Cfg, int NC>
+__device__ __forceinline__ void load_kcol_gather_c(double* s, const double* B, int64_t ld, int col0, int cols_total,
+                                                   int k0, int k_total, int tid, const GatherArgs& ga) {
+    constexpr int KB = Cfg::KB, LD = NC + 4;
+#pragma unroll
+    for (int c = tid; c < KB * (NC / 2); c += Cfg::THREADS) {
+        const int r = c / (NC / 2), c2 = c % (NC / 2);
+        const int gk = k0 + r, gc = col0 + 2 * c2;
+        int bytes = (gk < k_total) ? (cols_total - gc) * 8 : 0;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const double* src = B;
+        if (bytes) src = (gk >= ga.kg0 && gc < ga.ng) ? ga.G + ga.rowoff[gk - ga.kg0] + gc : B + (int64_t)gk * ld + gc;
+        cp_async16_zfill(s + r * LD + 2 * c2, src, bytes);
+    }
+}
+
 // D[m0.., n0..] = alpha op(A) op(B) + beta C for one BM x BNT tile.  `smem` = TileGeom<Cfg, BNT>::SMEM_BYTES, 16 B
 // aligned.  BNT = 128 or 64 for CfgBig (the narrow tile halves the work per CTA and is used by the triangular-solve
 // steps when the right-hand sides give fewer 128-column strips than the GPU has SMs), 64 for CfgSmall.
 // Every thread of the Cfg::THREADS-thread CTA must call this (it contains __syncthreads).
 // In-place note: a CTA reads all of its A / B slabs before the epilogue writes D, so D may alias rows of A
 // or B that only THIS tile reads (used by the panel solve and the triangular solves).
-template <typename Cfg, bool TA, bool TB, int BNT>
-__device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem) {
+template <typename Cfg, bool TA, bool TB, int BNT, bool GATHER = false>
+__device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem, const GatherArgs* ga = nullptr) {
+    static_assert(!GATHER || !TB, "gathered rows are rows of a k x n operand");
     using G_ = TileGeom<Cfg, BNT>;
     constexpr int KB = Cfg::KB, NST = Cfg::NST;
     constexpr int WN = BNT / Cfg::WARPS_N;    // columns per warp
@@ -154,6 +181,7 @@ __device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem) {
         if (TA) load_kcol_c<Cfg, BM>(sA, g.A, g.lda, m0, g.m, kt * KB, g.k, tid);
         else    load_rowk_c<Cfg, BM>(sA, g.A, g.lda, m0, g.m, kt * KB, g.k, tid);
         if (TB) load_rowk_c<Cfg, BNT>(sB, g.B, g.ldb, n0, g.n, kt * KB, g.k, tid);
+        else if (GATHER && (kt + 1) * KB > ga->kg0) load_kcol_gather_c<Cfg, BNT>(sB, g.B, g.ldb, n0, g.n, kt * KB, g.k, tid, *ga);
         else    load_kcol_c<Cfg, BNT>(sB, g.B, g.ldb, n0, g.n, kt * KB, g.k, tid);
     };
 #pragma unroll

@@ -58,12 +58,17 @@ __device__ __forceinline__ double error_cov_entry(const GmgKrigeDesc& d, int a, 
 // A thread owns two adjacent columns (one 16-byte load and one 16-byte store per row and matrix when the leading
 // dimensions and base pointers allow it) of eight rows, all loads issued before the first store, so that a CTA moves 64 KB instead of the 4 KB of the first
 // version (one row, one column per thread: 8.4 M CTAs for 480 months, bound by the CTA launch rate at 1.8 TB/s).
+// t_from > 0: only the columns >= t_from of T are written (S as always) and the grid's LAST column block is the one
+// that holds them (`tail_block`, or -1 when it is one of the S blocks anyway) - gmg_krige_solve_f64, whose solve reads
+// C[idx, :] itself.
 __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ C, int64_t M, int64_t ldc,
-                                                     const GmgKrigeDesc* __restrict__ descs) {
+                                                     const GmgKrigeDesc* __restrict__ descs, int64_t t_from,
+                                                     int tail_block) {
     const GmgKrigeDesc d = descs[blockIdx.z];
     const int a0 = blockIdx.y * kGatherRows;
     if (a0 >= d.n) return;
-    const int64_t m0 = 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+    const int64_t xblk = (tail_block >= 0 && blockIdx.x == gridDim.x - 1) ? tail_block : blockIdx.x;
+    const int64_t m0 = 2 * (xblk * (int64_t)blockDim.x + threadIdx.x);
     const bool vec = (((ldc | d.ldt | d.lds | d.ldx) & 1) == 0) &&
                      (((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(d.T) |
                         reinterpret_cast<uintptr_t>(d.S) | reinterpret_cast<uintptr_t>(d.Cx)) & 15) == 0);
@@ -85,7 +90,9 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
         crow[r] = C + min(max(d.idx[arow[r]], (int64_t)0), top) * ldc;
     }
     // ---- T = [C[idx, :] | 1 | y] (and the C_cross copy of the full-solve paths) ----------------------------------
-    if (m0 + 1 < M && vec) {
+    if (m0 + 1 < t_from) {
+        // nothing of T for these two columns
+    } else if (m0 + 1 < M && vec) {
         double2 v[kGatherRows];
 #pragma unroll
         for (int r = 0; r < kGatherRows; ++r) v[r] = *reinterpret_cast<const double2*>(crow[r] + m0);
@@ -101,7 +108,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int64_t m = m0 + k;
-                if (m < M) {
+                if (m < t_from) {
+                } else if (m < M) {
                     const double v = crow[r][m];
                     if (d.Cx) d.Cx[(int64_t)a * d.ldx + m] = v;
                     d.T[(int64_t)a * d.ldt + m] = v;
@@ -314,6 +322,11 @@ __global__ void __launch_bounds__(256) weights_kernel(const double* __restrict__
 
 extern "C" {
 
+// dense_f64.cu (library-internal, not part of the public header)
+int gmg_internal_potrf_solve_gathered(const GmgSolveDesc* descs, int batch, int64_t n_max, int64_t nrhs_max,
+                                      const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* kd, cudaStream_t stream);
+
+
 int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs, int batch,
                                  int64_t n_max, gmg_stream_t stream) {
     if (!C) return -1;
@@ -324,9 +337,28 @@ int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const 
     if (n_max <= 0 || n_max > 65535 || n_max > M) return -6;
     dim3 grid((unsigned)gmg_ceil_div(M + 2, kGatherCols), (unsigned)gmg_ceil_div(n_max, kGatherRows),
               (unsigned)batch);                                               // columns M, M + 1: the extra RHS
-    gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C, M, ldc, descs);
+    gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C, M, ldc, descs, 0, -1);
     GMG_LAUNCH_CHECK();
     return GMG_OK;
+}
+
+int gmg_krige_solve_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* kd, const GmgSolveDesc* sd, int batch,
+                        int64_t n_max, gmg_stream_t stream) {
+    if (!C) return -1;
+    if (M <= 0) return -2;
+    if (ldc < M) return -3;
+    if (!kd) return -4;
+    if (!sd) return -5;
+    if (batch <= 0 || batch > 65535) return -6;
+    if (n_max <= 0 || n_max > 65535 || n_max > M) return -7;
+    // the on-the-fly rows are fetched with 16-byte cp.async: two columns per chunk, never straddling column M
+    if ((M & 1) || (ldc & 1) || (reinterpret_cast<uintptr_t>(C) & 15)) return GMG_ERR_UNSUPPORTED;
+    const int64_t sblocks = gmg_ceil_div(n_max, kGatherCols), tail = M / kGatherCols;
+    const bool extra = tail >= sblocks;
+    dim3 grid((unsigned)(sblocks + (extra ? 1 : 0)), (unsigned)gmg_ceil_div(n_max, kGatherRows), (unsigned)batch);
+    gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C, M, ldc, kd, M, extra ? (int)tail : -1);
+    GMG_LAUNCH_CHECK();
+    return gmg_internal_potrf_solve_gathered(sd, batch, n_max, M + 2, C, M, ldc, kd, (cudaStream_t)stream);
 }
 
 int gmg_krige_error_cov_lower_f64(const GmgKrigeDesc* descs, int b, int64_t n, double* out, int64_t ldo,

@@ -253,6 +253,17 @@ typedef struct GmgKrigeDesc {
 int gmg_krige_gather_batched_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* descs,
                                  int batch, int64_t n_max, gmg_stream_t stream);
 
+/* gather + Cholesky + forward triangular solve of a batch of kriging systems as ONE call on one GPU: S = C[idx, idx] + E
+ * is assembled, and the overlapped factor + forward-solve pipeline of gmg_potrf_solve_f64 runs with the right-hand
+ * sides [C[idx, :] | 1 | y] of every block row read from C ITSELF inside the solve step (only the two extra columns
+ * of T are written beforehand) - the n x M copy of C[idx, :] that gmg_krige_gather_batched_f64 writes, and the solve
+ * then reads back, never exists.  Results (S = L L^T, T = L^-1 [Cx | 1 | y], *info) are bit-identical to
+ * gmg_krige_gather_batched_f64 + gmg_potrf_solve_f64.  kd[b] and sd[b] describe the same system: sd[b].S = kd[b].S,
+ * sd[b].R = kd[b].T, sd[b].nrhs = M + 2; kd[b].Cx is not written.  Needs an even M and ldc and a 16-byte aligned C
+ * (GMG_ERR_UNSUPPORTED otherwise: use the two separate calls).  replaces kriging.py:337-343, :571-585. */
+int gmg_krige_solve_f64(const double* C, int64_t M, int64_t ldc, const GmgKrigeDesc* kd, const GmgSolveDesc* sd, int batch,
+                        int64_t n_max, gmg_stream_t stream);
+
 /* field = W y, variance = diag(C) - rowdot(W, Cx^T) [- 2 alpha], constraint mask = rowdot(W_simple,
  * Cx^T) / diag(C), alpha = Lagrange multiplier column, without forming W (M x n) or the reference's
  * M x M temporaries (kriging.py:417, :434-435, :487-491, :677-679, :699-701, :772-776).  Ordinary

@@ -631,6 +631,48 @@ def _one_entry_off(E):
     return E
 
 
+def test_rhs_gather_fused_into_the_solve_is_bit_identical(K, monkeypatch):
+    """`gmg_krige_solve_f64` reads the right-hand sides C[idx, :] of every block row inside the forward-solve step instead
+    of from a copy written by the gather kernel.  Same bits as gather + `gmg_potrf_solve_f64`: results, the solved
+    right-hand sides T and the factors S - ragged batch (sizes around the 128-block and 512-column boundaries, one
+    larger than the K limit of the two-CTA tile), simple and ordinary, no error covariance; a covariance of odd order
+    takes the separate calls by itself."""
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    cov = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, delta_x_method="Met_Office",
+                                   precision=np.float64).cov_ns_device
+    probs = []
+    for m, n in enumerate((1, 127, 129, 511, 513, 1341, 2300)):
+        idx, obs = synth.month_observations(m, cov.shape[0], n_min=n, n_max=n + 1)
+        E = None if m == 2 else synth.hadcrut_style_error_cov(idx, lons.size, seed=m)
+        probs.append((idx.astype(np.int64), obs.astype(np.float64), E))
+    for ordinary in (True, False):
+        fused = quiet(lambda: dn.KrigeBatch(cov, probs, ordinary=ordinary).run())
+        with monkeypatch.context() as mp:
+            mp.setattr(dn, "FUSED_RHS_GATHER", False)
+            plain = quiet(lambda: dn.KrigeBatch(cov, probs, ordinary=ordinary).run())
+        assert not fused.lu_fallback and not plain.lu_fallback
+        assert np.array_equal(fused.out.cpu().numpy(), plain.out.cpu().numpy())
+        for b in range(len(probs)):
+            n = fused.ns[b]
+            assert np.array_equal(fused._T_view(b)[:, :fused.nrhs].cpu().numpy(), plain._T_view(b)[:, :plain.nrhs].cpu().numpy()), b
+            assert np.array_equal(np.tril(fused.S(b)[:, :n].cpu().numpy()), np.tril(plain.S(b)[:, :n].cpu().numpy())), b
+    # odd order: 2591 cells
+    import torch
+
+    odd = cov[:2591, :2591].contiguous()
+    p2 = [(np.sort(np.random.default_rng(1).choice(2591, 300, replace=False)).astype(np.int64),
+           np.random.default_rng(2).standard_normal(300), None)]
+    a = quiet(lambda: dn.KrigeBatch(odd, p2, ordinary=True).run())
+    with monkeypatch.context() as mp:
+        mp.setattr(dn, "FUSED_RHS_GATHER", False)
+        b_ = quiet(lambda: dn.KrigeBatch(odd, p2, ordinary=True).run())
+    assert np.array_equal(a.out.cpu().numpy(), b_.out.cpu().numpy())
+
+
 def test_pipelined_driver_many_small_months(K):
     """40 problems take the pipelined route of `krige_batch` (ramped chunks, uploads on the side stream into the two
     persistent arenas, everything of a chunk in one blob, result planes copied home per chunk); a second call reuses
