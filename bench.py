@@ -1002,11 +1002,13 @@ def run_stochastic(args, rank, world, device, barrier, max_over_ranks, local, dm
             warnings.simplefilter("ignore")
             return stochastic_ensemble(cov, idx, obs, E, mine, seed=20140371 + rank, return_device=dev_out)
 
-    for _ in range(2):
-        step(True)
-    barrier()
+    # (the clock sampler starts BEFORE the warm-up calls: this leg is bound by host launch latency - ~12 ms of small
+    # kernels per call - and the sampler's start-up, a subprocess spawn, otherwise lands inside the timed calls)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        for _ in range(3):
+            step(True)
+        barrier()
         e0.record()
         for _ in range(args.stochastic_steps):
             r = step(True)
