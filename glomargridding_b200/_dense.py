@@ -236,7 +236,7 @@ def factor_inplace(S: torch.Tensor, n: int, what: str = "matrix") -> dict:
     check(lib().gmg_potrf_solve_f64(None, dt.data_ptr(), 1, n, 0, None, 0, dev.stream_ptr()), "gmg_potrf_solve_f64")
     code = int(ws["info"].item())
     if code != 0:
-        raise np.linalg.LinAlgError(
+        raise NotPositiveDefinite(
             f"{what} is not positive definite (Cholesky pivot {code} of {n} is not positive); "
             "apply glomar_gridding.covariance_tools.eigenvalue_clip or use delta_x_method='Met_Office'")
     return ws
@@ -750,6 +750,10 @@ def factor_inplace_distributed(S: torch.Tensor, n: int, group=None, what: str = 
     return ws
 
 
+class NotPositiveDefinite(np.linalg.LinAlgError):
+    """Cholesky met a non-positive pivot (callers with an LU route catch exactly this)."""
+
+
 def _raise_unless_spd(info_t: torch.Tensor, n: int, group, what: str) -> None:
     """Factorisation status of a (possibly distributed) factorisation: only the owner of a block sees its pivots."""
     import torch.distributed as dist
@@ -759,7 +763,7 @@ def _raise_unless_spd(info_t: torch.Tensor, n: int, group, what: str) -> None:
         dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
     code = int(info.item())
     if code != 0:
-        raise np.linalg.LinAlgError(
+        raise NotPositiveDefinite(
             f"{what} is not positive definite (Cholesky pivot {code} of {n} is not positive); "
             "apply glomar_gridding.covariance_tools.eigenvalue_clip or use delta_x_method='Met_Office'")
 
@@ -773,7 +777,8 @@ def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.T
     column m reads its prior variance at diag_base[m * ldc + m].  Used by the column-sharded multi-GPU path.
     With an initialised process group of more than one rank the factorisation is the distributed one
     (`factor_inplace_distributed`; `group=False` forces the local, replicated factorisation).
-    Returns the (5, Mc) result rows.  Raises LinAlgError if S is not positive definite (no LU fallback here)."""
+    Returns the (5, Mc) result rows.  Raises `NotPositiveDefinite` (a LinAlgError) if S is not positive definite - on
+    every rank alike; `solve_prepared_lu` is the route for such a system."""
     n = S.shape[0]
     for name, t in (("S", S), ("T", T), ("diag_base", diag_base), ("y", y)):  # the kernels read double*
         if t.dtype != torch.float64:
@@ -818,4 +823,41 @@ def solve_prepared(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.T
             print(f"[solve_prepared] factor + forward solve + apply, n = {n}: {1e3 * (time.perf_counter() - t0):.1f} ms",
                   flush=True)
     torch.cuda.current_stream().synchronize()
+    return out
+
+
+def solve_prepared_lu(S: torch.Tensor, T: torch.Tensor, Mc: int, diag_base: torch.Tensor, ldc: int, y: torch.Tensor,
+                      ordinary: bool) -> torch.Tensor:
+    """`solve_prepared` for a system Cholesky rejected: S (FULL n x n matrix, both triangles; overwritten by its LU
+    factors) is factored by the blocked LU with partial pivoting on THIS GPU (every rank of a sharded solve factors its
+    own replica - 0.35 s at n = 20 000 - and solves its own columns), T <- S^-1 T, and the apply pass is the full-solve
+    one (it needs the untouched C_cross columns: a copy of T[:, :Mc] is kept).  What np.linalg.solve does
+    (reference kriging.py:343, :585).  Raises LinAlgError("Singular matrix") for an exactly zero pivot."""
+    n = S.shape[0]
+    for name, t in (("S", S), ("T", T), ("diag_base", diag_base), ("y", y)):
+        if t.dtype != torch.float64:
+            raise TypeError(f"solve_prepared_lu: {name} must be float64, got {t.dtype}")
+    assert S.stride(1) == 1 and T.stride(1) == 1 and S.stride(0) % 2 == 0 and T.stride(0) % 2 == 0
+    assert T.shape[1] >= Mc + 2
+    Cx = torch.empty((n, Mc + (Mc & 1)), dtype=torch.float64, device=S.device)
+    Cx[:, :Mc] = T[:, :Mc]
+    lin, pdb, ldp = gesv_ws(n)
+    linv = torch.empty(lin, dtype=torch.float64, device=S.device)
+    strip = torch.empty(pdb, dtype=torch.float64, device=S.device)
+    info = torch.zeros(1, dtype=torch.int32, device=S.device)
+    slabs = (n + SLAB - 1) // SLAB
+    partial = torch.empty(4 * slabs * Mc, dtype=torch.float64, device=S.device)
+    out = torch.empty((5, Mc), dtype=torch.float64, device=S.device)
+    sd = np.zeros(1, dtype=SOLVE_DESC)
+    sd[0] = (S.data_ptr(), S.stride(0), linv.data_ptr(), T.data_ptr(), T.stride(0), strip.data_ptr(), ldp,
+             info.data_ptr(), n, Mc + 2)
+    kd = np.zeros(1, dtype=KRIGE_DESC)
+    kd[0] = (0, 0, n, y.data_ptr(), 0, 0, Cx.data_ptr(), Cx.stride(0), T.data_ptr(), T.stride(0), partial.data_ptr(),
+             out.data_ptr(), n, int(ordinary))
+    sdt, kdt = _desc_tensor(sd, S.device), _desc_tensor(kd, S.device)
+    L, s = lib(), dev.stream_ptr()
+    check(L.gmg_gesv_blocked_f64(sdt.data_ptr(), 1, n, Mc + 2, s), "gmg_gesv_blocked_f64")
+    check(L.gmg_krige_apply_batched_f64(diag_base.data_ptr(), Mc, ldc, kdt.data_ptr(), 1, n, 0, s), "apply")
+    if int(info.item()) != 0:                       # (synchronises before the temporaries die)
+        raise np.linalg.LinAlgError("Singular matrix")
     return out

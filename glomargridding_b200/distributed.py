@@ -22,6 +22,8 @@ covariance that lives in row blocks (e.g. `EllipseCovarianceBuilder(..., rows=(r
 
 from __future__ import annotations
 
+from warnings import warn
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -152,8 +154,19 @@ def krige_sharded(cov_rows: torch.Tensor, r0: int, idx, obs, error_cov=None, met
     mark("local right-hand sides")
     nrows, N = cov_rows.shape
     # local column j has its prior variance at cov_rows[j, r0 + j]
-    out = dn.solve_prepared(S, T, nrows, cov_rows.view(-1)[r0:], cov_rows.stride(0), y, method == "ordinary",
-                            group=group if distributed_cholesky else False)
+    try:
+        out = dn.solve_prepared(S, T, nrows, cov_rows.view(-1)[r0:], cov_rows.stride(0), y, method == "ordinary",
+                                group=group if distributed_cholesky else False)
+    except dn.NotPositiveDefinite as err:
+        # The reference solves by LU whatever the matrix (np.linalg.solve, kriging.py:343, :585): an indefinite
+        # C[idx, idx] + E - the default displacement method's covariance without eigenvalue_clip - goes through the
+        # blocked LU with partial pivoting instead.  Every rank saw the same status (it is reduced over the group), so
+        # all of them re-assemble the system (the factorisation overwrote it) and take this route together.
+        warn(f"{err}; solving by LU with partial pivoting like the reference does - slow path")
+        del S, T
+        S = assemble_obs_system(cov_rows, r0, idx_t, error_cov, group)
+        T = local_rhs(cov_rows, idx_t, y)
+        out = dn.solve_prepared_lu(S, T, nrows, cov_rows.view(-1)[r0:], cov_rows.stride(0), y, method == "ordinary")
     mark("factor + forward solve + apply")
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world > 1:

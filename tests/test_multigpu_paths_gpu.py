@@ -401,3 +401,29 @@ def test_asymmetric_error_cov_in_few_entries_is_detected(cuda):
     kbs = dn.KrigeBatch(C, prob, ordinary=True, symmetry="assume").run()
     assert kbs.lu_fallback == []
     assert max_norm_rel(kbs.out[0, dn.OUT_FIELD].cpu().numpy(), want_sym["field"]) <= TOL
+
+
+def test_krige_sharded_indefinite_covariance_takes_the_lu_like_the_reference(cuda):
+    """The DEFAULT displacement method's covariance is indefinite: the reference solves it by LU all the same
+    (np.linalg.solve); `krige_sharded` warns, re-assembles the system and goes through the blocked LU - one rank here,
+    every rank alike in a group - and agrees with the oracle's (= the reference's) formulation."""
+    import warnings
+
+    from glomargridding_b200.distributed import krige_sharded
+    from glomargridding_b200.ellipse import EllipseCovarianceBuilder
+    from oracle import ordinary_kriging, simple_kriging
+
+    lats, lons = synth.global_grid(5.0)
+    Lx, Ly, th, sd = synth.ellipse_fields(lats, lons)
+    b = EllipseCovarianceBuilder(Lx, Ly, th, sd, lats, lons, v=1.5, precision=np.float64)     # Modified_Met_Office
+    C, cov = b.cov_ns_device, b.cov_ns
+    idx, obs = synth.fixed_observations(7, C.shape[0], 700)
+    E = synth.hadcrut_style_error_cov(idx, lons.size)
+    for method, oracle in (("ordinary", ordinary_kriging), ("simple", simple_kriging)):
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            got = krige_sharded(C, 0, idx, obs, E, method)
+            want = oracle(cov, idx, obs, E)
+        assert any("LU with partial pivoting" in str(x.message) for x in w)
+        assert max_norm_rel(got["field"], want["field"]) <= 1e-6
+        assert max_norm_rel(got["constraint_mask"], want["constraint_mask"]) <= 1e-6
