@@ -74,7 +74,7 @@ def parse_args():
     ap.add_argument("--nobs-1deg", type=int, default=20000)
     ap.add_argument("--krige-1deg-steps", type=int, default=3)
     ap.add_argument("--members", type=int, default=200)
-    ap.add_argument("--stochastic-steps", type=int, default=5)
+    ap.add_argument("--stochastic-steps", type=int, default=20)
     ap.add_argument("--cpu-cols-1deg", type=int, default=1024,
                     help="grid columns the CPU arm of the 1-degree kriging solves for (scaled to 64 800)")
     ap.add_argument("--ref-batches", type=int, default=2, help="2M-pair batches of the reference's own batched loop per step")
