@@ -133,3 +133,37 @@ def test_exact_symmetry_test_of_error_covariances():
     assert lib().gmg_host_rows_symmetric(None, 0, 4, 4, 0, 4) == -1
     assert lib().gmg_host_rows_symmetric(E.ctypes.data, 0, 4, 3, 0, 4) == -3
     assert lib().gmg_host_rows_symmetric(E.ctypes.data, 0, 4, 4, 2, 5) == -5
+
+
+def test_native_packers_of_the_upload_pipeline():
+    """`gmg_host_pack_f64` (float64 or float32 source, widened) and `gmg_host_pack_f32` (float32 kept float32): strided
+    blocks -> contiguous staging memory, any destination alignment, NaN preserved; and the blob layout rule of
+    `_group_doubles` (float32 groups padded to whole doubles)."""
+    from glomargridding_b200 import _dense as dn
+    from glomargridding_b200._lib import lib
+
+    L = lib()
+    rng = np.random.default_rng(3)
+    E = rng.standard_normal((301, 301))
+    E[5, 7] = np.nan
+    for dtype in (np.float64, np.float32):
+        Es = E.astype(dtype)
+        for (r0, r1, c) in ((0, 128, 128), (128, 256, 256), (256, 301, 301), (0, 77, 77), (10, 11, 3)):
+            blk = Es[r0:r1, :c]
+            for shift in (0, 1, 2, 3):
+                buf = np.zeros(blk.size + 8, dtype=np.float64)
+                assert L.gmg_host_pack_f64(blk.ctypes.data, int(dtype == np.float32), blk.shape[0], blk.shape[1],
+                                           blk.strides[0] // blk.itemsize, buf[shift:].ctypes.data) == 0
+                assert np.array_equal(buf[shift:shift + blk.size].reshape(blk.shape), blk.astype(np.float64), equal_nan=True)
+                assert not buf[shift + blk.size:].any() and not buf[:shift].any()
+                if dtype == np.float32:
+                    b32 = np.zeros(blk.size + 8, dtype=np.float32)
+                    assert L.gmg_host_pack_f32(blk.ctypes.data, blk.shape[0], blk.shape[1], blk.strides[0] // 4,
+                                               b32[shift:].ctypes.data) == 0
+                    assert np.array_equal(b32[shift:shift + blk.size].reshape(blk.shape), blk, equal_nan=True)
+                    assert not b32[shift + blk.size:].any() and not b32[:shift].any()
+    assert L.gmg_host_pack_f32(None, 1, 1, 1, E.ctypes.data) == -1
+    assert L.gmg_host_pack_f32(E.ctypes.data, 2, 4, 3, E.ctypes.data) == -3
+    a32, a64 = np.zeros((3, 5), dtype=np.float32), np.zeros((3, 5))
+    assert dn._group_doubles([a32, a32], True) == 15 and dn._group_doubles([a32], True) == 8      # 30 -> 15, 15 -> 8
+    assert dn._group_doubles([a32, a64], True) == 23 and dn._group_doubles([a32], False) == 15
