@@ -32,7 +32,8 @@ from . import _dense as dn
 from .kriging import _finish_uncertainty
 
 
-def assemble_obs_system(cov_rows: torch.Tensor, r0: int, idx: torch.Tensor, error_cov, group=None) -> torch.Tensor:
+def assemble_obs_system(cov_rows: torch.Tensor, r0: int, idx: torch.Tensor, error_cov, group=None,
+                        meanwhile=None) -> torch.Tensor:
     """S = C[idx, idx] + E on every rank from row-block shards of C.  `idx` must be sorted ascending (then the
     rows each rank contributes are contiguous in S).  `error_cov` (n x n, host numpy or tensor, identical on every
     rank, or None): each rank adds - and, for a host array, uploads - only the rows of E that belong to the
@@ -41,7 +42,8 @@ def assemble_obs_system(cov_rows: torch.Tensor, r0: int, idx: torch.Tensor, erro
 
     The upload of this rank's rows of E runs on a side stream while the rank cuts its rows of C[idx, idx] out of its
     row block; the only exchange is ONE all-gather, straight into the buffer that becomes S (rows padded to the
-    largest per-rank count, compacted in place when the counts differ)."""
+    largest per-rank count, compacted in place when the counts differ).  `meanwhile` (optional callable) is run while
+    the all-gather is in flight - `krige_sharded` builds its right-hand sides there."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n = idx.numel()
     nrows = cov_rows.shape[0]
@@ -58,7 +60,11 @@ def assemble_obs_system(cov_rows: torch.Tensor, r0: int, idx: torch.Tensor, erro
         counts = ct.cpu().tolist()
     cap = max(counts)
     rank = dist.get_rank(group) if world > 1 else 0
-    buf = torch.zeros((world * cap, ldn), dtype=cov_rows.dtype, device=cov_rows.device)
+    # (no 3.2 GB memset at n = 20 000: every entry that is read later is written below - the pieces by their owners, the
+    # rest by the all-gather - except the padding column of an odd n)
+    buf = torch.empty((world * cap, ldn), dtype=cov_rows.dtype, device=cov_rows.device)
+    if ldn != n:
+        buf[:, n:] = 0
     piece = buf[rank * cap: rank * cap + (hi - lo), :n]
     if own.numel():
         piece.copy_(cov_rows[(idx[own] - r0).unsqueeze(1), idx.unsqueeze(0)])   # (n_mine, n), one fused gather (async)
@@ -84,8 +90,13 @@ def assemble_obs_system(cov_rows: torch.Tensor, r0: int, idx: torch.Tensor, erro
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         piece += e_rows.to(piece.dtype)
+    work = None
     if world > 1:
-        dist.all_gather_into_tensor(buf, buf[rank * cap:(rank + 1) * cap].clone(), group=group)
+        work = dist.all_gather_into_tensor(buf, buf[rank * cap:(rank + 1) * cap].clone(), group=group, async_op=True)
+    if meanwhile is not None:
+        meanwhile()
+    if work is not None:
+        work.wait()
     if sum(counts) != n:
         raise ValueError("the row blocks of the ranks do not cover every observation index")
     if all(c == cap for c in counts):
@@ -148,10 +159,11 @@ def krige_sharded(cov_rows: torch.Tensor, r0: int, idx, obs, error_cov=None, met
         raise ValueError("idx must be sorted ascending and unique for the sharded path")
     idx_t = torch.from_numpy(idx_np).to(device)
     y = torch.from_numpy(np.asarray(obs, dtype=np.float64)).to(device)
-    S = assemble_obs_system(cov_rows, r0, idx_t, error_cov, group)       # rows of an even-stride buffer
-    mark("assemble S (gather + E upload + all_gather)")
-    T = local_rhs(cov_rows, idx_t, y)
-    mark("local right-hand sides")
+    rhs = []
+    S = assemble_obs_system(cov_rows, r0, idx_t, error_cov, group,       # rows of an even-stride buffer
+                            meanwhile=lambda: rhs.append(local_rhs(cov_rows, idx_t, y)))
+    T = rhs[0]
+    mark("assemble S (gather + E upload + all_gather) with the local right-hand sides built meanwhile")
     nrows, N = cov_rows.shape
     # local column j has its prior variance at cov_rows[j, r0 + j]
     try:
