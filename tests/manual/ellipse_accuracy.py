@@ -3,8 +3,8 @@
 Used to judge kernel variants (GLOMAR_B200_LIB=<variant .so>)."""
 import os, sys
 import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
 from conftest import load_golden, max_rel
 from glomargridding_b200 import synthetic as synth

@@ -3,7 +3,7 @@
 covariance per member)."""
 import json, os, sys, time, warnings
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from glomargridding_b200 import synthetic as synth
 from glomargridding_b200.batched import stochastic_ensemble
