@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 2) potrf_diag_kernel(const GmgSo
     double* G = Dinv + NSB * SB * SB;            // [SB][DIAG_G_LD]
     double* rd = G + SB * DIAG_G_LD;             // [SB] reciprocal diagonal of the current sub-block
     __shared__ int s_info;
+    __shared__ double s_piv, s_col[SB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_info = 0;
     for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
@@ -79,40 +80,41 @@ __global__ void __launch_bounds__(DIAG_THREADS, 2) potrf_diag_kernel(const GmgSo
 
     for (int kb = 0; kb < NSB; ++kb) {
         const int k0 = kb * SB;
-        // (1) 16 x 16 diagonal sub-block, right-looking, in the registers of one warp: lane l holds row l & 15,
-        //     column values travel by shuffle (no shared-memory round trips on the critical path)
-        if (warp == 0) {
-            const int l = lane & (SB - 1);
-            double r[SB];
+        // (1) 16 x 16 diagonal sub-block, right-looking, ONE ELEMENT PER THREAD on warps 0..7 (thread 16 i + c holds
+        //     A[i][c]); per column: the pivot travels through shared memory, every thread of the column scales its own
+        //     entry, the column is posted, every thread right of it applies its one FMA.  Two 256-thread named barriers
+        //     per column.  (Round 1 / early round 2 ran this in the registers of a single warp with shuffles: 1 430
+        //     straight-line instructions executed by one warp while fifteen waited - a third of the kernel's time, ncu
+        //     r02.)  Same operations on the same operands: the factor is bit-identical.
+        if (tid < SB * SB) {
+            const int i = tid >> 4, c = tid & (SB - 1);
+            const bool low = c <= i;
+            double v = low ? AT(k0 + i, k0 + c) : 0.0;
             double my_rinv = 0.0;
 #pragma unroll
-            for (int c = 0; c < SB; ++c) r[c] = (c <= l) ? AT(k0 + l, k0 + c) : 0.0;
-#pragma unroll
             for (int j = 0; j < SB; ++j) {
-                const double piv = __shfl_sync(0xffffffffu, r[j], j);
-                if (!(piv > 0.0) && lane == 0 && s_info == 0) s_info = k0g + k0 + j + 1;   // also NaN
-                // 1/sqrt(piv) without libm calls (a call would spill the row registers): MUFU seed, one cubic
-                // step (< 2^-64), and sqrt(piv) = piv * rinv with one Heron correction
-                double rinv;
-                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(piv));
-                const double e = fma(-(piv * rinv), rinv, 1.0);
-                rinv = fma(rinv * e, fma(e, 0.375, 0.5), rinv);
-                double sq = piv * rinv;
-                sq = fma(fma(-sq, sq, piv), 0.5 * rinv, sq);
-                r[j] = (l == j) ? sq : r[j] * rinv;                  // column j of L (zero above the diagonal)
-                if (l == j) my_rinv = rinv;
-#pragma unroll
-                for (int k = j + 1; k < SB; ++k) {
-                    const double lkj = __shfl_sync(0xffffffffu, r[j], k);
-                    if (l >= k) r[k] = fma(-r[j], lkj, r[k]);
+                if (i == j && c == j) s_piv = v;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (c == j && i >= j) {
+                    const double piv = s_piv;
+                    if (!(piv > 0.0) && i == j && s_info == 0) s_info = k0g + k0 + j + 1;   // also NaN
+                    // 1/sqrt(piv) without libm calls: MUFU seed, one cubic step (< 2^-64), and sqrt(piv) = piv * rinv
+                    // with one Heron correction
+                    double rinv;
+                    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(piv));
+                    const double e = fma(-(piv * rinv), rinv, 1.0);
+                    rinv = fma(rinv * e, fma(e, 0.375, 0.5), rinv);
+                    double sq = piv * rinv;
+                    sq = fma(fma(-sq, sq, piv), 0.5 * rinv, sq);
+                    v = (i == j) ? sq : v * rinv;                        // column j of L
+                    if (i == j) my_rinv = rinv;
+                    s_col[i] = v;
                 }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (c > j && low) v = fma(-s_col[i], s_col[c], v);      // A[i][c] -= L[i][j] L[c][j]
             }
-            if (lane < SB) {
-#pragma unroll
-                for (int c = 0; c < SB; ++c)
-                    if (c <= l) AT(k0 + l, k0 + c) = r[c];
-                rd[l] = my_rinv;                                     // reciprocal diagonal 1 / L_ll
-            }
+            if (low) AT(k0 + i, k0 + c) = v;
+            if (i == c) rd[i] = my_rinv;                                 // reciprocal diagonal 1 / L_ii
         }
         __syncthreads();
         // (2) warp 0 inverts the sub-block (lane j = column j of the inverse, forward substitution in registers);
