@@ -502,7 +502,7 @@ def run_reference(args):
         line[key] = {"metric": names[key], "value": cb["value"], "unit": cb["unit"], "cpu_baseline": cb,
                      "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -756,7 +756,7 @@ def run_b200(args):
         "cpu_baseline": cpu, "fp64_peaks": fp64_peaks, "kriging": kriging, "kriging_1deg": kriging_1deg,
         "stochastic": stochastic, "ellipse_fit": ellipse_fit,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -1111,9 +1111,28 @@ def run_ellipse_fit(args, rank, world, device, barrier, max_over_ranks, local):
             "roofline": None, "e2e": e2e}
 
 
-if __name__ == "__main__":
+def emit(line):
+    """The one JSON line, written to the process's ORIGINAL stdout (see `main`)."""
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
+_JSON_FD = 1
+
+
+def main():
+    # stdout carries the JSON line and nothing else: file descriptor 1 points at stderr for the whole run (library
+    # banners, the reference's own print() calls - e.g. cov_2_cor's "Numerical error correction applied" - and
+    # anything a child writes land there), and `emit` writes the line to a duplicate of the original descriptor
+    global _JSON_FD
     a = parse_args()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)
+
+
+if __name__ == "__main__":
+    main()
