@@ -5,9 +5,12 @@ for f in sys.argv[1:]:
     r = d["roofline"]
     print(f"{f}: n_gpus {d['n_gpus']}")
     print(f"  cov {d['value']:.4g} {d['unit']}  {d['ms_per_step']:.2f} ms/step  kernel {r['kernel_ms']:.2f} ms  frac {r['frac']:.3f} (hbm {r['hbm']['frac']:.3f})  e2e {d['e2e']['value']:.3g}")
-    for k in ("kriging", "kriging_1deg", "stochastic", "ellipse_fit"):
+    for k in ("kriging", "kriging_1deg", "stochastic", "ellipse_fit", "notebook"):
         s = d.get(k)
         if not s:
+            continue
+        if "error" in s:
+            print(f"  {k}: ERROR {s['error']}")
             continue
         e = s.get("e2e") or {}
         f32 = (e.get("float32_error_cov") or {}).get("value")
