@@ -222,3 +222,61 @@ def test_builder_fits_every_cell_like_the_reference(E, builder, tag):
         one = b.fit_ellipse_model(k, m, estimate_SE=None, **kw)
     assert np.allclose(one["ModelParams"][:-1], got[k][:-1], rtol=1e-12) and one["Success"] == want[k, -2]
     assert one["Correlation"].shape == b.xy_shape
+
+
+def _correlation_distance(cov1, cov2):
+    """Correlation matrix distance of the reference's own test (`test/test_ellipse.py:23-34`)."""
+    from glomargridding_b200.utils import cov_2_cor
+
+    cor1, cor2 = cov_2_cor(cov1), cov_2_cor(cov2)
+    return 1 - np.trace(cor1 @ cor2) / (np.linalg.norm(cor1, ord="fro") * np.linalg.norm(cor2, ord="fro"))
+
+
+@pytest.mark.parametrize("ci, v, p, size", [(0, 1.5, {"Lx": 1500, "Ly": 800, "theta": np.pi / 3, "stdev": 0.6}, (10, 6)),
+                                            (1, 1.5, {"Lx": 3600, "Ly": 1700, "theta": 0.2, "stdev": 1.2}, (8, 8))])
+def test_const_ellipse_round_trip_like_the_reference(E, ci, v, p, size):
+    """The reference's own self-consistency test (`test/test_ellipse.py:85-174`: same parameters, sizes and thresholds)
+    with every step on the device path: covariance of constant ellipse parameters -> eigenvalue clip (99 %) -> 5 000
+    draws -> `EllipseBuilder.compute_params` -> `EllipseCovarianceBuilder` from the fitted parameters -> clip.  The
+    rebuilt covariance must match the sample covariance of the draws (rtol 5e-2, correlation matrix distance < 1e-4)
+    AND what the unmodified reference rebuilds from the same draws (`tests/golden/make_golden_const_ellipse.py`, which
+    also says why the draws come from the symmetric square root and not from numpy's SVD-based sampler)."""
+    from glomargridding_b200.covariance_tools import eigenvalue_clip
+
+    g = load_golden("const_ellipse.npz")
+    n = 5_000
+    lats, lons = np.arange(size[0], dtype=np.float32), np.arange(size[1], dtype=np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        true_cov = eigenvalue_clip(
+            E.EllipseCovarianceBuilder(np.full(size, p["Lx"]), np.full(size, p["Ly"]), np.full(size, p["theta"]),
+                                       np.full(size, p["stdev"]), v=v, lons=lons, lats=lats).cov_ns,
+            method="explained_variance", target_variance_fraction=0.99)
+        assert np.abs(true_cov - g[f"c{ci}_true_cov"]).max() <= 1e-4 * np.abs(true_cov).max()  # float32 builder default
+        w, V = np.linalg.eigh(g[f"c{ci}_true_cov"])                       # the draws of the fixture, to rounding
+        data = np.random.default_rng(2).standard_normal((n, w.size)) @ ((V * np.sqrt(np.clip(w, 0.0, None))) @ V.T)
+        in_cov = np.cov(data.T)
+        assert np.allclose(in_cov, g[f"c{ci}_in_cov"], rtol=1e-7, atol=1e-10)
+        coords = {"time": _Coord(np.arange(n)), "longitude": _Coord(lons), "latitude": _Coord(lats)}
+        model = E.EllipseModel(anisotropic=True, rotated=True, physical_distance=True, v=v, unit_sigma=True)
+        b = E.EllipseBuilder(data.reshape((n, *size)), coords)
+        params = b.compute_params(default_value=[0.0] * model.supercategory_n_params, matern_ellipse=model,
+                                  bounds=[(300.0, 30000.0), (300.0, 30000.0), (-2.0 * np.pi, 2.0 * np.pi)],
+                                  guesses=[300.0, 300.0, 0.0], max_distance=10_000.0,
+                                  delta_x_method="Modified_Met_Office")
+        val = lambda k: np.asarray(getattr(params[k], "values", params[k]))  # noqa: E731
+        cov = eigenvalue_clip(
+            E.EllipseCovarianceBuilder(val("Lx"), val("Ly"), val("theta"), val("standard_deviation"), lons=lons,
+                                       lats=lats, v=v).cov_ns,
+            method="explained_variance", target_variance_fraction=0.99)
+    # the reference's own assertions
+    assert np.allclose(cov, in_cov, rtol=5e-2)
+    assert _correlation_distance(in_cov, cov) < 1e-4
+    # ... and cell by cell against the unmodified reference's fit of the same draws
+    want = g[f"c{ci}_rows"]
+    got = np.column_stack([val(k).reshape(-1) for k in ("Lx", "Ly", "theta", "standard_deviation")])
+    rel = np.abs(got - want[:, :4]) / np.abs(want[:, :4])
+    dcov = float(np.abs(cov - g[f"c{ci}_cov"]).max() / np.abs(cov).max())
+    print(f"const ellipse {size}: parameters vs reference median {np.median(rel):.2e} max {rel.max():.2e}; "
+          f"rebuilt covariance vs reference {dcov:.2e}")
+    assert np.median(rel) <= 1e-4 and rel.max() <= 2e-2 and dcov <= 1e-3
