@@ -50,7 +50,11 @@ constexpr int DIAG_G_LD = NB - SB + 1;          // staging of one block row of L
 // 97 KB in all, so two of them - or one and a 92 KB GEMM CTA of the solve stream - fit on an SM (round 1 / early
 // round 2: 163 KB, one CTA per SM, 480 months = 3.2 waves of 134 us per block step with the rest of the SM idle).
 constexpr int DIAG_ROWS = NB / 2;
-constexpr size_t DIAG_SMEM = (size_t)(DIAG_ROWS * DIAG_LD + NSB * SB * SB + SB * DIAG_G_LD + SB) * sizeof(double);
+// inverted diagonal sub-blocks, rows padded to 17: in the block-row products of the inverse the lanes of a half warp read
+// 16 different ROWS of one sub-block at the same column - with a leading dimension of 16 doubles that is one bank, 16-way
+// (ncu r02b: 14 % of the kernel's stall samples on that one line)
+constexpr int DINV_LD = SB + 1;
+constexpr size_t DIAG_SMEM = (size_t)(DIAG_ROWS * DIAG_LD + NSB * SB * DINV_LD + SB * DIAG_G_LD + SB) * sizeof(double);
 __device__ __forceinline__ int diag_at(int i, int j) {           // element (i, j), j <= i, of the folded lower triangle
     return i < DIAG_ROWS ? i * DIAG_LD + (NB - j) : (NB - 1 - i) * DIAG_LD + j;
 }
@@ -63,8 +67,8 @@ __global__ void __launch_bounds__(DIAG_THREADS, 2) potrf_diag_kernel(const GmgSo
     const int nb = min(NB, d.n - k0g);
     extern __shared__ __align__(16) double sm[];
     double* A = sm;                              // [DIAG_ROWS][DIAG_LD], folded lower triangle (see diag_at)
-    double* Dinv = A + DIAG_ROWS * DIAG_LD;      // [NSB][SB][SB] inverted diagonal sub-blocks
-    double* G = Dinv + NSB * SB * SB;            // [SB][DIAG_G_LD]
+    double* Dinv = A + DIAG_ROWS * DIAG_LD;      // [NSB][SB][DINV_LD] inverted diagonal sub-blocks
+    double* G = Dinv + NSB * SB * DINV_LD;       // [SB][DIAG_G_LD]
     double* rd = G + SB * DIAG_G_LD;             // [SB] reciprocal diagonal of the current sub-block
     __shared__ int s_info;
     __shared__ double s_piv, s_col[SB];
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 2) potrf_diag_kernel(const GmgSo
 #pragma unroll
                     for (int k = 0; k < i; ++k) acc = fma(-AT(k0 + i, k0 + k), x[k], acc);
                     x[i] = (i < lane) ? 0.0 : acc * rd[i];
-                    Dinv[(kb * SB + i) * SB + lane] = x[i];
+                    Dinv[(kb * SB + i) * DINV_LD + lane] = x[i];
                 }
             }
         } else {
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 2) potrf_diag_kernel(const GmgSo
     //      X_ij = -Dinv_i (L_i,j..i-1 X_j..i-1,j)
     for (int e = tid; e < NSB * SB * SB; e += DIAG_THREADS) {
         const int kb = e / (SB * SB), i = (e / SB) % SB, j = e % SB;
-        if (j <= i) AT(kb * SB + i, kb * SB + j) = Dinv[e];
+        if (j <= i) AT(kb * SB + i, kb * SB + j) = Dinv[(kb * SB + i) * DINV_LD + j];
     }
     __syncthreads();
     for (int bi = 1; bi < NSB; ++bi) {
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 2) potrf_diag_kernel(const GmgSo
         for (int e = tid; e < SB * ncols; e += DIAG_THREADS) {
             const int r = e % SB, c = e / SB;
             double s = 0.0;
-            for (int q = 0; q <= r; ++q) s = fma(Dinv[(bi * SB + r) * SB + q], G[q * DIAG_G_LD + c], s);
+            for (int q = 0; q <= r; ++q) s = fma(Dinv[(bi * SB + r) * DINV_LD + q], G[q * DIAG_G_LD + c], s);
             AT(i0 + r, c) = -s;
         }
         __syncthreads();

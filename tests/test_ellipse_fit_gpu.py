@@ -279,4 +279,5 @@ def test_const_ellipse_round_trip_like_the_reference(E, ci, v, p, size):
     dcov = float(np.abs(cov - g[f"c{ci}_cov"]).max() / np.abs(cov).max())
     print(f"const ellipse {size}: parameters vs reference median {np.median(rel):.2e} max {rel.max():.2e}; "
           f"rebuilt covariance vs reference {dcov:.2e}")
-    assert np.median(rel) <= 1e-4 and rel.max() <= 2e-2 and dcov <= 1e-3
+    # measured on B200: parameters 6e-8 .. 1.3e-7 median, 1.9e-6 max; rebuilt covariance 2-3e-7 (float32 builder default)
+    assert np.median(rel) <= 1e-5 and rel.max() <= 1e-4 and dcov <= 1e-5
