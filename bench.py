@@ -759,6 +759,7 @@ def run_b200(args):
             notebook = run_notebook(args, rank, world, device, barrier, local)
         except Exception as e:
             notebook = {"error": repr(e)}
+        barrier()                  # the other ranks wait here, so that every rank leaves the process group together
 
     if rank != 0:
         if world > 1:

@@ -6,7 +6,7 @@
 TAG=${1:-r02}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --months 120 --month-steps 1 --no-kriging-1deg --no-stochastic --no-ellipse-fit --no-fp64-peaks > gpurun_out/${TAG}_launches.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --months 120 --month-steps 1 --no-kriging-1deg --no-stochastic --no-ellipse-fit --no-notebook --no-fp64-peaks > gpurun_out/${TAG}_launches.log 2>&1
 for NU in 2.2 1.5; do
   ncu --set full --clock-control none --import-source on -k regex:ellipse_cov_tile -c 1 -s 1 -f \
       -o gpurun_out/${TAG}_ellipse_full_nu${NU} python tools/profile_ellipse.py --nu $NU --rows 64800 --reps 2 \
