@@ -62,11 +62,21 @@ def launches():
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(PR, f"{TAG}_launches.md"), "w") as f:
         f.write(f"# {TAG}: launch list of `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --months 120 "
-                "--month-steps 1 --no-kriging-1deg --no-stochastic --no-ellipse-fit --no-fp64-peaks`\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 900` (per-launch times are "
-                "cold-cache and serialised: read the SHARES).  Includes warm-up launches.\n\n"
+                "--month-steps 1 --no-kriging-1deg --no-stochastic --no-ellipse-fit --no-notebook --no-fp64-peaks`\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 900` (per-launch times are "
+                "cold-cache and serialised: read the SHARES).  Includes warm-up launches: 3 + 2 covariance builds and the 64-row "
+                "probe of the builder, 2 + 1 month batches of 120.\n\n"
                 "| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k[:90]}` | {c} | {t:.3f} | {100 * t / tot:.1f}% |\n")
+        gemm = sum(t for k, (c, t) in agg.items() if any(x in k for x in ("trsm_", "potrf_colupdate", "potrf_panel", "potrf_update")))
+        month = sum(t for k, (c, t) in agg.items() if not k.startswith(("ellipse_", "matern_")))
+        tile = sum(t for k, (c, t) in agg.items() if k.startswith("ellipse_cov_tile_kernel<3"))
+        cov = sum(t for k, (c, t) in agg.items() if k.startswith(("ellipse_", "matern_")))
+        f.write("\nPer bench step the captured launches are: one covariance build = 1 tile kernel + prepare; one batch of 120 "
+                "months = 13 solve steps, 12 column updates, 13 diagonal blocks, 12 panels, 13 coefficient strips, gather, "
+                "reduce, finalize.\n"
+                f"Share of the covariance step held by the tile kernel: {100 * tile / cov:.1f} %; share of the month step held "
+                f"by the DMMA GEMM kernels (solve steps + column updates + panels + strips): {100 * gemm / month:.0f} %.\n")
 
 
 def kernels():
