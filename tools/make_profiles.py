@@ -98,6 +98,8 @@ def kernels():
                            "fp64_pipe_pct_of_peak": num(k["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"][0]) / 100,
                            "issue_active_pct": num(k["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]) / 100,
                            "source": f"gpurun_out/{fn} (ncu --set full, one launch of the full 1-degree build)"}
+    if len(lines) == 1:
+        return                              # no capture of this tag under gpurun_out/: keep the tracked summary
     with open(os.path.join(PR, f"{TAG}_kernels.md"), "w") as f:
         f.write("\n".join(lines) + "\n")
     if traffic:
