@@ -145,6 +145,30 @@ __device__ __forceinline__ void load_kcol_gather_c(double* s, const double* B, i
     }
 }
 
+// The DMMAs of one k-slab for the first V row fragments of a warp (V is a compile-time count: no predicates - ptxas turns
+// `if (i < valid) dmma` into PREDICATED DMMAs, which still take their turn on the tensor pipe: profiles/
+// r02b_ragged_fragments_ab.txt).  Fragment i of warp row wm holds tile rows i * RSTEP + wm * 8 .. + 7.
+template <int V, int MI, int NJ, int KB, bool TA, bool TB, int LDA, int LDB, int LDK_, int RSTEP, int WN>
+__device__ __forceinline__ void mma_slab(double (&acc)[MI][NJ][2], const double* __restrict__ sA,
+                                         const double* __restrict__ sB, int wm, int wn, int grp, int t4) {
+#pragma unroll
+    for (int k4 = 0; k4 < KB / 4; ++k4) {
+        double a[V], b[NJ];
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            a[i] = TA ? sA[(k4 * 4 + t4) * LDA + i * RSTEP + wm * 8 + grp]
+                      : sA[(i * RSTEP + wm * 8 + grp) * LDK_ + k4 * 4 + t4];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+            b[j] = TB ? sB[(wn * WN + j * 8 + grp) * LDK_ + k4 * 4 + t4]
+                      : sB[(k4 * 4 + t4) * LDB + wn * WN + j * 8 + grp];
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
 // D[m0.., n0..] = alpha op(A) op(B) + beta C for one BM x BNT tile.  `smem` = TileGeom<Cfg, BNT>::SMEM_BYTES, 16 B
 // aligned.  BNT = 128 or 64 for CfgBig (the narrow tile halves the work per CTA and is used by the triangular-solve
 // steps when the right-hand sides give fewer 128-column strips than the GPU has SMs), 64 for CfgSmall.
@@ -174,6 +198,17 @@ __device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem, c
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // Rows of the tile are dealt to the warps in 8-row DMMA fragments ROUND ROBIN: fragment i of warp row wm holds tile rows
+    // i * RSTEP + wm * 8 .. + 7 (RSTEP = 8 x warps along m = 32 for the 4 x 4 and 4 x 2 layouts).  A tile on the ragged
+    // bottom edge of a matrix (the last block row of a system whose order is not a multiple of 128: half a tile on average,
+    // and the forward-solve step with the longest K) then has the same number of valid fragments in every warp, and each
+    // warp issues only those.  Skipped fragments feed rows the epilogue never stores; every stored element sees the same
+    // operations in the same order as with contiguous bands, so results are bit-identical.
+    constexpr int RSTEP = WARPS_M * 8;
+    static_assert(MI == 4 || MI == 1, "fragment-count dispatch below is written for 4 or 1 row fragments per warp");
+    const int rows_left = g.m - m0 - wm * 8;
+    const int mi_valid = rows_left <= 0 ? 0 : (rows_left > (MI - 1) * RSTEP ? MI : (rows_left + RSTEP - 1) / RSTEP);
+
     const int nk = (g.k + KB - 1) / KB;
     auto load_stage = [&](int kt) {
         double* sA = smem + (size_t)(kt % NST) * G_::STAGE_DOUBLES;
@@ -196,22 +231,15 @@ __device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem, c
         cp_commit();
         const double* sA = smem + (size_t)(kt % NST) * G_::STAGE_DOUBLES;
         const double* sB = sA + G_::A_DOUBLES;
-#pragma unroll
-        for (int k4 = 0; k4 < KB / 4; ++k4) {
-            double a[MI], b[NJ];
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-                a[i] = TA ? sA[(k4 * 4 + t4) * LDA + wm * (MI * 8) + i * 8 + grp]
-                          : sA[(wm * (MI * 8) + i * 8 + grp) * LDK_ + k4 * 4 + t4];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j)
-                b[j] = TB ? sB[(wn * WN + j * 8 + grp) * LDK_ + k4 * 4 + t4]
-                          : sB[(k4 * 4 + t4) * LDB + wn * WN + j * 8 + grp];
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+#define GMG_SLAB(V) mma_slab<V, MI, NJ, KB, TA, TB, LDA, LDB, LDK_, RSTEP, WN>(acc, sA, sB, wm, wn, grp, t4)
+        if (mi_valid == MI) {
+            GMG_SLAB(MI);
+        } else if constexpr (MI == 4) {          // ragged bottom edge: the same count of valid fragments in every warp (+- 1)
+            if (mi_valid == 3) GMG_SLAB(3);
+            else if (mi_valid == 2) GMG_SLAB(2);
+            else if (mi_valid == 1) GMG_SLAB(1);
         }
+#undef GMG_SLAB
     }
     cp_wait<0>();
     __syncthreads();                         // all warps done with shared memory (callers may reuse it)
@@ -220,7 +248,7 @@ __device__ void gemm_tile_cfg(const TileArgs& g, int m0, int n0, double* smem, c
                         ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
-        const int row = m0 + wm * (MI * 8) + i * 8 + grp;
+        const int row = m0 + i * RSTEP + wm * 8 + grp;
         if (row >= g.m) continue;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
