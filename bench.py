@@ -42,8 +42,8 @@ DFMA_PEAK_TFLOPS = 34.2     # plain DFMA, same file
 # instruction count of the shipped kernel, which is then frozen as the algorithmic figure"): frozen at the round-1
 # kernel's count - 50 FP64 pipe instructions per pair for general nu (degree-7 Matern table), 43 for the closed forms
 # (profiles/r01_kernels.md).  Each holds one FP64 issue slot and is counted as one FMA slot (2 flop)
-# against the DFMA rate measured in the run.  The kernel shipped now executes K1_FP64_EXECUTED of them (degree-6
-# table, round 2): doing the same job with fewer instructions shows up as time, not as a smaller numerator.
+# against the DFMA rate measured in the run.  The kernel shipped now executes K1_FP64_EXECUTED of them (degree-5
+# table with 32 sub-intervals per octave, round 2; 94 per two pairs in the SASS of the row loop): doing the same job with fewer instructions shows up as time, not as a smaller numerator.
 K1_FP64_INSTR_PER_PAIR = {"table": 50.0, "closed": 43.0}
 K1_FP64_EXECUTED = {"table": 47.0, "closed": 43.0}
 
