@@ -27,6 +27,16 @@ def test_library_exports_every_declared_symbol():
     assert b"invalid argument" in L.gmg_strerror(-3)
 
 
+def test_every_entry_point_is_mapped_to_the_reference_in_integration_md():
+    """INTEGRATION.md's table says, for each exported entry point, which reference lines it replaces (or that it has no
+    counterpart); a new export without a row fails here."""
+    from glomargridding_b200._lib import exported_symbols
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in exported_symbols() if s not in text and not (s.startswith("gmg_ipc_") and "gmg_ipc_" in text)]
+    assert not missing, missing
+
+
 def test_argument_validation_without_gpu():
     """Bad arguments are rejected before any CUDA call: negative return = 1-based argument index."""
     from glomargridding_b200._lib import lib
