@@ -1258,7 +1258,9 @@ def run_ellipse_fit(args, rank, world, device, barrier, max_over_ranks, local):
 
 def emit(line):
     """The one JSON line, written to the process's ORIGINAL stdout (see `main`)."""
-    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+    data = (json.dumps(line) + "\n").encode()
+    while data:                                   # a pipe may take a 12 KB line in pieces
+        data = data[os.write(_JSON_FD, data):]
 
 
 _JSON_FD = 1
